@@ -1,0 +1,192 @@
+/*
+ * smcb200.h - C-ABI of the B200-native likelihood-tempered SMC hot path.
+ *
+ * One shared library (libsmcb200.so, hand-written sm_100a CUDA) replaces the
+ * body of the reference sampler loop.  The reference has no FFI; its de-facto
+ * interface is a handful of Python call sites, cited per entry point below
+ * (paths relative to the upstream repository):
+ *
+ *   EX/main = SMC_example/Micmem_SMC_main.py      EX/lik = SMC_example/Micmem_likelihood.py
+ *   EX/set  = SMC_example/Micmem_settings.py      ME/lik = SMC_methanation/methanation_set_likelihood.py
+ *   ME/fun  = SMC_methanation/methanation_functions.py
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - Pointers named *_dev are device pointers owned by the caller (the Python
+ *     host keeps them alive as torch tensors); *_host are host pointers.
+ *   - Particle state is SoA: theta_dev[k*ld + i] is parameter k of local
+ *     particle i (ld >= n, the leading dimension in elements).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Every call is asynchronous on that stream unless it says "synchronous".
+ *   - Every function returns 0 on success or a negative SMCB_ERR_* code; the
+ *     message is available from smcb_last_error().  A non-finite likelihood is
+ *     a value (-inf), never an error.
+ *   - The library allocates device scratch only in smcb_create / smcb_reserve /
+ *     smcb_set_data_*; nothing is allocated on the hot path.
+ *   - There is no CPU fallback: without a CUDA device smcb_create fails.
+ */
+#ifndef SMCB200_H
+#define SMCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMCB_OK 0
+#define SMCB_ERR_INVALID (-1)     /* bad argument                               */
+#define SMCB_ERR_CUDA (-2)        /* a CUDA runtime call failed                 */
+#define SMCB_ERR_STATE (-3)       /* call order (e.g. data not set, no reserve) */
+#define SMCB_ERR_UNSUPPORTED (-4) /* size / option outside what is compiled in  */
+
+/* likelihood models */
+#define SMCB_MODEL_MM_PROGRESS 1 /* EX/lik:35-77: six progress curves, scipy-RK45 twin */
+#define SMCB_MODEL_MM_RATE 2     /* synthetic rate-law observations (S_i, v_i)         */
+#define SMCB_MODEL_KINETIC_RK 3  /* methanation-style plug-flow reactor, fixed-step RK4 */
+
+/* resampling prefix-sum arithmetic */
+#define SMCB_SCAN_SEQUENTIAL 0 /* the reference's sequentially rounded FP64 sum (EX/main:165-174), bit-exact */
+#define SMCB_SCAN_FIXED 1      /* exact 2^-62 fixed-point parallel scan, independent of sharding */
+
+#define SMCB_MAX_DIM 32        /* max estimated parameters d                  */
+#define SMCB_MAX_CAND 16       /* max tempering candidates per pass           */
+
+typedef struct smcb_handle smcb_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int smcb_version(void);
+/* Replaces ray.init (EX/main:56): binds the handle to one CUDA device. */
+int smcb_create(int device, smcb_handle** out);
+int smcb_destroy(smcb_handle* h);
+const char* smcb_last_error(const smcb_handle* h); /* h may be NULL: last create error */
+/* Size the scratch for at most n_max local particles / slots and d_max parameters. */
+int smcb_reserve(smcb_handle* h, int64_t n_max, int d_max);
+/* Number of kernels this handle has launched so far (for bench.py's gpu_launches). */
+int64_t smcb_launch_count(const smcb_handle* h);
+
+/* ---- data (replaces the module globals `dataset`, `n_ex`, `datapoint`, EX/set:103-115) - */
+/* t, P: [n_ex][n_t] row-major; S0: [n_ex].  Synchronous (copies to the device). */
+int smcb_set_data_mm_progress(smcb_handle* h, const double* t_host, const double* P_host,
+                              const double* S0_host, int n_ex, int n_t);
+/* S, v: [n_obs].  precision: 64 = FP64 arithmetic, 32 = FP32 arithmetic with FP32 accumulation
+ * in 64-observation tiles and FP64 across tiles. */
+int smcb_set_data_mm_rate(smcb_handle* h, const double* S_host, const double* v_host,
+                          int64_t n_obs, int precision);
+/* Methanation-style reactor (ME/lik:44-66,204-208,289-298; reactor definition in DESIGN.md).
+ * cond: [n_cond][SMCB_KIN_NCOND_FIELDS] row-major operating conditions
+ *       (Ca,Cb,Cc,Cd,Ce inlet [mol/m3], T_in [K], T_jacket [K], u_in [m/s], void, length [m]);
+ * obs:  [5][n_cond] outlet flows [sccm] (the layout of ME's `data.csv`);
+ * base: [n_pairs*2+1] full parameter vector (A_j,E_j pairs then sigma) used for positions that
+ *       are not estimated; est_pos: [d] positions of the estimated parameters in that vector
+ *       (ME/fun:80 `p_pred_bases[:, est_position] = particle`). */
+#define SMCB_KIN_NCOND_FIELDS 10
+int smcb_set_data_kinetic(smcb_handle* h, const double* cond_host, const double* obs_host, int n_cond,
+                          const double* base_host, int n_pairs, const int* est_pos_host, int d,
+                          int n_steps);
+
+/* ---- K1: per-particle log-likelihood (replaces sim_particle, EX/lik:79-92, ME/fun:70-92) */
+/* lk_dev[i] = log-likelihood of particle i for i<n.  active_dev (may be NULL) is a byte mask:
+ * particles with active==0 are skipped and lk_dev[i] is left untouched. */
+int smcb_loglik(smcb_handle* h, int model, const double* theta_dev, int64_t ld, int64_t n, int d,
+                const uint8_t* active_dev, double* lk_dev, void* stream);
+/* Model predictions for a few particles (the `C_l_` the reference returns for its parity plots,
+ * EX/lik:74-77): pred_dev[i][n_ex][n_t].  MM_PROGRESS only. */
+int smcb_predict_mm_progress(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n,
+                             double* pred_dev, void* stream);
+/* Work counters of the last MM_PROGRESS sweep: out_host[0]=RHS evaluations, [1]=accepted steps,
+ * [2]=rejected steps, [3]=failed solves.  Synchronous. */
+int smcb_loglik_stats(smcb_handle* h, int64_t* out_host);
+
+/* ---- K2: tempering reductions (replaces EX/main:116-134) --------------------------------- */
+/* out_dev[0] = max_i lk[i]  (NaN-free input assumed; -inf allowed). */
+int smcb_lk_max(smcb_handle* h, const double* lk_dev, int64_t n, double* out_dev, void* stream);
+/* For each candidate increment gm_k (k<n_cand<=SMCB_MAX_CAND, host array):
+ *   out_dev[2k] = sum_i exp((lk_i-max)*gm_k),  out_dev[2k+1] = sum_i exp((lk_i-max)*gm_k)^2.
+ * max_dev points to the (already all-reduced) maximum on the device. */
+int smcb_temper_sums(smcb_handle* h, const double* lk_dev, int64_t n, const double* max_dev,
+                     const double* gm_host, int n_cand, double* out_dev, void* stream);
+
+/* ---- K3: residual-systematic resampling (replaces EX/main:147-184) ----------------------- */
+/* Normalised weights p_weight_i = exp((lk_i-max)*gm)/sum_w  (EX/main:124-130). */
+int smcb_weights(smcb_handle* h, const double* lk_dev, int64_t n, const double* max_dev, double gm,
+                 const double* sum_w_dev, double* w_dev, void* stream);
+/* From normalised weights to copy counts.
+ *   n_total  : global particle count N (inv_Np = 1/N), n: local particles,
+ *   u0       : the single U[0,1) draw (EX/main:156),
+ *   mode     : SMCB_SCAN_SEQUENTIAL or SMCB_SCAN_FIXED,
+ *   carry_host[2] (SEQUENTIAL, may be NULL = {0, u0/N}): running sum and threshold entering this
+ *              shard; on return (synchronous in that case) holds the values leaving it,
+ *   carry_q  (FIXED): exclusive prefix of the fixed-point residual totals of lower ranks,
+ *   id_offset: global index of this shard's first particle (the very first particle of the run
+ *              starts with zero thresholds crossed, which matters only when u0 == 0),
+ *   counts_dev int32[n]: copies per particle (floor + crossing),
+ *   totals_dev: int64[2] = {sum of floor counts, sum of fixed-point residuals (FIXED) or crossings
+ *              (SEQUENTIAL)} of this shard. */
+int smcb_resample_counts(smcb_handle* h, const double* w_dev, int64_t n, int64_t n_total, double u0,
+                         int mode, double* carry_host, uint64_t carry_q, int64_t id_offset,
+                         int32_t* counts_dev, int64_t* totals_dev, void* stream);
+/* First half of the FIXED mode for sharded runs: floor counts and fixed-point residuals only.
+ * totals_dev int64[2] = {sum floor, sum q}.  Call smcb_resample_counts afterwards with carry_q. */
+int smcb_resample_totals(smcb_handle* h, const double* w_dev, int64_t n, int64_t n_total,
+                         int64_t* totals_dev, void* stream);
+/* Expand counts into the non-decreasing ancestor vector: ancestors_dev[s] for s<m is the local
+ * index of the particle copied into slot s.  If sum(counts) < m the tail is padded with the last
+ * ancestor; copies beyond m are dropped.  filled_dev int64[1] = sum(counts). */
+int smcb_ancestors(smcb_handle* h, const int32_t* counts_dev, int64_t n, int64_t m,
+                   int32_t* ancestors_dev, int64_t* filled_dev, void* stream);
+/* Vectorised gather of particle state: dst[k*ld_dst+s] = src[k*ld_src+anc[s]] for k<rows, s<m. */
+int smcb_gather(smcb_handle* h, const double* src_dev, int64_t ld_src, const int32_t* ancestors_dev,
+                int64_t m, int rows, double* dst_dev, int64_t ld_dst, void* stream);
+
+/* ---- K4: Metropolis-Hastings mutation (replaces EX/main:209-249) ------------------------- */
+/* Column sums: out_dev[k] = sum_i theta[k][i]. */
+int smcb_colsum(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n, int d,
+                double* out_dev, void* stream);
+/* Centred second moments: out_dev[a*d+b] = sum_i (theta[a][i]-mean[a])*(theta[b][i]-mean[b]).
+ * mean_dev: device pointer to d doubles (the all-reduced mean). */
+int smcb_centered_moments(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n, int d,
+                          const double* mean_dev, double* out_dev, void* stream);
+/* Proposal: prop = theta + (z @ F) * ratio, z ~ N(0,I_d)  (EX/main:220), followed by the box test
+ * of the uniform prior (EX/main:224-228): inbox[i] = all_k low_k <= prop_k <= high_k; out-of-box
+ * proposals are replaced by the current particle.
+ *   F_host[d*d] row-major factor (x = z @ F), low_host/high_host[d].
+ *   z_dev: external normals [n][d] row-major (parity mode) or NULL = Philox4x32-10 keyed by
+ *   (seed, global particle id = id_offset+i, stage, sweep). */
+int smcb_mh_propose(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n, int d,
+                    const double* F_host, double ratio, const double* low_host, const double* high_host,
+                    const double* z_dev, uint64_t seed, uint64_t id_offset, uint32_t stage, uint32_t sweep,
+                    double* prop_dev, int64_t ld_prop, uint8_t* inbox_dev, void* stream);
+/* Accept step (EX/main:231-241): r = exp((lk2-lk1)*gamma)*inbox >= u; theta/lk updated in place;
+ * moved_dev[i] |= r; counts_dev int64[3] += {accepted this sweep, newly moved, in-box proposals
+ * (= likelihood evaluations this sweep performed)}.
+ *   u_dev: external uniforms [n] or NULL = Philox (same key, separate stream id). */
+int smcb_mh_accept(smcb_handle* h, double* theta_dev, int64_t ld, double* lk_dev, const double* prop_dev,
+                   int64_t ld_prop, const double* lk2_dev, const uint8_t* inbox_dev, int64_t n, int d,
+                   double gamma, const double* u_dev, uint64_t seed, uint64_t id_offset, uint32_t stage,
+                   uint32_t sweep, uint8_t* moved_dev, int64_t* counts_dev, void* stream);
+/* Several MH sweeps fused in one launch with a frozen proposal factor (documented deviation from
+ * the per-sweep covariance refresh of EX/main:212): propose + box + likelihood + accept, particle
+ * state held in registers.  KINETIC_RK.  counts_dev int64[3] as for smcb_mh_accept. */
+int smcb_mh_fused(smcb_handle* h, int model, double* theta_dev, int64_t ld, double* lk_dev, int64_t n, int d,
+                  const double* F_host, double ratio, const double* low_host, const double* high_host,
+                  double gamma, int n_sweeps, uint64_t seed, uint64_t id_offset, uint32_t stage,
+                  uint32_t sweep0, uint8_t* moved_dev, int64_t* counts_dev, void* stream);
+
+/* ---- utilities ---------------------------------------------------------------------------- */
+/* Philox draws exactly as the kernels make them, for tests: z_dev [n][d], u_dev [n] (either NULL). */
+int smcb_philox_draws(smcb_handle* h, int64_t n, int d, uint64_t seed, uint64_t id_offset, uint32_t stage,
+                      uint32_t sweep, double* z_dev, double* u_dev, void* stream);
+/* Uniform prior sample: theta[k][i] = low_k + (high_k-low_k)*U, Philox keyed (seed, id, 0xFFFFFFFF, k). */
+int smcb_sample_uniform_box(smcb_handle* h, double* theta_dev, int64_t ld, int64_t n, int d,
+                            const double* low_host, const double* high_host, uint64_t seed,
+                            uint64_t id_offset, void* stream);
+/* Sustained FP64 FMA and FP32 FMA rates of this device (micro-benchmark, used as the roofline
+ * denominator for the compute-bound likelihood kernels): out_host[0]=FP64 FLOP/s, [1]=FP32 FLOP/s.
+ * Synchronous. */
+int smcb_measure_fma_peak(smcb_handle* h, double* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMCB200_H */

@@ -309,3 +309,39 @@ def run(loglik, p_pred, low, high, cfg: Settings, stream, lk0=None, hook=None):
             break
         gamma_old = gamma_new
     return p_pred, lk, tr
+
+
+# --------------------------------------------------------------------------- fixed-point scan twin
+TWO62 = 1 << 62
+
+
+def resample_fixed(p_weight, u0, N=None):
+    """The engine's FIXED scan arithmetic, restated with exact Python/NumPy integers.
+
+    Same floor counts and residuals as the reference (`trunc(w*N)`, `w - p_is*inv_Np`), but the
+    residuals are quantised to 2^-62 fixed point (round-to-nearest-even, negatives clamped to 0),
+    summed exactly, and particle j receives `cross(s_j) - cross(s_{j-1})` extra copies where
+    `cross(s) = floor((s*N - u0q)/2^62) + 1` counts thresholds (u0+k)/N <= s.  No rounding depends on
+    the order of summation, so the result is independent of blocking and sharding.
+    Returns (ancestors, counts, info).
+    """
+    w = np.array(p_weight, dtype=np.float64)
+    n = w.shape[0]
+    N = n if N is None else N
+    inv_Np = 1 / N
+    fl = np.trunc(w * N)
+    resid = w - fl * inv_Np
+    rq = np.maximum(resid * float(TWO62), 0.0)
+    q = np.rint(rq).astype(np.uint64).astype(object)       # exact Python ints
+    u0q = int(np.rint(u0 * float(TWO62)))
+    s = 0
+    c_prev = 0          # nothing is crossed before the first particle
+    counts = np.zeros(n, dtype=np.int64)
+    for j in range(n):
+        s += int(q[j])
+        x = s * N
+        c = 0 if x < u0q else ((x - u0q) >> 62) + 1
+        counts[j] = int(fl[j]) + (c - c_prev)
+        c_prev = c
+    ancestors = np.repeat(np.arange(n, dtype=np.int64), counts)
+    return ancestors, counts, dict(n_floor=int(fl.sum()), q_total=s, n_filled=int(counts.sum()))

@@ -1,0 +1,247 @@
+// C-ABI entry points that are not kernels themselves: lifetime, scratch, data upload, dispatch.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <vector>
+
+#include "common.cuh"
+
+char g_create_err[512] = {0};
+
+int smcb_fail(smcb_handle* h, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    char* dst = h ? h->err : g_create_err;
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+namespace {
+
+template <typename T>
+int dev_alloc(smcb_handle* h, T** p, size_t count) {
+    if (*p) {
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    if (count == 0) return SMCB_OK;
+    CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+    return SMCB_OK;
+}
+
+template <typename T>
+void dev_free(T** p) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+}
+
+// ---- FMA peak micro-benchmarks ---------------------------------------------------------------
+__global__ void fma64_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void fma32_kernel(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-9f, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+          a7 = a0 + 7;
+    const float m = 1.0000001f, c = 1e-9f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace
+
+extern "C" int smcb_version(void) { return SMCB_VERSION; }
+
+extern "C" const char* smcb_last_error(const smcb_handle* h) { return h ? h->err : g_create_err; }
+
+extern "C" int64_t smcb_launch_count(const smcb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int smcb_create(int device, smcb_handle** out) {
+    if (out == nullptr) return smcb_fail(nullptr, SMCB_ERR_INVALID, "smcb_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return smcb_fail(nullptr, SMCB_ERR_CUDA,
+                         "smcb_create: no CUDA device (%s); this library has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count)
+        return smcb_fail(nullptr, SMCB_ERR_INVALID, "smcb_create: device %d out of range [0,%d)", device, count);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return smcb_fail(nullptr, SMCB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess)
+        return smcb_fail(nullptr, SMCB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return smcb_fail(nullptr, SMCB_ERR_UNSUPPORTED,
+                         "smcb_create: device is sm_%d%d; this library is built for sm_100a (B200) only",
+                         prop.major, prop.minor);
+    smcb_handle* h = new smcb_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    e = cudaMalloc(reinterpret_cast<void**>(&h->stats), 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(h->stats, 0, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->seq_carry), 4 * sizeof(double));
+    if (e != cudaSuccess) {
+        smcb_fail(nullptr, SMCB_ERR_CUDA, "smcb_create: cudaMalloc: %s", cudaGetErrorString(e));
+        delete h;
+        return SMCB_ERR_CUDA;
+    }
+    *out = h;
+    return SMCB_OK;
+}
+
+extern "C" int smcb_destroy(smcb_handle* h) {
+    if (!h) return SMCB_OK;
+    cudaSetDevice(h->device);
+    dev_free(&h->ssr); dev_free(&h->partial); dev_free(&h->stats); dev_free(&h->task_counter);
+    dev_free(&h->floor_cnt); dev_free(&h->resid_q); dev_free(&h->resid_f); dev_free(&h->tile_tot);
+    dev_free(&h->tile_tot2); dev_free(&h->mark); dev_free(&h->seq_carry);
+    dev_free(&h->mmp.t); dev_free(&h->mmp.P); dev_free(&h->mmp.S0);
+    dev_free(&h->mmr.S); dev_free(&h->mmr.v); dev_free(&h->mmr.Sv32);
+    dev_free(&h->kin.cond); dev_free(&h->kin.obs); dev_free(&h->kin.base); dev_free(&h->kin.est_pos);
+    delete h;
+    return SMCB_OK;
+}
+
+extern "C" int smcb_reserve(smcb_handle* h, int64_t n_max, int d_max) {
+    REQUIRE(h, h != nullptr, SMCB_ERR_INVALID, "null handle");
+    REQUIRE(h, n_max > 0 && d_max >= 1 && d_max <= SMCB_MAX_DIM, SMCB_ERR_INVALID, "bad sizes");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rows = 1;
+    if (h->mmp.n_ex > rows) rows = h->mmp.n_ex;
+    if (h->kin.n_cond > rows) rows = h->kin.n_cond;
+    int rc;
+    if ((rc = dev_alloc(h, &h->ssr, (size_t)rows * n_max))) return rc;
+    h->ssr_rows = rows;
+    h->partial_len = (int64_t)h->sm_count * 8 * 80 + 8192;
+    if ((rc = dev_alloc(h, &h->partial, (size_t)h->partial_len))) return rc;
+    if ((rc = dev_alloc(h, &h->floor_cnt, (size_t)n_max))) return rc;
+    if ((rc = dev_alloc(h, &h->resid_q, (size_t)n_max))) return rc;
+    if ((rc = dev_alloc(h, &h->resid_f, (size_t)n_max))) return rc;
+    if ((rc = dev_alloc(h, &h->mark, (size_t)n_max))) return rc;
+    const size_t tiles = (size_t)(n_max + 2047) / 2048 + 8;
+    if ((rc = dev_alloc(h, &h->tile_tot, 2 * tiles))) return rc;
+    if ((rc = dev_alloc(h, &h->tile_tot2, 2 * tiles))) return rc;
+    h->n_max = n_max;
+    h->d_max = d_max;
+    return SMCB_OK;
+}
+
+extern "C" int smcb_set_data_mm_progress(smcb_handle* h, const double* t_host, const double* P_host,
+                                         const double* S0_host, int n_ex, int n_t) {
+    REQUIRE(h, h && t_host && P_host && S0_host, SMCB_ERR_INVALID, "null pointer");
+    REQUIRE(h, n_ex >= 1 && n_t >= 2, SMCB_ERR_INVALID, "need n_ex>=1 and n_t>=2");
+    for (int e = 0; e < n_ex; ++e)
+        for (int i = 1; i < n_t; ++i)
+            REQUIRE(h, t_host[e * n_t + i] > t_host[e * n_t + i - 1], SMCB_ERR_INVALID,
+                    "t must be strictly increasing within an experiment");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc;
+    const size_t m = (size_t)n_ex * n_t;
+    if ((rc = dev_alloc(h, &h->mmp.t, m))) return rc;
+    if ((rc = dev_alloc(h, &h->mmp.P, m))) return rc;
+    if ((rc = dev_alloc(h, &h->mmp.S0, (size_t)n_ex))) return rc;
+    CUDA_TRY(h, cudaMemcpy(h->mmp.t, t_host, m * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->mmp.P, P_host, m * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->mmp.S0, S0_host, n_ex * sizeof(double), cudaMemcpyHostToDevice));
+    h->mmp.n_ex = n_ex;
+    h->mmp.n_t = n_t;
+    if (h->n_max > 0 && n_ex > h->ssr_rows) return smcb_reserve(h, h->n_max, h->d_max);
+    return SMCB_OK;
+}
+
+extern "C" int smcb_set_data_mm_rate(smcb_handle* h, const double* S_host, const double* v_host, int64_t n_obs,
+                                     int precision) {
+    REQUIRE(h, h && S_host && v_host && n_obs > 0, SMCB_ERR_INVALID, "bad argument");
+    REQUIRE(h, precision == 32 || precision == 64, SMCB_ERR_INVALID, "precision must be 32 or 64");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc;
+    if ((rc = dev_alloc(h, &h->mmr.S, (size_t)n_obs))) return rc;
+    if ((rc = dev_alloc(h, &h->mmr.v, (size_t)n_obs))) return rc;
+    if ((rc = dev_alloc(h, &h->mmr.Sv32, (size_t)n_obs))) return rc;
+    CUDA_TRY(h, cudaMemcpy(h->mmr.S, S_host, n_obs * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->mmr.v, v_host, n_obs * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<float2> packed((size_t)n_obs);
+    for (int64_t i = 0; i < n_obs; ++i) packed[i] = make_float2((float)S_host[i], (float)v_host[i]);
+    CUDA_TRY(h, cudaMemcpy(h->mmr.Sv32, packed.data(), n_obs * sizeof(float2), cudaMemcpyHostToDevice));
+    h->mmr.n_obs = n_obs;
+    h->mmr.precision = precision;
+    return SMCB_OK;
+}
+
+extern "C" int smcb_loglik(smcb_handle* h, int model, const double* theta_dev, int64_t ld, int64_t n, int d,
+                           const uint8_t* active_dev, double* lk_dev, void* stream) {
+    REQUIRE(h, h && theta_dev && lk_dev, SMCB_ERR_INVALID, "null pointer");
+    REQUIRE(h, n >= 0 && ld >= n, SMCB_ERR_INVALID, "need 0<=n<=ld");
+    cudaStream_t st = as_stream(stream);
+    switch (model) {
+        case SMCB_MODEL_MM_PROGRESS:
+            REQUIRE(h, d == 3, SMCB_ERR_INVALID, "MM_PROGRESS expects d=3 (Vmax, Km, sigma)");
+            return launch_loglik_mm_progress(h, theta_dev, ld, n, active_dev, lk_dev, nullptr, st);
+        case SMCB_MODEL_MM_RATE:
+            REQUIRE(h, d == 3, SMCB_ERR_INVALID, "MM_RATE expects d=3 (Vmax, Km, sigma)");
+            return launch_loglik_mm_rate(h, theta_dev, ld, n, active_dev, lk_dev, st);
+        case SMCB_MODEL_KINETIC_RK:
+            return launch_loglik_kinetic(h, theta_dev, ld, n, d, active_dev, lk_dev, st);
+        default:
+            return smcb_fail(h, SMCB_ERR_INVALID, "smcb_loglik: unknown model %d", model);
+    }
+}
+
+extern "C" int smcb_predict_mm_progress(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n,
+                                        double* pred_dev, void* stream) {
+    REQUIRE(h, h && theta_dev && pred_dev && n > 0 && ld >= n, SMCB_ERR_INVALID, "bad argument");
+    return launch_loglik_mm_progress(h, theta_dev, ld, n, nullptr, nullptr, pred_dev, as_stream(stream));
+}
+
+extern "C" int smcb_loglik_stats(smcb_handle* h, int64_t* out_host) {
+    REQUIRE(h, h && out_host, SMCB_ERR_INVALID, "null pointer");
+    CUDA_TRY(h, cudaMemcpy(out_host, h->stats, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return SMCB_OK;
+}
+
+extern "C" int smcb_measure_fma_peak(smcb_handle* h, double* out_host) {
+    REQUIRE(h, h && out_host, SMCB_ERR_INVALID, "null pointer");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int threads = 256, blocks = h->sm_count * 8, iters = 1 << 15;
+    double* buf = nullptr;
+    CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&buf), (size_t)threads * blocks * sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float ms = 0.f;
+    for (int rep = 0; rep < 2; ++rep) {   // first repetition warms up
+        cudaEventRecord(e0);
+        fma64_kernel<<<blocks, threads>>>(buf, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    h->launches += 2;
+    out_host[0] = 2.0 * 8 * (double)iters * threads * blocks / (ms * 1e-3);
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(e0);
+        fma32_kernel<<<blocks, threads>>>(reinterpret_cast<float*>(buf), iters * 4);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    h->launches += 2;
+    out_host[1] = 2.0 * 8 * (double)iters * 4 * threads * blocks / (ms * 1e-3);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    CUDA_TRY(h, cudaGetLastError());
+    return SMCB_OK;
+}

@@ -1,0 +1,136 @@
+// Shared declarations for libsmcb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/smcb200.h"
+
+#define SMCB_VERSION 100
+#define FULL_MASK 0xffffffffu
+
+struct MmProgressData {
+    double* t = nullptr;   // [n_ex][n_t]
+    double* P = nullptr;   // [n_ex][n_t]
+    double* S0 = nullptr;  // [n_ex]
+    int n_ex = 0, n_t = 0;
+};
+
+struct MmRateData {
+    double* S = nullptr;   // [n_obs] FP64
+    double* v = nullptr;
+    float2* Sv32 = nullptr;  // [n_obs] packed (S, v) FP32
+    int64_t n_obs = 0;
+    int precision = 64;
+    double sum_v2 = 0.0;   // sum v^2 (host, FP64)
+};
+
+struct KineticData {
+    double* cond = nullptr;   // [n_cond][SMCB_KIN_NCOND_FIELDS]
+    double* obs = nullptr;    // [5][n_cond]
+    double* base = nullptr;   // [n_pairs*2+1]
+    int* est_pos = nullptr;   // [d]
+    int n_cond = 0, n_pairs = 0, d = 0, n_steps = 0;
+};
+
+struct smcb_handle {
+    int device = 0;
+    int sm_count = 0;
+    int64_t launches = 0;
+    char err[512] = {0};
+    // scratch (smcb_reserve)
+    int64_t n_max = 0;
+    int d_max = 0;
+    double* ssr = nullptr;           // [n_ex][n_max]   per-(experiment,particle) residual sums
+    int64_t ssr_rows = 0;
+    double* partial = nullptr;       // block partials for reductions
+    int64_t partial_len = 0;
+    unsigned long long* stats = nullptr;  // 4 counters (device)
+    int* task_counter = nullptr;     // dynamic task queue head
+    int32_t* floor_cnt = nullptr;    // [n_max]
+    uint64_t* resid_q = nullptr;     // [n_max] fixed-point residuals
+    double* resid_f = nullptr;       // [n_max] FP64 residuals (sequential mode)
+    int64_t* tile_tot = nullptr;     // [2*tiles] tile totals (floor, q)
+    int64_t* tile_tot2 = nullptr;    // second tile array (ancestor expansion)
+    int32_t* mark = nullptr;         // [n_max] head marks for the ancestor fill
+    double* seq_carry = nullptr;     // [4] sequential-scan carry (device)
+    MmProgressData mmp;
+    MmRateData mmr;
+    KineticData kin;
+};
+
+extern char g_create_err[512];
+
+int smcb_fail(smcb_handle* h, int code, const char* fmt, ...);
+
+#define CUDA_TRY(h, expr)                                                                  \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return smcb_fail((h), SMCB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,           \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);                  \
+    } while (0)
+
+#define LAUNCH_CHECK(h)                                                                    \
+    do {                                                                                   \
+        (h)->launches++;                                                                   \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess)                                                             \
+            return smcb_fail((h), SMCB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",       \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);                  \
+    } while (0)
+
+#define REQUIRE(h, cond, code, msg)                                                        \
+    do {                                                                                   \
+        if (!(cond)) return smcb_fail((h), (code), "%s: %s", __func__, (msg));             \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ------------------------------------------------------------------ warp / block reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+// Block-wide sum of K doubles per thread; result valid in thread 0.  smem: K*32 doubles.
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double* smem) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) smem[k * 32 + wid] = v[k];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double x = (lane < nw) ? smem[k * 32 + lane] : 0.0;
+            v[k] = warp_sum(x);
+        }
+    }
+    __syncthreads();
+}
+
+// kernels implemented across translation units
+int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, int64_t n,
+                              const uint8_t* active, double* lk, double* pred, cudaStream_t st);
+int launch_loglik_mm_rate(smcb_handle* h, const double* theta, int64_t ld, int64_t n,
+                          const uint8_t* active, double* lk, cudaStream_t st);
+int launch_loglik_kinetic(smcb_handle* h, const double* theta, int64_t ld, int64_t n, int d,
+                          const uint8_t* active, double* lk, cudaStream_t st);

@@ -1,0 +1,377 @@
+// K4: Metropolis-Hastings mutation.  Replaces SMC_example/Micmem_SMC_main.py:209-249:
+//   cov = np.cov(p_filt.T, bias=True) * w_cov          -> colsum + centred second moments (two-pass,
+//                                                         like np.cov), factorised on the host (d<=32)
+//   p_pred = p_filt + MVN(0,cov,N) * mhstep_ratio      -> smcb_mh_propose (z @ F, z from Philox or given)
+//   p0 = prior(p_pred) > 0; replace out-of-box         -> same kernel (closed box test)
+//   r = exp((lk2-lk1)*gamma)*p0 >= U; select; r_ac     -> smcb_mh_accept
+#include "common.cuh"
+#include "philox.cuh"
+
+int final_colsum(smcb_handle* h, const double* partial, int nb, int ncol, double* out, cudaStream_t st);
+
+namespace {
+
+constexpr int MB = 256;
+
+struct MhParams {
+    double F[SMCB_MAX_DIM * SMCB_MAX_DIM];   // row-major, x = z @ F
+    double low[SMCB_MAX_DIM];
+    double high[SMCB_MAX_DIM];
+};
+
+struct MeanVec {
+    double m[SMCB_MAX_DIM];
+};
+
+// ---- column sums ------------------------------------------------------------------------------
+// grid = (blocks, d): block (b, k) reduces a strided slice of row k
+__global__ void __launch_bounds__(MB)
+colsum_partial_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, double* __restrict__ partial) {
+    __shared__ double sm[32];
+    const int k = blockIdx.y, d = gridDim.y;
+    const double* row = theta + (int64_t)k * ld;
+    double v[1] = {0.0};
+    const int64_t stride = (int64_t)gridDim.x * MB;
+    for (int64_t i = (int64_t)blockIdx.x * MB + threadIdx.x; i < n; i += stride) v[0] += row[i];
+    block_sum<1>(v, sm);
+    if (threadIdx.x == 0) partial[(int64_t)blockIdx.x * d + k] = v[0];
+}
+
+// ---- centred second moments, small d: every thread keeps the D(D+1)/2 upper triangle ------------
+template <int D>
+__global__ void __launch_bounds__(MB)
+moments_small_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const double* __restrict__ mean,
+                     double* __restrict__ partial) {
+    constexpr int NP = D * (D + 1) / 2;
+    __shared__ double sm[NP * 32];
+    double mu[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) mu[a] = mean[a];
+    double acc[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) acc[q] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * MB;
+    for (int64_t i = (int64_t)blockIdx.x * MB + threadIdx.x; i < n; i += stride) {
+        double x[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) x[a] = theta[(int64_t)a * ld + i] - mu[a];
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int b = a; b < D; ++b) {
+                acc[q] = fma(x[a], x[b], acc[q]);
+                ++q;
+            }
+    }
+    block_sum<NP>(acc, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) partial[(int64_t)blockIdx.x * NP + q] = acc[q];
+    }
+}
+
+// ---- centred second moments, general d<=32: particles staged in shared memory, one (a,b) pair
+// per thread (threads >= d(d+1)/2 idle).  Block = 544 threads covers d=32 (528 pairs).
+constexpr int GEN_THREADS = 544;
+constexpr int GEN_TILE = 64;   // particles per shared-memory tile
+__global__ void __launch_bounds__(GEN_THREADS)
+moments_general_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, int d,
+                       const double* __restrict__ mean, double* __restrict__ partial) {
+    __shared__ double sx[SMCB_MAX_DIM][GEN_TILE + 1];
+    const int npair = d * (d + 1) / 2;
+    int a = 0, b = 0;
+    if ((int)threadIdx.x < npair) {   // unrank (a<=b) from the linear upper-triangle index
+        int q = threadIdx.x;
+        while (q >= d - a) {
+            q -= d - a;
+            ++a;
+        }
+        b = a + q;
+    }
+    double acc = 0.0;
+    const int64_t n_tiles = (n + GEN_TILE - 1) / GEN_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i0 = tile * GEN_TILE;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < d * GEN_TILE; idx += GEN_THREADS) {
+            const int k = idx / GEN_TILE, j = idx - k * GEN_TILE;
+            sx[k][j] = (i0 + j < n) ? theta[(int64_t)k * ld + i0 + j] - mean[k] : 0.0;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < npair) {
+#pragma unroll 8
+            for (int j = 0; j < GEN_TILE; ++j) acc = fma(sx[a][j], sx[b][j], acc);
+        }
+    }
+    if ((int)threadIdx.x < npair) partial[(int64_t)blockIdx.x * npair + threadIdx.x] = acc;
+}
+
+// expand packed upper triangle to a full symmetric d x d matrix
+__global__ void unpack_sym_kernel(const double* __restrict__ packed, int d, double* __restrict__ out) {
+    const int t = threadIdx.x;
+    if (t >= d * d) return;
+    int a = t / d, b = t - a * d;
+    if (a > b) {
+        const int c = a;
+        a = b;
+        b = c;
+    }
+    const int q = a * d - a * (a - 1) / 2 + (b - a);
+    out[t] = packed[q];
+}
+
+// ---- proposal -------------------------------------------------------------------------------------
+// DT>0: compile-time dimension (registers, fully unrolled); DT==0: run-time d<=32 (local array).
+template <int DT>
+__global__ void __launch_bounds__(MB)
+propose_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, int d_rt, const __grid_constant__ MhParams prm,
+               double ratio, const double* __restrict__ z_ext, uint64_t seed, uint64_t id_offset, uint32_t stage,
+               uint32_t sweep, double* __restrict__ prop, int64_t ld_prop, uint8_t* __restrict__ inbox) {
+    const int64_t i = (int64_t)blockIdx.x * MB + threadIdx.x;
+    if (i >= n) return;
+    const int d = DT ? DT : d_rt;
+    double step[DT ? DT : SMCB_MAX_DIM];
+#pragma unroll
+    for (int k = 0; k < (DT ? DT : SMCB_MAX_DIM); ++k) step[k] = 0.0;
+    // x = z @ F  accumulated row by row (j outer) so only two normals are live at a time
+#pragma unroll
+    for (int j = 0; j < d; j += 2) {
+        double z0, z1 = 0.0;
+        if (z_ext != nullptr) {
+            z0 = z_ext[i * d + j];
+            if (j + 1 < d) z1 = z_ext[i * d + j + 1];
+        } else {
+            philox_normal2(seed, id_offset + (uint64_t)i, stage, sweep, (uint32_t)(j >> 1), &z0, &z1);
+        }
+#pragma unroll
+        for (int k = 0; k < d; ++k) step[k] += z0 * prm.F[j * d + k];
+        if (j + 1 < d) {
+#pragma unroll
+            for (int k = 0; k < d; ++k) step[k] += z1 * prm.F[(j + 1) * d + k];
+        }
+    }
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+        const double cur = theta[(int64_t)k * ld + i];
+        const double x = __dadd_rn(cur, __dmul_rn(step[k], ratio));   // p_filt + MVN*mhstep_ratio
+        step[k] = x;
+        ok = ok && (x >= prm.low[k]) && (x <= prm.high[k]);          // closed box (uniform pdf > 0)
+    }
+#pragma unroll
+    for (int k = 0; k < d; ++k)
+        prop[(int64_t)k * ld_prop + i] = ok ? step[k] : theta[(int64_t)k * ld + i];
+    inbox[i] = ok ? 1 : 0;
+}
+
+// ---- accept ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MB)
+accept_kernel(double* __restrict__ theta, int64_t ld, double* __restrict__ lk, const double* __restrict__ prop,
+              int64_t ld_prop, const double* __restrict__ lk2, const uint8_t* __restrict__ inbox, int64_t n, int d,
+              double gamma, const double* __restrict__ u_ext, uint64_t seed, uint64_t id_offset, uint32_t stage,
+              uint32_t sweep, uint8_t* __restrict__ moved, unsigned long long* __restrict__ counts) {
+    __shared__ long long sm[3][32];
+    const int64_t i = (int64_t)blockIdx.x * MB + threadIdx.x;
+    long long acc = 0, newly = 0, evald = 0;
+    if (i < n) {
+        const double u = (u_ext != nullptr)
+                             ? u_ext[i]
+                             : philox_uniform(seed, id_offset + (uint64_t)i, stage, sweep, SMCB_SLOT_UNIFORM);
+        double pp = 0.0;
+        double l2 = 0.0;
+        if (inbox[i]) {
+            evald = 1;
+            l2 = lk2[i];
+            pp = exp(__dmul_rn(__dsub_rn(l2, lk[i]), gamma));   // exp(px*gamma_new)*p0
+        }
+        const bool r = pp >= u;   // NaN compares false, as in NumPy
+        if (r) {
+            acc = 1;
+            if (inbox[i]) {
+                for (int k = 0; k < d; ++k) theta[(int64_t)k * ld + i] = prop[(int64_t)k * ld_prop + i];
+                lk[i] = l2;
+            }
+            if (!moved[i]) {
+                moved[i] = 1;
+                newly = 1;
+            }
+        }
+    }
+    acc = warp_sum_ll(acc);
+    newly = warp_sum_ll(newly);
+    evald = warp_sum_ll(evald);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        sm[0][wid] = acc;
+        sm[1][wid] = newly;
+        sm[2][wid] = evald;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        acc = (lane < MB / 32) ? sm[0][lane] : 0;
+        newly = (lane < MB / 32) ? sm[1][lane] : 0;
+        evald = (lane < MB / 32) ? sm[2][lane] : 0;
+        acc = warp_sum_ll(acc);
+        newly = warp_sum_ll(newly);
+        evald = warp_sum_ll(evald);
+        if (lane == 0) {
+            if (acc) atomicAdd(&counts[0], (unsigned long long)acc);
+            if (newly) atomicAdd(&counts[1], (unsigned long long)newly);
+            if (evald) atomicAdd(&counts[2], (unsigned long long)evald);
+        }
+    }
+}
+
+__global__ void philox_draws_kernel(int64_t n, int d, uint64_t seed, uint64_t id_offset, uint32_t stage,
+                                    uint32_t sweep, double* __restrict__ z, double* __restrict__ u) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (z != nullptr) {
+        for (int j = 0; j < d; j += 2) {
+            double z0, z1;
+            philox_normal2(seed, id_offset + (uint64_t)i, stage, sweep, (uint32_t)(j >> 1), &z0, &z1);
+            z[i * d + j] = z0;
+            if (j + 1 < d) z[i * d + j + 1] = z1;
+        }
+    }
+    if (u != nullptr) u[i] = philox_uniform(seed, id_offset + (uint64_t)i, stage, sweep, SMCB_SLOT_UNIFORM);
+}
+
+struct BoxParams {
+    double low[SMCB_MAX_DIM];
+    double high[SMCB_MAX_DIM];
+};
+
+__global__ void sample_box_kernel(double* __restrict__ theta, int64_t ld, int64_t n, int d, const BoxParams bx,
+                                  uint64_t seed, uint64_t id_offset) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < d; ++k) {
+        const double u = philox_uniform(seed, id_offset + (uint64_t)i, 0xFFFFFFFFu, (uint32_t)k, 0u);
+        theta[(int64_t)k * ld + i] = bx.low[k] + (bx.high[k] - bx.low[k]) * u;
+    }
+}
+
+inline int moments_grid(const smcb_handle* h, int64_t n) {
+    int64_t nb = (n + MB - 1) / MB;
+    const int64_t cap = (int64_t)h->sm_count * 4;
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    return (int)nb;
+}
+
+}  // namespace
+
+extern "C" int smcb_colsum(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n, int d, double* out_dev,
+                           void* stream) {
+    REQUIRE(h, h && theta_dev && out_dev && n > 0 && d >= 1 && d <= SMCB_MAX_DIM && ld >= n, SMCB_ERR_INVALID,
+            "bad argument");
+    REQUIRE(h, h->partial != nullptr, SMCB_ERR_STATE, "smcb_reserve has not been called");
+    cudaStream_t st = as_stream(stream);
+    const int nb = moments_grid(h, n);
+    colsum_partial_kernel<<<dim3(nb, d), MB, 0, st>>>(theta_dev, ld, n, h->partial);
+    LAUNCH_CHECK(h);
+    return final_colsum(h, h->partial, nb, d, out_dev, st);
+}
+
+extern "C" int smcb_centered_moments(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n, int d,
+                                     const double* mean_dev, double* out_dev, void* stream) {
+    REQUIRE(h, h && theta_dev && mean_dev && out_dev && n > 0 && d >= 1 && d <= SMCB_MAX_DIM && ld >= n,
+            SMCB_ERR_INVALID, "bad argument");
+    REQUIRE(h, h->partial != nullptr, SMCB_ERR_STATE, "smcb_reserve has not been called");
+    cudaStream_t st = as_stream(stream);
+    const int npair = d * (d + 1) / 2;
+    int nb = moments_grid(h, n);
+    switch (d) {
+#define CASE(D)                                                                                        \
+    case D:                                                                                            \
+        moments_small_kernel<D><<<nb, MB, 0, st>>>(theta_dev, ld, n, mean_dev, h->partial);            \
+        break;
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6)
+#undef CASE
+        default: {
+            const int64_t tiles = (n + GEN_TILE - 1) / GEN_TILE;
+            nb = (int)((tiles < (int64_t)h->sm_count * 2) ? tiles : (int64_t)h->sm_count * 2);
+            moments_general_kernel<<<nb, GEN_THREADS, 0, st>>>(theta_dev, ld, n, d, mean_dev, h->partial);
+        }
+    }
+    LAUNCH_CHECK(h);
+    double* packed = h->partial + (int64_t)nb * npair;
+    int rc = final_colsum(h, h->partial, nb, npair, packed, st);
+    if (rc) return rc;
+    unpack_sym_kernel<<<1, 1024, 0, st>>>(packed, d, out_dev);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+extern "C" int smcb_mh_propose(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n, int d,
+                               const double* F_host, double ratio, const double* low_host, const double* high_host,
+                               const double* z_dev, uint64_t seed, uint64_t id_offset, uint32_t stage,
+                               uint32_t sweep, double* prop_dev, int64_t ld_prop, uint8_t* inbox_dev, void* stream) {
+    REQUIRE(h, h && theta_dev && F_host && low_host && high_host && prop_dev && inbox_dev, SMCB_ERR_INVALID,
+            "null pointer");
+    REQUIRE(h, n > 0 && d >= 1 && d <= SMCB_MAX_DIM && ld >= n && ld_prop >= n, SMCB_ERR_INVALID, "bad size");
+    REQUIRE(h, sweep < (1u << 24), SMCB_ERR_INVALID, "sweep index too large");
+    MhParams prm;
+    memset(&prm, 0, sizeof(prm));
+    memcpy(prm.F, F_host, sizeof(double) * d * d);
+    memcpy(prm.low, low_host, sizeof(double) * d);
+    memcpy(prm.high, high_host, sizeof(double) * d);
+    const unsigned grid = (unsigned)((n + MB - 1) / MB);
+    cudaStream_t st = as_stream(stream);
+#define PROPOSE(DT)                                                                                              \
+    propose_kernel<DT><<<grid, MB, 0, st>>>(theta_dev, ld, n, d, prm, ratio, z_dev, seed, id_offset, stage, sweep, \
+                                            prop_dev, ld_prop, inbox_dev)
+    switch (d) {
+        case 1: PROPOSE(1); break;
+        case 2: PROPOSE(2); break;
+        case 3: PROPOSE(3); break;
+        case 4: PROPOSE(4); break;
+        case 5: PROPOSE(5); break;
+        case 6: PROPOSE(6); break;
+        case 8: PROPOSE(8); break;
+        default: PROPOSE(0);
+    }
+#undef PROPOSE
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+extern "C" int smcb_mh_accept(smcb_handle* h, double* theta_dev, int64_t ld, double* lk_dev, const double* prop_dev,
+                              int64_t ld_prop, const double* lk2_dev, const uint8_t* inbox_dev, int64_t n, int d,
+                              double gamma, const double* u_dev, uint64_t seed, uint64_t id_offset, uint32_t stage,
+                              uint32_t sweep, uint8_t* moved_dev, int64_t* counts_dev, void* stream) {
+    REQUIRE(h, h && theta_dev && lk_dev && prop_dev && lk2_dev && inbox_dev && moved_dev && counts_dev,
+            SMCB_ERR_INVALID, "null pointer");
+    REQUIRE(h, n > 0 && d >= 1 && d <= SMCB_MAX_DIM && ld >= n && ld_prop >= n, SMCB_ERR_INVALID, "bad size");
+    accept_kernel<<<(unsigned)((n + MB - 1) / MB), MB, 0, as_stream(stream)>>>(
+        theta_dev, ld, lk_dev, prop_dev, ld_prop, lk2_dev, inbox_dev, n, d, gamma, u_dev, seed, id_offset, stage,
+        sweep, moved_dev, reinterpret_cast<unsigned long long*>(counts_dev));
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+extern "C" int smcb_philox_draws(smcb_handle* h, int64_t n, int d, uint64_t seed, uint64_t id_offset, uint32_t stage,
+                                 uint32_t sweep, double* z_dev, double* u_dev, void* stream) {
+    REQUIRE(h, h && n > 0 && d >= 1 && d <= SMCB_MAX_DIM, SMCB_ERR_INVALID, "bad argument");
+    philox_draws_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(n, d, seed, id_offset, stage,
+                                                                                  sweep, z_dev, u_dev);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+extern "C" int smcb_sample_uniform_box(smcb_handle* h, double* theta_dev, int64_t ld, int64_t n, int d,
+                                       const double* low_host, const double* high_host, uint64_t seed,
+                                       uint64_t id_offset, void* stream) {
+    REQUIRE(h, h && theta_dev && low_host && high_host && n > 0 && d >= 1 && d <= SMCB_MAX_DIM && ld >= n,
+            SMCB_ERR_INVALID, "bad argument");
+    BoxParams bx;
+    memset(&bx, 0, sizeof(bx));
+    memcpy(bx.low, low_host, sizeof(double) * d);
+    memcpy(bx.high, high_host, sizeof(double) * d);
+    sample_box_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(theta_dev, ld, n, d, bx, seed,
+                                                                                id_offset);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}

@@ -1,0 +1,478 @@
+// K3: residual-systematic resampling.  Replaces the serial Python loop of the reference
+// (SMC_example/Micmem_SMC_main.py:147-184):
+//
+//     p_is = trunc(w*N);  w -= p_is*inv_Np;  wrand = u0*inv_Np
+//     for j: sum += w[j];  if sum >= wrand: p_is[j]++, wrand += inv_Np;  emit p_is[j] copies of j
+//
+// Two prefix-sum arithmetics:
+//   SEQUENTIAL  one warp walks the residuals with the reference's sequentially rounded FP64
+//               running sum and sequentially incremented threshold: bit-exact ancestors.
+//   FIXED       residuals are quantised to 2^-62 fixed point and summed exactly in integers with
+//               a blocked parallel scan; the number of thresholds (u0+k)/N at or below a prefix s
+//               is cross(s) = floor((s*N - u0q)/2^62)+1, evaluated in 128-bit integers.  The
+//               result is independent of block structure and of how particles are sharded.
+// Copy counts are expanded to the (non-decreasing) ancestor vector by marking the first slot of
+// each surviving particle and running a max-scan; particle state then moves with one gather.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SB = 256;               // scan block
+constexpr int IPT = 8;                // items per thread
+constexpr int TILE = SB * IPT;        // 2048
+constexpr double TWO62 = 4611686018427387904.0;
+
+// ---------------------------------------------------------------------------------------------
+// block-wide exclusive scan of one value per thread (sum for uint64/int64, max for int32)
+struct OpAdd {
+    template <typename T>
+    __device__ __forceinline__ T operator()(T a, T b) const { return a + b; }
+};
+struct OpMax {
+    template <typename T>
+    __device__ __forceinline__ T operator()(T a, T b) const { return a > b ? a : b; }
+};
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_exclusive_scan(T v, T identity, Op op, T* smem /*[32]*/, T* block_total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    T incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T up = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl = op(up, incl);
+    }
+    if (lane == 31) smem[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        T w = (lane < SB / 32) ? smem[lane] : identity;
+        T wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T up = __shfl_up_sync(FULL_MASK, wi, o);
+            if (lane >= o) wi = op(up, wi);
+        }
+        if (lane < SB / 32) smem[lane] = wi;   // inclusive over warps
+    }
+    __syncthreads();
+    T excl = __shfl_up_sync(FULL_MASK, incl, 1);
+    if (lane == 0) excl = identity;
+    if (wid > 0) excl = op(smem[wid - 1], excl);
+    *block_total = smem[SB / 32 - 1];
+    __syncthreads();
+    return excl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prepare: floor counts and residuals from normalised weights; per-tile totals
+template <int MODE>
+__global__ void __launch_bounds__(SB)
+prepare_kernel(const double* __restrict__ w, int64_t n, double Nd, double inv_Np,
+               int32_t* __restrict__ floor_cnt, double* __restrict__ resid_f,
+               uint64_t* __restrict__ resid_q, int64_t* __restrict__ tile_tot) {
+    __shared__ long long sm_f[32];
+    __shared__ long long sm_q[32];
+    const int64_t base = (int64_t)blockIdx.x * TILE;
+    long long tf = 0, tq = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const int64_t j = base + (int64_t)k * SB + threadIdx.x;   // coalesced
+        if (j < n) {
+            const double wj = w[j];
+            const double fl = trunc(__dmul_rn(wj, Nd));              // np.trunc(p_weight*n_particle)
+            const double r = __dsub_rn(wj, __dmul_rn(fl, inv_Np));   // p_weight - p_is*inv_Np
+            const int32_t c = (int32_t)fl;
+            floor_cnt[j] = c;
+            tf += c;
+            if (MODE == SMCB_SCAN_SEQUENTIAL) {
+                resid_f[j] = r;
+            } else {
+                double rq = r * TWO62;
+                rq = (rq > 0.0) ? rq : 0.0;
+                const uint64_t q = (uint64_t)__double2ull_rn(rq);
+                resid_q[j] = q;
+                tq += (long long)q;
+            }
+        }
+    }
+    tf = warp_sum_ll(tf);
+    tq = warp_sum_ll(tq);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        sm_f[wid] = tf;
+        sm_q[wid] = tq;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        tf = (lane < SB / 32) ? sm_f[lane] : 0;
+        tq = (lane < SB / 32) ? sm_q[lane] : 0;
+        tf = warp_sum_ll(tf);
+        tq = warp_sum_ll(tq);
+        if (lane == 0) {
+            tile_tot[2 * (int64_t)blockIdx.x] = tf;
+            tile_tot[2 * (int64_t)blockIdx.x + 1] = tq;
+        }
+    }
+}
+
+// exclusive scan over tile totals (pairs), single block; totals written to totals_out[0..1].
+__global__ void __launch_bounds__(SB)
+scan_tiles_pair_kernel(int64_t* __restrict__ tile_tot, int64_t n_tiles, int64_t carry0, int64_t carry1,
+                       int64_t* __restrict__ totals_out) {
+    __shared__ long long sm[32];
+    long long run0 = carry0, run1 = carry1;
+    for (int64_t b0 = 0; b0 < n_tiles; b0 += SB) {
+        const int64_t i = b0 + threadIdx.x;
+        long long v0 = 0, v1 = 0;
+        if (i < n_tiles) {
+            v0 = tile_tot[2 * i];
+            v1 = tile_tot[2 * i + 1];
+        }
+        long long t0, t1;
+        long long e0 = block_exclusive_scan<long long>(v0, 0LL, OpAdd(), sm, &t0);
+        long long e1 = block_exclusive_scan<long long>(v1, 0LL, OpAdd(), sm, &t1);
+        if (i < n_tiles) {
+            tile_tot[2 * i] = run0 + e0;
+            tile_tot[2 * i + 1] = run1 + e1;
+        }
+        run0 += t0;
+        run1 += t1;
+    }
+    if (threadIdx.x == 0 && totals_out != nullptr) {
+        totals_out[0] = run0 - carry0;
+        totals_out[1] = run1 - carry1;
+    }
+}
+
+__global__ void totals_from_tiles_kernel(const int64_t* __restrict__ tile_tot, int64_t n_tiles,
+                                         int64_t* __restrict__ totals_out) {
+    // single thread block, tiny: plain ordered sum of the *unscanned* tile totals
+    __shared__ long long sm[32];
+    long long a = 0, b = 0;
+    for (int64_t i = threadIdx.x; i < n_tiles; i += blockDim.x) {
+        a += tile_tot[2 * i];
+        b += tile_tot[2 * i + 1];
+    }
+    a = warp_sum_ll(a);
+    b = warp_sum_ll(b);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sm[wid] = a;
+    __syncthreads();
+    long long ta = 0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) ta += sm[k];
+    __syncthreads();
+    if (lane == 0) sm[wid] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long tb = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tb += sm[k];
+        totals_out[0] = ta;
+        totals_out[1] = tb;
+    }
+}
+
+// number of thresholds (u0 + k)/N, k>=0, at or below the fixed-point prefix s
+__device__ __forceinline__ long long crossings(uint64_t s, uint64_t N, uint64_t u0q) {
+    const uint64_t lo = s * N;
+    const uint64_t hi = __umul64hi(s, N);
+    if (hi == 0 && lo < u0q) return 0;
+    const uint64_t dlo = lo - u0q;
+    const uint64_t dhi = hi - (lo < u0q ? 1 : 0);
+    return (long long)((dhi << 2) | (dlo >> 62)) + 1;
+}
+
+// FIXED mode: counts[j] = floor[j] + cross(s_j) - cross(s_{j-1}),  s = exact prefix of q
+__global__ void __launch_bounds__(SB)
+counts_fixed_kernel(const int32_t* __restrict__ floor_cnt, const uint64_t* __restrict__ resid_q, int64_t n,
+                    const int64_t* __restrict__ tile_base, uint64_t N, uint64_t u0q, int first_shard,
+                    int32_t* __restrict__ counts) {
+    __shared__ unsigned long long sm[32];
+    const int64_t base = (int64_t)blockIdx.x * TILE + (int64_t)threadIdx.x * IPT;   // blocked layout
+    unsigned long long q[IPT];
+    unsigned long long tsum = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        q[k] = (base + k < n) ? resid_q[base + k] : 0ULL;
+        tsum += q[k];
+    }
+    unsigned long long btot;
+    unsigned long long excl = block_exclusive_scan<unsigned long long>(tsum, 0ULL, OpAdd(), sm, &btot);
+    unsigned long long s = (unsigned long long)tile_base[2 * (int64_t)blockIdx.x + 1] + excl;
+    long long c_prev = crossings(s, N, u0q);
+    if (first_shard && base == 0) c_prev = 0;   // nothing is crossed before the first particle of the run
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        s += q[k];
+        const long long c = crossings(s, N, u0q);
+        if (base + k < n) counts[base + k] = floor_cnt[base + k] + (int32_t)(c - c_prev);
+        c_prev = c;
+    }
+}
+
+// SEQUENTIAL mode: one warp; lane 0 carries the reference's running sum and threshold.
+constexpr int SEQ_CHUNK = 1024;
+__global__ void __launch_bounds__(32)
+counts_sequential_kernel(const int32_t* __restrict__ floor_cnt, const double* __restrict__ resid_f, int64_t n,
+                         double inv_Np, double* __restrict__ carry /*[2]: sum, wrand*/,
+                         int32_t* __restrict__ counts, int64_t* __restrict__ totals_out) {
+    __shared__ double s_w[SEQ_CHUNK];
+    __shared__ unsigned char s_c[SEQ_CHUNK];
+    const int lane = threadIdx.x;
+    double run = carry[0], wrand = carry[1];
+    long long ncross = 0, nfloor = 0;
+    for (int64_t b0 = 0; b0 < n; b0 += SEQ_CHUNK) {
+        const int m = (int)((n - b0 < SEQ_CHUNK) ? (n - b0) : SEQ_CHUNK);
+        for (int i = lane; i < m; i += 32) s_w[i] = resid_f[b0 + i];
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll 8
+            for (int i = 0; i < m; ++i) {
+                run = __dadd_rn(run, s_w[i]);
+                const bool hit = run >= wrand;
+                s_c[i] = hit ? 1 : 0;
+                if (hit) {
+                    wrand = __dadd_rn(wrand, inv_Np);
+                    ++ncross;
+                }
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) {
+            const int32_t f = floor_cnt[b0 + i];
+            counts[b0 + i] = f + s_c[i];
+            nfloor += f;
+        }
+        __syncwarp();
+    }
+    nfloor = warp_sum_ll(nfloor);
+    if (lane == 0) {
+        carry[0] = run;
+        carry[1] = wrand;
+        totals_out[0] = nfloor;
+        totals_out[1] = ncross;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ancestor expansion
+__global__ void __launch_bounds__(SB)
+count_tiles_kernel(const int32_t* __restrict__ counts, int64_t n, int64_t* __restrict__ tile_tot) {
+    __shared__ long long sm[32];
+    const int64_t base = (int64_t)blockIdx.x * TILE;
+    long long t = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const int64_t j = base + (int64_t)k * SB + threadIdx.x;
+        if (j < n) t += counts[j];
+    }
+    t = warp_sum_ll(t);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sm[wid] = t;
+    __syncthreads();
+    if (wid == 0) {
+        t = (lane < SB / 32) ? sm[lane] : 0;
+        t = warp_sum_ll(t);
+        if (lane == 0) {
+            tile_tot[2 * (int64_t)blockIdx.x] = t;
+            tile_tot[2 * (int64_t)blockIdx.x + 1] = 0;
+        }
+    }
+}
+
+// mark[offset_j] = j+1 for every particle with count_j>0 and offset_j<m
+__global__ void __launch_bounds__(SB)
+mark_heads_kernel(const int32_t* __restrict__ counts, int64_t n, const int64_t* __restrict__ tile_base,
+                  int64_t m, int32_t* __restrict__ mark) {
+    __shared__ long long sm[32];
+    const int64_t base = (int64_t)blockIdx.x * TILE + (int64_t)threadIdx.x * IPT;
+    int32_t c[IPT];
+    long long tsum = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        c[k] = (base + k < n) ? counts[base + k] : 0;
+        tsum += c[k];
+    }
+    long long btot;
+    long long off = tile_base[2 * (int64_t)blockIdx.x] +
+                    block_exclusive_scan<long long>(tsum, 0LL, OpAdd(), sm, &btot);
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        if (c[k] > 0 && off < m) mark[off] = (int32_t)(base + k) + 1;
+        off += c[k];
+    }
+}
+
+__global__ void __launch_bounds__(SB)
+max_tiles_kernel(const int32_t* __restrict__ mark, int64_t m, int32_t* __restrict__ tile_max) {
+    __shared__ int sm[32];
+    const int64_t base = (int64_t)blockIdx.x * TILE;
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        const int64_t j = base + (int64_t)k * SB + threadIdx.x;
+        if (j < m) t = max(t, mark[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(FULL_MASK, t, o));
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sm[wid] = t;
+    __syncthreads();
+    if (wid == 0) {
+        t = (lane < SB / 32) ? sm[lane] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = max(t, __shfl_xor_sync(FULL_MASK, t, o));
+        if (lane == 0) tile_max[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(SB) scan_tiles_max_kernel(int32_t* __restrict__ tile_max, int64_t n_tiles) {
+    __shared__ int sm[32];
+    int run = 0;
+    for (int64_t b0 = 0; b0 < n_tiles; b0 += SB) {
+        const int64_t i = b0 + threadIdx.x;
+        int v = (i < n_tiles) ? tile_max[i] : 0;
+        int tot;
+        int e = block_exclusive_scan<int>(v, 0, OpMax(), sm, &tot);
+        if (i < n_tiles) tile_max[i] = max(run, e);
+        run = max(run, tot);
+    }
+}
+
+__global__ void __launch_bounds__(SB)
+fill_ancestors_kernel(const int32_t* __restrict__ mark, int64_t m, const int32_t* __restrict__ tile_max,
+                      int32_t* __restrict__ anc) {
+    __shared__ int sm[32];
+    const int64_t base = (int64_t)blockIdx.x * TILE + (int64_t)threadIdx.x * IPT;
+    int v[IPT];
+    int tmax = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        v[k] = (base + k < m) ? mark[base + k] : 0;
+        tmax = max(tmax, v[k]);
+    }
+    int btot;
+    int run = max(tile_max[blockIdx.x], block_exclusive_scan<int>(tmax, 0, OpMax(), sm, &btot));
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        run = max(run, v[k]);
+        if (base + k < m) anc[base + k] = (run > 0 ? run : 1) - 1;
+    }
+}
+
+// dst[k][s] = src[k][anc[s]]
+__global__ void __launch_bounds__(256)
+gather_kernel(const double* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ anc, int64_t m, int rows,
+              double* __restrict__ dst, int64_t ld_dst) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m) return;
+    const int64_t a = anc[s];
+    int k = 0;
+    for (; k + 4 <= rows; k += 4) {
+        const double v0 = src[(int64_t)(k + 0) * ld_src + a];
+        const double v1 = src[(int64_t)(k + 1) * ld_src + a];
+        const double v2 = src[(int64_t)(k + 2) * ld_src + a];
+        const double v3 = src[(int64_t)(k + 3) * ld_src + a];
+        dst[(int64_t)(k + 0) * ld_dst + s] = v0;
+        dst[(int64_t)(k + 1) * ld_dst + s] = v1;
+        dst[(int64_t)(k + 2) * ld_dst + s] = v2;
+        dst[(int64_t)(k + 3) * ld_dst + s] = v3;
+    }
+    for (; k < rows; ++k) dst[(int64_t)k * ld_dst + s] = src[(int64_t)k * ld_src + a];
+}
+
+inline int64_t tiles_of(int64_t n) { return (n + TILE - 1) / TILE; }
+
+}  // namespace
+
+extern "C" int smcb_resample_totals(smcb_handle* h, const double* w_dev, int64_t n, int64_t n_total,
+                                    int64_t* totals_dev, void* stream) {
+    REQUIRE(h, h && w_dev && totals_dev && n > 0 && n_total >= n, SMCB_ERR_INVALID, "bad argument");
+    REQUIRE(h, h->floor_cnt != nullptr && n <= h->n_max, SMCB_ERR_STATE, "smcb_reserve too small");
+    REQUIRE(h, n_total < (1LL << 31), SMCB_ERR_UNSUPPORTED, "n_total must be below 2^31");
+    cudaStream_t st = as_stream(stream);
+    const int64_t nt = tiles_of(n);
+    prepare_kernel<SMCB_SCAN_FIXED><<<(unsigned)nt, SB, 0, st>>>(w_dev, n, (double)n_total, 1.0 / (double)n_total,
+                                                               h->floor_cnt, h->resid_f, h->resid_q, h->tile_tot);
+    LAUNCH_CHECK(h);
+    totals_from_tiles_kernel<<<1, SB, 0, st>>>(h->tile_tot, nt, totals_dev);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+extern "C" int smcb_resample_counts(smcb_handle* h, const double* w_dev, int64_t n, int64_t n_total, double u0,
+                                    int mode, double* carry_host, uint64_t carry_q, int64_t id_offset,
+                                    int32_t* counts_dev, int64_t* totals_dev, void* stream) {
+    REQUIRE(h, h && w_dev && counts_dev && totals_dev && n > 0 && n_total >= n, SMCB_ERR_INVALID, "bad argument");
+    REQUIRE(h, h->floor_cnt != nullptr && n <= h->n_max, SMCB_ERR_STATE, "smcb_reserve too small");
+    REQUIRE(h, n_total < (1LL << 31), SMCB_ERR_UNSUPPORTED, "n_total must be below 2^31");
+    REQUIRE(h, u0 >= 0.0 && u0 < 1.0, SMCB_ERR_INVALID, "u0 must lie in [0,1)");
+    cudaStream_t st = as_stream(stream);
+    const int64_t nt = tiles_of(n);
+    const double Nd = (double)n_total;
+    const double inv_Np = 1.0 / Nd;   // Micmem_settings.py:17
+    if (mode == SMCB_SCAN_SEQUENTIAL) {
+        prepare_kernel<SMCB_SCAN_SEQUENTIAL><<<(unsigned)nt, SB, 0, st>>>(w_dev, n, Nd, inv_Np, h->floor_cnt,
+                                                                        h->resid_f, h->resid_q, h->tile_tot);
+        LAUNCH_CHECK(h);
+        double carry[2] = {0.0, u0 * inv_Np};   // wrand = rand()*inv_Np (Micmem_SMC_main.py:156)
+        if (carry_host != nullptr) {
+            carry[0] = carry_host[0];
+            carry[1] = carry_host[1];
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(h->seq_carry, carry, sizeof(carry), cudaMemcpyHostToDevice, st));
+        counts_sequential_kernel<<<1, 32, 0, st>>>(h->floor_cnt, h->resid_f, n, inv_Np, h->seq_carry, counts_dev,
+                                                  totals_dev);
+        LAUNCH_CHECK(h);
+        if (carry_host != nullptr) {
+            CUDA_TRY(h, cudaMemcpyAsync(carry_host, h->seq_carry, sizeof(carry), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(h, cudaStreamSynchronize(st));
+        }
+        return SMCB_OK;
+    }
+    REQUIRE(h, mode == SMCB_SCAN_FIXED, SMCB_ERR_INVALID, "unknown scan mode");
+    prepare_kernel<SMCB_SCAN_FIXED><<<(unsigned)nt, SB, 0, st>>>(w_dev, n, Nd, inv_Np, h->floor_cnt, h->resid_f,
+                                                               h->resid_q, h->tile_tot);
+    LAUNCH_CHECK(h);
+    scan_tiles_pair_kernel<<<1, SB, 0, st>>>(h->tile_tot, nt, 0, (int64_t)carry_q, totals_dev);
+    LAUNCH_CHECK(h);
+    const uint64_t u0q = (uint64_t)llrint(u0 * TWO62);
+    counts_fixed_kernel<<<(unsigned)nt, SB, 0, st>>>(h->floor_cnt, h->resid_q, n, h->tile_tot, (uint64_t)n_total,
+                                                    u0q, id_offset == 0 ? 1 : 0, counts_dev);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+extern "C" int smcb_ancestors(smcb_handle* h, const int32_t* counts_dev, int64_t n, int64_t m,
+                              int32_t* ancestors_dev, int64_t* filled_dev, void* stream) {
+    REQUIRE(h, h && counts_dev && ancestors_dev && n > 0 && m > 0, SMCB_ERR_INVALID, "bad argument");
+    REQUIRE(h, h->mark != nullptr && n <= h->n_max && m <= h->n_max, SMCB_ERR_STATE, "smcb_reserve too small");
+    cudaStream_t st = as_stream(stream);
+    const int64_t nt = tiles_of(n), mt = tiles_of(m);
+    count_tiles_kernel<<<(unsigned)nt, SB, 0, st>>>(counts_dev, n, h->tile_tot);
+    LAUNCH_CHECK(h);
+    scan_tiles_pair_kernel<<<1, SB, 0, st>>>(h->tile_tot, nt, 0, 0, h->tile_tot2);
+    LAUNCH_CHECK(h);
+    if (filled_dev != nullptr)
+        CUDA_TRY(h, cudaMemcpyAsync(filled_dev, h->tile_tot2, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(h, cudaMemsetAsync(h->mark, 0, sizeof(int32_t) * m, st));
+    mark_heads_kernel<<<(unsigned)nt, SB, 0, st>>>(counts_dev, n, h->tile_tot, m, h->mark);
+    LAUNCH_CHECK(h);
+    int32_t* tile_max = reinterpret_cast<int32_t*>(h->tile_tot2 + 2);
+    max_tiles_kernel<<<(unsigned)mt, SB, 0, st>>>(h->mark, m, tile_max);
+    LAUNCH_CHECK(h);
+    scan_tiles_max_kernel<<<1, SB, 0, st>>>(tile_max, mt);
+    LAUNCH_CHECK(h);
+    fill_ancestors_kernel<<<(unsigned)mt, SB, 0, st>>>(h->mark, m, tile_max, ancestors_dev);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+extern "C" int smcb_gather(smcb_handle* h, const double* src_dev, int64_t ld_src, const int32_t* ancestors_dev,
+                           int64_t m, int rows, double* dst_dev, int64_t ld_dst, void* stream) {
+    REQUIRE(h, h && src_dev && ancestors_dev && dst_dev && m > 0 && rows > 0, SMCB_ERR_INVALID, "bad argument");
+    gather_kernel<<<(unsigned)((m + 255) / 256), 256, 0, as_stream(stream)>>>(src_dev, ld_src, ancestors_dev, m, rows,
+                                                                            dst_dev, ld_dst);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}

@@ -1,0 +1,573 @@
+"""Host side of the tempered-SMC sampler loop.
+
+`Engine.run` is the drop-in for the body of the reference driver
+(`SMC_example/Micmem_SMC_main.py:98-262`, same loop in
+`SMC_methanation/SMC_methanation_main.py:194-418`): prior particles + likelihood + settings in,
+posterior particles + tempering schedule + log-evidence out.  The stage-level methods
+(`sim_particle`, `temper`, `resample`, `mh_sweep`) keep the reference's script shape usable.
+
+All arithmetic over particles happens in libsmcb200.so (hand-written sm_100a kernels) through
+ctypes; torch owns the device buffers and supplies streams and (for sharded runs)
+`torch.distributed` collectives.  The host only sees O(1) scalars per stage.
+
+Particle state is one SoA tensor `state[d+1, n_local]` (rows 0..d-1 parameters, row d the
+log-likelihood) so resampling moves everything with a single gather.  With `world > 1` particles
+are sharded in contiguous blocks; global particle id = rank * n_local + i.
+"""
+import math
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from .settings import Settings
+
+_SCAN = {"sequential": _lib.SCAN_SEQUENTIAL, "fixed": _lib.SCAN_FIXED}
+_TWO62 = 1 << 62
+
+
+# ------------------------------------------------------------------------------------ collectives
+class LocalComm:
+    """Single-process stand-in (world = 1)."""
+    rank, world = 0, 1
+
+    def all_reduce_max(self, t):
+        return t
+
+    def all_reduce_sum(self, t):
+        return t
+
+    def all_gather_i64(self, t):
+        return t.reshape(1, -1)
+
+    def all_to_all(self, out, inp, out_splits, in_splits):
+        out.copy_(inp)
+
+    def broadcast(self, t, src):
+        return t
+
+    def barrier(self):
+        pass
+
+
+class TorchComm:
+    """`torch.distributed` (NCCL over NVLink on GPUs; gloo in CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def all_reduce_max(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_gather_i64(self, t):
+        out = torch.empty((self.world, t.numel()), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=self.group)
+        return out
+
+    def all_to_all(self, out, inp, out_splits, in_splits):
+        self.dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits,
+                                    group=self.group)
+
+    def broadcast(self, t, src):
+        self.dist.broadcast(t, src=src, group=self.group)
+        return t
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+
+def fixed_crossings(s, N, u0q):
+    """Thresholds (u0+k)/N, k>=0, at or below the fixed-point prefix s (mirrors resample.cu)."""
+    x = s * N
+    return 0 if x < u0q else ((x - u0q) >> 62) + 1
+
+
+def migration_plan(floor_tot, q_tot, N, n_local, u0, world):
+    """Where every shard's copies go (pure integer host logic, identical on all ranks).
+
+    floor_tot[r], q_tot[r]: per-shard sums of floor counts / fixed-point residuals.
+    Returns dict with, per rank r: carry_q[r], first global slot O[r], number of slots M[r] it fills
+    (after clamping to N and padding the tail), and send[r][q] = number of slots rank r sends to q.
+    """
+    u0q = int(round(u0 * _TWO62)) if not isinstance(u0, int) else u0
+    carry_q, O, M = [], [], []
+    pre_q = 0
+    pre_f = 0
+    for r in range(world):
+        carry_q.append(pre_q)
+        c0 = fixed_crossings(pre_q, N, u0q) if r > 0 else 0
+        c1 = fixed_crossings(pre_q + int(q_tot[r]), N, u0q)
+        O.append(pre_f + c0)
+        M.append(int(floor_tot[r]) + c1 - c0)
+        pre_q += int(q_tot[r])
+        pre_f += int(floor_tot[r])
+    plan = _plan_from_offsets(O, M, N, n_local, world)
+    plan.update(carry_q=carry_q, u0q=u0q)
+    return plan
+
+
+# ------------------------------------------------------------------------------------ results
+@dataclass
+class StageRecord:
+    step: int
+    gamma: float
+    ess: float
+    max_lk: float
+    n_backoff: int
+    n_mh: int
+    moved: int
+    log_evidence: float
+    mhstep_ratio: float
+    filled: int
+
+
+@dataclass
+class Result:
+    particles: np.ndarray            # [N, d] posterior particles (this rank's shard when sharded)
+    lk: np.ndarray                   # [N]
+    betas: list
+    ess: list
+    log_evidence: float
+    n_moved: list
+    n_mh: list
+    stages: list
+    n_eval: int                      # particle log-likelihood evaluations performed on the device (global)
+    n_eval_reference: int            # what the reference would have evaluated: N * (1 + sweeps)
+    seconds: float                   # device time first sweep -> end of gamma=1 block
+    reached_one: bool
+    ancestors: list = field(default_factory=list)
+
+
+# ------------------------------------------------------------------------------------ engine
+class Engine:
+    def __init__(self, likelihood, prior, settings=None, device=None, comm=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("a CUDA device is required: the sampler path has no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = (settings or Settings()).validate()
+        self.lik, self.prior = likelihood, prior
+        self.d = prior.d
+        if likelihood.d != self.d:
+            raise ValueError(f"prior has {self.d} parameters, likelihood expects {likelihood.d}")
+        self.comm = comm or LocalComm()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        torch.cuda.set_device(self.device)
+        h = _lib.p_void()
+        rc = self.lib.smcb_create(self.device.index, _lib.C.byref(h))
+        if rc != 0:
+            raise _lib.SmcbError(rc, self.lib.smcb_last_error(None).decode())
+        self.h = h
+        likelihood.upload(self.lib, self.h)
+        N, W = self.cfg.n_particle, self.comm.world
+        if N % W != 0:
+            raise ValueError("n_particle must be divisible by the number of ranks")
+        self.N, self.n = N, N // W
+        self.id_offset = self.comm.rank * self.n
+        # a shard may have to expand up to N copies when it holds all the weight
+        self.cap = self.n if W == 1 else N
+        self._ck(self.lib.smcb_reserve(self.h, max(self.cap, self.n), self.d))
+        dev, f64 = self.device, torch.float64
+        D1 = self.d + 1
+        self.state = torch.zeros((D1, self.n), dtype=f64, device=dev)
+        self.state2 = torch.zeros((D1, self.n), dtype=f64, device=dev)
+        self.prop = torch.zeros((self.d, self.n), dtype=f64, device=dev)
+        self.lk2 = torch.zeros(self.n, dtype=f64, device=dev)
+        self.w = torch.zeros(self.n, dtype=f64, device=dev)
+        self.inbox = torch.zeros(self.n, dtype=torch.uint8, device=dev)
+        self.moved = torch.zeros(self.n, dtype=torch.uint8, device=dev)
+        self.counts = torch.zeros(self.n, dtype=torch.int32, device=dev)
+        self.anc = torch.zeros(self.cap, dtype=torch.int32, device=dev)
+        self.scal = torch.zeros(64, dtype=f64, device=dev)       # [0]=max, [2:34]=tempering sums
+        self.mom = torch.zeros(self.d + self.d * self.d, dtype=f64, device=dev)
+        self.icnt = torch.zeros(8, dtype=torch.int64, device=dev)  # [0:3] MH counters, [4:6] totals, [6] filled
+        self.sendbuf = None
+        self._low = np.ascontiguousarray(prior.low)
+        self._high = np.ascontiguousarray(prior.high)
+
+    # -------------------------------------------------------------------------------- helpers
+    def _ck(self, rc):
+        _lib.check(self.h, rc)
+
+    @property
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.smcb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_count(self):
+        return int(self.lib.smcb_launch_count(self.h))
+
+    @property
+    def theta(self):
+        return self.state[: self.d]
+
+    @property
+    def lk(self):
+        return self.state[self.d]
+
+    # -------------------------------------------------------------------------------- particles
+    def set_particles(self, particles):
+        """particles: [n_local, d] (reference layout, AoS) host or device array of this shard."""
+        p = torch.as_tensor(particles, dtype=torch.float64)
+        if p.shape != (self.n, self.d):
+            raise ValueError(f"expected particles of shape {(self.n, self.d)}, got {tuple(p.shape)}")
+        self.state[: self.d].copy_(p.to(self.device, non_blocking=True).t())
+
+    def sample_prior(self, seed=None):
+        """Uniform box prior drawn on the device with Philox (keyed by global particle id)."""
+        seed = self.cfg.seed if seed is None else seed
+        self._ck(self.lib.smcb_sample_uniform_box(self.h, self.state.data_ptr(), self.n, self.n, self.d,
+                                                  self._low.ctypes.data, self._high.ctypes.data, seed,
+                                                  self.id_offset, self._stream))
+
+    def particles(self):
+        """[n_local, d] tensor (AoS copy of the current shard)."""
+        return self.state[: self.d].t().contiguous()
+
+    # -------------------------------------------------------------------------------- K1
+    def loglik_into(self, theta, lk_out, active=None):
+        n = theta.shape[1]
+        self._ck(self.lib.smcb_loglik(self.h, self.lik.model_id, theta.data_ptr(), theta.stride(0), n, self.d,
+                                      active.data_ptr() if active is not None else None, lk_out.data_ptr(),
+                                      self._stream))
+
+    def sim_particle(self, particle=None):
+        """Reference surface (`sim_particle(particle) -> llk`, Micmem_likelihood.py:79-92): evaluates
+        all local particles; returns the log-likelihood tensor (device)."""
+        if particle is not None:
+            self.set_particles(particle)
+        self.loglik_into(self.theta, self.lk)
+        return self.lk
+
+    # -------------------------------------------------------------------------------- K2
+    def temper(self, gamma_old):
+        """Next gamma by the configured rule.  Returns dict(gamma_new, gm, ess, sum_w, max_lk, n_backoff)
+        and leaves max in scal[0], the accepted sum_w in scal[1]."""
+        cfg, N = self.cfg, self.N
+        st = self._stream
+        self._ck(self.lib.smcb_lk_max(self.h, self.lk.data_ptr(), self.n, self.scal.data_ptr(), st))
+        self.comm.all_reduce_max(self.scal[0:1])
+        sums = self.scal[2:2 + 2 * _lib.MAX_CAND]
+
+        def eval_batch(gms):
+            g = np.ascontiguousarray(gms, dtype=np.float64)
+            self._ck(self.lib.smcb_temper_sums(self.h, self.lk.data_ptr(), self.n, self.scal.data_ptr(),
+                                               g.ctypes.data, len(g), sums.data_ptr(), st))
+            self.comm.all_reduce_sum(sums[: 2 * len(g)])
+            host = self.scal[: 2 + 2 * len(g)].cpu().numpy()   # one D2H: max + sums
+            return float(host[0]), host[2:]
+
+        if cfg.temper_rule == "backoff":
+            # candidate list of the reference's geometric back-off (Micmem_SMC_main.py:111-141)
+            g_new = gamma_old + cfg.d_gamma_max
+            if g_new > 1.0:
+                g_new = 1.0
+            cands = []
+            for _ in range(cfg.gm_reduction_itr):
+                cands.append(g_new)
+                g_new = (g_new - gamma_old) * cfg.gm_reduction_rate + gamma_old
+            g_after_last = g_new
+            k_acc, max_lk = None, None
+            for b0 in range(0, len(cands), cfg.cand_batch):
+                batch = cands[b0:b0 + cfg.cand_batch]
+                max_lk, s = eval_batch([g - gamma_old for g in batch])
+                for k in range(len(batch)):
+                    s1, s2 = float(s[2 * k]), float(s[2 * k + 1])
+                    ess = 1.0 / (s2 / (s1 * s1)) / N
+                    if ess > cfg.ess_limit:
+                        k_acc = b0 + k
+                        break
+                if k_acc is not None:
+                    break
+            if k_acc is None:
+                # the reference keeps the weights of the last tested increment but a gamma reduced once more
+                k, k_acc = len(batch) - 1, len(cands) - 1
+                gamma_new, n_back = g_after_last, len(cands)
+            else:
+                k = k_acc - b0
+                gamma_new, n_back = cands[k_acc], k_acc
+            gm = cands[k_acc] - gamma_old
+            s1, s2 = float(s[2 * k]), float(s[2 * k + 1])
+            ess = 1.0 / (s2 / (s1 * s1)) / N
+            self.scal[1:2].copy_(sums[2 * k:2 * k + 1])
+            return dict(gamma_new=gamma_new, gm=gm, ess=ess, sum_w=s1, max_lk=max_lk, n_backoff=n_back)
+
+        # bisection on ESS/N = ess_limit (north_star's alternative rule)
+        hi = 1.0 - gamma_old
+        max_lk, s = eval_batch([hi])
+
+        def ess_of(s, k=0):
+            return (s[2 * k] * s[2 * k]) / s[2 * k + 1] / N
+
+        if ess_of(s) >= cfg.ess_limit:
+            gm, gamma_new = hi, 1.0
+        else:
+            lo = 0.0
+            for _ in range(cfg.bisect_iters):
+                mid = 0.5 * (lo + hi)
+                _, s = eval_batch([mid])
+                if ess_of(s) >= cfg.ess_limit:
+                    lo = mid
+                else:
+                    hi = mid
+                if hi - lo <= 1e-12:
+                    break
+            gm = lo
+            _, s = eval_batch([gm])
+            gamma_new = gamma_old + gm
+        self.scal[1:2].copy_(sums[0:1])
+        return dict(gamma_new=gamma_new, gm=gm, ess=float(ess_of(s)), sum_w=float(s[0]), max_lk=max_lk, n_backoff=0)
+
+    # -------------------------------------------------------------------------------- K3
+    def resample(self, gm, u0, weights=None):
+        """Residual-systematic resampling of the current state with increment `gm` (weights
+        exp((lk-max)*gm)/sum_w from scal[0], scal[1]) or explicit normalised `weights`.
+        Returns the number of slots filled before clamping; new state replaces the old."""
+        st, lib, h = self._stream, self.lib, self.h
+        mode = _SCAN[self.cfg.scan_mode]
+        if weights is not None:
+            self.w.copy_(torch.as_tensor(weights, dtype=torch.float64))
+        else:
+            self._ck(lib.smcb_weights(h, self.lk.data_ptr(), self.n, self.scal.data_ptr(), gm,
+                                      self.scal[1:].data_ptr(), self.w.data_ptr(), st))
+        tot = self.icnt[4:6]
+        filled_t = self.icnt[6:7]
+        D1, W = self.d + 1, self.comm.world
+        if W == 1:
+            self._ck(lib.smcb_resample_counts(h, self.w.data_ptr(), self.n, self.N, u0, mode, None, 0, 0,
+                                              self.counts.data_ptr(), tot.data_ptr(), st))
+            self._ck(lib.smcb_ancestors(h, self.counts.data_ptr(), self.n, self.n, self.anc.data_ptr(),
+                                        filled_t.data_ptr(), st))
+            self._ck(lib.smcb_gather(h, self.state.data_ptr(), self.n, self.anc.data_ptr(), self.n, D1,
+                                     self.state2.data_ptr(), self.n, st))
+            self.state, self.state2 = self.state2, self.state
+            return None   # filled count stays on the device (icnt[6]); read lazily
+        # ---- sharded: cross-GPU exclusive scan of shard totals, then all-to-all migration ----
+        rank = self.comm.rank
+        if mode == _lib.SCAN_FIXED:
+            self._ck(lib.smcb_resample_totals(h, self.w.data_ptr(), self.n, self.N, tot.data_ptr(), st))
+            allt = self.comm.all_gather_i64(tot).cpu().numpy()
+            plan = migration_plan(allt[:, 0], allt[:, 1], self.N, self.n, u0, W)
+            self._ck(lib.smcb_resample_counts(h, self.w.data_ptr(), self.n, self.N, u0, mode, None,
+                                              plan["carry_q"][rank], self.id_offset, self.counts.data_ptr(),
+                                              tot.data_ptr(), st))
+        else:
+            # the reference's running sum is inherently serial: shards take turns, passing the carry
+            carry = np.array([0.0, u0 * (1.0 / self.N)], dtype=np.float64)
+            carry_t = torch.zeros(2, dtype=torch.float64, device=self.device)
+            for r in range(W):
+                if r == rank:
+                    self._ck(lib.smcb_resample_counts(h, self.w.data_ptr(), self.n, self.N, u0, mode,
+                                                      carry.ctypes.data, 0, self.id_offset, self.counts.data_ptr(),
+                                                      tot.data_ptr(), st))
+                    carry_t.copy_(torch.from_numpy(carry))
+                self.comm.broadcast(carry_t, src=r)
+                carry = carry_t.cpu().numpy().copy()
+            allt = self.comm.all_gather_i64(tot).cpu().numpy()   # [W, 2] = (floor sum, crossings)
+            O, M, pre = [], [], 0
+            for r in range(W):
+                O.append(pre)
+                M.append(int(allt[r, 0] + allt[r, 1]))
+                pre += M[-1]
+            plan = _plan_from_offsets(O, M, self.N, self.n, W)
+        m_loc = plan["M"][rank]
+        send = plan["send"][rank]
+        recv = [plan["send"][r][rank] for r in range(W)]
+        if self.sendbuf is None:
+            self.sendbuf = torch.empty(D1 * self.cap, dtype=torch.float64, device=self.device)
+            self.recvbuf = torch.empty(D1 * self.n, dtype=torch.float64, device=self.device)
+        if m_loc > 0:
+            self._ck(lib.smcb_ancestors(h, self.counts.data_ptr(), self.n, m_loc, self.anc.data_ptr(),
+                                        filled_t.data_ptr(), st))
+            off = 0
+            for q in range(W):   # one contiguous [d+1][len] chunk per destination
+                if send[q]:
+                    self._ck(lib.smcb_gather(h, self.state.data_ptr(), self.n, self.anc[off:].data_ptr(), send[q],
+                                             D1, self.sendbuf[D1 * off:].data_ptr(), send[q], st))
+                    off += send[q]
+        self.comm.all_to_all(self.recvbuf[: D1 * sum(recv)], self.sendbuf[: D1 * sum(send)],
+                             [D1 * c for c in recv], [D1 * c for c in send])
+        off = 0
+        for r in range(W):
+            if recv[r]:
+                self.state2[:, off:off + recv[r]].copy_(self.recvbuf[D1 * off: D1 * (off + recv[r])].view(D1, recv[r]))
+                off += recv[r]
+        self.state, self.state2 = self.state2, self.state
+        return plan["filled"]
+
+    # -------------------------------------------------------------------------------- K4
+    def proposal_factor(self):
+        """cov = np.cov(p_filt.T, bias=True) * w_cov, factorised the way NumPy's legacy
+        multivariate_normal does (SVD): x = z @ (sqrt(s)[:,None] * Vt)."""
+        st, d = self._stream, self.d
+        self._ck(self.lib.smcb_colsum(self.h, self.state.data_ptr(), self.n, self.n, d, self.mom.data_ptr(), st))
+        mean = self.mom[:d]
+        self.comm.all_reduce_sum(mean)
+        mean.div_(float(self.N))
+        cov_t = self.mom[d:d + d * d]
+        self._ck(self.lib.smcb_centered_moments(self.h, self.state.data_ptr(), self.n, self.n, d, mean.data_ptr(),
+                                                cov_t.data_ptr(), st))
+        self.comm.all_reduce_sum(cov_t)
+        cov = cov_t.cpu().numpy().reshape(d, d) / float(self.N)
+        cov = cov * self.cfg.w_cov(d)
+        (u, s, v) = np.linalg.svd(cov)
+        return np.ascontiguousarray(np.sqrt(s)[:, None] * v), cov
+
+    def mh_sweep(self, gamma, F, ratio, stage, sweep, Z=None, U=None):
+        """One sweep: propose, evaluate in-box proposals, accept.  MH counters accumulate in icnt[0:2]."""
+        st, lib, h, d = self._stream, self.lib, self.h, self.d
+        seed = self.cfg.seed
+        z_ptr = u_ptr = None
+        if Z is not None:
+            Zt = torch.as_tensor(Z, dtype=torch.float64).to(self.device).contiguous()
+            z_ptr = Zt.data_ptr()
+        if U is not None:
+            Ut = torch.as_tensor(U, dtype=torch.float64).to(self.device).contiguous()
+            u_ptr = Ut.data_ptr()
+        F = np.ascontiguousarray(F, dtype=np.float64)
+        self._ck(lib.smcb_mh_propose(h, self.state.data_ptr(), self.n, self.n, d, F.ctypes.data, ratio,
+                                     self._low.ctypes.data, self._high.ctypes.data, z_ptr, seed, self.id_offset,
+                                     stage, sweep, self.prop.data_ptr(), self.n, self.inbox.data_ptr(), st))
+        self.loglik_into(self.prop, self.lk2, active=self.inbox)
+        self._ck(lib.smcb_mh_accept(h, self.state.data_ptr(), self.n, self.lk.data_ptr(), self.prop.data_ptr(),
+                                    self.n, self.lk2.data_ptr(), self.inbox.data_ptr(), self.n, d, gamma, u_ptr,
+                                    seed, self.id_offset, stage, sweep, self.moved.data_ptr(),
+                                    self.icnt.data_ptr(), st))
+
+    def mh_fused(self, gamma, F, ratio, stage, sweep0, n_sweeps):
+        F = np.ascontiguousarray(F, dtype=np.float64)
+        self._ck(self.lib.smcb_mh_fused(self.h, self.lik.model_id, self.state.data_ptr(), self.n, self.lk.data_ptr(),
+                                        self.n, self.d, F.ctypes.data, ratio, self._low.ctypes.data,
+                                        self._high.ctypes.data, gamma, n_sweeps, self.cfg.seed, self.id_offset,
+                                        stage, sweep0, self.moved.data_ptr(), self.icnt.data_ptr(), self._stream))
+
+    # -------------------------------------------------------------------------------- the loop
+    def run(self, particles=None, stream=None, keep_ancestors=False, hook=None):
+        """Tempered SMC from gamma=0 to gamma=1.
+
+        particles: [n_local, d] initial (prior) particles, or None to use what `set_particles` /
+                   `sample_prior` left on the device.
+        stream:    optional object with u0(), normals(N, d), uniforms(N) supplying the random inputs
+                   (parity mode); default is one seeded host draw for u0 and Philox on the device.
+        """
+        cfg, N, d = self.cfg, self.N, self.d
+        if particles is not None:
+            self.set_particles(particles)
+        host_rng = np.random.RandomState(cfg.seed)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        self.sim_particle()
+        n_eval, n_sweeps_total = N, 0    # evaluations actually performed (global); in-box proposals only
+        gamma_old, logZ = 0.0, 0.0
+        stages, ancestors = [], []
+        reached = False
+        for step in range(1, cfg.itr_max):
+            t = self.temper(gamma_old)
+            gamma_new, gm = t["gamma_new"], t["gm"]
+            logZ += math.log(t["sum_w"] / N) + gm * t["max_lk"]
+            u0 = float(stream.u0()) if stream is not None else float(host_rng.rand())
+            filled = self.resample(gm, u0)
+            if keep_ancestors and self.comm.world == 1:
+                ancestors.append(self.anc[: self.n].cpu().numpy().astype(np.int64))
+            self.moved.zero_()
+            self.icnt[:4].zero_()
+            ratio = 1.0
+            if gamma_new >= 1.0:
+                n_mh, r_th = cfg.ad_mhstep_num, cfg.r_threshold_f
+            else:
+                n_mh, r_th = cfg.mhstep_num, cfg.r_threshold
+            n_run, moved, stage_evals = 0, 0, 0
+            if cfg.fused_sweeps > 0:
+                F, _ = self.proposal_factor()
+                done = 0
+                while done < n_mh:
+                    k = min(cfg.fused_sweeps, n_mh - done)
+                    self.mh_fused(gamma_new, F, ratio, step, done, k)
+                    done += k
+                    n_run += k
+                    cnt = self.icnt[:4].clone()
+                    self.comm.all_reduce_sum(cnt)
+                    c = cnt.cpu().numpy()
+                    moved, stage_evals = int(c[1]), int(c[2])
+                    if cfg.early_exit and moved > r_th * N:
+                        break
+                    if done < n_mh:
+                        F, _ = self.proposal_factor()
+            else:
+                for j in range(n_mh):
+                    F, cov = self.proposal_factor()
+                    Z = stream.normals(N, d) if stream is not None else None
+                    U = stream.uniforms(N) if stream is not None else None
+                    if Z is not None and self.comm.world > 1:
+                        lo = self.id_offset
+                        Z, U = Z[lo:lo + self.n], U[lo:lo + self.n]
+                    if hook is not None:
+                        hook("sweep", step=step, j=j, engine=self, F=F, cov=cov, gamma=gamma_new, ratio=ratio)
+                    self.mh_sweep(gamma_new, F, ratio, step, j, Z, U)
+                    n_run += 1
+                    cnt = self.icnt[:4].clone()
+                    self.comm.all_reduce_sum(cnt)
+                    c = cnt.cpu().numpy()
+                    moved, stage_evals = int(c[1]), int(c[2])
+                    if cfg.early_exit and moved > r_th * N:
+                        break
+                    if moved < cfg.r_threshold_min * N:
+                        ratio = ratio * 0.5
+            n_eval += stage_evals
+            n_sweeps_total += n_run
+            if filled is None:
+                filled = int(self.icnt[6].item())
+            stages.append(StageRecord(step, gamma_new, t["ess"], t["max_lk"], t["n_backoff"], n_run, moved, logZ,
+                                      ratio, filled))
+            if hook is not None:
+                hook("stage", step=step, engine=self, gamma=gamma_new)
+            if gamma_new == 1.0:
+                reached = True
+                break
+            gamma_old = gamma_new
+        ev1.record()
+        ev1.synchronize()
+        secs = ev0.elapsed_time(ev1) * 1e-3
+        return Result(particles=self.particles().cpu().numpy(), lk=self.lk.cpu().numpy().copy(),
+                      betas=[s.gamma for s in stages], ess=[s.ess for s in stages], log_evidence=logZ,
+                      n_moved=[s.moved for s in stages], n_mh=[s.n_mh for s in stages], stages=stages,
+                      n_eval=n_eval, n_eval_reference=N * (1 + n_sweeps_total),
+                      seconds=secs, reached_one=reached, ancestors=ancestors)
+
+
+def _plan_from_offsets(O, M, N, n_local, world):
+    filled = sum(M)
+    O, M = list(O), list(M)
+    for r in range(world):
+        lo, hi = min(O[r], N), min(O[r] + M[r], N)
+        O[r], M[r] = lo, hi - lo
+    if filled < N:
+        last = max((r for r in range(world) if M[r] > 0), default=world - 1)
+        M[last] += N - (O[last] + M[last])
+    send = [[0] * world for _ in range(world)]
+    for r in range(world):
+        for q in range(world):
+            lo = max(O[r], q * n_local)
+            hi = min(O[r] + M[r], (q + 1) * n_local)
+            send[r][q] = max(0, hi - lo)
+    return dict(O=O, M=M, send=send, filled=filled)

@@ -1,0 +1,106 @@
+"""Likelihood specifications (the data a model needs on the device).
+
+The reference's "plugin" is `sim_particle(particle) -> (llk, C_l_)` plus module globals holding the
+data (`SMC_example/Micmem_likelihood.py:79-92`, `Micmem_settings.py:103-115`;
+`SMC_methanation/methanation_functions.py:70-92`).  Here a likelihood is a small object that
+uploads its data once; the engine then evaluates all particles with one kernel launch.
+"""
+import os
+
+import numpy as np
+
+from . import _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class MMProgress:
+    """Michaelis-Menten progress curves, scipy-RK45 arithmetic (Micmem_likelihood.py:14-77)."""
+    model_id = _lib.MODEL_MM_PROGRESS
+    d = 3
+    names = ("Vmax", "Km", "sigma")
+
+    def __init__(self, t, P_obs, S0):
+        self.t, self.P_obs, self.S0 = _f64(t), _f64(P_obs), _f64(S0)
+        if self.t.ndim != 2 or self.t.shape != self.P_obs.shape or self.S0.shape != (self.t.shape[0],):
+            raise ValueError("t, P_obs must be [n_ex, n_t] and S0 [n_ex]")
+
+    @classmethod
+    def from_csv(cls, base_path="data/mm_pseudo_data", n_ex=6):
+        """Loads `{base_path}_{i}.csv` with columns t,S_true,P_true,P_obs exactly as
+        Micmem_settings.py:103-115 does (S0 = first S_true)."""
+        import pandas as pd
+        t, P, S0 = [], [], []
+        for i in range(n_ex):
+            df = pd.read_csv(f"{base_path}_{i}.csv")
+            t.append(df["t"].values)
+            P.append(df["P_obs"].values)
+            S0.append(df["S_true"].iloc[0])
+        return cls(np.array(t), np.array(P), np.array(S0))
+
+    @property
+    def n_obs(self):
+        return self.t.size
+
+    def upload(self, lib, handle):
+        _lib.check(handle, lib.smcb_set_data_mm_progress(
+            handle, self.t.ctypes.data, self.P_obs.ctypes.data, self.S0.ctypes.data,
+            self.t.shape[0], self.t.shape[1]))
+
+
+class MMRate:
+    """Rate-law observations (S_i, v_i), v ~ N(Vmax*S/(Km+S), sigma^2)."""
+    model_id = _lib.MODEL_MM_RATE
+    d = 3
+    names = ("Vmax", "Km", "sigma")
+
+    def __init__(self, S, v, precision=64):
+        self.S, self.v, self.precision = _f64(S), _f64(v), int(precision)
+        if self.S.ndim != 1 or self.S.shape != self.v.shape:
+            raise ValueError("S and v must be 1-D arrays of equal length")
+
+    @classmethod
+    def synthetic(cls, n_obs=10000, Vmax=1.2, Km=0.5, sigma=0.02, seed=20250205, precision=64):
+        rs = np.random.RandomState(seed)
+        S = np.exp(rs.uniform(np.log(0.05), np.log(20.0), n_obs))
+        v = Vmax * S / (Km + S) + sigma * rs.standard_normal(n_obs)
+        return cls(S, v, precision)
+
+    @property
+    def n_obs(self):
+        return self.S.size
+
+    def upload(self, lib, handle):
+        _lib.check(handle, lib.smcb_set_data_mm_rate(handle, self.S.ctypes.data, self.v.ctypes.data,
+                                                     self.S.size, self.precision))
+
+
+class KineticRK:
+    """Methanation-style reactor, fixed-step RK4 (physics: methanation_set_likelihood.py:44-66,
+    204-208,289-298; reactor definition: DESIGN.md)."""
+    model_id = _lib.MODEL_KINETIC_RK
+
+    def __init__(self, cond, obs, base, est_pos, n_steps=50, names=None):
+        self.cond, self.obs, self.base = _f64(cond), _f64(obs), _f64(base)
+        self.est_pos = np.ascontiguousarray(est_pos, dtype=np.int32)
+        self.n_steps = int(n_steps)
+        if self.cond.ndim != 2 or self.cond.shape[1] != _lib.KIN_NCOND_FIELDS:
+            raise ValueError(f"cond must be [n_cond, {_lib.KIN_NCOND_FIELDS}]")
+        if self.obs.shape != (5, self.cond.shape[0]):
+            raise ValueError("obs must be [5, n_cond]")
+        if (self.base.size - 1) % 8 != 0:
+            raise ValueError("base must hold 8*M kinetic parameters followed by sigma")
+        self.n_pairs = (self.base.size - 1) // 2
+        self.d = int(self.est_pos.size)
+        self.names = tuple(names) if names is not None else tuple(f"p{i}" for i in self.est_pos)
+
+    @property
+    def n_obs(self):
+        return self.obs.size
+
+    def upload(self, lib, handle):
+        _lib.check(handle, lib.smcb_set_data_kinetic(
+            handle, self.cond.ctypes.data, self.obs.ctypes.data, self.cond.shape[0], self.base.ctypes.data,
+            self.n_pairs, self.est_pos.ctypes.data, self.d, self.n_steps))

@@ -1,0 +1,57 @@
+"""Sampler settings with the reference's names and defaults.
+
+Mirrors the hyper-parameter block of `SMC_example/Micmem_settings.py:15-31,90` (identical in
+`SMC_methanation/methanation_set_conditon.py:107-125`).  Fields below the divider are additions of
+this engine; their defaults reproduce the reference's behaviour.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class Settings:
+    n_particle: int = 1000
+    ess_limit: float = 0.5
+    mhstep_factor: float = 0.5          # diagonal of w_cov
+    mhstep_factor_cov: float = 0.5      # off-diagonal of w_cov
+    ad_mhstep_num: int = 20             # max MH sweeps once gamma == 1
+    mhstep_num: int = 5                 # max MH sweeps while gamma < 1
+    mhstep_ratio: float = 1.0           # reset to 1.0 at every stage (Micmem_SMC_main.py:190)
+    r_threshold: float = 0.5
+    r_threshold_f: float = 0.7
+    r_threshold_min: float = 0.1
+    d_gamma_max: float = 1
+    gm_reduction_itr: int = 80
+    gm_reduction_rate: float = 0.7
+    itr_max: int = 50
+    n_cores: int = 30                   # accepted for compatibility; unused (no ray pool)
+    # ------------------------------------------------------------------ engine additions
+    seed: int = 20250205
+    temper_rule: str = "backoff"        # "backoff" (reference) | "bisect" (ESS bisection)
+    scan_mode: str = "fixed"            # "fixed" (parallel, shard-invariant) | "sequential" (bit-exact reference sum)
+    cand_batch: int = 8                 # tempering candidates evaluated per pass (<=16)
+    early_exit: bool = True             # stop sweeps when moved fraction exceeds r_threshold (reference)
+    fused_sweeps: int = 0               # >0: run this many sweeps per launch with a frozen proposal factor
+    bisect_iters: int = 60
+
+    @property
+    def inv_Np(self):
+        return 1 / self.n_particle
+
+    def w_cov(self, d):
+        """`w_cov` of Micmem_settings.py:93-96."""
+        w = np.full((d, d), self.mhstep_factor_cov, dtype=np.float64)
+        np.fill_diagonal(w, self.mhstep_factor)
+        return w
+
+    def validate(self):
+        if self.n_particle < 1:
+            raise ValueError("n_particle must be positive")
+        if not (1 <= self.cand_batch <= 16):
+            raise ValueError("cand_batch must be in 1..16")
+        if self.temper_rule not in ("backoff", "bisect"):
+            raise ValueError("temper_rule must be 'backoff' or 'bisect'")
+        if self.scan_mode not in ("fixed", "sequential"):
+            raise ValueError("scan_mode must be 'fixed' or 'sequential'")
+        return self

@@ -1,0 +1,97 @@
+"""Oracle self-consistency (CPU only): resampling twins, tempering rules, Philox, kinetic model."""
+import numpy as np
+import pytest
+
+from oracle import kinetic, philox, smc
+
+
+def _weights(n, seed, conc=0.3):
+    rs = np.random.RandomState(seed)
+    return rs.dirichlet(np.full(n, conc))
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (7, 2), (1000, 3), (4096, 4)])
+def test_sequential_resample_properties(n, seed):
+    w = _weights(n, seed)
+    anc, counts, info = smc.resample_sequential(w, 0.37)
+    assert np.all(np.diff(anc) >= 0)
+    assert abs(info["n_filled"] - n) <= 1
+    assert np.all(counts >= np.trunc(w * n))           # at least the floor copies
+    assert np.all(counts <= np.trunc(w * n) + 1)
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (7, 2), (1000, 3), (4096, 4), (5000, 5)])
+def test_fixed_scan_agrees_with_sequential(n, seed):
+    """The exact fixed-point scan gives the reference's ancestors except for ~1e-13 near-ties."""
+    for u0 in (0.0, 0.37, 0.999999):
+        w = _weights(n, seed)
+        a1, c1, _ = smc.resample_sequential(w, u0)
+        a2, c2, i2 = smc.resample_fixed(w, u0)
+        assert np.array_equal(c1, c2)
+        assert abs(i2["n_filled"] - n) <= 1          # u0 == 0 over-fills by one, exactly like the reference
+
+
+def test_degenerate_weights():
+    w = np.zeros(100)
+    w[17] = 1.0
+    for f in (smc.resample_sequential, smc.resample_fixed):
+        anc, counts, _ = f(w, 0.5)
+        assert counts[17] == 100 and counts.sum() == 100
+    w = np.full(64, 1 / 64)
+    for f in (smc.resample_sequential, smc.resample_fixed):
+        anc, counts, _ = f(w, 0.25)
+        assert counts.sum() in (63, 64, 65)
+
+
+def test_fit_ancestors():
+    assert np.array_equal(smc.fit_ancestors([0, 0, 2], 5), [0, 0, 2, 2, 2])
+    assert np.array_equal(smc.fit_ancestors([0, 1, 2, 3], 3), [0, 1, 2])
+
+
+def test_backoff_candidates_match_loop():
+    cfg = smc.Settings()
+    rs = np.random.RandomState(0)
+    lk = rs.normal(0, 50, 1000)
+    t = smc.temper_backoff(lk, 0.1, cfg)
+    cands = smc.backoff_candidates(0.1, cfg)
+    assert t["gamma_new"] == cands[t["n_backoff"]]
+    assert t["ess"] > cfg.ess_limit
+
+
+def test_bisect_hits_target():
+    rs = np.random.RandomState(1)
+    lk = rs.normal(0, 30, 5000)
+    t = smc.temper_bisect(lk, 0.0, 0.5)
+    assert abs(t["ess"] - 0.5) < 1e-6 and 0 < t["gamma_new"] < 1
+
+
+def test_philox_known_answer_and_moments():
+    # Random123 known-answer test for philox4x32-10: zero counter, zero key
+    c = philox.philox4x32_10(np.zeros(1, np.uint32), np.zeros(1, np.uint32), np.zeros(1, np.uint32),
+                             np.zeros(1, np.uint32), 0, 0)
+    assert [int(x[0]) for x in c] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    ids = np.arange(200000, dtype=np.uint64)
+    Z = philox.normals(20250205, ids, 3, 1, 3)
+    U = philox.uniforms(20250205, ids, 3, 1)
+    assert abs(Z.mean()) < 0.01 and abs(Z.std() - 1) < 0.01
+    assert abs(np.corrcoef(Z.T)[0, 1]) < 0.01
+    assert abs(U.mean() - 0.5) < 0.005 and U.min() >= 0 and U.max() < 1
+
+
+def test_kinetic_model_sane():
+    cond = kinetic.synthetic_conditions(30)
+    base = kinetic.base_vector(4)
+    F50 = kinetic.outlet_flows(base[None, :], cond, 50)[0]
+    F400 = kinetic.outlet_flows(base[None, :], cond, 400)[0]
+    assert np.all(F50 > 0)
+    assert np.abs(F50 - F400).max() < 1e-3                 # RK4 with 50 steps is converged
+    # carbon balance: CO2 + CH4 out == CO2 in (sccm)
+    Cb_in = cond[:, 1] * kinetic.S_TUBE * cond[:, 7] * 60 * kinetic.R * 1e6 / kinetic.P_STP * 298
+    assert np.allclose(F50[1] + F50[2], Cb_in, rtol=1e-9)
+    obs = kinetic.synthetic_observations(cond, base)
+    low, high = kinetic.reference_box()
+    rs = np.random.RandomState(0)
+    th = rs.uniform(low, high, (300, 5))
+    lk = kinetic.loglik(th, cond, obs, base, kinetic.EST_POSITION)
+    lk_true = kinetic.loglik(base[None, kinetic.EST_POSITION], cond, obs, base, kinetic.EST_POSITION)[0]
+    assert np.all(np.isfinite(lk)) and lk_true > np.max(lk) - 5
