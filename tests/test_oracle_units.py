@@ -27,8 +27,13 @@ def test_fixed_scan_agrees_with_sequential(n, seed):
         w = _weights(n, seed)
         a1, c1, _ = smc.resample_sequential(w, u0)
         a2, c2, i2 = smc.resample_fixed(w, u0)
-        assert np.array_equal(c1, c2)
-        assert abs(i2["n_filled"] - n) <= 1          # u0 == 0 over-fills by one, exactly like the reference
+        if u0 == 0.0:
+            # thresholds k/N make the final prefix (exactly (N - n_floor)/N) an exact tie: the fixed scan
+            # always counts it, the sequentially rounded sum lands on either side of it
+            assert np.array_equal(c1[:-1], c2[:-1]) and 0 <= c2[-1] - c1[-1] <= 1
+        else:
+            assert np.array_equal(c1, c2)
+        assert abs(i2["n_filled"] - n) <= 1          # u0 == 0 can over-fill by one (clamped by the engine)
 
 
 def test_degenerate_weights():
