@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""Benchmark of the tempered-SMC hot path (BASELINE.json metric: particle-loglik evals/s, time-to-beta=1).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One "step" = one complete pass of the hot path over one batch of particles: a whole tempered-SMC
+run (first likelihood sweep -> tempering -> residual-systematic resampling -> MH sweeps, repeated
+until beta = 1) started from prior particles that are already resident in HBM.  `value` is the
+number of per-particle log-likelihood evaluations the device performed divided by the device time
+(CUDA events, max over ranks); `time_to_beta1_s` is the average step time.  `e2e` is the same
+metric through the public call `smcb200.run(likelihood, prior, host_particles, settings)`: engine
+construction, H2D of the particles from pinned host memory, the run, D2H of posterior particles.
+
+Workloads (BASELINE.json configs):
+  mm_progress   config 2: Michaelis-Menten progress curves (the reference's six CSVs, 240
+                observations), 2^20 particles per GPU, FP64, scipy-RK45-twin arithmetic.  DEFAULT.
+  mm_rate       config 4 shape: 10 000 rate-law observations, 2^22 particles per GPU (--particles)
+  kinetic       config 3: methanation-style reactor, d=5, 30 conditions, RK4 x 50, 2^18 particles
+  kinetic32     config 5: 32-parameter kinetic family, 10 fused MH sweeps per stage, 2^20 particles
+With N > 1 (torchrun) particles are sharded, per-GPU count fixed => "scaling": "weak".
+
+`--impl reference` times the reference's CPU implementation of the same path (the oracle's
+restatement: scipy RK45 likelihood fanned out over all host cores + the NumPy sampler-loop body) on
+a bounded sample; only rank 0 works.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "mm_reference_run.npz")
+METRIC = "particle_loglik_evals_per_s"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="mm_progress", choices=["mm_progress", "mm_rate", "kinetic", "kinetic32"])
+    ap.add_argument("--particles", type=int, default=0, help="particles per GPU (0 = workload default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------ workloads
+def make_workload(pkg, name, n_per_gpu):
+    if name.startswith("kinetic"):
+        # synthetic operating conditions / observations: fixture written by tests/golden/make_kinetic_fixture.py
+        kf = np.load(os.path.join(ROOT, "tests", "golden", "kinetic_synth.npz"))
+    if name == "mm_progress":
+        g = np.load(GOLDEN)
+        lik = pkg.MMProgress(g["data_t"], g["data_P"], g["data_S0"])
+        prior = pkg.UniformBox([0, 0, 0], [10, 10, 10], names=["Vmax", "Km", "sigma"])
+        n = n_per_gpu or (1 << 20)
+        cfg = dict()
+        desc = "Michaelis-Menten tempered SMC, 6x40 progress-curve observations (reference CSVs), FP64 scipy-RK45 twin"
+    elif name == "mm_rate":
+        lik = pkg.MMRate.synthetic(10000, precision=32)
+        prior = pkg.UniformBox([0, 0, 0], [10, 10, 10], names=["Vmax", "Km", "sigma"])
+        n = n_per_gpu or (1 << 22)
+        cfg = dict()
+        desc = "synthetic Michaelis-Menten rate law, 10k observations, FP32 terms / FP64 accumulation"
+    elif name == "kinetic":
+        cond, base, obs, low, high = kf["cond"], kf["base4"], kf["obs4"], kf["low4"], kf["high4"]
+        lik = pkg.KineticRK(cond, obs, base, kf["est4"], n_steps=50)
+        prior = pkg.UniformBox(low, high, names=["Af", "Eaf", "Ar", "Ear", "sigma"])
+        n = n_per_gpu or (1 << 18)
+        cfg = dict()
+        desc = "methanation-style plug-flow reactor, d=5, 30 conditions, RK4 x 50 steps, FP64"
+    else:
+        cond, base, obs = kf["cond"], kf["base16"], kf["obs16"]
+        est = np.arange(32, dtype=np.int32)
+        lo, hi = base[:32] * 0.8, base[:32] * 1.2
+        lik = pkg.KineticRK(cond, obs, base, est, n_steps=50)
+        prior = pkg.UniformBox(np.minimum(lo, hi), np.maximum(lo, hi))
+        n = n_per_gpu or (1 << 20)
+        cfg = dict(fused_sweeps=10, mhstep_num=10, ad_mhstep_num=10, early_exit=False)
+        desc = "32-parameter kinetic family (4 LH channels), 30 conditions, RK4 x 50, 10 fused MH sweeps/stage"
+    return lik, prior, n, cfg, desc
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------ CPU baseline
+def _cpu_chunk(args):
+    from oracle import mm
+    P, t, Pobs, S0 = args
+    return mm.sweep_progress(P, t, Pobs, S0, which="scipy")
+
+
+def cpu_sweep(pool, cores, P, data):
+    chunks = [c for c in np.array_split(P, cores * 4) if len(c)]
+    return np.concatenate(pool.map(_cpu_chunk, [(c, *data) for c in chunks]))
+
+
+def cpu_baseline_mm_progress(target_s=15.0):
+    """The reference's likelihood (scipy RK45 through the oracle) on all host cores, one chunk of
+    particles per task, over a strided sample of every particle cloud the reference's own N=1000
+    run evaluated (prior cloud ... posterior cloud: the golden fixture's 34 sweeps)."""
+    import multiprocessing as mp
+    g = np.load(GOLDEN)
+    data = (g["data_t"], g["data_P"], g["data_S0"])
+    cores = os.cpu_count() or 1
+    allp = g["sweeps_in"].reshape(-1, 3)
+    stride = max(1, int(math.ceil(len(allp) / (cores * 110.0 * target_s))))
+    P = allp[::stride]
+    with mp.get_context("fork").Pool(cores) as pool:
+        cpu_sweep(pool, cores, P[: cores * 4], data)          # warm the workers
+        t0 = time.perf_counter()
+        cpu_sweep(pool, cores, P, data)
+        dt = time.perf_counter() - t0
+    return {"value": len(P) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(P)} of the 34000 particle evaluations of the reference's own N=1000 run "
+                      f"(every {stride}th, all 34 sweeps), scipy solve_ivp RK45 via oracle.mm, {dt:.1f} s"}
+
+
+def run_reference_arm(args):
+    """CPU implementation of the hot path (oracle restatement of the reference) on a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import smc
+    g = np.load(GOLDEN)
+    data = (g["data_t"], g["data_P"], g["data_S0"])
+    cores = os.cpu_count() or 1
+    M = min(1000, max(64, 40 * cores))         # particles per step: ~0.3-3 s of work per step on all cores
+    # particle cloud: a mid-run cloud of the reference's own run, so the RK step counts are representative
+    cfg = smc.Settings(n_particle=M)
+    times = []
+    with mp.get_context("fork").Pool(cores) as pool:
+        loglik = lambda th: cpu_sweep(pool, cores, th, data)
+        rs = np.random.RandomState(1)
+        sweeps = g["sweeps_in"]
+        for it in range(args.warmup + args.steps):
+            cloud = sweeps[(it * 5) % len(sweeps)][:M]
+            t0 = time.perf_counter()
+            lk = loglik(cloud)                                                        # sim_particle
+            t = smc.temper_backoff(lk, 0.0, cfg)                                      # tempering
+            anc = smc.fit_ancestors(smc.resample_sequential(t["p_weight"], rs.rand())[0], M)   # resampling
+            p_filt, lk1 = cloud[anc], lk[anc]
+            F = smc.proposal_factor(smc.particle_cov(p_filt) * cfg.w_cov(3))
+            smc.mh_sweep(p_filt, lk1, t["gamma_new"], F, rs.standard_normal((M, 3)), rs.uniform(0, 1, M), 1.0,
+                         loglik, np.zeros(3), np.full(3, 10.0))                       # one MH sweep
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    val = 2 * M * len(times) / total
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "mm_progress: Michaelis-Menten tempered SMC, reference CSV data, FP64",
+                       "particles_per_step": M, "evals_per_step": 2 * M},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"per step: likelihood sweep + tempering + resampling + one MH sweep (2 "
+                                       f"likelihood sweeps) over {M} particles of the reference run's clouds; "
+                                       "oracle restatement (scipy RK45), multiprocessing over all cores"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ roofline helpers
+def mm_progress_flops(stats_delta, n_particle_evals, n_ex, n_t):
+    """Algorithmic FP64 flop of the progress-curve likelihood from the device's own work counters
+    (DESIGN.md 'K1 work model'): 84 flop per step attempt (6 RHS x 3, stage sums 35, y_new 11, error
+    norm 13, controller 7), 34 per accepted step (dense-output Q), 18 per observation, 30 per solve
+    (initial step)."""
+    fev, acc, rej = (int(x) for x in stats_delta[:3])
+    return 84.0 * (acc + rej) + 34.0 * acc + 18.0 * n_particle_evals * n_ex * n_t + 30.0 * n_particle_evals * n_ex
+
+
+def gather_microbench(pkg, eng, torch, flush):
+    """HBM leg: resample-gather of the full particle state with the ancestors of a real stage,
+    inputs flushed from L2.  Algorithmic bytes per particle: 4 (ancestor) + 2*(d+1)*8."""
+    n, D1 = eng.n, eng.d + 1
+    ms = []
+    for _ in range(5):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng._ck(eng.lib.smcb_gather(eng.h, eng.state.data_ptr(), n, eng.anc.data_ptr(), n, D1, eng.state2.data_ptr(), n,
+                                    eng._stream))
+        e1.record()
+        e1.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    best = float(np.median(ms))
+    nbytes = n * (4 + 2 * D1 * 8)
+    return best, nbytes
+
+
+# ------------------------------------------------------------------------------------ main arm
+def main():
+    args = parse()
+    if args.cpu_baseline_only:
+        print(json.dumps(cpu_baseline_mm_progress()), flush=True)
+        return
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import smcb200 as pkg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sampler path has no CPU fallback")
+    torch.cuda.set_device(local)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        comm = pkg.TorchComm()
+    n_gpus = world
+
+    lik, prior, n_loc, cfg_kw, desc = make_workload(pkg, args.workload, args.particles)
+    N = n_loc * world
+    cfg = pkg.Settings(n_particle=N, **cfg_kw)
+    eng = pkg.Engine(lik, prior, cfg, comm=comm)
+    eng.sample_prior()
+    prior_dev = eng.state[: eng.d].clone()            # prior particles resident in HBM
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
+
+    def flush():
+        flush_buf.fill_(1)                            # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        eng.state[: eng.d].copy_(prior_dev)
+        return eng.run()
+
+    for _ in range(args.warmup):
+        flush()
+        res = step()
+    eng.enable_profiling(True)
+    stats0 = eng.loglik_stats() if args.workload == "mm_progress" else None
+    launches0 = eng.launch_count()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_total, evals, stages, sweeps = 0.0, 0, 0, 0
+    barrier()
+    for _ in range(args.steps):
+        flush()                                       # L2 flushed between timed iterations (untimed)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = step()
+        e1.record()
+        e1.synchronize()
+        barrier()
+        ms_total += e0.elapsed_time(e1)
+        evals += res.n_eval
+        stages += len(res.betas)
+        sweeps += sum(res.n_mh)
+        assert res.reached_one, "tempering did not reach beta = 1"
+    clk = clocks.stop() if rank == 0 else None
+    launches = eng.launch_count() - launches0
+    prof = eng.profile_summary()
+    eng.enable_profiling(False)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_total], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    secs = ms_total * 1e-3
+    value = evals / secs
+
+    # ---- roofline of the dominant kernel (rank 0's shard) ---------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    fma = np.zeros(2)
+    eng._ck(eng.lib.smcb_measure_fma_peak(eng.h, fma.ctypes.data))
+    n_lik, ms_lik = prof.get("loglik", (0, 0.0))
+    if "mh_fused" in prof:
+        n_lik, ms_lik = n_lik + prof["mh_fused"][0], ms_lik + prof["mh_fused"][1]
+    roofline = {"bound": "fp64", "kernel": "likelihood", "achieved": None, "peak": fma[0] / 1e12, "unit": "TFLOP/s",
+                "frac": None, "traffic": None,
+                "peak_source": "FP64 FMA micro-benchmark run in this process (smcb_measure_fma_peak); "
+                               "MEASURED_PEAKS.json has no FP64 figure",
+                "share_of_step": ms_lik / ms_total if ms_total else None,
+                "avg_launch_ms": ms_lik / max(n_lik, 1), "launches": n_lik}
+    if args.workload == "mm_progress":
+        d_stats = eng.loglik_stats()[4:8] - stats0[4:8]
+        local_evals = evals // world
+        flops = mm_progress_flops(d_stats, local_evals, lik.t.shape[0], lik.t.shape[1])
+        roofline.update(kernel="mm_progress_kernel<0> (+ finalize)", achieved=flops / (ms_lik * 1e-3) / 1e12,
+                        rhs_evals_per_particle_eval=float(d_stats[0]) / max(local_evals, 1),
+                        rejected_step_fraction=float(d_stats[2]) / max(float(d_stats[1] + d_stats[2]), 1.0))
+        roofline["frac"] = roofline["achieved"] / roofline["peak"]
+    g_ms, g_bytes = gather_microbench(pkg, eng, torch, flush)
+    roofline_hbm = {"bound": "hbm", "kernel": "gather_kernel (resampling gather of particle state)",
+                    "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "launch_ms": g_ms, "bytes": g_bytes}
+
+    # ---- end to end through the public API, host buffers ----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_p = torch.empty((n_loc, eng.d), dtype=torch.float64).pin_memory()
+        host_p.copy_(prior_dev.t())
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+        e_evals, e_t = 0, 0.0
+        for it in range(1 + max(1, min(args.steps, 2))):
+            barrier()
+            t0 = time.perf_counter()
+            r = pkg.run(lik, prior, particles=host_p, settings=cfg, comm=comm)     # H2D + run + D2H inside
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                import torch.distributed as dist
+                tt = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            if it > 0:
+                e_evals += r.n_eval
+                e_t += dt
+        e2e = {"value": e_evals / e_t, "unit": UNIT, "h2d_bytes_per_step": int(N * prior.d * 8),
+               "d2h_bytes_per_step": int(N * (prior.d + 1) * 8), "seconds_per_step": e_t / max(1, min(args.steps, 2)),
+               "api": "smcb200.run(likelihood, prior, pinned host particles, settings) -> Result (host arrays)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "mm_progress":
+        # separate process: the worker pool forks, which must not happen under a live CUDA context
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only"], capture_output=True,
+                             text=True, timeout=600)
+        cpu = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {"error": out.stderr[-300:]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.workload != "mm_rate" else "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {desc}", "particles_total": N, "particles_per_gpu": n_loc,
+                           "d": prior.d, "observations": int(lik.n_obs), "temper_rule": cfg.temper_rule,
+                           "scan_mode": cfg.scan_mode, "l2": "256 MiB flush between timed steps",
+                           "step": "one full tempered-SMC run, prior -> beta=1"},
+                "time_to_beta1_s": secs / args.steps, "stages_per_step": stages / args.steps,
+                "mh_sweeps_per_step": sweeps / args.steps, "evals_per_step": evals / args.steps,
+                "log_evidence": res.log_evidence, "posterior_mean": [float(x) for x in res.particles.mean(0)],
+                "roofline": roofline, "roofline_hbm": roofline_hbm,
+                "kernel_ms": {k: {"groups": v[0], "ms": v[1]} for k, v in prof.items()},
+                "fp32_fma_peak_tflops": fma[1] / 1e12,
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -94,8 +94,9 @@ int smcb_loglik(smcb_handle* h, int model, const double* theta_dev, int64_t ld, 
  * EX/lik:74-77): pred_dev[i][n_ex][n_t].  MM_PROGRESS only. */
 int smcb_predict_mm_progress(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n,
                              double* pred_dev, void* stream);
-/* Work counters of the last MM_PROGRESS sweep: out_host[0]=RHS evaluations, [1]=accepted steps,
- * [2]=rejected steps, [3]=failed solves.  Synchronous. */
+/* Work counters of MM_PROGRESS sweeps, out_host int64[8]: [0]=RHS evaluations, [1]=accepted steps,
+ * [2]=rejected steps, [3]=failed solves of the last sweep; [4..7] the same four accumulated over
+ * every sweep since smcb_create.  Synchronous. */
 int smcb_loglik_stats(smcb_handle* h, int64_t* out_host);
 
 /* ---- K2: tempering reductions (replaces EX/main:116-134) --------------------------------- */

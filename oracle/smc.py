@@ -218,6 +218,30 @@ class ReferenceStream:
         return self.rs.uniform(0, 1, N)
 
 
+class PhiloxStream:
+    """The engine's default randomness, restated: u0 from a seeded legacy RandomState on the host,
+    normals/uniforms from Philox keyed by (seed, global particle id, stage, sweep)."""
+
+    def __init__(self, seed=20250205):
+        from . import philox
+        self.philox, self.seed = philox, seed
+        self.rs = np.random.RandomState(seed)
+        self.stage, self.sweep = 0, 0
+
+    def u0(self):
+        self.stage += 1
+        self.sweep = 0
+        return self.rs.rand()
+
+    def normals(self, N, d):
+        return self.philox.normals(self.seed, np.arange(N, dtype=np.uint64), self.stage, self.sweep, d)
+
+    def uniforms(self, N):
+        u = self.philox.uniforms(self.seed, np.arange(N, dtype=np.uint64), self.stage, self.sweep)
+        self.sweep += 1
+        return u
+
+
 class ArrayStream:
     """Hands out pre-generated arrays (shared verbatim with the device path in tests)."""
 
@@ -249,8 +273,12 @@ class Trace:
     n_eval: int = 0
 
 
-def run(loglik, p_pred, low, high, cfg: Settings, stream, lk0=None, hook=None):
-    """Whole tempered-SMC run.  Returns (particles, lk, Trace)."""
+def run(loglik, p_pred, low, high, cfg: Settings, stream, lk0=None, hook=None, resampler=None, early_exit=True):
+    """Whole tempered-SMC run.  Returns (particles, lk, Trace).
+
+    resampler: `resample_sequential` (the reference, default) or `resample_fixed` (the engine's
+    shard-invariant arithmetic); early_exit=False runs all nMH sweeps (BASELINE config 5)."""
+    resampler = resampler or resample_sequential
     p_pred = np.array(p_pred, dtype=np.float64)
     N, d = p_pred.shape
     tr = Trace()
@@ -264,7 +292,7 @@ def run(loglik, p_pred, low, high, cfg: Settings, stream, lk0=None, hook=None):
         gamma_new = t["gamma_new"]
         # log-evidence increment (the reference computes sum_weight and discards it, :127)
         logZ += math.log(t["sum_weight"] / N) + t["gm_used"] * t["max_lk"]
-        anc, counts, info = resample_sequential(t["p_weight"], stream.u0())
+        anc, counts, info = resampler(t["p_weight"], stream.u0())
         anc = fit_ancestors(anc, N)
         p_filt = p_pred[anc]
         lk1 = lk[anc]
@@ -288,7 +316,7 @@ def run(loglik, p_pred, low, high, cfg: Settings, stream, lk0=None, hook=None):
             tr.n_eval += N          # the reference evaluates all N (out-of-box ones at the old point)
             r_ac = np.maximum(r_ac, r)
             n_run += 1
-            if r_ac.sum() > r_th * N:
+            if early_exit and r_ac.sum() > r_th * N:
                 break
             if r_ac.sum() < cfg.r_threshold_min * N:
                 mhstep_ratio = mhstep_ratio * 0.5

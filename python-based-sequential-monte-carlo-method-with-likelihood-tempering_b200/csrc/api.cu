@@ -207,7 +207,7 @@ extern "C" int smcb_predict_mm_progress(smcb_handle* h, const double* theta_dev,
 
 extern "C" int smcb_loglik_stats(smcb_handle* h, int64_t* out_host) {
     REQUIRE(h, h && out_host, SMCB_ERR_INVALID, "null pointer");
-    CUDA_TRY(h, cudaMemcpy(out_host, h->stats, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(out_host, h->stats, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost));
     return SMCB_OK;
 }
 

@@ -268,6 +268,10 @@ mm_progress_kernel(const double* __restrict__ theta, int64_t ld, int64_t n,
         atomicAdd(&stats[1], n_acc);
         atomicAdd(&stats[2], n_rej);
         if (n_fail) atomicAdd(&stats[3], n_fail);
+        atomicAdd(&stats[4], n_fev);   // cumulative since smcb_create (never reset by a sweep)
+        atomicAdd(&stats[5], n_acc);
+        atomicAdd(&stats[6], n_rej);
+        if (n_fail) atomicAdd(&stats[7], n_fail);
     }
 }
 

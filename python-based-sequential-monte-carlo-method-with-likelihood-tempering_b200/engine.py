@@ -14,8 +14,8 @@ Particle state is one SoA tensor `state[d+1, n_local]` (rows 0..d-1 parameters, 
 log-likelihood) so resampling moves everything with a single gather.  With `world > 1` particles
 are sharded in contiguous blocks; global particle id = rank * n_local + i.
 """
+import contextlib
 import math
-import time
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -192,6 +192,7 @@ class Engine:
         self.mom = torch.zeros(self.d + self.d * self.d, dtype=f64, device=dev)
         self.icnt = torch.zeros(8, dtype=torch.int64, device=dev)  # [0:3] MH counters, [4:6] totals, [6] filled
         self.sendbuf = None
+        self.prof = None          # name -> list of (start, end) CUDA events when profiling is on
         self._low = np.ascontiguousarray(prior.low)
         self._high = np.ascontiguousarray(prior.high)
 
@@ -216,6 +217,33 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.smcb_launch_count(self.h))
+
+    def loglik_stats(self):
+        """int64[8] work counters of the MM progress-curve kernel (see smcb_loglik_stats)."""
+        out = np.zeros(8, dtype=np.int64)
+        self._ck(self.lib.smcb_loglik_stats(self.h, out.ctypes.data))
+        return out
+
+    # -------------------------------------------------------------------------------- device timers
+    def enable_profiling(self, on=True):
+        """Bracket every kernel group with CUDA events on the launching stream (bench.py's roofline)."""
+        self.prof = {} if on else None
+
+    @contextlib.contextmanager
+    def _timed(self, name):
+        if self.prof is None:
+            yield
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        self.prof.setdefault(name, []).append((e0, e1))
+
+    def profile_summary(self):
+        """{name: (launch groups, total ms)}; synchronises."""
+        torch.cuda.synchronize(self.device)
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (self.prof or {}).items()}
 
     @property
     def theta(self):
@@ -247,9 +275,10 @@ class Engine:
     # -------------------------------------------------------------------------------- K1
     def loglik_into(self, theta, lk_out, active=None):
         n = theta.shape[1]
-        self._ck(self.lib.smcb_loglik(self.h, self.lik.model_id, theta.data_ptr(), theta.stride(0), n, self.d,
-                                      active.data_ptr() if active is not None else None, lk_out.data_ptr(),
-                                      self._stream))
+        with self._timed("loglik"):
+            self._ck(self.lib.smcb_loglik(self.h, self.lik.model_id, theta.data_ptr(), theta.stride(0), n, self.d,
+                                          active.data_ptr() if active is not None else None, lk_out.data_ptr(),
+                                          self._stream))
 
     def sim_particle(self, particle=None):
         """Reference surface (`sim_particle(particle) -> llk`, Micmem_likelihood.py:79-92): evaluates
@@ -265,14 +294,16 @@ class Engine:
         and leaves max in scal[0], the accepted sum_w in scal[1]."""
         cfg, N = self.cfg, self.N
         st = self._stream
-        self._ck(self.lib.smcb_lk_max(self.h, self.lk.data_ptr(), self.n, self.scal.data_ptr(), st))
+        with self._timed("temper"):
+            self._ck(self.lib.smcb_lk_max(self.h, self.lk.data_ptr(), self.n, self.scal.data_ptr(), st))
         self.comm.all_reduce_max(self.scal[0:1])
         sums = self.scal[2:2 + 2 * _lib.MAX_CAND]
 
         def eval_batch(gms):
             g = np.ascontiguousarray(gms, dtype=np.float64)
-            self._ck(self.lib.smcb_temper_sums(self.h, self.lk.data_ptr(), self.n, self.scal.data_ptr(),
-                                               g.ctypes.data, len(g), sums.data_ptr(), st))
+            with self._timed("temper"):
+                self._ck(self.lib.smcb_temper_sums(self.h, self.lk.data_ptr(), self.n, self.scal.data_ptr(),
+                                                   g.ctypes.data, len(g), sums.data_ptr(), st))
             self.comm.all_reduce_sum(sums[: 2 * len(g)])
             host = self.scal[: 2 + 2 * len(g)].cpu().numpy()   # one D2H: max + sums
             return float(host[0]), host[2:]
@@ -348,18 +379,21 @@ class Engine:
         if weights is not None:
             self.w.copy_(torch.as_tensor(weights, dtype=torch.float64))
         else:
-            self._ck(lib.smcb_weights(h, self.lk.data_ptr(), self.n, self.scal.data_ptr(), gm,
-                                      self.scal[1:].data_ptr(), self.w.data_ptr(), st))
+            with self._timed("weights"):
+                self._ck(lib.smcb_weights(h, self.lk.data_ptr(), self.n, self.scal.data_ptr(), gm,
+                                          self.scal[1:].data_ptr(), self.w.data_ptr(), st))
         tot = self.icnt[4:6]
         filled_t = self.icnt[6:7]
         D1, W = self.d + 1, self.comm.world
         if W == 1:
-            self._ck(lib.smcb_resample_counts(h, self.w.data_ptr(), self.n, self.N, u0, mode, None, 0, 0,
-                                              self.counts.data_ptr(), tot.data_ptr(), st))
-            self._ck(lib.smcb_ancestors(h, self.counts.data_ptr(), self.n, self.n, self.anc.data_ptr(),
-                                        filled_t.data_ptr(), st))
-            self._ck(lib.smcb_gather(h, self.state.data_ptr(), self.n, self.anc.data_ptr(), self.n, D1,
-                                     self.state2.data_ptr(), self.n, st))
+            with self._timed("resample_scan"):
+                self._ck(lib.smcb_resample_counts(h, self.w.data_ptr(), self.n, self.N, u0, mode, None, 0, 0,
+                                                  self.counts.data_ptr(), tot.data_ptr(), st))
+                self._ck(lib.smcb_ancestors(h, self.counts.data_ptr(), self.n, self.n, self.anc.data_ptr(),
+                                            filled_t.data_ptr(), st))
+            with self._timed("resample_gather"):
+                self._ck(lib.smcb_gather(h, self.state.data_ptr(), self.n, self.anc.data_ptr(), self.n, D1,
+                                         self.state2.data_ptr(), self.n, st))
             self.state, self.state2 = self.state2, self.state
             return None   # filled count stays on the device (icnt[6]); read lazily
         # ---- sharded: cross-GPU exclusive scan of shard totals, then all-to-all migration ----
@@ -420,13 +454,15 @@ class Engine:
         """cov = np.cov(p_filt.T, bias=True) * w_cov, factorised the way NumPy's legacy
         multivariate_normal does (SVD): x = z @ (sqrt(s)[:,None] * Vt)."""
         st, d = self._stream, self.d
-        self._ck(self.lib.smcb_colsum(self.h, self.state.data_ptr(), self.n, self.n, d, self.mom.data_ptr(), st))
+        with self._timed("moments"):
+            self._ck(self.lib.smcb_colsum(self.h, self.state.data_ptr(), self.n, self.n, d, self.mom.data_ptr(), st))
         mean = self.mom[:d]
         self.comm.all_reduce_sum(mean)
         mean.div_(float(self.N))
         cov_t = self.mom[d:d + d * d]
-        self._ck(self.lib.smcb_centered_moments(self.h, self.state.data_ptr(), self.n, self.n, d, mean.data_ptr(),
-                                                cov_t.data_ptr(), st))
+        with self._timed("moments"):
+            self._ck(self.lib.smcb_centered_moments(self.h, self.state.data_ptr(), self.n, self.n, d,
+                                                    mean.data_ptr(), cov_t.data_ptr(), st))
         self.comm.all_reduce_sum(cov_t)
         cov = cov_t.cpu().numpy().reshape(d, d) / float(self.N)
         cov = cov * self.cfg.w_cov(d)
@@ -445,21 +481,25 @@ class Engine:
             Ut = torch.as_tensor(U, dtype=torch.float64).to(self.device).contiguous()
             u_ptr = Ut.data_ptr()
         F = np.ascontiguousarray(F, dtype=np.float64)
-        self._ck(lib.smcb_mh_propose(h, self.state.data_ptr(), self.n, self.n, d, F.ctypes.data, ratio,
-                                     self._low.ctypes.data, self._high.ctypes.data, z_ptr, seed, self.id_offset,
-                                     stage, sweep, self.prop.data_ptr(), self.n, self.inbox.data_ptr(), st))
+        with self._timed("propose"):
+            self._ck(lib.smcb_mh_propose(h, self.state.data_ptr(), self.n, self.n, d, F.ctypes.data, ratio,
+                                         self._low.ctypes.data, self._high.ctypes.data, z_ptr, seed, self.id_offset,
+                                         stage, sweep, self.prop.data_ptr(), self.n, self.inbox.data_ptr(), st))
         self.loglik_into(self.prop, self.lk2, active=self.inbox)
-        self._ck(lib.smcb_mh_accept(h, self.state.data_ptr(), self.n, self.lk.data_ptr(), self.prop.data_ptr(),
-                                    self.n, self.lk2.data_ptr(), self.inbox.data_ptr(), self.n, d, gamma, u_ptr,
-                                    seed, self.id_offset, stage, sweep, self.moved.data_ptr(),
-                                    self.icnt.data_ptr(), st))
+        with self._timed("accept"):
+            self._ck(lib.smcb_mh_accept(h, self.state.data_ptr(), self.n, self.lk.data_ptr(), self.prop.data_ptr(),
+                                        self.n, self.lk2.data_ptr(), self.inbox.data_ptr(), self.n, d, gamma, u_ptr,
+                                        seed, self.id_offset, stage, sweep, self.moved.data_ptr(),
+                                        self.icnt.data_ptr(), st))
 
     def mh_fused(self, gamma, F, ratio, stage, sweep0, n_sweeps):
         F = np.ascontiguousarray(F, dtype=np.float64)
-        self._ck(self.lib.smcb_mh_fused(self.h, self.lik.model_id, self.state.data_ptr(), self.n, self.lk.data_ptr(),
-                                        self.n, self.d, F.ctypes.data, ratio, self._low.ctypes.data,
-                                        self._high.ctypes.data, gamma, n_sweeps, self.cfg.seed, self.id_offset,
-                                        stage, sweep0, self.moved.data_ptr(), self.icnt.data_ptr(), self._stream))
+        with self._timed("mh_fused"):
+            self._ck(self.lib.smcb_mh_fused(self.h, self.lik.model_id, self.state.data_ptr(), self.n,
+                                            self.lk.data_ptr(), self.n, self.d, F.ctypes.data, ratio,
+                                            self._low.ctypes.data, self._high.ctypes.data, gamma, n_sweeps,
+                                            self.cfg.seed, self.id_offset, stage, sweep0, self.moved.data_ptr(),
+                                            self.icnt.data_ptr(), self._stream))
 
     # -------------------------------------------------------------------------------- the loop
     def run(self, particles=None, stream=None, keep_ancestors=False, hook=None):

@@ -1,0 +1,212 @@
+"""End-to-end parity of the sampler loop on the B200 (through the Python surface that sits on the C-ABI).
+
+* the reference's own run (golden fixture, same data / particles / uniforms / normals): beta schedule,
+  ESS, max likelihood, moved counts, sweeps per stage, ancestors, final particles, log-evidence;
+* the engine's default randomness (Philox) against the oracle loop fed by the NumPy Philox twin;
+* full-size (2^20) runs through size-independent properties.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kinetic, mm, smc
+
+pytestmark = pytest.mark.gpu
+
+REL_FP64 = 1e-5   # north_star bar for log-weights, beta schedule, log-evidence, posterior means
+
+
+def _oracle_replay(golden):
+    st = smc.ReferenceStream(int(golden["seed"]))
+    pp = st.prior_uniform([0, 0, 0], [10, 10, 10], 1000)
+    k = [0]
+
+    def ll(p):
+        k[0] += 1
+        return golden["sweeps_out"][k[0] - 1]
+
+    return smc.run(ll, pp, np.zeros(3), np.full(3, 10.0), smc.Settings(), st)
+
+
+@pytest.mark.parametrize("scan_mode", ["sequential", "fixed"])
+def test_reference_run_is_reproduced(golden, mm_engine_factory, scan_mode):
+    """BASELINE config 1: the reference's MM run (N=1000, seed 20250205), same random inputs."""
+    eng = mm_engine_factory(1000, scan_mode=scan_mode)
+    st = smc.ReferenceStream(int(golden["seed"]))
+    prior = st.prior_uniform([0, 0, 0], [10, 10, 10], 1000)
+    assert np.array_equal(prior, golden["prior_particles"])
+    seen = []
+
+    def hook(kind, **kw):
+        if kind == "sweep":
+            seen.append(kw["engine"].particles().cpu().numpy())
+
+    res = eng.run(prior, stream=st, keep_ancestors=True, hook=hook)
+    T = golden["stage_table"]
+    assert res.reached_one and len(res.betas) == len(T) == 14
+    assert np.array_equal(np.array(res.betas), T[:, 4])                      # beta schedule: identical
+    assert np.abs(np.array(res.ess) / T[:, 2] - 1).max() < 1e-9
+    assert np.abs(np.array([s.max_lk for s in res.stages]) / T[:, 3] - 1).max() < 1e-9
+    assert np.array_equal(np.array(res.n_moved), T[:, 5])
+    assert np.array_equal(np.array(res.n_mh) - 1, T[:, 1])
+    _, _, tr = _oracle_replay(golden)
+    for a, b in zip(res.ancestors, tr.ancestors):
+        assert np.array_equal(a, b)                                           # ancestors: bit-exact
+    assert abs(res.log_evidence - tr.log_evidence[-1]) < 1e-8 * abs(tr.log_evidence[-1])
+    assert abs(res.log_evidence - 567.031312) < 1e-5
+    assert np.abs(res.particles - golden["final_particles"]).max() < 1e-9
+    assert np.abs(res.lk / golden["final_lk"] - 1).max() < 1e-9
+    assert np.abs(res.particles.mean(0) / golden["final_particles"].mean(0) - 1).max() < REL_FP64
+    assert res.n_eval_reference == 34 * 1000 and res.n_eval <= res.n_eval_reference
+    # every particle matrix that went into a sweep equals the reference's (sweeps_in[1:] are proposals;
+    # the engine's state before sweep j equals the reference's p_filt, checked through the final state)
+    assert len(seen) == 33
+    eng.close()
+
+
+def test_script_shape_surface(golden, mm_engine_factory, pkg):
+    """sim_particle / cal_prior keep the reference's call shape (Micmem_likelihood.py:79-92)."""
+    from importlib import import_module
+    eng = mm_engine_factory(1000)
+    surf = import_module(pkg.__name__ + ".reference_api").ReferenceSurface(eng)
+    llk, C = surf.sim_particle(golden["prior_particles"], with_predictions=True)
+    assert np.abs(llk / golden["sweeps_out"][0] - 1).max() < 1e-9
+    assert np.abs(C[:8] - golden["pmodel0"]).max() < 1e-11
+    pr = surf.cal_prior(np.array([[1.0, 1.0, 1.0], [11.0, 1.0, 1.0], [10.0, 0.0, 5.0]]))
+    assert list(pr > 0) == [True, False, True]
+    eng.close()
+
+
+def _rate_problem(pkg, n_obs, precision=64):
+    lik = pkg.MMRate.synthetic(n_obs, precision=precision)
+    prior = pkg.UniformBox([0, 0, 0], [10, 10, 10])
+    return lik, prior
+
+
+@pytest.mark.parametrize("scan_mode", ["fixed", "sequential"])
+def test_philox_run_matches_oracle_loop_mm_rate(pkg, scan_mode):
+    """Default engine path (device Philox, device prior sample) vs the oracle loop with the NumPy
+    Philox twin: same schedule, same ancestors, same posterior."""
+    N, n_obs, seed = 4096, 300, 20250205
+    lik, prior = _rate_problem(pkg, n_obs)
+    cfg = pkg.Settings(n_particle=N, scan_mode=scan_mode, seed=seed)
+    eng = pkg.Engine(lik, prior, cfg)
+    eng.sample_prior()
+    p0 = eng.particles().cpu().numpy()
+    from oracle import philox
+    assert np.array_equal(p0, philox.uniform_box(seed, np.arange(N, dtype=np.uint64), prior.low, prior.high))
+    res = eng.run(keep_ancestors=True)
+    rs = smc.resample_fixed if scan_mode == "fixed" else smc.resample_sequential
+    p, lk, tr = smc.run(lambda th: mm.loglik_rate(th, lik.S, lik.v), p0, prior.low, prior.high,
+                        smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=rs)
+    assert np.array_equal(np.array(res.betas), np.array(tr.gamma))
+    assert res.n_mh == tr.n_mh and res.n_moved == tr.moved
+    for a, b in zip(res.ancestors, tr.ancestors):
+        assert np.array_equal(a, b)
+    assert np.abs(np.array(res.ess) / np.array(tr.ess) - 1).max() < 1e-9
+    assert abs(res.log_evidence / tr.log_evidence[-1] - 1) < 1e-9
+    assert np.abs(res.particles - p).max() < 1e-9 and np.abs(res.lk / lk - 1).max() < 1e-9
+    assert np.abs(res.particles.mean(0) / p.mean(0) - 1).max() < REL_FP64
+    eng.close()
+
+
+def test_bisection_rule_matches_oracle(pkg):
+    N = 2048
+    lik, prior = _rate_problem(pkg, 200)
+    eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N, temper_rule="bisect"))
+    eng.sample_prior()
+    eng.sim_particle()
+    lk = eng.lk.cpu().numpy()
+    t = eng.temper(0.0)
+    o = smc.temper_bisect(lk, 0.0, 0.5)
+    assert abs(t["gamma_new"] / o["gamma_new"] - 1) < 1e-9 and abs(t["ess"] - 0.5) < 1e-6
+    eng.close()
+
+
+def test_kinetic_run_matches_oracle_loop(pkg):
+    """BASELINE config 3 shape at a size the oracle can follow: methanation-style reactor, d=5."""
+    N, seed = 1024, 20250205
+    cond = kinetic.synthetic_conditions(8)
+    base = kinetic.base_vector(4)
+    obs = kinetic.synthetic_observations(cond, base, n_steps=20)
+    low, high = kinetic.reference_box()
+    lik = pkg.KineticRK(cond, obs, base, kinetic.EST_POSITION, n_steps=20)
+    prior = pkg.UniformBox(low, high)
+    eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N, seed=seed))
+    eng.sample_prior()
+    p0 = eng.particles().cpu().numpy()
+    res = eng.run(keep_ancestors=True)
+    p, lk, tr = smc.run(lambda th: kinetic.loglik(th, cond, obs, base, kinetic.EST_POSITION, 20), p0, low, high,
+                        smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed)
+    assert res.reached_one
+    assert np.array_equal(np.array(res.betas), np.array(tr.gamma))
+    for a, b in zip(res.ancestors, tr.ancestors):
+        assert np.array_equal(a, b)
+    assert abs(res.log_evidence / tr.log_evidence[-1] - 1) < 1e-8
+    assert np.abs(res.particles / p - 1).max() < 1e-8
+    assert np.abs(res.particles.mean(0) / p.mean(0) - 1).max() < REL_FP64
+    eng.close()
+
+
+def test_fused_sweeps_match_oracle_with_frozen_factor(pkg):
+    """smcb_mh_fused: k sweeps in one launch, proposal factor frozen (documented deviation)."""
+    N, seed, k = 512, 11, 3
+    cond = kinetic.synthetic_conditions(6)
+    base = kinetic.base_vector(4)
+    obs = kinetic.synthetic_observations(cond, base, n_steps=10)
+    low, high = kinetic.reference_box()
+    lik = pkg.KineticRK(cond, obs, base, kinetic.EST_POSITION, n_steps=10)
+    eng = pkg.Engine(lik, pkg.UniformBox(low, high), pkg.Settings(n_particle=N, seed=seed))
+    eng.sample_prior()
+    eng.sim_particle()
+    X, lk1 = eng.particles().cpu().numpy(), eng.lk.cpu().numpy().copy()
+    F, _ = eng.proposal_factor()
+    gamma, ratio, stage = 0.01, 0.25, 4
+    eng.moved.zero_()
+    eng.icnt.zero_()
+    eng.mh_fused(gamma, F, ratio, stage, 0, k)
+    from oracle import philox
+    ids = np.arange(N, dtype=np.uint64)
+    r_ac = np.zeros(N, dtype=np.int32)
+    n_in = 0
+    for s in range(k):
+        Z, U = philox.normals(seed, ids, stage, s, 5), philox.uniforms(seed, ids, stage, s)
+        X, lk1, r, ne = smc.mh_sweep(X, lk1, gamma, F, Z, U, ratio,
+                                     lambda th: kinetic.loglik(th, cond, obs, base, kinetic.EST_POSITION, 10), low, high)
+        r_ac = np.maximum(r_ac, r)
+        n_in += ne
+    assert np.array_equal(eng.moved.cpu().numpy(), r_ac.astype(np.uint8))
+    c = eng.icnt.cpu().numpy()
+    assert c[1] == r_ac.sum() and c[2] == n_in
+    assert np.abs(eng.particles().cpu().numpy() / X - 1).max() < 1e-9
+    assert np.abs(eng.lk.cpu().numpy() / lk1 - 1).max() < 1e-9
+    eng.close()
+
+
+def test_full_size_run_properties(pkg, golden):
+    """BASELINE config 2: MM progress curves, 2^20 particles, FP64.  The oracle cannot follow 3.6e7
+    scipy solves, so check what must hold at any size: schedule monotone to exactly 1, ESS above the
+    limit, ancestors sorted, posterior agreeing with the reference's N=1000 posterior within Monte
+    Carlo error, log-evidence agreeing with the reference-run value."""
+    N = 1 << 20
+    lik = pkg.MMProgress(golden["data_t"], golden["data_P"], golden["data_S0"])
+    prior = pkg.UniformBox([0, 0, 0], [10, 10, 10])
+    eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N))
+    eng.sample_prior()
+    res = eng.run()
+    b = np.array(res.betas)
+    assert res.reached_one and b[-1] == 1.0 and np.all(np.diff(b) > 0)
+    assert np.all(np.array(res.ess) > 0.5)
+    assert all(s.filled in (N - 1, N, N + 1) for s in res.stages)
+    anc = eng.anc[:N].cpu().numpy()
+    assert np.all(np.diff(anc) >= 0)
+    ref = golden["final_particles"]
+    se = ref.std(0) / np.sqrt(500.0)              # the reference cloud has ~657 distinct ancestors
+    assert np.all(np.abs(res.particles.mean(0) - ref.mean(0)) < 5 * se)
+    assert abs(res.log_evidence - 567.03) < 0.5
+    # spot-check the device likelihood of 256 posterior particles against scipy (the reference arithmetic)
+    idx = np.random.RandomState(0).choice(N, 256, replace=False)
+    d = (golden["data_t"], golden["data_P"], golden["data_S0"])
+    want = np.array([mm.loglik_progress_scipy(p, *d) for p in res.particles[idx]])
+    assert np.abs(res.lk[idx] / want - 1).max() < 1e-9
+    eng.close()

@@ -1,0 +1,351 @@
+"""Per-kernel parity: every C-ABI entry point on the B200 against the CPU oracle / the golden run of the
+unmodified reference, on the same inputs.  Bars (BASELINE.json north_star): ancestor indices and
+all integer work bit-exact; FP64 quantities within 1e-5 relative (the tests assert far tighter bounds
+where the arithmetic allows and say so), FP32 within 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kinetic, mm, philox, smc
+
+pytestmark = pytest.mark.gpu
+
+REL_FP64 = 1e-5   # north_star bar
+REL_FP32 = 1e-3
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from _abi import Abi
+    a = Abi(1 << 21, 32)
+    yield a
+    a.close()
+
+
+@pytest.fixture(scope="module")
+def mm_abi(abi, golden):
+    t, P, S0 = (np.ascontiguousarray(golden[k]) for k in ("data_t", "data_P", "data_S0"))
+    abi.ck(abi.lib.smcb_set_data_mm_progress(abi.h, t.ctypes.data, P.ctypes.data, S0.ctypes.data, t.shape[0],
+                                             t.shape[1]))
+    return abi
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    same_inf = np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b))
+    den = np.maximum(np.abs(b), 1e-300)
+    r = np.abs(a - b) / den
+    r[same_inf] = 0.0
+    return r
+
+
+# ------------------------------------------------------------------------------------ K1 MM progress
+@pytest.mark.parametrize("sweep", [0, 1, 5, 20, 33])
+def test_mm_progress_matches_reference_sweeps(mm_abi, golden, sweep):
+    """Every particle of sweeps the reference itself evaluated (prior cloud ... posterior cloud)."""
+    P, want = golden["sweeps_in"][sweep], golden["sweeps_out"][sweep]
+    got = mm_abi.loglik(1, P)
+    rel = _rel(got, want)
+    assert rel.max() < REL_FP64
+    assert rel.max() < 1e-9, rel.max()      # the DOPRI5 twin is operation-for-operation; only pow() ulps differ
+    st = mm_abi.stats()
+    assert st[3] == 0 and st[0] > 6 * 1000 * 8
+
+
+def test_mm_progress_known_answers_and_edge_cases(mm_abi, golden):
+    th = np.array([[1.2, 0.5, 0.02], [1.0, 0.4, 0.05], [1.0, 0.4, 0.0], [1.0, 0.4, -1.0], [0.0, 1.0, 1.0],
+                   [5.0, 1e-9, 0.1], [1e-12, 5.0, 0.3], [10.0, 10.0, 10.0]])
+    got = mm_abi.loglik(1, th)
+    d = (golden["data_t"], golden["data_P"], golden["data_S0"])
+    want = np.array([mm.loglik_progress_scipy(p, *d) for p in th])
+    assert abs(got[0] - 593.9635684697922) < 1e-7 and abs(got[1] - 424.5676547271564) < 1e-7
+    assert got[2] == -np.inf and got[3] == -np.inf            # sigma <= 0 (Micmem_likelihood.py:53-54)
+    assert _rel(got, want).max() < 1e-8
+
+
+def test_mm_progress_active_mask_and_ragged_sizes(mm_abi, golden):
+    P = golden["sweeps_in"][0]
+    full = mm_abi.loglik(1, P)
+    for n in (1, 31, 33, 127, 129, 1000):
+        assert np.array_equal(mm_abi.loglik(1, P[:n]), full[:n])      # independent of launch shape
+    act = (np.arange(1000) % 3 == 0).astype(np.uint8)
+    part = mm_abi.loglik(1, P, active=act)
+    assert np.array_equal(part[act == 1], full[act == 1]) and np.all(part[act == 0] == 0.0)
+
+
+def test_mm_progress_predictions(mm_abi, golden):
+    P = golden["prior_particles"][:8]
+    th = mm_abi.t(P.T)
+    pred = mm_abi.zeros(8, 6, 40)
+    mm_abi.ck(mm_abi.lib.smcb_predict_mm_progress(mm_abi.h, th.data_ptr(), 8, 8, pred.data_ptr(), None))
+    got = pred.cpu().numpy()
+    want = golden["pmodel0"]
+    assert np.abs(got - want).max() < 1e-11
+
+
+# ------------------------------------------------------------------------------------ K1 MM rate
+@pytest.mark.parametrize("n_obs", [1, 63, 2048, 10000])
+def test_mm_rate_fp64_and_fp32(abi, n_obs):
+    rs = np.random.RandomState(3)
+    S = np.exp(rs.uniform(np.log(0.05), np.log(20.0), n_obs))
+    v = 1.2 * S / (0.5 + S) + 0.02 * rs.standard_normal(n_obs)
+    th = rs.uniform(0, 10, (777, 3))
+    th[5, 2] = 0.0
+    want = mm.loglik_rate(th, S, v)
+    for prec, tol in ((64, 1e-12), (32, REL_FP32)):
+        abi.ck(abi.lib.smcb_set_data_mm_rate(abi.h, S.ctypes.data, v.ctypes.data, n_obs, prec))
+        got = abi.loglik(2, th)
+        assert got[5] == -np.inf
+        assert _rel(got, want).max() < tol, (prec, _rel(got, want).max())
+
+
+# ------------------------------------------------------------------------------------ K1' kinetic
+@pytest.mark.parametrize("n_pairs,d", [(4, 5), (16, 32)])
+def test_kinetic_matches_oracle(abi, n_pairs, d):
+    cond = kinetic.synthetic_conditions(30)
+    base = kinetic.base_vector(n_pairs)
+    obs = kinetic.synthetic_observations(cond, base)
+    if n_pairs == 4:
+        est = np.array(kinetic.EST_POSITION, dtype=np.int32)
+        low, high = kinetic.reference_box()
+    else:
+        est = np.arange(32, dtype=np.int32)
+        low, high = base[:32] * 0.9, base[:32] * 1.1
+        low, high = np.minimum(low, high), np.maximum(low, high)
+    abi.ck(abi.lib.smcb_set_data_kinetic(abi.h, cond.ctypes.data, obs.ctypes.data, 30, base.ctypes.data, n_pairs,
+                                         est.ctypes.data, d, 50))
+    rs = np.random.RandomState(1)
+    th = rs.uniform(low, high, (300, d))
+    th[0] = base[est]
+    want = kinetic.loglik(th, cond, obs, base, est, 50)
+    got = abi.loglik(3, th)
+    assert np.all(np.isfinite(got))
+    assert _rel(got, want).max() < 1e-9, _rel(got, want).max()
+
+
+# ------------------------------------------------------------------------------------ K2 tempering
+@pytest.mark.parametrize("n", [1, 2, 777, 1000, (1 << 20) + 3])
+def test_temper_reductions(abi, n):
+    rs = np.random.RandomState(n % 1000)
+    lk = rs.normal(300, 80, n)
+    if n > 10:
+        lk[3] = -np.inf
+        lk[7] = -618002.599096893
+    t = abi.t(lk)
+    out = abi.zeros(40)
+    abi.ck(abi.lib.smcb_lk_max(abi.h, t.data_ptr(), n, out.data_ptr(), None))
+    assert out[0].item() == lk.max()
+    gms = np.array([1.0 * 0.7 ** k for k in range(0, 32, 2)])
+    for nc in (1, 2, 3, 8, 16):
+        g = np.ascontiguousarray(gms[:nc])
+        abi.ck(abi.lib.smcb_temper_sums(abi.h, t.data_ptr(), n, out.data_ptr(), g.ctypes.data, nc,
+                                        out[2:].data_ptr(), None))
+        got = out[2:2 + 2 * nc].cpu().numpy()
+        for k in range(nc):
+            w = np.exp((lk - lk.max()) * g[k])
+            assert abs(got[2 * k] - w.sum()) <= 1e-12 * w.sum()
+            assert abs(got[2 * k + 1] - (w * w).sum()) <= 1e-12 * (w * w).sum()
+
+
+def test_weights_kernel_matches_numpy(abi):
+    rs = np.random.RandomState(0)
+    lk = rs.normal(300, 80, 5000)
+    t, out, w = abi.t(lk), abi.zeros(4), abi.zeros(5000)
+    gm = 0.0023263051398720674
+    ref = np.exp((lk - lk.max()) * gm)
+    out[0], out[1] = lk.max(), ref.sum()
+    abi.ck(abi.lib.smcb_weights(abi.h, t.data_ptr(), 5000, out.data_ptr(), gm, out[1:].data_ptr(), w.data_ptr(), None))
+    assert _rel(w.cpu().numpy(), ref / ref.sum()).max() < 4e-16      # exp() within an ulp
+
+
+# ------------------------------------------------------------------------------------ K3 resampling
+def _weights(n, seed, conc=0.3):
+    return np.random.RandomState(seed).dirichlet(np.full(n, conc))
+
+
+def _resample(abi, w, u0, mode, n_total=None, carry_q=0, id_offset=0, m=None):
+    n = w.shape[0]
+    n_total = n if n_total is None else n_total
+    m = n if m is None else m
+    wt = abi.t(w)
+    counts = abi.zeros(n, dtype=torch.int32)
+    tot = abi.zeros(2, dtype=torch.int64)
+    abi.ck(abi.lib.smcb_resample_counts(abi.h, wt.data_ptr(), n, n_total, u0, mode, None, carry_q, id_offset,
+                                        counts.data_ptr(), tot.data_ptr(), None))
+    anc = abi.zeros(m, dtype=torch.int32)
+    filled = abi.zeros(1, dtype=torch.int64)
+    abi.ck(abi.lib.smcb_ancestors(abi.h, counts.data_ptr(), n, m, anc.data_ptr(), filled.data_ptr(), None))
+    torch.cuda.synchronize()
+    return counts.cpu().numpy().astype(np.int64), anc.cpu().numpy().astype(np.int64), tot.cpu().numpy(), int(filled.item())
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (7, 2), (1000, 3), (2048, 4), (2049, 5), (5000, 6), (65536, 7)])
+@pytest.mark.parametrize("u0", [0.0, 0.37, 0.999999])
+def test_resample_sequential_is_bit_exact(abi, n, seed, u0):
+    """Same weights, same uniform -> the reference's ancestors, bit for bit (Micmem_SMC_main.py:147-184)."""
+    w = _weights(n, seed)
+    a_ref, c_ref, info = smc.resample_sequential(w, u0)
+    c, a, tot, filled = _resample(abi, w, u0, 0)
+    assert np.array_equal(c, c_ref)
+    assert filled == info["n_filled"] and tot[0] == info["n_floor"] and tot[1] == info["n_cross"]
+    assert np.array_equal(a, smc.fit_ancestors(a_ref, n))
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (7, 2), (1000, 3), (2048, 4), (2049, 5), (5000, 6), (65536, 7)])
+@pytest.mark.parametrize("u0", [0.0, 0.37, 0.999999])
+def test_resample_fixed_matches_integer_twin(abi, n, seed, u0):
+    w = _weights(n, seed)
+    a_ref, c_ref, info = smc.resample_fixed(w, u0)
+    c, a, tot, filled = _resample(abi, w, u0, 1)
+    assert np.array_equal(c, c_ref)
+    assert tot[0] == info["n_floor"] and tot[1] == info["q_total"]
+    assert np.array_equal(a, smc.fit_ancestors(a_ref, n))
+
+
+def test_resample_golden_stage_weights(abi, golden):
+    """Weights of the reference's first stage (from its own likelihoods) and its own rand() draw."""
+    lk = golden["sweeps_out"][0]
+    t = smc.temper_backoff(lk, 0.0, smc.Settings())
+    u0 = float(golden["draws_rand"][0])
+    a_ref, c_ref, _ = smc.resample_sequential(t["p_weight"], u0)
+    for mode in (0, 1):
+        c, a, _, _ = _resample(abi, t["p_weight"], u0, mode)
+        assert np.array_equal(c, c_ref) and np.array_equal(a, a_ref)
+    assert len(np.unique(a_ref)) == 783           # SURVEY.md 6.2, stage 1 distinct ancestors
+
+
+def test_resample_degenerate_and_padding(abi):
+    w = np.zeros(3000)
+    w[1717] = 1.0
+    for mode in (0, 1):
+        c, a, _, filled = _resample(abi, w, 0.5, mode)
+        assert c[1717] == 3000 and c.sum() == 3000 and np.all(a == 1717)
+    # under-filled output is padded with the last ancestor, over-filled output is cut
+    counts = np.array([2, 0, 1, 0], dtype=np.int32)
+    ct = abi.t(counts, torch.int32)
+    for m, want in ((6, [0, 0, 2, 2, 2, 2]), (2, [0, 0]), (3, [0, 0, 2])):
+        anc = abi.zeros(m, dtype=torch.int32)
+        filled = abi.zeros(1, dtype=torch.int64)
+        abi.ck(abi.lib.smcb_ancestors(abi.h, ct.data_ptr(), 4, m, anc.data_ptr(), filled.data_ptr(), None))
+        assert anc.cpu().tolist() == want and filled.item() == 3
+
+
+def test_resample_fixed_is_shard_invariant(abi):
+    """Counts computed shard by shard with the carried fixed-point prefix equal the unsharded counts."""
+    n, W = 1 << 16, 4
+    w = _weights(n, 11)
+    u0 = 0.6180339887
+    c_full, _, tot_full, _ = _resample(abi, w, u0, 1)
+    nl = n // W
+    carry, got = 0, []
+    for r in range(W):
+        wt = abi.t(w[r * nl:(r + 1) * nl])
+        tot = abi.zeros(2, dtype=torch.int64)
+        abi.ck(abi.lib.smcb_resample_totals(abi.h, wt.data_ptr(), nl, n, tot.data_ptr(), None))
+        c, _, tot2, _ = _resample(abi, w[r * nl:(r + 1) * nl], u0, 1, n_total=n, carry_q=carry, id_offset=r * nl)
+        assert np.array_equal(tot.cpu().numpy(), tot2)
+        carry += int(tot2[1])
+        got.append(c)
+    assert np.array_equal(np.concatenate(got), c_full) and carry == tot_full[1]
+
+
+def test_resample_full_size_properties(abi):
+    """2^20 particles (BASELINE config 2 size): size-independent properties."""
+    n = 1 << 20
+    rs = np.random.RandomState(5)
+    lk = rs.normal(0, 3, n)
+    w = np.exp(lk - lk.max())
+    w /= w.sum()
+    c, a, tot, filled = _resample(abi, w, 0.123456789, 1)
+    assert abs(filled - n) <= 1 and c.sum() == filled
+    assert np.all(np.diff(a) >= 0) and a.min() >= 0 and a.max() < n
+    assert np.array_equal(np.bincount(a, minlength=n)[: n - 1], c[: n - 1])
+    fl = np.trunc(w * n)
+    assert np.all(c >= fl) and np.all(c <= fl + 1)
+    # sequential mode agrees except at ~1e-13 near-ties
+    c2, a2, _, _ = _resample(abi, w, 0.123456789, 0)
+    assert (c != c2).sum() <= 2
+    # gather: checksum of checksums
+    D1 = 4
+    src = torch.arange(D1 * n, dtype=torch.float64, device=abi.dev).reshape(D1, n)
+    dst = torch.zeros_like(src)
+    at = abi.t(a, torch.int32)
+    abi.ck(abi.lib.smcb_gather(abi.h, src.data_ptr(), n, at.data_ptr(), n, D1, dst.data_ptr(), n, None))
+    want = src[:, at.long()]
+    assert torch.equal(dst, want)
+
+
+# ------------------------------------------------------------------------------------ K4 MH
+@pytest.mark.parametrize("d,n", [(1, 100), (3, 1000), (5, 4097), (8, 3000), (32, 2500)])
+def test_moments_match_numpy_cov(abi, d, n):
+    rs = np.random.RandomState(d)
+    X = rs.normal(0, 1, (n, d)) @ rs.normal(0, 1, (d, d)) + rs.uniform(1e3, 1e6, d)   # large offsets (H4)
+    th = abi.t(X.T)
+    mom = abi.zeros(d + d * d)
+    abi.ck(abi.lib.smcb_colsum(abi.h, th.data_ptr(), n, n, d, mom.data_ptr(), None))
+    mean = mom[:d] / n
+    assert _rel(mean.cpu().numpy(), X.mean(axis=0)).max() < 1e-13
+    mom[:d] = mean
+    abi.ck(abi.lib.smcb_centered_moments(abi.h, th.data_ptr(), n, n, d, mom.data_ptr(), mom[d:].data_ptr(), None))
+    cov = mom[d:].cpu().numpy().reshape(d, d) / n
+    want = np.atleast_2d(np.cov(X.T, bias=True))
+    assert np.abs(cov - want).max() <= 1e-10 * np.abs(want).max()
+    assert np.array_equal(cov, cov.T)
+
+
+def test_philox_draws_match_numpy_twin(abi):
+    n, d, seed = 5000, 5, 20250205
+    z, u = abi.zeros(n, d), abi.zeros(n)
+    abi.ck(abi.lib.smcb_philox_draws(abi.h, n, d, seed, 1 << 33, 7, 3, z.data_ptr(), u.data_ptr(), None))
+    ids = np.arange(n, dtype=np.uint64) + np.uint64(1 << 33)
+    assert np.array_equal(u.cpu().numpy(), philox.uniforms(seed, ids, 7, 3))
+    assert np.abs(z.cpu().numpy() - philox.normals(seed, ids, 7, 3, d)).max() < 1e-13
+    th = abi.zeros(3, n)
+    low, high = np.array([0.0, -5.0, 2.0]), np.array([10.0, 5.0, 2.5])
+    abi.ck(abi.lib.smcb_sample_uniform_box(abi.h, th.data_ptr(), n, n, 3, low.ctypes.data, high.ctypes.data, seed,
+                                           1 << 33, None))
+    assert np.array_equal(th.cpu().numpy().T, philox.uniform_box(seed, ids, low, high))
+
+
+@pytest.mark.parametrize("d", [3, 5, 32])
+def test_propose_and_accept_match_oracle(abi, d):
+    """Same particles, same normals, same uniforms -> same proposals, same accept decisions."""
+    n = 3001
+    rs = np.random.RandomState(d)
+    X = rs.uniform(0, 10, (n, d))
+    lk1 = rs.normal(100, 5, n)
+    A = rs.normal(0, 1, (d, d))
+    F = smc.proposal_factor(A @ A.T / d * 0.5)
+    Z, U = rs.standard_normal((n, d)), rs.uniform(0, 1, n)
+    low, high = np.zeros(d), np.full(d, 10.0)
+    lk2_all = rs.normal(100, 5, n)
+    gamma, ratio = 0.37, 0.5
+
+    def fake_loglik(p):
+        return lk2_all
+
+    p_new, lk_new, r, n_in = smc.mh_sweep(X, lk1, gamma, F, Z, U, ratio, fake_loglik, low, high)
+    step = np.dot(Z, F)
+    prop_ref = X + step * ratio
+    inbox_ref = smc.in_box(prop_ref, low, high)
+    prop_ref = np.where(inbox_ref[:, None], prop_ref, X)
+
+    th, lk, prop = abi.t(X.T), abi.t(lk1), abi.zeros(d, n)
+    inbox, moved = abi.zeros(n, dtype=torch.uint8), abi.zeros(n, dtype=torch.uint8)
+    cnt = abi.zeros(4, dtype=torch.int64)
+    Fc = np.ascontiguousarray(F)
+    abi.ck(abi.lib.smcb_mh_propose(abi.h, th.data_ptr(), n, n, d, Fc.ctypes.data, ratio, low.ctypes.data,
+                                   high.ctypes.data, abi.t(Z).data_ptr(), 1, 0, 1, 0, prop.data_ptr(), n,
+                                   inbox.data_ptr(), None))
+    assert np.array_equal(inbox.cpu().numpy().astype(bool), inbox_ref)
+    got_prop = prop.cpu().numpy().T
+    # z @ F is accumulated in the same order as np.dot for d<=8 up to FMA contraction
+    assert np.abs(got_prop - prop_ref).max() < 1e-13 * 10
+    abi.ck(abi.lib.smcb_mh_accept(abi.h, th.data_ptr(), n, lk.data_ptr(), prop.data_ptr(), n, abi.t(lk2_all).data_ptr(),
+                                  inbox.data_ptr(), n, d, gamma, abi.t(U).data_ptr(), 1, 0, 1, 0, moved.data_ptr(),
+                                  cnt.data_ptr(), None))
+    assert np.array_equal(moved.cpu().numpy(), r.astype(np.uint8))
+    c = cnt.cpu().numpy()
+    assert c[0] == r.sum() and c[1] == r.sum() and c[2] == n_in
+    assert np.array_equal(lk.cpu().numpy(), lk_new)
+    assert np.abs(th.cpu().numpy().T - p_new).max() < 1e-12
