@@ -249,7 +249,7 @@ __global__ void sample_box_kernel(double* __restrict__ theta, int64_t ld, int64_
     if (i >= n) return;
     for (int k = 0; k < d; ++k) {
         const double u = philox_uniform(seed, id_offset + (uint64_t)i, 0xFFFFFFFFu, (uint32_t)k, 0u);
-        theta[(int64_t)k * ld + i] = bx.low[k] + (bx.high[k] - bx.low[k]) * u;
+        theta[(int64_t)k * ld + i] = __dadd_rn(bx.low[k], __dmul_rn(bx.high[k] - bx.low[k], u));   // no FMA: same bits as NumPy
     }
 }
 

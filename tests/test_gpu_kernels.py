@@ -120,7 +120,32 @@ def test_kinetic_matches_oracle(abi, n_pairs, d):
     want = kinetic.loglik(th, cond, obs, base, est, 50)
     got = abi.loglik(3, th)
     assert np.all(np.isfinite(got))
-    assert _rel(got, want).max() < 1e-9, _rel(got, want).max()
+    # A few percent of the wide reference prior box are fast-kinetics particles for which the explicit
+    # fixed-step march is numerically unstable: there the result is sensitive to single ulps (the oracle
+    # disagrees with *itself* when a parameter moves by one ulp).  Those particles carry likelihoods
+    # ~1e6 below the mode (zero weight); parity is asserted on the well-conditioned ones.
+    th_ulp = th.copy()
+    th_ulp[:, 0] = np.nextafter(th_ulp[:, 0], np.inf)
+    sens = _rel(kinetic.loglik(th_ulp, cond, obs, base, est, 50), want)
+    good = sens < 1e-12
+    assert good.mean() > 0.9 and good[0]
+    assert _rel(got, want)[good].max() < 1e-9, _rel(got, want)[good].max()
+    assert np.all(want[~good] < want[0] - 100) and np.all(got[~good] < want[0] - 100)
+    assert _rel(got, want)[~good].max() < 0.5
+
+
+def test_kinetic_fixture_known_answers(abi):
+    """tests/golden/kinetic_synth.npz: oracle likelihoods committed with their inputs."""
+    import os
+    kf = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kinetic_synth.npz"))
+    for tag, n_pairs, est in (("4", 4, kf["est4"]), ("16", 16, np.arange(32, dtype=np.int32))):
+        cond, base, obs = (np.ascontiguousarray(kf[k]) for k in ("cond", "base" + tag, "obs" + tag))
+        est = np.ascontiguousarray(est, dtype=np.int32)
+        abi.ck(abi.lib.smcb_set_data_kinetic(abi.h, cond.ctypes.data, obs.ctypes.data, 30, base.ctypes.data, n_pairs,
+                                             est.ctypes.data, len(est), 50))
+        got, want = abi.loglik(3, kf["theta" + tag]), kf["lk" + tag]
+        rel = _rel(got, want)
+        assert np.median(rel) < 1e-12 and (rel < 1e-9).mean() > 0.9, (np.median(rel), rel.max())
 
 
 # ------------------------------------------------------------------------------------ K2 tempering
@@ -334,16 +359,18 @@ def test_propose_and_accept_match_oracle(abi, d):
     inbox, moved = abi.zeros(n, dtype=torch.uint8), abi.zeros(n, dtype=torch.uint8)
     cnt = abi.zeros(4, dtype=torch.int64)
     Fc = np.ascontiguousarray(F)
+    Zt, Ut, lk2t = abi.t(Z), abi.t(U), abi.t(lk2_all)      # keep the device copies alive across the launches
     abi.ck(abi.lib.smcb_mh_propose(abi.h, th.data_ptr(), n, n, d, Fc.ctypes.data, ratio, low.ctypes.data,
-                                   high.ctypes.data, abi.t(Z).data_ptr(), 1, 0, 1, 0, prop.data_ptr(), n,
+                                   high.ctypes.data, Zt.data_ptr(), 1, 0, 1, 0, prop.data_ptr(), n,
                                    inbox.data_ptr(), None))
     assert np.array_equal(inbox.cpu().numpy().astype(bool), inbox_ref)
     got_prop = prop.cpu().numpy().T
     # z @ F is accumulated in the same order as np.dot for d<=8 up to FMA contraction
     assert np.abs(got_prop - prop_ref).max() < 1e-13 * 10
-    abi.ck(abi.lib.smcb_mh_accept(abi.h, th.data_ptr(), n, lk.data_ptr(), prop.data_ptr(), n, abi.t(lk2_all).data_ptr(),
-                                  inbox.data_ptr(), n, d, gamma, abi.t(U).data_ptr(), 1, 0, 1, 0, moved.data_ptr(),
+    abi.ck(abi.lib.smcb_mh_accept(abi.h, th.data_ptr(), n, lk.data_ptr(), prop.data_ptr(), n, lk2t.data_ptr(),
+                                  inbox.data_ptr(), n, d, gamma, Ut.data_ptr(), 1, 0, 1, 0, moved.data_ptr(),
                                   cnt.data_ptr(), None))
+    torch.cuda.synchronize()
     assert np.array_equal(moved.cpu().numpy(), r.astype(np.uint8))
     c = cnt.cpu().numpy()
     assert c[0] == r.sum() and c[1] == r.sum() and c[2] == n_in
