@@ -90,13 +90,26 @@ int smcb_set_data_kinetic(smcb_handle* h, const double* cond_host, const double*
  * particles with active==0 are skipped and lk_dev[i] is left untouched. */
 int smcb_loglik(smcb_handle* h, int model, const double* theta_dev, int64_t ld, int64_t n, int d,
                 const uint8_t* active_dev, double* lk_dev, void* stream);
+/* The same sweep with early rejection: lkmin_dev[i] (may be NULL = smcb_loglik) is a value below which
+ * the caller does not need lk_dev[i] exactly (smcb_mh_threshold).  A particle whose log-likelihood is
+ * PROVEN to lie below lkmin_dev[i] - from an upper bound that only uses the residuals accumulated so
+ * far - may stop early and report -inf; every other particle reports its exact value.  MM_PROGRESS
+ * uses it; the other models ignore lkmin_dev. */
+int smcb_loglik_bounded(smcb_handle* h, int model, const double* theta_dev, int64_t ld, int64_t n, int d,
+                        const uint8_t* active_dev, const double* lkmin_dev, double* lk_dev, void* stream);
+/* Tunables.  SMCB_PARAM_MM_BUDGET: attempted RK steps after which the bulk MM_PROGRESS kernel hands a
+ * solve to the tail kernel (default 256; results do not depend on it). */
+#define SMCB_PARAM_MM_BUDGET 1
+int smcb_set_param(smcb_handle* h, int key, double value);
 /* Model predictions for a few particles (the `C_l_` the reference returns for its parity plots,
  * EX/lik:74-77): pred_dev[i][n_ex][n_t].  MM_PROGRESS only. */
 int smcb_predict_mm_progress(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n,
                              double* pred_dev, void* stream);
-/* Work counters of MM_PROGRESS sweeps, out_host int64[8]: [0]=RHS evaluations, [1]=accepted steps,
- * [2]=rejected steps, [3]=failed solves of the last sweep; [4..7] the same four accumulated over
- * every sweep since smcb_create.  Synchronous. */
+/* Work counters of MM_PROGRESS sweeps, out_host int64[16]: [0]=RHS evaluations, [1]=accepted steps,
+ * [2]=rejected steps, [3]=failed solves of the last sweep; [4..7] the same four accumulated over every
+ * sweep since smcb_create; [8]/[9] particles reported -inf by early rejection (last sweep / accumulated);
+ * [10] largest number of attempted steps of one solve in the last sweep; [11]/[12] solves deferred to
+ * the tail kernel; [13]/[14] particles the tail kernel processed; [15] unused.  Synchronous. */
 int smcb_loglik_stats(smcb_handle* h, int64_t* out_host);
 
 /* ---- K2: tempering reductions (replaces EX/main:116-134) --------------------------------- */
@@ -159,13 +172,22 @@ int smcb_mh_propose(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t
                     const double* z_dev, uint64_t seed, uint64_t id_offset, uint32_t stage, uint32_t sweep,
                     double* prop_dev, int64_t ld_prop, uint8_t* inbox_dev, void* stream);
 /* Accept step (EX/main:231-241): r = exp((lk2-lk1)*gamma)*inbox >= u; theta/lk updated in place;
- * moved_dev[i] |= r; counts_dev int64[3] += {accepted this sweep, newly moved, in-box proposals
- * (= likelihood evaluations this sweep performed)}.
+ * moved_dev[i] |= r; counts_dev int64[4] += {accepted this sweep, newly moved, in-box proposals
+ * (= likelihood evaluations this sweep requested), in-box proposals whose lk2 is -inf (= rejected early
+ * by smcb_loglik_bounded before every observation was integrated)}.
  *   u_dev: external uniforms [n] or NULL = Philox (same key, separate stream id). */
 int smcb_mh_accept(smcb_handle* h, double* theta_dev, int64_t ld, double* lk_dev, const double* prop_dev,
                    int64_t ld_prop, const double* lk2_dev, const uint8_t* inbox_dev, int64_t n, int d,
                    double gamma, const double* u_dev, uint64_t seed, uint64_t id_offset, uint32_t stage,
                    uint32_t sweep, uint8_t* moved_dev, int64_t* counts_dev, void* stream);
+/* Early-rejection threshold for smcb_loglik_bounded: with u the uniform smcb_mh_accept will draw for
+ * particle i (same u_dev / Philox key), the proposal is certainly rejected if
+ *     lk2 < lkmin[i] = lk1[i] + log(u)/gamma - margin,   margin = 1e-9*(1 + |lk1| + |log u|/gamma),
+ * because then exp((lk2-lk1)*gamma) < u even after rounding.  u == 0, gamma <= 0 or a non-finite lk1 give
+ * -inf (never reject early).  Out-of-box particles (inbox == 0) get -inf as well; they are not evaluated. */
+int smcb_mh_threshold(smcb_handle* h, const double* lk_dev, const uint8_t* inbox_dev, int64_t n, double gamma,
+                      const double* u_dev, uint64_t seed, uint64_t id_offset, uint32_t stage, uint32_t sweep,
+                      double* lkmin_dev, void* stream);
 /* Several MH sweeps fused in one launch with a frozen proposal factor (documented deviation from
  * the per-sweep covariance refresh of EX/main:212): propose + box + likelihood + accept, particle
  * state held in registers.  KINETIC_RK.  counts_dev int64[3] as for smcb_mh_accept. */

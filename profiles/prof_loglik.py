@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Likelihood-kernel micro-run for profiling (ncu) and for quick timing while tuning K1.
 
-    python profiles/prof_loglik.py [log2_particles=20] [reps=3] [model=mm_progress|mm_rate32|mm_rate64|kinetic|kinetic32]
+    python profiles/prof_loglik.py [log2_particles=20] [reps=3] [model=mm_progress|mm_rate32|mm_rate64|kinetic|kinetic32] [budget]
 
 Evaluates (a) a prior cloud (Philox uniform box) and (b) a posterior-like cloud (for MM: a Gaussian
 around the reference posterior) and prints the CUDA-event time of each sweep and the device work
@@ -37,6 +37,8 @@ else:
     lik = pkg.KineticRK(kf["cond"], kf["obs16"], b, np.arange(32, dtype=np.int32), n_steps=50)
     prior = pkg.UniformBox(np.minimum(b[:32] * 0.8, b[:32] * 1.2), np.maximum(b[:32] * 0.8, b[:32] * 1.2))
 eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N))
+if len(sys.argv) > 4:   # deferral budget of the bulk MM_PROGRESS kernel
+    eng._ck(eng.lib.smcb_set_param(eng.h, 1, float(sys.argv[4])))
 
 
 def sweep(tag):
@@ -50,7 +52,8 @@ def sweep(tag):
         extra = ""
         if model == "mm_progress":
             st = eng.loglik_stats()
-            extra = f" rhs/particle={st[0] / N:.1f} acc={st[1] / N:.1f} rej={st[2] / N:.1f} fail={st[3]}"
+            extra = (f" rhs/particle={st[0] / N:.1f} acc={st[1] / N:.1f} rej={st[2] / N:.1f} fail={st[3]}"
+                     f" max_attempts={st[10]} deferred_solves={st[11]} tail_particles={st[13]}")
         print(f"{model} {tag} N=2^{lg} rep{r}: {ms:.3f} ms  {N / ms * 1e3:.4g} evals/s{extra}", flush=True)
 
 

@@ -25,6 +25,8 @@ _SIGNATURES = {
     "smcb_set_data_mm_rate": [p_void, p_void, p_void, c_i64, c_int],
     "smcb_set_data_kinetic": [p_void, p_void, p_void, c_int, p_void, c_int, p_void, c_int, c_int],
     "smcb_loglik": [p_void, c_int, p_void, c_i64, c_i64, c_int, p_void, p_void, p_void],
+    "smcb_loglik_bounded": [p_void, c_int, p_void, c_i64, c_i64, c_int, p_void, p_void, p_void, p_void],
+    "smcb_set_param": [p_void, c_int, c_dbl],
     "smcb_predict_mm_progress": [p_void, p_void, c_i64, c_i64, p_void, p_void],
     "smcb_loglik_stats": [p_void, p_void],
     "smcb_lk_max": [p_void, p_void, c_i64, p_void, p_void],
@@ -41,6 +43,7 @@ _SIGNATURES = {
                         c_u32, c_u32, p_void, c_i64, p_void, p_void],
     "smcb_mh_accept": [p_void, p_void, c_i64, p_void, p_void, c_i64, p_void, p_void, c_i64, c_int, c_dbl, p_void,
                        c_u64, c_u64, c_u32, c_u32, p_void, p_void, p_void],
+    "smcb_mh_threshold": [p_void, p_void, p_void, c_i64, c_dbl, p_void, c_u64, c_u64, c_u32, c_u32, p_void, p_void],
     "smcb_mh_fused": [p_void, c_int, p_void, c_i64, p_void, c_i64, c_int, p_void, c_dbl, p_void, p_void, c_dbl,
                       c_int, c_u64, c_u64, c_u32, c_u32, p_void, p_void, p_void],
     "smcb_philox_draws": [p_void, c_i64, c_int, c_u64, c_u64, c_u32, c_u32, p_void, p_void, p_void],
@@ -55,6 +58,8 @@ MODEL_MM_PROGRESS, MODEL_MM_RATE, MODEL_KINETIC_RK = 1, 2, 3
 SCAN_SEQUENTIAL, SCAN_FIXED = 0, 1
 MAX_DIM, MAX_CAND = 32, 16
 KIN_NCOND_FIELDS = 10
+PARAM_MM_BUDGET = 1
+N_STATS = 16
 
 
 def library_path():

@@ -89,9 +89,11 @@ extern "C" int smcb_create(int device, smcb_handle** out) {
     smcb_handle* h = new smcb_handle();
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
-    e = cudaMalloc(reinterpret_cast<void**>(&h->stats), 8 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(h->stats, 0, 8 * sizeof(unsigned long long));
+    e = cudaMalloc(reinterpret_cast<void**>(&h->stats), SMCB_N_STATS * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(h->stats, 0, SMCB_N_STATS * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->seq_carry), 4 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mm_ctl), 4 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(h->mm_ctl, 0, 4 * sizeof(unsigned));
     if (e != cudaSuccess) {
         smcb_fail(nullptr, SMCB_ERR_CUDA, "smcb_create: cudaMalloc: %s", cudaGetErrorString(e));
         delete h;
@@ -104,7 +106,7 @@ extern "C" int smcb_create(int device, smcb_handle** out) {
 extern "C" int smcb_destroy(smcb_handle* h) {
     if (!h) return SMCB_OK;
     cudaSetDevice(h->device);
-    dev_free(&h->ssr); dev_free(&h->partial); dev_free(&h->stats); dev_free(&h->task_counter);
+    dev_free(&h->ssr); dev_free(&h->partial); dev_free(&h->stats); dev_free(&h->mm_ctl); dev_free(&h->mm_defer); dev_free(&h->mm_cutlim);
     dev_free(&h->floor_cnt); dev_free(&h->resid_q); dev_free(&h->resid_f); dev_free(&h->tile_tot);
     dev_free(&h->tile_tot2); dev_free(&h->mark); dev_free(&h->seq_carry);
     dev_free(&h->mmp.t); dev_free(&h->mmp.P); dev_free(&h->mmp.S0);
@@ -130,6 +132,8 @@ extern "C" int smcb_reserve(smcb_handle* h, int64_t n_max, int d_max) {
     if ((rc = dev_alloc(h, &h->resid_q, (size_t)n_max))) return rc;
     if ((rc = dev_alloc(h, &h->resid_f, (size_t)n_max))) return rc;
     if ((rc = dev_alloc(h, &h->mark, (size_t)n_max))) return rc;
+    if ((rc = dev_alloc(h, &h->mm_defer, (size_t)n_max))) return rc;
+    if ((rc = dev_alloc(h, &h->mm_cutlim, (size_t)n_max))) return rc;
     const size_t tiles = (size_t)(n_max + 2047) / 2048 + 8;
     if ((rc = dev_alloc(h, &h->tile_tot, 2 * tiles))) return rc;
     if ((rc = dev_alloc(h, &h->tile_tot2, 2 * tiles))) return rc;
@@ -157,6 +161,8 @@ extern "C" int smcb_set_data_mm_progress(smcb_handle* h, const double* t_host, c
     CUDA_TRY(h, cudaMemcpy(h->mmp.S0, S0_host, n_ex * sizeof(double), cudaMemcpyHostToDevice));
     h->mmp.n_ex = n_ex;
     h->mmp.n_t = n_t;
+    h->mm_bulk_blocks_per_sm = 0;   // shared-memory footprint changed: query the occupancy again
+    h->mm_smem_set = false;
     if (h->n_max > 0 && n_ex > h->ssr_rows) return smcb_reserve(h, h->n_max, h->d_max);
     return SMCB_OK;
 }
@@ -182,13 +188,19 @@ extern "C" int smcb_set_data_mm_rate(smcb_handle* h, const double* S_host, const
 
 extern "C" int smcb_loglik(smcb_handle* h, int model, const double* theta_dev, int64_t ld, int64_t n, int d,
                            const uint8_t* active_dev, double* lk_dev, void* stream) {
+    return smcb_loglik_bounded(h, model, theta_dev, ld, n, d, active_dev, nullptr, lk_dev, stream);
+}
+
+extern "C" int smcb_loglik_bounded(smcb_handle* h, int model, const double* theta_dev, int64_t ld, int64_t n, int d,
+                                   const uint8_t* active_dev, const double* lkmin_dev, double* lk_dev,
+                                   void* stream) {
     REQUIRE(h, h && theta_dev && lk_dev, SMCB_ERR_INVALID, "null pointer");
     REQUIRE(h, n >= 0 && ld >= n, SMCB_ERR_INVALID, "need 0<=n<=ld");
     cudaStream_t st = as_stream(stream);
     switch (model) {
         case SMCB_MODEL_MM_PROGRESS:
             REQUIRE(h, d == 3, SMCB_ERR_INVALID, "MM_PROGRESS expects d=3 (Vmax, Km, sigma)");
-            return launch_loglik_mm_progress(h, theta_dev, ld, n, active_dev, lk_dev, nullptr, st);
+            return launch_loglik_mm_progress(h, theta_dev, ld, n, active_dev, lkmin_dev, lk_dev, nullptr, st);
         case SMCB_MODEL_MM_RATE:
             REQUIRE(h, d == 3, SMCB_ERR_INVALID, "MM_RATE expects d=3 (Vmax, Km, sigma)");
             return launch_loglik_mm_rate(h, theta_dev, ld, n, active_dev, lk_dev, st);
@@ -199,15 +211,27 @@ extern "C" int smcb_loglik(smcb_handle* h, int model, const double* theta_dev, i
     }
 }
 
+extern "C" int smcb_set_param(smcb_handle* h, int key, double value) {
+    REQUIRE(h, h != nullptr, SMCB_ERR_INVALID, "null handle");
+    switch (key) {
+        case SMCB_PARAM_MM_BUDGET:
+            REQUIRE(h, value >= 1 && value <= 1e9, SMCB_ERR_INVALID, "MM_BUDGET must be in [1, 1e9]");
+            h->mm_budget = (int)value;
+            return SMCB_OK;
+        default:
+            return smcb_fail(h, SMCB_ERR_INVALID, "smcb_set_param: unknown key %d", key);
+    }
+}
+
 extern "C" int smcb_predict_mm_progress(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n,
                                         double* pred_dev, void* stream) {
     REQUIRE(h, h && theta_dev && pred_dev && n > 0 && ld >= n, SMCB_ERR_INVALID, "bad argument");
-    return launch_loglik_mm_progress(h, theta_dev, ld, n, nullptr, nullptr, pred_dev, as_stream(stream));
+    return launch_loglik_mm_progress(h, theta_dev, ld, n, nullptr, nullptr, nullptr, pred_dev, as_stream(stream));
 }
 
 extern "C" int smcb_loglik_stats(smcb_handle* h, int64_t* out_host) {
     REQUIRE(h, h && out_host, SMCB_ERR_INVALID, "null pointer");
-    CUDA_TRY(h, cudaMemcpy(out_host, h->stats, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(out_host, h->stats, SMCB_N_STATS * sizeof(int64_t), cudaMemcpyDeviceToHost));
     return SMCB_OK;
 }
 

@@ -8,7 +8,8 @@
 
 #include "../../include/smcb200.h"
 
-#define SMCB_VERSION 100
+#define SMCB_VERSION 101
+#define SMCB_N_STATS 16
 #define FULL_MASK 0xffffffffu
 
 struct MmProgressData {
@@ -47,8 +48,13 @@ struct smcb_handle {
     int64_t ssr_rows = 0;
     double* partial = nullptr;       // block partials for reductions
     int64_t partial_len = 0;
-    unsigned long long* stats = nullptr;  // 4 counters (device)
-    int* task_counter = nullptr;     // dynamic task queue head
+    unsigned long long* stats = nullptr;  // SMCB_N_STATS counters (device)
+    unsigned* mm_ctl = nullptr;      // [0] solve-queue head, [1] number of deferred particles (MM_PROGRESS)
+    unsigned* mm_defer = nullptr;    // [n_max] particles handed to the tail kernel
+    double* mm_cutlim = nullptr;     // [n_max] per-particle residual limit of a bounded sweep
+    int mm_budget = 256;             // attempted steps after which the bulk kernel defers a solve
+    int mm_bulk_blocks_per_sm = 0;   // occupancy of the bulk kernel (queried once)
+    bool mm_smem_set = false;
     int32_t* floor_cnt = nullptr;    // [n_max]
     uint64_t* resid_q = nullptr;     // [n_max] fixed-point residuals
     double* resid_f = nullptr;       // [n_max] FP64 residuals (sequential mode)
@@ -129,7 +135,8 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* smem) {
 
 // kernels implemented across translation units
 int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, int64_t n,
-                              const uint8_t* active, double* lk, double* pred, cudaStream_t st);
+                              const uint8_t* active, const double* lkmin, double* lk, double* pred,
+                              cudaStream_t st);
 int launch_loglik_mm_rate(smcb_handle* h, const double* theta, int64_t ld, int64_t n,
                           const uint8_t* active, double* lk, cudaStream_t st);
 int launch_loglik_kinetic(smcb_handle* h, const double* theta, int64_t ld, int64_t n, int d,

@@ -1,298 +1,401 @@
 // K1: Michaelis-Menten log-likelihoods.
 //
-// MM_PROGRESS replaces `log_likelihood_mm_multi` / `simulate_mm_on_grid` / `mm_ode`
-// (reference SMC_example/Micmem_likelihood.py:14-77).  The reference integrates
-// dS/dt = -Vmax*S/(Km+S) with scipy's adaptive RK45 at rtol=1e-3, atol=1e-6 and reads the
-// solution through the quartic dense output, so the likelihood is defined by that controller.
-// The device code below takes the same steps (scipy/_ivp/rk.py:61-180,538-567,
-// common.py:110-134, ivp.py:712-728) in FP64.
+// MM_PROGRESS replaces `log_likelihood_mm_multi` / `simulate_mm_on_grid` / `mm_ode` and the ray fan-out
+// of `sim_particle` (reference SMC_example/Micmem_likelihood.py:14-92).  The arithmetic of one solve -
+// scipy's adaptive RK45 taken step for step - lives in mm_solver.cuh; this file is the mapping onto the
+// machine.
 //
-// Mapping: one *lane* integrates one (particle, experiment) solve at a time.  Solves need
-// 40..3000 RHS evaluations depending on (Vmax, Km), so a static lane->solve map would leave
-// most of a warp idle.  Instead every block owns a contiguous range of solves and its lanes
-// pull the next one from a shared-memory queue head (warp-aggregated atomic) whenever they
-// finish; the step body itself is executed convergently by all lanes that hold a solve.
-// Observation data (t, P_obs, S0) is staged once per block in shared memory.
+// Work is a list of n_ex*n solves (experiment-major: solve g = e*n + p), each 10 .. 1e5 attempted steps
+// depending on (Vmax, Km): in a prior cloud the median solve takes 12 attempts, one in a thousand takes
+// more than 800 and the worst of 2^20 particles takes ~1e5 strictly sequential ones.  Three kernels:
+//
+//   mm_bulk_kernel      persistent warps, one solve per lane.  A warp draws runs of consecutive solves
+//                       from a global queue; a lane whose solve ends waits until REFILL_MIN lanes of its
+//                       warp are free (or none is busy) and they are then set up together, so neither
+//                       the set-up code nor the step code runs for a handful of lanes.  Consecutive solves
+//                       belong to consecutive particles of the same experiment: coalesced parameter
+//                       loads, broadcast reads of the observation grid in shared memory, and (near the
+//                       posterior) the same accept/reject sequence in every lane.  A solve that needs
+//                       more than `budget` attempts is abandoned and marked DEFERRED, which bounds the
+//                       drain time of the kernel.
+//   mm_finalize_kernel  one thread per particle: sums the experiments in the reference's order
+//                       (Micmem_likelihood.py:70-73) or queues the particle for the tail kernel.
+//   mm_tail_kernel      one thread per queued particle, deferred solves restarted without a budget.
+//                       These few threads are latency-bound (~0.3 us per step); the grid is sized so that
+//                       they do not compete for the FP64 pipe.
+//
+// Early rejection (MH sweeps).  Residuals only accumulate, so with c0 = -n_t/2 log(2 pi sigma^2)
+//     n_ex*c0 - ssr_e/(2 sigma^2)                                   (one solve alone)
+//     sum_finished (c0 - ssr_e/(2 sigma^2)) + n_unfinished*c0       (finalize / tail)
+// are upper bounds of the particle's log-likelihood.  Given lkmin[p] (smcb_mh_threshold: the value below
+// which the Metropolis test of Micmem_SMC_main.py:231-236 is certain to reject, with a safety margin) a
+// solve stops as soon as a bound falls below it and the particle reports -inf: the accept/reject
+// decision, hence the whole run, is exactly what it would have been.  Stiff proposals are almost always
+// hopeless ones, so this removes the serial tail from MH sweeps; the first sweep has no threshold and
+// keeps it.
 #include "common.cuh"
+#include "mm_solver.cuh"
 
 namespace {
 
-constexpr double RTOL = 1e-3, ATOL = 1e-6, SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;
+using mmsolve::Solve;
 
-// Dormand-Prince tableau exactly as scipy spells it (rk.py:538-567); the quotients are
-// evaluated by the compiler in FP64 just as CPython evaluates them.
-constexpr double C2 = 1.0 / 5, C3 = 3.0 / 10, C4 = 4.0 / 5, C5 = 8.0 / 9;
-constexpr double A21 = 1.0 / 5;
-constexpr double A31 = 3.0 / 40, A32 = 9.0 / 40;
-constexpr double A41 = 44.0 / 45, A42 = -56.0 / 15, A43 = 32.0 / 9;
-constexpr double A51 = 19372.0 / 6561, A52 = -25360.0 / 2187, A53 = 64448.0 / 6561, A54 = -212.0 / 729;
-constexpr double A61 = 9017.0 / 3168, A62 = -355.0 / 33, A63 = 46732.0 / 5247, A64 = 49.0 / 176,
-                 A65 = -5103.0 / 18656;
-constexpr double B1 = 35.0 / 384, B3 = 500.0 / 1113, B4 = 125.0 / 192, B5 = -2187.0 / 6784, B6 = 11.0 / 84;
-constexpr double E1 = -71.0 / 57600, E3 = 71.0 / 16695, E4 = -71.0 / 1920, E5 = 17253.0 / 339200,
-                 E6 = -22.0 / 525, E7 = 1.0 / 40;
-// dense-output matrix P (7 x 4); row 2 is zero.
-constexpr double P11 = 1.0, P12 = -8048581381.0 / 2820520608, P13 = 8663915743.0 / 2820520608,
-                 P14 = -12715105075.0 / 11282082432;
-constexpr double P32 = 131558114200.0 / 32700410799, P33 = -68118460800.0 / 10900136933,
-                 P34 = 87487479700.0 / 32700410799;
-constexpr double P42 = -1754552775.0 / 470086768, P43 = 14199869525.0 / 1410260304,
-                 P44 = -10690763975.0 / 1880347072;
-constexpr double P52 = 127303824393.0 / 49829197408, P53 = -318862633887.0 / 49829197408,
-                 P54 = 701980252875.0 / 199316789632;
-constexpr double P62 = -282668133.0 / 205662961, P63 = 2019193451.0 / 616988883,
-                 P64 = -1453857185.0 / 822651844;
-constexpr double P72 = 40617522.0 / 29380423, P73 = -110615467.0 / 29380423, P74 = 69997945.0 / 29380423;
+constexpr int BULK_BLOCK = 128;
+constexpr int BULK_CHUNK = 128;     // solves a warp takes from the queue at a time
+constexpr int REFILL_MIN = 8;       // free lanes needed before a warp stops to set up new solves
+constexpr int TAIL_BLOCK = 32;
+constexpr double DEFERRED = -1.0;   // marker in the per-solve result array (a residual sum is >= 0)
 
-__device__ __forceinline__ double mm_rhs(double nVmax, double Km, double S) {
-    // python: -Vmax * S / (Km + S)  ==  ((-Vmax)*S)/(Km+S)
-    return (nVmax * S) / (Km + S);
+__device__ __forceinline__ void stage_data(double* s_t, double* s_P, double* s_S0, const double* g_t,
+                                           const double* g_P, const double* g_S0, int n_ex, int n_t) {
+    for (int i = threadIdx.x; i < n_ex * n_t; i += blockDim.x) {
+        s_t[i] = g_t[i];
+        s_P[i] = g_P[i];
+    }
+    for (int i = threadIdx.x; i < n_ex; i += blockDim.x) s_S0[i] = g_S0[i];
+    __syncthreads();
 }
 
-__device__ __forceinline__ double ulp10(double t) {
-    // 10 * |nextafter(t, +inf) - t|
-    double nx = __longlong_as_double(__double_as_longlong(t) + (t >= 0.0 ? 1 : -1));
-    if (t == 0.0) nx = __longlong_as_double(1LL);
-    return 10.0 * fabs(nx - t);
+// counters: see smcb_loglik_stats
+__device__ __forceinline__ void flush_stats(unsigned long long* stats, unsigned n_set, unsigned n_acc,
+                                            unsigned n_rej, unsigned n_fail, unsigned n_def, unsigned mx) {
+    if (stats == nullptr) return;
+    const unsigned long long w_fev =
+        (unsigned long long)warp_sum_ll(2LL * n_set + 6LL * ((long long)n_acc + n_rej));
+    const unsigned long long w_acc = (unsigned long long)warp_sum_ll((long long)n_acc);
+    const unsigned long long w_rej = (unsigned long long)warp_sum_ll((long long)n_rej);
+    const unsigned long long w_fail = (unsigned long long)warp_sum_ll((long long)n_fail);
+    const unsigned long long w_def = (unsigned long long)warp_sum_ll((long long)n_def);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, o));
+    if ((threadIdx.x & 31) == 0) {
+        if (w_fev) { atomicAdd(&stats[0], w_fev); atomicAdd(&stats[4], w_fev); }
+        if (w_acc) { atomicAdd(&stats[1], w_acc); atomicAdd(&stats[5], w_acc); }
+        if (w_rej) { atomicAdd(&stats[2], w_rej); atomicAdd(&stats[6], w_rej); }
+        if (w_fail) { atomicAdd(&stats[3], w_fail); atomicAdd(&stats[7], w_fail); }
+        if (w_def) { atomicAdd(&stats[11], w_def); atomicAdd(&stats[12], w_def); }
+        if (mx) atomicMax(&stats[10], (unsigned long long)mx);
+    }
 }
 
-struct SolveState {
-    double nVmax, Km, S0;
-    double t, y, f, h_abs;
-    double acc;      // residual sum of squares
-    int i_eval;      // next t_eval index
-    int task;        // -1 = none
-    int e;
-};
+// ------------------------------------------------------------------------------ prep (bounded sweeps)
+// cutlim[p] = residual sum of squares above which ONE solve alone proves lk[p] < lkmin[p]:
+//   n_ex*c0 - ssr/(2 sigma^2) < lkmin   <=>   ssr > (n_ex*c0 - lkmin) * 2 sigma^2
+__global__ void mm_prep_kernel(const double* __restrict__ theta, int64_t ld, int64_t n,
+                               const uint8_t* __restrict__ active, const double* __restrict__ lkmin, int n_ex,
+                               int n_t, double* __restrict__ cutlim) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || (active != nullptr && !active[p])) return;
+    const double sigma = theta[2 * ld + p];
+    double cl = INFINITY;
+    const double thr = lkmin[p];
+    if (sigma > 0 && thr > -INFINITY) {
+        const double s2 = sigma * sigma;
+        const double c0 = -0.5 * n_t * log(2 * M_PI * s2);
+        cl = (n_ex * c0 - thr) * (2 * s2);   // negative: hopeless before any residual (NaN compares false)
+    }
+    cutlim[p] = cl;
+}
 
-constexpr int BLOCK = 128;
-
-// MODE 0: residual sum of squares into ssr[e*n + p];  MODE 1: predictions P_model into pred.
-template <int MODE>
-__global__ void __launch_bounds__(BLOCK)
-mm_progress_kernel(const double* __restrict__ theta, int64_t ld, int64_t n,
-                   const uint8_t* __restrict__ active, const double* __restrict__ g_t,
-                   const double* __restrict__ g_P, const double* __restrict__ g_S0, int n_ex, int n_t,
-                   int tasks_per_block, double* __restrict__ out, unsigned long long* __restrict__ stats) {
+// ------------------------------------------------------------------------------ bulk
+template <bool BOUNDED>
+__global__ void __launch_bounds__(BULK_BLOCK)
+mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const uint8_t* __restrict__ active,
+               const double* __restrict__ cutlim, const double* __restrict__ g_t, const double* __restrict__ g_P,
+               const double* __restrict__ g_S0, int n_ex, int n_t, unsigned budget, double* __restrict__ ssr_out,
+               unsigned* __restrict__ queue, unsigned long long* __restrict__ stats) {
     extern __shared__ double smem[];
     double* s_t = smem;
     double* s_P = smem + (size_t)n_ex * n_t;
     double* s_S0 = s_P + (size_t)n_ex * n_t;
-    __shared__ int s_next;
+    stage_data(s_t, s_P, s_S0, g_t, g_P, g_S0, n_ex, n_t);
 
-    for (int i = threadIdx.x; i < n_ex * n_t; i += BLOCK) {
-        s_t[i] = g_t[i];
-        s_P[i] = g_P[i];
-    }
-    for (int i = threadIdx.x; i < n_ex; i += BLOCK) s_S0[i] = g_S0[i];
-    const int64_t total = n * (int64_t)n_ex;
-    const int64_t task_lo = (int64_t)blockIdx.x * tasks_per_block;
-    int64_t rem = total - task_lo;
-    const int n_tasks = (int)(rem < tasks_per_block ? rem : tasks_per_block);
-    if (threadIdx.x == 0) s_next = 0;
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31;
+    const unsigned total = n * (unsigned)n_ex;
+    const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned w_cur = 0, w_end = 0;   // the warp's current run of solves (warp-uniform)
+    bool drained = false;            // queue exhausted (warp-uniform)
 
-    SolveState st;
-    st.task = -1;
-    bool exhausted = false;
-    unsigned long long n_fev = 0, n_acc = 0, n_rej = 0, n_fail = 0;
-    int64_t p = 0;
+    Solve s;
+    s.nVmax = -1.0; s.Km = 1.0; s.S0 = 0.0; s.t = 0.0; s.y = 0.0; s.f = 0.0; s.h_abs = 0.0; s.ssr = 0.0;
+    s.cut_lim = INFINITY; s.i_eval = 0;
+    bool have = false;
+    unsigned task = 0, n_att = 0;
     const double* tt = s_t;
     const double* pp = s_P;
+    unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, n_def = 0, mx = 0;
 
-    while (true) {
-        // ---- refill: lanes without a solve pull the next task of this block --------------
-        while (true) {
-            const bool want = (st.task < 0) && !exhausted;
-            const unsigned need = __ballot_sync(FULL_MASK, want);
-            if (need == 0) break;
-            const int leader = __ffs(need) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(&s_next, __popc(need));
-            base = __shfl_sync(FULL_MASK, base, leader);
-            if (want) {
-                const int tsk = base + __popc(need & lt_mask);
-                if (tsk >= n_tasks) {
-                    exhausted = true;
-                } else {
-                    const int64_t g = task_lo + tsk;
-                    p = g / n_ex;
-                    const int e = (int)(g - p * n_ex);
+    for (;;) {
+        const unsigned busy = __ballot_sync(FULL_MASK, have);
+        unsigned want = drained ? 0u : (~busy);
+        if (want != 0 && (__popc(want) >= REFILL_MIN || busy == 0)) {
+            // ---- 1. hand out solves until every free lane holds a live one (or the queue is empty) ----
+            bool got = false;
+            unsigned e = 0, p = 0;
+            while (want != 0) {
+                if (w_cur == w_end) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(queue, (unsigned)BULK_CHUNK);
+                    base = __shfl_sync(FULL_MASK, base, 0);
+                    if (base >= total) {
+                        drained = true;
+                        break;
+                    }
+                    w_cur = base;
+                    w_end = (total - base < (unsigned)BULK_CHUNK) ? total : base + BULK_CHUNK;
+                }
+                const unsigned avail = w_end - w_cur;
+                const unsigned rank = __popc(want & lt_mask);
+                const bool mine = ((want >> lane) & 1u) && rank < avail;
+                const unsigned g = w_cur + rank;
+                const unsigned n_want = __popc(want);
+                w_cur += (n_want < avail) ? n_want : avail;
+                bool ok = false;
+                if (mine) {
+                    e = g / n;
+                    p = g - e * n;
                     if (active == nullptr || active[p]) {
-                        st.task = tsk;
-                        st.e = e;
-                        st.nVmax = -theta[p];
-                        st.Km = theta[ld + p];
-                        st.S0 = s_S0[e];
-                        tt = s_t + (size_t)e * n_t;
-                        pp = s_P + (size_t)e * n_t;
-                        st.t = tt[0];
-                        st.y = st.S0;
-                        st.acc = 0.0;
-                        st.i_eval = 0;
-                        st.f = mm_rhs(st.nVmax, st.Km, st.y);
-                        // select_initial_step (common.py:110-134), n=1, direction=+1, order=4
-                        const double t_bound = tt[n_t - 1];
-                        const double interval = fabs(t_bound - st.t);
-                        const double scale = ATOL + fabs(st.y) * RTOL;
-                        const double d0 = fabs(st.y / scale);
-                        const double d1 = fabs(st.f / scale);
-                        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-                        h0 = (interval < h0) ? interval : h0;
-                        const double y1 = st.y + h0 * st.f;
-                        const double f1 = mm_rhs(st.nVmax, st.Km, y1);
-                        const double d2 = fabs((f1 - st.f) / scale) / h0;
-                        double h1;
-                        if (d1 <= 1e-15 && d2 <= 1e-15) {
-                            h1 = h0 * 1e-3;
-                            h1 = (h1 > 1e-6) ? h1 : 1e-6;
-                        } else {
-                            const double dm = (d2 > d1) ? d2 : d1;
-                            h1 = pow(0.01 / dm, 1.0 / 5.0);
-                        }
-                        double hh = 100 * h0;
-                        hh = (h1 < hh) ? h1 : hh;
-                        hh = (interval < hh) ? interval : hh;
-                        st.h_abs = hh;
-                        n_fev += 2;
-                        if (interval == 0.0) {   // degenerate grid: nothing to integrate
-                            if (MODE == 0) out[(int64_t)e * n + p] = 0.0;
-                            st.task = -1;
+                        if (theta[2 * ld + p] > 0) {   // sigma <= 0: finalize reports -inf
+                            ok = true;
+                            if (BOUNDED) {
+                                s.cut_lim = cutlim[p];
+                                if (s.cut_lim < 0) {   // hopeless before any residual
+                                    ssr_out[g] = INFINITY;
+                                    ok = false;
+                                }
+                            }
                         }
                     }
+                    if (ok) {
+                        got = true;
+                        task = g;
+                    }
+                }
+                want &= ~__ballot_sync(FULL_MASK, ok);
+            }
+            // ---- 2. set the new solves up together ------------------------------------------------
+            if (got) {
+                s.nVmax = -theta[p];
+                s.Km = theta[ld + p];
+                s.S0 = s_S0[e];
+                tt = s_t + (size_t)e * n_t;
+                pp = s_P + (size_t)e * n_t;
+                n_att = 0;
+                n_set++;
+                if (mmsolve::setup(s, tt, n_t)) {
+                    have = true;
+                } else {
+                    ssr_out[task] = INFINITY;
+                    n_fail++;
                 }
             }
         }
-        const bool have = st.task >= 0;
-        if (!__any_sync(FULL_MASK, have)) break;   // all lanes exhausted and idle
-
+        if (__ballot_sync(FULL_MASK, have) == 0) {
+            if (drained) break;
+            continue;
+        }
         if (have) {
-            // ---- one step attempt (rk.py:111-176) ----------------------------------------
-            const double t_bound = tt[n_t - 1];
-            const double t = st.t, y = st.y;
-            const double min_step = ulp10(t);
-            double h_abs = st.h_abs;
-            // the clamp `h_abs < min_step -> min_step` applies at the start of a scipy step
-            // (before the first attempt); a *rejected* attempt that drops below fails instead.
-            // st.h_abs < 0 encodes "inside a step, after a rejection".
-            bool rejected = false;
-            if (h_abs < 0) {
-                rejected = true;
-                h_abs = -h_abs;
-            } else if (h_abs < min_step) {
-                h_abs = min_step;
-            }
-            if (h_abs < min_step) {
-                // TOO_SMALL_STEP: scipy returns a short solution and the reference would raise.
-                n_fail++;
-                if (MODE == 0) out[(int64_t)st.e * n + p] = INFINITY;
-                st.task = -1;
-            } else {
-                double t_new = t + h_abs;
-                if (t_new - t_bound > 0) t_new = t_bound;
-                const double h = t_new - t;
-                h_abs = fabs(h);
-                const double k1 = st.f;
-                const double k2 = mm_rhs(st.nVmax, st.Km, y + (k1 * A21) * h);
-                const double k3 = mm_rhs(st.nVmax, st.Km, y + (k1 * A31 + k2 * A32) * h);
-                const double k4 = mm_rhs(st.nVmax, st.Km, y + (k1 * A41 + k2 * A42 + k3 * A43) * h);
-                const double k5 = mm_rhs(st.nVmax, st.Km, y + (k1 * A51 + k2 * A52 + k3 * A53 + k4 * A54) * h);
-                const double k6 =
-                    mm_rhs(st.nVmax, st.Km, y + (k1 * A61 + k2 * A62 + k3 * A63 + k4 * A64 + k5 * A65) * h);
-                const double y_new = y + h * (k1 * B1 + k3 * B3 + k4 * B4 + k5 * B5 + k6 * B6);
-                const double k7 = mm_rhs(st.nVmax, st.Km, y_new);
-                n_fev += 6;
-                const double ay = fabs(y), ayn = fabs(y_new);
-                const double scale = ATOL + ((ayn > ay || ayn != ayn) ? ayn : ay) * RTOL;
-                const double err =
-                    fabs(((k1 * E1 + k3 * E3 + k4 * E4 + k5 * E5 + k6 * E6 + k7 * E7) * h) / scale);
-                if (err < 1.0) {
-                    double factor;
-                    if (err == 0.0) {
-                        factor = MAX_FACTOR;
-                    } else {
-                        factor = SAFETY * pow(err, -0.2);
-                        factor = (factor < MAX_FACTOR) ? factor : MAX_FACTOR;
-                    }
-                    if (rejected) factor = (factor < 1.0) ? factor : 1.0;
-                    st.h_abs = h_abs * factor;
-                    n_acc++;
-                    // ---- dense output for every t_eval in (t_old, t_new] (ivp.py:712-728) ----
-                    int i = st.i_eval;
-                    if (i < n_t && tt[i] <= t_new) {
-                        const double q1 = k1 * P11;
-                        const double q2 = k1 * P12 + k3 * P32 + k4 * P42 + k5 * P52 + k6 * P62 + k7 * P72;
-                        const double q3 = k1 * P13 + k3 * P33 + k4 * P43 + k5 * P53 + k6 * P63 + k7 * P73;
-                        const double q4 = k1 * P14 + k3 * P34 + k4 * P44 + k5 * P54 + k6 * P64 + k7 * P74;
-                        do {
-                            const double x = (tt[i] - t) / h;
-                            const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
-                            const double S = h * (q1 * x + q2 * x2 + q3 * x3 + q4 * x4) + y;
-                            const double Pm = st.S0 - S;
-                            if (MODE == 0) {
-                                const double r = pp[i] - Pm;
-                                st.acc += r * r;
-                            } else {
-                                out[(p * n_ex + st.e) * (int64_t)n_t + i] = Pm;
-                            }
-                            ++i;
-                        } while (i < n_t && tt[i] <= t_new);
-                        st.i_eval = i;
-                    }
-                    st.t = t_new;
-                    st.y = y_new;
-                    st.f = k7;
-                    if (t_new - t_bound >= 0) {   // finished
-                        if (MODE == 0) out[(int64_t)st.e * n + p] = st.acc;
-                        st.task = -1;
-                    }
-                } else {
-                    double factor = SAFETY * pow(err, -0.2);
-                    factor = (factor > MIN_FACTOR) ? factor : MIN_FACTOR;
-                    st.h_abs = -(h_abs * factor);   // stay inside this scipy step
-                    n_rej++;
-                }
+            const int st = mmsolve::attempt<false>(s, tt, pp, n_t, nullptr, n_acc, n_rej);
+            ++n_att;
+            if (st != mmsolve::RUNNING) {
+                ssr_out[task] = (st == mmsolve::DONE) ? s.ssr : INFINITY;
+                if (st == mmsolve::FAILED) n_fail++;
+                mx = max(mx, n_att);
+                have = false;
+            } else if (n_att >= budget) {
+                ssr_out[task] = DEFERRED;
+                n_def++;
+                have = false;
             }
         }
     }
-    // ---- work counters ---------------------------------------------------------------------
-    n_fev = warp_sum_ll((long long)n_fev);
-    n_acc = warp_sum_ll((long long)n_acc);
-    n_rej = warp_sum_ll((long long)n_rej);
-    n_fail = warp_sum_ll((long long)n_fail);
-    if (lane == 0 && stats != nullptr) {
-        atomicAdd(&stats[0], n_fev);
-        atomicAdd(&stats[1], n_acc);
-        atomicAdd(&stats[2], n_rej);
-        if (n_fail) atomicAdd(&stats[3], n_fail);
-        atomicAdd(&stats[4], n_fev);   // cumulative since smcb_create (never reset by a sweep)
-        atomicAdd(&stats[5], n_acc);
-        atomicAdd(&stats[6], n_rej);
-        if (n_fail) atomicAdd(&stats[7], n_fail);
+    flush_stats(stats, n_set, n_acc, n_rej, n_fail, n_def, mx);
+}
+
+// ------------------------------------------------------------------------------ finalize
+template <bool BOUNDED>
+__global__ void __launch_bounds__(256)
+mm_finalize_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const uint8_t* __restrict__ active,
+                   const double* __restrict__ lkmin, int n_ex, int n_t, const double* __restrict__ ssr,
+                   double* __restrict__ lk, unsigned* __restrict__ defer_list, unsigned* __restrict__ defer_count,
+                   unsigned long long* __restrict__ stats) {
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool cut = false;
+    if (p < n && (active == nullptr || active[p])) {
+        const double sigma = theta[2 * ld + p];
+        if (sigma <= 0) {   // Micmem_likelihood.py:53-54
+            lk[p] = -INFINITY;
+        } else {
+            const double s2 = sigma * sigma;
+            const double c0 = -0.5 * n_t * log(2 * M_PI * s2);
+            const double inv_den = 1.0 / (2 * s2);
+            double total = 0.0;
+            int n_def = 0;
+            for (int e = 0; e < n_ex; ++e) {
+                const double v = ssr[(size_t)e * n + p];
+                if (v < 0) ++n_def;
+                else total += c0 - v * inv_den;   // logL_i, summed in experiment order (:70-73)
+            }
+            if (n_def == 0 || total == -INFINITY) {
+                lk[p] = total;
+                cut = BOUNDED && total == -INFINITY;
+            } else if (BOUNDED && total + n_def * c0 < lkmin[p]) {
+                lk[p] = -INFINITY;
+                cut = true;
+            } else {
+                defer_list[atomicAdd(defer_count, 1u)] = p;
+            }
+        }
+    }
+    if (BOUNDED) {
+        const unsigned m = __ballot_sync(FULL_MASK, cut);
+        if (m != 0 && (threadIdx.x & 31) == 0) {
+            atomicAdd(&stats[8], (unsigned long long)__popc(m));
+            atomicAdd(&stats[9], (unsigned long long)__popc(m));
+        }
     }
 }
 
-// lk[p] = sum_e [ -0.5*n_t*log(2*pi*sigma^2) - ssr_e/(2 sigma^2) ]   (Micmem_likelihood.py:70-73)
-__global__ void mm_progress_finalize(const double* __restrict__ theta, int64_t ld, int64_t n,
-                                     const uint8_t* __restrict__ active, const double* __restrict__ ssr,
-                                     int n_ex, int n_t, double* __restrict__ lk) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    if (active != nullptr && !active[p]) return;
-    const double sigma = theta[2 * ld + p];
-    if (sigma <= 0) {   // Micmem_likelihood.py:53-54
-        lk[p] = -INFINITY;
-        return;
+// ------------------------------------------------------------------------------ tail
+template <bool BOUNDED>
+__global__ void __launch_bounds__(TAIL_BLOCK)
+mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const double* __restrict__ lkmin,
+               const double* __restrict__ g_t, const double* __restrict__ g_P, const double* __restrict__ g_S0,
+               int n_ex, int n_t, double* __restrict__ ssr, double* __restrict__ lk,
+               const unsigned* __restrict__ defer_list, const unsigned* __restrict__ defer_count,
+               unsigned long long* __restrict__ stats) {
+    const unsigned count = *defer_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && stats != nullptr) {
+        stats[13] = count;
+        atomicAdd(&stats[14], (unsigned long long)count);
     }
-    const double s2 = sigma * sigma;
-    const double c0 = -0.5 * n_t * log(2 * M_PI * s2);
-    const double den = 2 * s2;
-    double total = 0.0;
-    for (int e = 0; e < n_ex; ++e) total += c0 - ssr[(int64_t)e * n + p] / den;
-    lk[p] = total;
+    if (blockIdx.x * TAIL_BLOCK >= count) return;   // nothing for this block: skip the staging too
+    extern __shared__ double smem[];
+    double* s_t = smem;
+    double* s_P = smem + (size_t)n_ex * n_t;
+    double* s_S0 = s_P + (size_t)n_ex * n_t;
+    stage_data(s_t, s_P, s_S0, g_t, g_P, g_S0, n_ex, n_t);
+
+    Solve s;
+    s.nVmax = -1.0; s.Km = 1.0; s.S0 = 0.0; s.t = 0.0; s.y = 0.0; s.f = 0.0; s.h_abs = 0.0; s.ssr = 0.0;
+    s.cut_lim = INFINITY; s.i_eval = 0;
+    bool have = false, p_valid = false, finished = false;
+    unsigned idx = blockIdx.x * TAIL_BLOCK + threadIdx.x, p = 0;
+    const unsigned stride = gridDim.x * TAIL_BLOCK;
+    int e_cur = 0, e_scan = 0, n_left = 0;
+    double c0 = 0.0, inv_den = 0.0, two_s2 = 0.0, thr = -INFINITY, total_fin = 0.0;
+    const double* tt = s_t;
+    const double* pp = s_P;
+    unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, n_cut = 0, n_att = 0, mx = 0;
+
+    for (;;) {
+        if (!have && !finished) {
+            // next deferred solve of my particle; when it has none left, write its likelihood and take
+            // the next particle of the list
+            for (;;) {
+                if (!p_valid) {
+                    if (idx >= count) {
+                        finished = true;
+                        break;
+                    }
+                    p = defer_list[idx];
+                    idx += stride;
+                    p_valid = true;
+                    const double sigma = theta[2 * ld + p];
+                    const double s2 = sigma * sigma;
+                    c0 = -0.5 * n_t * log(2 * M_PI * s2);
+                    inv_den = 1.0 / (2 * s2);
+                    two_s2 = 2 * s2;
+                    thr = BOUNDED ? lkmin[p] : -INFINITY;
+                    s.nVmax = -theta[p];
+                    s.Km = theta[ld + p];
+                    total_fin = 0.0;
+                    n_left = 0;
+                    for (int e = 0; e < n_ex; ++e) {
+                        const double v = ssr[(size_t)e * n + p];
+                        if (v < 0) ++n_left;
+                        else total_fin += c0 - v * inv_den;
+                    }
+                    e_scan = 0;
+                }
+                while (e_scan < n_ex && !(ssr[(size_t)e_scan * n + p] < 0)) ++e_scan;
+                if (e_scan < n_ex) {
+                    e_cur = e_scan++;
+                    s.S0 = s_S0[e_cur];
+                    tt = s_t + (size_t)e_cur * n_t;
+                    pp = s_P + (size_t)e_cur * n_t;
+                    // ssr_e > cut_lim  <=>  total_fin + n_left*c0 - ssr_e*inv_den < thr
+                    s.cut_lim = (BOUNDED && thr > -INFINITY) ? (total_fin + n_left * c0 - thr) * two_s2
+                                                            : INFINITY;
+                    n_att = 0;
+                    n_set++;
+                    if (mmsolve::setup(s, tt, n_t)) {
+                        have = true;
+                        break;
+                    }
+                    n_fail++;
+                    lk[p] = -INFINITY;
+                    p_valid = false;
+                    continue;
+                }
+                // all experiments of this particle are in: ordered sum, as the reference adds them
+                double total = 0.0;
+                for (int e = 0; e < n_ex; ++e) total += c0 - ssr[(size_t)e * n + p] * inv_den;
+                lk[p] = total;
+                p_valid = false;
+            }
+        }
+        if (__ballot_sync(FULL_MASK, have) == 0) break;
+        if (have) {
+            const int st = mmsolve::attempt<false>(s, tt, pp, n_t, nullptr, n_acc, n_rej);
+            ++n_att;
+            if (st != mmsolve::RUNNING) {
+                mx = max(mx, n_att);
+                have = false;
+                if (st == mmsolve::DONE) {
+                    ssr[(size_t)e_cur * n + p] = s.ssr;
+                    total_fin += c0 - s.ssr * inv_den;
+                    --n_left;
+                } else {
+                    if (st == mmsolve::FAILED) n_fail++;
+                    else n_cut++;
+                    lk[p] = -INFINITY;
+                    p_valid = false;
+                }
+            }
+        }
+    }
+    flush_stats(stats, n_set, n_acc, n_rej, n_fail, 0u, mx);
+    if (BOUNDED) {
+        const unsigned long long w_cut = (unsigned long long)warp_sum_ll((long long)n_cut);
+        if (w_cut != 0 && threadIdx.x == 0) {
+            atomicAdd(&stats[8], w_cut);
+            atomicAdd(&stats[9], w_cut);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ predictions
+// P_model of every (particle, experiment): pred[(p*n_ex + e)*n_t + i]  (the `C_l_` of sim_particle)
+__global__ void __launch_bounds__(128)
+mm_predict_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const double* __restrict__ g_t,
+                  const double* __restrict__ g_S0, int n_ex, int n_t, double* __restrict__ pred) {
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n * (unsigned)n_ex) return;
+    const unsigned p = g / n_ex, e = g - p * n_ex;
+    Solve s;
+    s.nVmax = -theta[p];
+    s.Km = theta[ld + p];
+    s.S0 = g_S0[e];
+    s.cut_lim = INFINITY;
+    const double* tt = g_t + (size_t)e * n_t;
+    double* out = pred + (size_t)g * n_t;
+    unsigned a = 0, r = 0;
+    int st = mmsolve::setup(s, tt, n_t) ? mmsolve::RUNNING : mmsolve::FAILED;
+    if (st == mmsolve::FAILED) s.i_eval = 0;
+    while (st == mmsolve::RUNNING) st = mmsolve::attempt<true>(s, tt, nullptr, n_t, out, a, r);
+    if (st == mmsolve::FAILED)   // scipy would return a short solution here
+        for (int i = s.i_eval; i < n_t; ++i) out[i] = NAN;
 }
 
 // ------------------------------------------------------------------------------ MM_RATE
@@ -398,38 +501,80 @@ mm_rate_kernel_f32(const double* __restrict__ theta, int64_t ld, int64_t n,
 
 }  // namespace
 
+// sweep-local counters, the solve queue and the deferred-particle list head
+__global__ void mm_reset_kernel(unsigned long long* stats, unsigned* ctl) {
+    if (threadIdx.x < 4) stats[threadIdx.x] = 0;
+    if (threadIdx.x == 8 || threadIdx.x == 10 || threadIdx.x == 11 || threadIdx.x == 13) stats[threadIdx.x] = 0;
+    if (threadIdx.x < 2) ctl[threadIdx.x] = 0;
+}
+
 int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, int64_t n,
-                              const uint8_t* active, double* lk, double* pred, cudaStream_t st) {
+                              const uint8_t* active, const double* lkmin, double* lk, double* pred,
+                              cudaStream_t st) {
     const MmProgressData& D = h->mmp;
     REQUIRE(h, D.t != nullptr, SMCB_ERR_STATE, "smcb_set_data_mm_progress has not been called");
     if (n == 0) return SMCB_OK;
     const size_t smem = ((size_t)2 * D.n_ex * D.n_t + D.n_ex) * sizeof(double);
     REQUIRE(h, smem <= 200 * 1024, SMCB_ERR_UNSUPPORTED, "data set too large for shared-memory staging");
-    const int64_t total = n * (int64_t)D.n_ex;
-    int tasks_per_block = BLOCK * 8;
-    // keep at least ~4 blocks per SM in flight for small n
-    while (tasks_per_block > BLOCK && total / tasks_per_block < (int64_t)h->sm_count * 4) tasks_per_block >>= 1;
-    const int64_t grid = (total + tasks_per_block - 1) / tasks_per_block;
-    REQUIRE(h, grid < (1LL << 31), SMCB_ERR_UNSUPPORTED, "too many particles for one launch");
+    REQUIRE(h, n * (int64_t)D.n_ex < (1LL << 31), SMCB_ERR_UNSUPPORTED, "too many solves for one launch");
+    const unsigned un = (unsigned)n;
     if (pred != nullptr) {
-        CUDA_TRY(h, cudaFuncSetAttribute(mm_progress_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
-        mm_progress_kernel<1><<<(unsigned)grid, BLOCK, smem, st>>>(theta, ld, n, active, D.t, D.P, D.S0, D.n_ex,
-                                                                 D.n_t, tasks_per_block, pred, nullptr);
+        const unsigned tasks = un * (unsigned)D.n_ex;
+        mm_predict_kernel<<<(tasks + 127) / 128, 128, 0, st>>>(theta, ld, un, D.t, D.S0, D.n_ex, D.n_t, pred);
         LAUNCH_CHECK(h);
         return SMCB_OK;
     }
-    REQUIRE(h, h->ssr != nullptr && n <= h->n_max && D.n_ex <= h->ssr_rows, SMCB_ERR_STATE,
-            "smcb_reserve too small for this sweep");
-    CUDA_TRY(h, cudaMemsetAsync(h->stats, 0, 4 * sizeof(unsigned long long), st));
-    CUDA_TRY(h, cudaFuncSetAttribute(mm_progress_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    mm_progress_kernel<0><<<(unsigned)grid, BLOCK, smem, st>>>(theta, ld, n, active, D.t, D.P, D.S0, D.n_ex, D.n_t,
-                                                             tasks_per_block, h->ssr, h->stats);
+    REQUIRE(h, h->n_max >= n && h->ssr_rows >= D.n_ex && h->mm_defer != nullptr, SMCB_ERR_STATE,
+            "smcb_reserve(n_max >= n) must be called before smcb_loglik");
+    const bool bounded = lkmin != nullptr;
+    if (smem > 48 * 1024 && !h->mm_smem_set) {
+        CUDA_TRY(h, cudaFuncSetAttribute(mm_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(h, cudaFuncSetAttribute(mm_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(h, cudaFuncSetAttribute(mm_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(h, cudaFuncSetAttribute(mm_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->mm_smem_set = true;
+    }
+    if (h->mm_bulk_blocks_per_sm == 0) {
+        int a = 0, b = 0;
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, mm_bulk_kernel<false>, BULK_BLOCK, smem));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, mm_bulk_kernel<true>, BULK_BLOCK, smem));
+        h->mm_bulk_blocks_per_sm = (a < b ? a : b) > 0 ? (a < b ? a : b) : 1;
+    }
+    unsigned* queue = h->mm_ctl;
+    unsigned* defer_count = h->mm_ctl + 1;
+    mm_reset_kernel<<<1, 32, 0, st>>>(h->stats, h->mm_ctl);
     LAUNCH_CHECK(h);
-    const int fb = 256;
-    mm_progress_finalize<<<(unsigned)((n + fb - 1) / fb), fb, 0, st>>>(theta, ld, n, active, h->ssr, D.n_ex, D.n_t,
-                                                                     lk);
+    if (bounded) {
+        mm_prep_kernel<<<(un + 255) / 256, 256, 0, st>>>(theta, ld, n, active, lkmin, D.n_ex, D.n_t, h->mm_cutlim);
+        LAUNCH_CHECK(h);
+    }
+    const unsigned tasks = un * (unsigned)D.n_ex;
+    unsigned grid = (unsigned)(h->sm_count * h->mm_bulk_blocks_per_sm);
+    const unsigned need = (tasks + BULK_BLOCK - 1) / BULK_BLOCK;
+    if (need < grid) grid = need;
+    const unsigned budget = (unsigned)h->mm_budget;
+    if (bounded)
+        mm_bulk_kernel<true><<<grid, BULK_BLOCK, smem, st>>>(theta, ld, un, active, h->mm_cutlim, D.t, D.P, D.S0,
+                                                           D.n_ex, D.n_t, budget, h->ssr, queue, h->stats);
+    else
+        mm_bulk_kernel<false><<<grid, BULK_BLOCK, smem, st>>>(theta, ld, un, active, nullptr, D.t, D.P, D.S0,
+                                                            D.n_ex, D.n_t, budget, h->ssr, queue, h->stats);
+    LAUNCH_CHECK(h);
+    // 12 warps per SM keep the latency-bound tail solves clear of each other on the FP64 pipe
+    const unsigned tail_grid = (unsigned)h->sm_count * 12;
+    if (bounded) {
+        mm_finalize_kernel<true><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, active, lkmin, D.n_ex, D.n_t, h->ssr,
+                                                                  lk, h->mm_defer, defer_count, h->stats);
+        LAUNCH_CHECK(h);
+        mm_tail_kernel<true><<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, lkmin, D.t, D.P, D.S0, D.n_ex, D.n_t,
+                                                                 h->ssr, lk, h->mm_defer, defer_count, h->stats);
+    } else {
+        mm_finalize_kernel<false><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, active, nullptr, D.n_ex, D.n_t,
+                                                                   h->ssr, lk, h->mm_defer, defer_count, h->stats);
+        LAUNCH_CHECK(h);
+        mm_tail_kernel<false><<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, nullptr, D.t, D.P, D.S0, D.n_ex,
+                                                                  D.n_t, h->ssr, lk, h->mm_defer, defer_count, h->stats);
+    }
     LAUNCH_CHECK(h);
     return SMCB_OK;
 }

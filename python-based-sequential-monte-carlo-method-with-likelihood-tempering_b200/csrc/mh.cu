@@ -171,9 +171,9 @@ accept_kernel(double* __restrict__ theta, int64_t ld, double* __restrict__ lk, c
               int64_t ld_prop, const double* __restrict__ lk2, const uint8_t* __restrict__ inbox, int64_t n, int d,
               double gamma, const double* __restrict__ u_ext, uint64_t seed, uint64_t id_offset, uint32_t stage,
               uint32_t sweep, uint8_t* __restrict__ moved, unsigned long long* __restrict__ counts) {
-    __shared__ long long sm[3][32];
+    __shared__ long long sm[4][32];
     const int64_t i = (int64_t)blockIdx.x * MB + threadIdx.x;
-    long long acc = 0, newly = 0, evald = 0;
+    long long acc = 0, newly = 0, evald = 0, ninf = 0;
     if (i < n) {
         const double u = (u_ext != nullptr)
                              ? u_ext[i]
@@ -183,6 +183,7 @@ accept_kernel(double* __restrict__ theta, int64_t ld, double* __restrict__ lk, c
         if (inbox[i]) {
             evald = 1;
             l2 = lk2[i];
+            ninf = (l2 == -INFINITY);   // rejected early by smcb_loglik_bounded (or a genuinely impossible proposal)
             pp = exp(__dmul_rn(__dsub_rn(l2, lk[i]), gamma));   // exp(px*gamma_new)*p0
         }
         const bool r = pp >= u;   // NaN compares false, as in NumPy
@@ -201,26 +202,56 @@ accept_kernel(double* __restrict__ theta, int64_t ld, double* __restrict__ lk, c
     acc = warp_sum_ll(acc);
     newly = warp_sum_ll(newly);
     evald = warp_sum_ll(evald);
+    ninf = warp_sum_ll(ninf);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) {
         sm[0][wid] = acc;
         sm[1][wid] = newly;
         sm[2][wid] = evald;
+        sm[3][wid] = ninf;
     }
     __syncthreads();
     if (wid == 0) {
         acc = (lane < MB / 32) ? sm[0][lane] : 0;
         newly = (lane < MB / 32) ? sm[1][lane] : 0;
         evald = (lane < MB / 32) ? sm[2][lane] : 0;
+        ninf = (lane < MB / 32) ? sm[3][lane] : 0;
         acc = warp_sum_ll(acc);
         newly = warp_sum_ll(newly);
         evald = warp_sum_ll(evald);
+        ninf = warp_sum_ll(ninf);
         if (lane == 0) {
             if (acc) atomicAdd(&counts[0], (unsigned long long)acc);
             if (newly) atomicAdd(&counts[1], (unsigned long long)newly);
             if (evald) atomicAdd(&counts[2], (unsigned long long)evald);
+            if (ninf) atomicAdd(&counts[3], (unsigned long long)ninf);
         }
     }
+}
+
+// ---- early-rejection threshold -----------------------------------------------------------------------
+// accept_kernel takes a proposal iff exp((lk2-lk1)*gamma) >= u.  If lk2 < lk1 + log(u)/gamma - margin the
+// left side is below u*exp(-margin*gamma), a relative gap (>= 1e-9) far wider than the rounding of the
+// subtraction, the product and exp(), so the test fails for certain.
+__global__ void __launch_bounds__(MB)
+threshold_kernel(const double* __restrict__ lk, const uint8_t* __restrict__ inbox, int64_t n, double gamma,
+                 const double* __restrict__ u_ext, uint64_t seed, uint64_t id_offset, uint32_t stage, uint32_t sweep,
+                 double* __restrict__ lkmin) {
+    const int64_t i = (int64_t)blockIdx.x * MB + threadIdx.x;
+    if (i >= n) return;
+    double thr = -INFINITY;
+    if (inbox == nullptr || inbox[i]) {
+        const double u = (u_ext != nullptr)
+                             ? u_ext[i]
+                             : philox_uniform(seed, id_offset + (uint64_t)i, stage, sweep, SMCB_SLOT_UNIFORM);
+        const double l1 = lk[i];
+        if (u > 0.0 && gamma > 0.0 && isfinite(l1)) {
+            const double lu = log(u) / gamma;   // <= 0 (u < 1); u >= 1 gives lu >= 0: any finite lk2 might still pass
+            thr = l1 + lu - 1e-9 * (1.0 + fabs(l1) + fabs(lu));
+            if (!(thr == thr)) thr = -INFINITY;
+        }
+    }
+    lkmin[i] = thr;
 }
 
 __global__ void philox_draws_kernel(int64_t n, int d, uint64_t seed, uint64_t id_offset, uint32_t stage,
@@ -334,6 +365,16 @@ extern "C" int smcb_mh_propose(smcb_handle* h, const double* theta_dev, int64_t 
         default: PROPOSE(0);
     }
 #undef PROPOSE
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+extern "C" int smcb_mh_threshold(smcb_handle* h, const double* lk_dev, const uint8_t* inbox_dev, int64_t n, double gamma,
+                                 const double* u_dev, uint64_t seed, uint64_t id_offset, uint32_t stage,
+                                 uint32_t sweep, double* lkmin_dev, void* stream) {
+    REQUIRE(h, h && lk_dev && lkmin_dev && n > 0, SMCB_ERR_INVALID, "bad argument");
+    threshold_kernel<<<(unsigned)((n + MB - 1) / MB), MB, 0, as_stream(stream)>>>(lk_dev, inbox_dev, n, gamma, u_dev, seed,
+                                                                              id_offset, stage, sweep, lkmin_dev);
     LAUNCH_CHECK(h);
     return SMCB_OK;
 }

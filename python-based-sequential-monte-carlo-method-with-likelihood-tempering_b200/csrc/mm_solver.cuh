@@ -1,0 +1,253 @@
+// One Michaelis-Menten progress-curve solve, as the reference defines it.
+//
+// The reference likelihood (SMC_example/Micmem_likelihood.py:14-33, 59-71) integrates
+//     dS/dt = -Vmax*S/(Km+S),  S(0) = S0
+// with scipy.integrate.solve_ivp(method="RK45") at the default tolerances (rtol 1e-3, atol 1e-6) and
+// reads S at the 40 observation times through the quartic dense output.  At rtol = 1e-3 the result
+// depends on the controller (up to 2.9e-3 relative away from a converged solve), so the
+// likelihood is *defined* by scipy's sequence of accepted and rejected steps.  This header takes the
+// same steps:
+//     tableau C/A/B/E/P                scipy/integrate/_ivp/rk.py:538-567
+//     select_initial_step              common.py:110-134
+//     step loop, accept/reject, factor rk.py:111-176  (SAFETY .9, MIN_FACTOR .2, MAX_FACTOR 10, exponent -1/5)
+//     stages, FSAL, error estimate     rk.py:61-109
+//     dense output at t_eval           rk.py:178-180,723-737 and ivp.py:712-728
+//
+// Arithmetic.  Same quantities, FP64 throughout, but spelt for the FP64 pipe of sm_100a instead of in
+// NumPy's operation order:
+//   * the stage derivatives are carried pre-multiplied by the step, K_j = h*k_j, so a stage argument
+//     is a pure FMA chain y + sum a_sj K_j, the error estimate is sum E_j K_j and the dense-output
+//     coefficients need no further scaling (92 FP64 operations per attempted step against ~130
+//     for the unscaled form);
+//   * S/(Km+S) by reciprocal: MUFU.RCP64H seed (rcp.approx.ftz.f64, 20 bits) and one cubically
+//     convergent correction r0*(1+e+e^2), e = 1-den*r0, folded into the product (error < 1 ulp);
+//   * err^(-1/5) from an FP32 lg2/ex2 seed and one FP64 correction instead of pow().
+// Every operation is within an ulp or two of the one scipy performs; over the reference's own 34
+// sweeps (prior cloud to posterior) the log-likelihoods agree with scipy's to better than 1e-9
+// relative (tests/test_gpu_kernels.py, tests/test_host_twin.py), far inside the 1e-5 bar.
+//
+// The functions are __host__ __device__ so that tests can compile this very arithmetic with g++
+// (tests/host_twin.cpp; the MUFU seeds are replaced by truncated host values, which the corrections
+// make irrelevant) and compare it with scipy without a GPU.  The product never runs the host build.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MM_HD __host__ __device__ __forceinline__
+#else
+#define MM_HD inline
+#endif
+
+namespace mmsolve {
+
+constexpr double RTOL = 1e-3, ATOL = 1e-6, SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;
+// 0.9*err^(-1/5) reaches MAX_FACTOR for err <= 0.09^5 and MIN_FACTOR for err >= 4.5^5
+constexpr double ERR_LO = 5.9049e-6, ERR_HI = 1845.28125;
+
+// Dormand-Prince coefficients spelt as scipy spells them; the quotients are evaluated in FP64.
+constexpr double A21 = 1.0 / 5;
+constexpr double A31 = 3.0 / 40, A32 = 9.0 / 40;
+constexpr double A41 = 44.0 / 45, A42 = -56.0 / 15, A43 = 32.0 / 9;
+constexpr double A51 = 19372.0 / 6561, A52 = -25360.0 / 2187, A53 = 64448.0 / 6561, A54 = -212.0 / 729;
+constexpr double A61 = 9017.0 / 3168, A62 = -355.0 / 33, A63 = 46732.0 / 5247, A64 = 49.0 / 176,
+                 A65 = -5103.0 / 18656;
+constexpr double B1 = 35.0 / 384, B3 = 500.0 / 1113, B4 = 125.0 / 192, B5 = -2187.0 / 6784, B6 = 11.0 / 84;
+constexpr double E1 = -71.0 / 57600, E3 = 71.0 / 16695, E4 = -71.0 / 1920, E5 = 17253.0 / 339200,
+                 E6 = -22.0 / 525, E7 = 1.0 / 40;
+// dense-output matrix P (7 x 4); row 2 is zero, P11 = 1.
+constexpr double P12 = -8048581381.0 / 2820520608, P13 = 8663915743.0 / 2820520608,
+                 P14 = -12715105075.0 / 11282082432;
+constexpr double P32 = 131558114200.0 / 32700410799, P33 = -68118460800.0 / 10900136933,
+                 P34 = 87487479700.0 / 32700410799;
+constexpr double P42 = -1754552775.0 / 470086768, P43 = 14199869525.0 / 1410260304,
+                 P44 = -10690763975.0 / 1880347072;
+constexpr double P52 = 127303824393.0 / 49829197408, P53 = -318862633887.0 / 49829197408,
+                 P54 = 701980252875.0 / 199316789632;
+constexpr double P62 = -282668133.0 / 205662961, P63 = 2019193451.0 / 616988883,
+                 P64 = -1453857185.0 / 822651844;
+constexpr double P72 = 40617522.0 / 29380423, P73 = -110615467.0 / 29380423, P74 = 69997945.0 / 29380423;
+
+// ---- seeds (the only lines that differ between the device and the host build) ------------------
+MM_HD double rcp_seed(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+#else
+    union { double d; uint64_t u; } v;
+    v.d = 1.0 / x;
+    v.u &= 0xFFFFFFFF00000000ull;   // what MUFU.RCP64H keeps
+    return v.d;
+#endif
+}
+MM_HD double rootm5_seed(double x) {
+#if defined(__CUDA_ARCH__)
+    return (double)exp2f(-0.2f * __log2f((float)x));
+#else
+    return (double)powf((float)x, -0.2f);
+#endif
+}
+
+// 1/x, error below one ulp for normal x: r0*(1+e+e^2) with e = 1 - x*r0  (|e| < 2^-20)
+MM_HD double rcp64(double x) {
+    const double r0 = rcp_seed(x);
+    const double e = fma(-x, r0, 1.0);
+    return fma(r0, fma(e, e, e), r0);
+}
+// c*S/(Km+S): the reciprocal correction is folded into the product so the chain after the seed is
+// three FMAs deep.
+MM_HD double mm_rate(double c, double Km, double S) {
+    const double den = Km + S;
+    const double r0 = rcp_seed(den);
+    const double q0 = (c * S) * r0;
+    const double e = fma(-den, r0, 1.0);
+    return fma(q0, fma(e, e, e), q0);
+}
+// x^(-1/5) for x in [1e-30, 1e30]: seed r (relative error ~2^-20), then with e = 1 - x*r^5
+// x^(-1/5) = r*(1-e)^(-1/5) = r*(1 + e/5 + 3e^2/25 + O(e^3)).
+MM_HD double rootm5(double x) {
+    const double r = rootm5_seed(x);
+    const double r2 = r * r, r4 = r2 * r2;
+    const double e = fma(-x * r, r4, 1.0);
+    return fma(r, e * fma(0.12, e, 0.2), r);
+}
+
+MM_HD double ulp10(double t) {
+    // 10 * |nextafter(t, +inf) - t|   (rk.py:113, direction = +1)
+    union { double d; int64_t i; } v;
+    v.d = t;
+    v.i += (t >= 0.0) ? 1 : -1;
+    if (t == 0.0) v.i = 1;
+    return 10.0 * fabs(v.d - t);
+}
+
+enum Status { RUNNING = 0, DONE = 1, FAILED = 2, CUT = 3 };
+
+struct Solve {
+    double nVmax, Km;   // -Vmax, Km of the particle
+    double S0;          // initial substrate of the experiment
+    double t, y, f;     // current time, state, f(t, y) (first-same-as-last)
+    double h_abs;       // next step size; negative = retry of the same scipy step after a rejection
+    double ssr;         // residual sum of squares so far
+    double cut_lim;     // stop (CUT) as soon as ssr exceeds this; +inf = never
+    int i_eval;         // next observation time to emit
+};
+
+// select_initial_step (common.py:110-134) for n = 1, direction = +1, order 4.  Returns false when no
+// positive step size results (Km + S0 = 0 gives NaN, with which scipy would loop forever).
+MM_HD bool setup(Solve& s, const double* tt, int n_t) {
+    const double t0 = tt[0], t_bound = tt[n_t - 1];
+    s.t = t0;
+    s.y = s.S0;
+    s.ssr = 0.0;
+    s.i_eval = 0;
+    const double y = s.S0;
+    const double f = mm_rate(s.nVmax, s.Km, y);
+    s.f = f;
+    const double interval = fabs(t_bound - t0);
+    const double iscale = rcp64(fma(fabs(y), RTOL, ATOL));
+    const double d0 = fabs(y * iscale);
+    const double d1 = fabs(f * iscale);
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    h0 = (interval < h0) ? interval : h0;
+    const double y1 = fma(h0, f, y);
+    const double f1 = mm_rate(s.nVmax, s.Km, y1);
+    const double d2 = fabs((f1 - f) * iscale) / h0;
+    double h1;
+    if (d1 <= 1e-15 && d2 <= 1e-15) {
+        h1 = h0 * 1e-3;
+        h1 = (h1 > 1e-6) ? h1 : 1e-6;
+    } else {
+        const double dm = ((d2 > d1) ? d2 : d1) * 100.0;   // (0.01/max(d1,d2))^(1/5) = (100 max)^(-1/5)
+        h1 = (dm > 1e-30 && dm < 1e30) ? rootm5(dm) : pow(dm, -0.2);
+    }
+    double hh = 100 * h0;
+    hh = (h1 < hh) ? h1 : hh;
+    hh = (interval < hh) ? interval : hh;
+    s.h_abs = hh;
+    return hh > 0.0;   // false for NaN
+}
+
+// One attempted step (rk.py:111-176).  PRED: write P_model = S0 - S(t_eval) to pred[i] instead of
+// accumulating residuals.  n_acc / n_rej count accepted / rejected attempts.
+template <bool PRED>
+MM_HD int attempt(Solve& s, const double* tt, const double* pp, int n_t, double* pred, unsigned& n_acc,
+                  unsigned& n_rej) {
+    const double t = s.t, y = s.y;
+    const double t_bound = tt[n_t - 1];
+    double ha = s.h_abs;
+    bool rejected = false;
+    if (ha < 0) {
+        rejected = true;
+        ha = -ha;
+    }
+    if (ha < fabs(t) * 4e-15 + 1e-290) {   // only then can 10*ulp(t) matter
+        const double min_step = ulp10(t);
+        // scipy clamps h_abs up to min_step when it enters a step; an attempt shrunk below min_step by
+        // a rejection fails instead (TOO_SMALL_STEP: short solution, the reference would raise).
+        if (!rejected && ha < min_step) ha = min_step;
+        if (ha < min_step) return FAILED;
+    }
+    double t_new = t + ha;
+    if (t_new - t_bound > 0) t_new = t_bound;
+    const double h = t_new - t;
+    ha = fabs(h);
+    const double hn = h * s.nVmax, Km = s.Km;
+    const double K1 = h * s.f;
+    const double K2 = mm_rate(hn, Km, fma(A21, K1, y));
+    const double K3 = mm_rate(hn, Km, fma(A32, K2, fma(A31, K1, y)));
+    const double K4 = mm_rate(hn, Km, fma(A43, K3, fma(A42, K2, fma(A41, K1, y))));
+    const double K5 = mm_rate(hn, Km, fma(A54, K4, fma(A53, K3, fma(A52, K2, fma(A51, K1, y)))));
+    const double K6 = mm_rate(hn, Km, fma(A65, K5, fma(A64, K4, fma(A63, K3, fma(A62, K2, fma(A61, K1, y))))));
+    const double y_new = fma(B6, K6, fma(B5, K5, fma(B4, K4, fma(B3, K3, fma(B1, K1, y)))));
+    const double k7 = mm_rate(s.nVmax, Km, y_new);
+    const double K7 = h * k7;
+    const double ay = fabs(y), ayn = fabs(y_new);
+    const double iscale = rcp64(fma((ayn > ay || ayn != ayn) ? ayn : ay, RTOL, ATOL));
+    const double ee = fma(E7, K7, fma(E6, K6, fma(E5, K5, fma(E4, K4, fma(E3, K3, E1 * K1)))));
+    const double err = fabs(ee * iscale);
+    // 0.9*err^(-1/5) where it is not clamped anyway
+    const double fr = SAFETY * rootm5(fmin(fmax(err, ERR_LO), ERR_HI));
+    if (err < 1.0) {
+        double factor = (err <= ERR_LO) ? MAX_FACTOR : fmin(MAX_FACTOR, fr);
+        if (rejected) factor = fmin(factor, 1.0);
+        s.h_abs = ha * factor;
+        n_acc++;
+        // dense output for every t_eval in (t_old, t_new] (ivp.py:712-728; t_eval[0] = t0 is emitted by
+        // the first step with x = 0)
+        int i = s.i_eval;
+        if (i < n_t && tt[i] <= t_new) {
+            const double q2 = fma(K7, P72, fma(K6, P62, fma(K5, P52, fma(K4, P42, fma(K3, P32, K1 * P12)))));
+            const double q3 = fma(K7, P73, fma(K6, P63, fma(K5, P53, fma(K4, P43, fma(K3, P33, K1 * P13)))));
+            const double q4 = fma(K7, P74, fma(K6, P64, fma(K5, P54, fma(K4, P44, fma(K3, P34, K1 * P14)))));
+            const double ih = rcp64(h);
+            double ssr = s.ssr;
+            do {
+                const double x = (tt[i] - t) * ih;
+                const double S = fma(x, fma(x, fma(x, fma(x, q4, q3), q2), K1), y);
+                const double Pm = s.S0 - S;   // Micmem_likelihood.py:32
+                if (PRED) {
+                    pred[i] = Pm;
+                } else {
+                    const double r = pp[i] - Pm;   // :68
+                    ssr = fma(r, r, ssr);
+                }
+                ++i;
+            } while (i < n_t && tt[i] <= t_new);
+            s.i_eval = i;
+            s.ssr = ssr;
+        }
+        s.t = t_new;
+        s.y = y_new;
+        s.f = k7;
+        if (!PRED && s.ssr > s.cut_lim) return CUT;
+        return (t_new - t_bound >= 0) ? DONE : RUNNING;
+    }
+    double factor = (err < ERR_HI) ? fmax(MIN_FACTOR, fr) : MIN_FACTOR;   // NaN error: MIN_FACTOR, as Python's max()
+    s.h_abs = -(ha * factor);
+    n_rej++;
+    return RUNNING;
+}
+
+}  // namespace mmsolve

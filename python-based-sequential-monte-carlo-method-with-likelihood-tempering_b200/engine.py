@@ -140,7 +140,8 @@ class Result:
     n_moved: list
     n_mh: list
     stages: list
-    n_eval: int                      # particle log-likelihood evaluations performed on the device (global)
+    n_eval: int                      # particle log-likelihood evaluations requested on the device (global)
+    n_eval_cut: int                  # of those, proposals whose rejection was proven before the last observation
     n_eval_reference: int            # what the reference would have evaluated: N * (1 + sweeps)
     seconds: float                   # device time first sweep -> end of gamma=1 block
     reached_one: bool
@@ -184,13 +185,14 @@ class Engine:
         self.prop = torch.zeros((self.d, self.n), dtype=f64, device=dev)
         self.lk2 = torch.zeros(self.n, dtype=f64, device=dev)
         self.w = torch.zeros(self.n, dtype=f64, device=dev)
+        self.lkmin = torch.zeros(self.n, dtype=f64, device=dev)
         self.inbox = torch.zeros(self.n, dtype=torch.uint8, device=dev)
         self.moved = torch.zeros(self.n, dtype=torch.uint8, device=dev)
         self.counts = torch.zeros(self.n, dtype=torch.int32, device=dev)
         self.anc = torch.zeros(self.cap, dtype=torch.int32, device=dev)
         self.scal = torch.zeros(64, dtype=f64, device=dev)       # [0]=max, [2:34]=tempering sums
         self.mom = torch.zeros(self.d + self.d * self.d, dtype=f64, device=dev)
-        self.icnt = torch.zeros(8, dtype=torch.int64, device=dev)  # [0:3] MH counters, [4:6] totals, [6] filled
+        self.icnt = torch.zeros(8, dtype=torch.int64, device=dev)  # [0:4] MH counters, [4:6] totals, [6] filled
         self.sendbuf = None
         self.prof = None          # name -> list of (start, end) CUDA events when profiling is on
         self._low = np.ascontiguousarray(prior.low)
@@ -219,8 +221,8 @@ class Engine:
         return int(self.lib.smcb_launch_count(self.h))
 
     def loglik_stats(self):
-        """int64[8] work counters of the MM progress-curve kernel (see smcb_loglik_stats)."""
-        out = np.zeros(8, dtype=np.int64)
+        """int64[16] work counters of the MM progress-curve kernels (see smcb_loglik_stats)."""
+        out = np.zeros(_lib.N_STATS, dtype=np.int64)
         self._ck(self.lib.smcb_loglik_stats(self.h, out.ctypes.data))
         return out
 
@@ -244,6 +246,11 @@ class Engine:
         """{name: (launch groups, total ms)}; synchronises."""
         torch.cuda.synchronize(self.device)
         return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (self.prof or {}).items()}
+
+    def profile_events(self, name):
+        """Per-launch-group device times [ms] of one kernel group, in launch order; synchronises."""
+        torch.cuda.synchronize(self.device)
+        return [a.elapsed_time(b) for a, b in (self.prof or {}).get(name, [])]
 
     @property
     def theta(self):
@@ -273,12 +280,15 @@ class Engine:
         return self.state[: self.d].t().contiguous()
 
     # -------------------------------------------------------------------------------- K1
-    def loglik_into(self, theta, lk_out, active=None):
+    def loglik_into(self, theta, lk_out, active=None, lkmin=None):
+        """lk_out[i] = log-likelihood of theta[:, i] (active: byte mask of the particles to evaluate;
+        lkmin: early-rejection thresholds, see smcb_loglik_bounded)."""
         n = theta.shape[1]
         with self._timed("loglik"):
-            self._ck(self.lib.smcb_loglik(self.h, self.lik.model_id, theta.data_ptr(), theta.stride(0), n, self.d,
-                                          active.data_ptr() if active is not None else None, lk_out.data_ptr(),
-                                          self._stream))
+            self._ck(self.lib.smcb_loglik_bounded(self.h, self.lik.model_id, theta.data_ptr(), theta.stride(0), n,
+                                                  self.d, active.data_ptr() if active is not None else None,
+                                                  lkmin.data_ptr() if lkmin is not None else None,
+                                                  lk_out.data_ptr(), self._stream))
 
     def sim_particle(self, particle=None):
         """Reference surface (`sim_particle(particle) -> llk`, Micmem_likelihood.py:79-92): evaluates
@@ -485,7 +495,14 @@ class Engine:
             self._ck(lib.smcb_mh_propose(h, self.state.data_ptr(), self.n, self.n, d, F.ctypes.data, ratio,
                                          self._low.ctypes.data, self._high.ctypes.data, z_ptr, seed, self.id_offset,
                                          stage, sweep, self.prop.data_ptr(), self.n, self.inbox.data_ptr(), st))
-        self.loglik_into(self.prop, self.lk2, active=self.inbox)
+        lkmin = None
+        if self.cfg.early_reject:
+            # value below which the accept test below is certain to fail: the likelihood kernel may stop there
+            lkmin = self.lkmin
+            with self._timed("propose"):
+                self._ck(lib.smcb_mh_threshold(h, self.lk.data_ptr(), self.inbox.data_ptr(), self.n, gamma, u_ptr, seed,
+                                               self.id_offset, stage, sweep, lkmin.data_ptr(), st))
+        self.loglik_into(self.prop, self.lk2, active=self.inbox, lkmin=lkmin)
         with self._timed("accept"):
             self._ck(lib.smcb_mh_accept(h, self.state.data_ptr(), self.n, self.lk.data_ptr(), self.prop.data_ptr(),
                                         self.n, self.lk2.data_ptr(), self.inbox.data_ptr(), self.n, d, gamma, u_ptr,
@@ -517,7 +534,8 @@ class Engine:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         self.sim_particle()
-        n_eval, n_sweeps_total = N, 0    # evaluations actually performed (global); in-box proposals only
+        n_eval, n_sweeps_total = N, 0    # evaluations requested (global): N + in-box proposals of every sweep
+        n_cut = 0                        # of those, proposals rejected early (reported -inf before all observations)
         gamma_old, logZ = 0.0, 0.0
         stages, ancestors = [], []
         reached = False
@@ -536,7 +554,7 @@ class Engine:
                 n_mh, r_th = cfg.ad_mhstep_num, cfg.r_threshold_f
             else:
                 n_mh, r_th = cfg.mhstep_num, cfg.r_threshold
-            n_run, moved, stage_evals = 0, 0, 0
+            n_run, moved, stage_evals, stage_cut = 0, 0, 0, 0
             if cfg.fused_sweeps > 0:
                 F, _ = self.proposal_factor()
                 done = 0
@@ -548,7 +566,7 @@ class Engine:
                     cnt = self.icnt[:4].clone()
                     self.comm.all_reduce_sum(cnt)
                     c = cnt.cpu().numpy()
-                    moved, stage_evals = int(c[1]), int(c[2])
+                    moved, stage_evals, stage_cut = int(c[1]), int(c[2]), int(c[3])
                     if cfg.early_exit and moved > r_th * N:
                         break
                     if done < n_mh:
@@ -568,12 +586,13 @@ class Engine:
                     cnt = self.icnt[:4].clone()
                     self.comm.all_reduce_sum(cnt)
                     c = cnt.cpu().numpy()
-                    moved, stage_evals = int(c[1]), int(c[2])
+                    moved, stage_evals, stage_cut = int(c[1]), int(c[2]), int(c[3])
                     if cfg.early_exit and moved > r_th * N:
                         break
                     if moved < cfg.r_threshold_min * N:
                         ratio = ratio * 0.5
             n_eval += stage_evals
+            n_cut += stage_cut
             n_sweeps_total += n_run
             if filled is None:
                 filled = int(self.icnt[6].item())
@@ -591,7 +610,7 @@ class Engine:
         return Result(particles=self.particles().cpu().numpy(), lk=self.lk.cpu().numpy().copy(),
                       betas=[s.gamma for s in stages], ess=[s.ess for s in stages], log_evidence=logZ,
                       n_moved=[s.moved for s in stages], n_mh=[s.n_mh for s in stages], stages=stages,
-                      n_eval=n_eval, n_eval_reference=N * (1 + n_sweeps_total),
+                      n_eval=n_eval, n_eval_cut=n_cut, n_eval_reference=N * (1 + n_sweeps_total),
                       seconds=secs, reached_one=reached, ancestors=ancestors)
 
 

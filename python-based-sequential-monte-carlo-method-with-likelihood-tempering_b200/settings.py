@@ -32,6 +32,7 @@ class Settings:
     scan_mode: str = "fixed"            # "fixed" (parallel, shard-invariant) | "sequential" (bit-exact reference sum)
     cand_batch: int = 8                 # tempering candidates evaluated per pass (<=16)
     early_exit: bool = True             # stop sweeps when moved fraction exceeds r_threshold (reference)
+    early_reject: bool = True           # let the likelihood stop once the MH rejection is certain (exact decisions)
     fused_sweeps: int = 0               # >0: run this many sweeps per launch with a frozen proposal factor
     bisect_iters: int = 60
 

@@ -1,0 +1,61 @@
+// Host build of the DEVICE solver arithmetic (csrc/mm_solver.cuh) for tests only.
+//
+// The kernels of loglik_mm.cu call mmsolve::setup / mmsolve::attempt; this file compiles the very same
+// header with g++ (FMA instructions on, no contraction of anything that is not spelt fma()) so that the
+// arithmetic the GPU performs can be compared with scipy without a GPU (tests/test_host_twin.py).  It is
+// test infrastructure: nothing in the product loads it.
+#include <math.h>
+#include <stdint.h>
+
+#include "../python-based-sequential-monte-carlo-method-with-likelihood-tempering_b200/csrc/mm_solver.cuh"
+
+extern "C" void twin_loglik(const double* theta, int64_t n, const double* t, const double* P, const double* S0,
+                            int n_ex, int n_t, double* lk, int64_t* counters, int32_t* steps) {
+    using namespace mmsolve;
+    for (int64_t p = 0; p < n; ++p) {
+        const double Vmax = theta[3 * p], Km = theta[3 * p + 1], sigma = theta[3 * p + 2];
+        if (sigma <= 0) {
+            lk[p] = -INFINITY;
+            continue;
+        }
+        const double s2 = sigma * sigma;
+        const double c0 = -0.5 * n_t * log(2 * M_PI * s2);
+        const double inv_den = 1.0 / (2 * s2);
+        double total = 0.0;
+        for (int e = 0; e < n_ex; ++e) {
+            Solve s;
+            s.nVmax = -Vmax;
+            s.Km = Km;
+            s.S0 = S0[e];
+            s.cut_lim = INFINITY;
+            unsigned n_acc = 0, n_rej = 0;
+            int st = setup(s, t + e * n_t, n_t) ? RUNNING : FAILED;
+            while (st == RUNNING) st = attempt<false>(s, t + e * n_t, P + e * n_t, n_t, nullptr, n_acc, n_rej);
+            if (counters) {
+                counters[0] += 2 + 6 * (int64_t)(n_acc + n_rej);
+                counters[1] += n_acc;
+                counters[2] += n_rej;
+                counters[3] += (st == FAILED);
+            }
+            if (steps) steps[p * n_ex + e] = (int32_t)(n_acc + n_rej);
+            total += (st == DONE) ? c0 - s.ssr * inv_den : -INFINITY;
+        }
+        lk[p] = total;
+    }
+}
+
+extern "C" void twin_predict(const double* theta, int64_t n, const double* t, const double* S0, int n_ex,
+                             int n_t, double* pred) {
+    using namespace mmsolve;
+    for (int64_t p = 0; p < n; ++p)
+        for (int e = 0; e < n_ex; ++e) {
+            Solve s;
+            s.nVmax = -theta[3 * p];
+            s.Km = theta[3 * p + 1];
+            s.S0 = S0[e];
+            s.cut_lim = INFINITY;
+            unsigned a = 0, r = 0;
+            int st = setup(s, t + e * n_t, n_t) ? RUNNING : FAILED;
+            while (st == RUNNING) st = attempt<true>(s, t + e * n_t, nullptr, n_t, pred + (p * n_ex + e) * n_t, a, r);
+        }
+}
