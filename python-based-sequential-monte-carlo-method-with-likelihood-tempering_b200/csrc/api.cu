@@ -132,7 +132,7 @@ extern "C" int smcb_reserve(smcb_handle* h, int64_t n_max, int d_max) {
     if ((rc = dev_alloc(h, &h->resid_q, (size_t)n_max))) return rc;
     if ((rc = dev_alloc(h, &h->resid_f, (size_t)n_max))) return rc;
     if ((rc = dev_alloc(h, &h->mark, (size_t)n_max))) return rc;
-    if ((rc = dev_alloc(h, &h->mm_defer, (size_t)n_max))) return rc;
+    if ((rc = dev_alloc(h, &h->mm_defer, (size_t)(rows + 1) * n_max))) return rc;   // deferred solves + particles
     if ((rc = dev_alloc(h, &h->mm_cutlim, (size_t)n_max))) return rc;
     const size_t tiles = (size_t)(n_max + 2047) / 2048 + 8;
     if ((rc = dev_alloc(h, &h->tile_tot, 2 * tiles))) return rc;

@@ -49,8 +49,8 @@ struct smcb_handle {
     double* partial = nullptr;       // block partials for reductions
     int64_t partial_len = 0;
     unsigned long long* stats = nullptr;  // SMCB_N_STATS counters (device)
-    unsigned* mm_ctl = nullptr;      // [0] solve-queue head, [1] number of deferred particles (MM_PROGRESS)
-    unsigned* mm_defer = nullptr;    // [n_max] particles handed to the tail kernel
+    unsigned* mm_ctl = nullptr;      // [0] solve-queue head, [1] deferred solves, [2] deferred particles (MM_PROGRESS)
+    unsigned* mm_defer = nullptr;    // [ssr_rows*n_max] deferred solves, then [n_max] their particles
     double* mm_cutlim = nullptr;     // [n_max] per-particle residual limit of a bounded sweep
     int mm_budget = 256;             // attempted steps after which the bulk kernel defers a solve
     int mm_bulk_blocks_per_sm = 0;   // occupancy of the bulk kernel (queried once)

@@ -19,14 +19,15 @@
 //                       more than `budget` attempts is abandoned and marked DEFERRED, which bounds the
 //                       drain time of the kernel.
 //   mm_finalize_kernel  one thread per particle: sums the experiments in the reference's order
-//                       (Micmem_likelihood.py:70-73) or queues the particle for the tail kernel.
-//   mm_tail_kernel      one thread per queued particle, deferred solves restarted without a budget.
-//                       These few threads are latency-bound (~0.3 us per step); the grid is sized so that
-//                       they do not compete for the FP64 pipe.
+//                       (Micmem_likelihood.py:70-73), or lists its deferred solves for the tail kernel.
+//   mm_tail_kernel      one lane per deferred solve, restarted without a budget.  These few thousand
+//                       solves are latency-bound (~0.45 us per step, measured); the grid is sized so that
+//                       they do not compete for the FP64 pipe.  mm_collect_kernel then sums their particles.
 //
 // Early rejection (MH sweeps).  Residuals only accumulate, so with c0 = -n_t/2 log(2 pi sigma^2)
 //     n_ex*c0 - ssr_e/(2 sigma^2)                                   (one solve alone)
-//     sum_finished (c0 - ssr_e/(2 sigma^2)) + n_unfinished*c0       (finalize / tail)
+//     sum_finished (c0 - ssr_e/(2 sigma^2)) + n_deferred*c0         (finalize; minus one deferred solve's
+//                                                                    own term in the tail kernel)
 // are upper bounds of the particle's log-likelihood.  Given lkmin[p] (smcb_mh_threshold: the value below
 // which the Metropolis test of Micmem_SMC_main.py:231-236 is certain to reject, with a safety margin) a
 // solve stops as soon as a bound falls below it and the particle reports -inf: the accept/reject
@@ -123,7 +124,9 @@ mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const u
     unsigned task = 0, n_att = 0;
     const double* tt = s_t;
     const double* pp = s_P;
-    unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, n_def = 0, mx = 0;
+    // work counters: a deferred solve is redone from scratch by the tail kernel, so its attempts here are
+    // dropped again (acc0/rej0 = counters when the solve started) and every step is counted once
+    unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, n_def = 0, mx = 0, acc0 = 0, rej0 = 0;
 
     for (;;) {
         const unsigned busy = __ballot_sync(FULL_MASK, have);
@@ -182,6 +185,8 @@ mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const u
                 pp = s_P + (size_t)e * n_t;
                 n_att = 0;
                 n_set++;
+                acc0 = n_acc;
+                rej0 = n_rej;
                 if (mmsolve::setup(s, tt, n_t)) {
                     have = true;
                 } else {
@@ -205,6 +210,9 @@ mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const u
             } else if (n_att >= budget) {
                 ssr_out[task] = DEFERRED;
                 n_def++;
+                n_set--;
+                n_acc = acc0;
+                n_rej = rej0;
                 have = false;
             }
         }
@@ -213,11 +221,16 @@ mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const u
 }
 
 // ------------------------------------------------------------------------------ finalize
+// One thread per particle.  No deferred solve: ordered sum -> lk.  Otherwise, unless the bound already
+// decides it, every deferred solve goes to solve_list (for mm_tail_kernel), the particle to part_list
+// (for mm_collect_kernel) and cutlim[p] becomes the residual limit of ONE deferred solve given what the
+// finished ones contributed:  total_finished + n_deferred*c0 - ssr_e/(2 sigma^2) < lkmin.
 template <bool BOUNDED>
 __global__ void __launch_bounds__(256)
 mm_finalize_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const uint8_t* __restrict__ active,
                    const double* __restrict__ lkmin, int n_ex, int n_t, const double* __restrict__ ssr,
-                   double* __restrict__ lk, unsigned* __restrict__ defer_list, unsigned* __restrict__ defer_count,
+                   double* __restrict__ lk, double* __restrict__ cutlim, unsigned* __restrict__ solve_list,
+                   unsigned* __restrict__ part_list, unsigned* __restrict__ ctl,
                    unsigned long long* __restrict__ stats) {
     const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
     bool cut = false;
@@ -236,14 +249,19 @@ mm_finalize_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, con
                 if (v < 0) ++n_def;
                 else total += c0 - v * inv_den;   // logL_i, summed in experiment order (:70-73)
             }
+            const double thr = BOUNDED ? lkmin[p] : -INFINITY;
             if (n_def == 0 || total == -INFINITY) {
                 lk[p] = total;
                 cut = BOUNDED && total == -INFINITY;
-            } else if (BOUNDED && total + n_def * c0 < lkmin[p]) {
+            } else if (BOUNDED && total + n_def * c0 < thr) {
                 lk[p] = -INFINITY;
                 cut = true;
             } else {
-                defer_list[atomicAdd(defer_count, 1u)] = p;
+                cutlim[p] = (BOUNDED && thr > -INFINITY) ? (total + n_def * c0 - thr) * (2 * s2) : INFINITY;
+                part_list[atomicAdd(&ctl[2], 1u)] = p;
+                unsigned at = atomicAdd(&ctl[1], (unsigned)n_def);
+                for (int e = 0; e < n_ex; ++e)
+                    if (ssr[(size_t)e * n + p] < 0) solve_list[at++] = (unsigned)e * n + p;
             }
         }
     }
@@ -257,17 +275,18 @@ mm_finalize_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, con
 }
 
 // ------------------------------------------------------------------------------ tail
-template <bool BOUNDED>
+// One lane per deferred solve, restarted from t0 without a budget.  These are the 1e3 .. 1e5-step solves:
+// each is a strictly serial chain (~870 cycles per attempted step), so the kernel's duration is the
+// longest one; blocks of one warp spread them over all SM sub-partitions.
 __global__ void __launch_bounds__(TAIL_BLOCK)
-mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const double* __restrict__ lkmin,
+mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const double* __restrict__ cutlim,
                const double* __restrict__ g_t, const double* __restrict__ g_P, const double* __restrict__ g_S0,
-               int n_ex, int n_t, double* __restrict__ ssr, double* __restrict__ lk,
-               const unsigned* __restrict__ defer_list, const unsigned* __restrict__ defer_count,
-               unsigned long long* __restrict__ stats) {
-    const unsigned count = *defer_count;
+               int n_ex, int n_t, double* __restrict__ ssr, const unsigned* __restrict__ solve_list,
+               const unsigned* __restrict__ ctl, unsigned long long* __restrict__ stats) {
+    const unsigned count = ctl[1];
     if (blockIdx.x == 0 && threadIdx.x == 0 && stats != nullptr) {
-        stats[13] = count;
-        atomicAdd(&stats[14], (unsigned long long)count);
+        stats[13] = ctl[2];
+        atomicAdd(&stats[14], (unsigned long long)ctl[2]);
     }
     if (blockIdx.x * TAIL_BLOCK >= count) return;   // nothing for this block: skip the staging too
     extern __shared__ double smem[];
@@ -279,98 +298,76 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
     Solve s;
     s.nVmax = -1.0; s.Km = 1.0; s.S0 = 0.0; s.t = 0.0; s.y = 0.0; s.f = 0.0; s.h_abs = 0.0; s.ssr = 0.0;
     s.cut_lim = INFINITY; s.i_eval = 0;
-    bool have = false, p_valid = false, finished = false;
-    unsigned idx = blockIdx.x * TAIL_BLOCK + threadIdx.x, p = 0;
+    bool have = false;
+    unsigned idx = blockIdx.x * TAIL_BLOCK + threadIdx.x, g = 0;
     const unsigned stride = gridDim.x * TAIL_BLOCK;
-    int e_cur = 0, e_scan = 0, n_left = 0;
-    double c0 = 0.0, inv_den = 0.0, two_s2 = 0.0, thr = -INFINITY, total_fin = 0.0;
     const double* tt = s_t;
     const double* pp = s_P;
-    unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, n_cut = 0, n_att = 0, mx = 0;
+    unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, n_att = 0, mx = 0;
 
     for (;;) {
-        if (!have && !finished) {
-            // next deferred solve of my particle; when it has none left, write its likelihood and take
-            // the next particle of the list
-            for (;;) {
-                if (!p_valid) {
-                    if (idx >= count) {
-                        finished = true;
-                        break;
-                    }
-                    p = defer_list[idx];
-                    idx += stride;
-                    p_valid = true;
-                    const double sigma = theta[2 * ld + p];
-                    const double s2 = sigma * sigma;
-                    c0 = -0.5 * n_t * log(2 * M_PI * s2);
-                    inv_den = 1.0 / (2 * s2);
-                    two_s2 = 2 * s2;
-                    thr = BOUNDED ? lkmin[p] : -INFINITY;
-                    s.nVmax = -theta[p];
-                    s.Km = theta[ld + p];
-                    total_fin = 0.0;
-                    n_left = 0;
-                    for (int e = 0; e < n_ex; ++e) {
-                        const double v = ssr[(size_t)e * n + p];
-                        if (v < 0) ++n_left;
-                        else total_fin += c0 - v * inv_den;
-                    }
-                    e_scan = 0;
-                }
-                while (e_scan < n_ex && !(ssr[(size_t)e_scan * n + p] < 0)) ++e_scan;
-                if (e_scan < n_ex) {
-                    e_cur = e_scan++;
-                    s.S0 = s_S0[e_cur];
-                    tt = s_t + (size_t)e_cur * n_t;
-                    pp = s_P + (size_t)e_cur * n_t;
-                    // ssr_e > cut_lim  <=>  total_fin + n_left*c0 - ssr_e*inv_den < thr
-                    s.cut_lim = (BOUNDED && thr > -INFINITY) ? (total_fin + n_left * c0 - thr) * two_s2
-                                                            : INFINITY;
-                    n_att = 0;
-                    n_set++;
-                    if (mmsolve::setup(s, tt, n_t)) {
-                        have = true;
-                        break;
-                    }
-                    n_fail++;
-                    lk[p] = -INFINITY;
-                    p_valid = false;
-                    continue;
-                }
-                // all experiments of this particle are in: ordered sum, as the reference adds them
-                double total = 0.0;
-                for (int e = 0; e < n_ex; ++e) total += c0 - ssr[(size_t)e * n + p] * inv_den;
-                lk[p] = total;
-                p_valid = false;
+        if (!have && idx < count) {
+            g = solve_list[idx];
+            idx += stride;
+            const unsigned e = g / n, p = g - e * n;
+            s.nVmax = -theta[p];
+            s.Km = theta[ld + p];
+            s.S0 = s_S0[e];
+            s.cut_lim = cutlim[p];
+            tt = s_t + (size_t)e * n_t;
+            pp = s_P + (size_t)e * n_t;
+            n_att = 0;
+            n_set++;
+            if (mmsolve::setup(s, tt, n_t)) {
+                have = true;
+            } else {
+                ssr[g] = INFINITY;
+                n_fail++;
             }
         }
-        if (__ballot_sync(FULL_MASK, have) == 0) break;
+        if (__ballot_sync(FULL_MASK, have) == 0) {
+            if (__ballot_sync(FULL_MASK, idx < count) == 0) break;
+            continue;
+        }
         if (have) {
             const int st = mmsolve::attempt<false>(s, tt, pp, n_t, nullptr, n_acc, n_rej);
             ++n_att;
             if (st != mmsolve::RUNNING) {
+                ssr[g] = (st == mmsolve::DONE) ? s.ssr : INFINITY;
+                if (st == mmsolve::FAILED) n_fail++;
                 mx = max(mx, n_att);
                 have = false;
-                if (st == mmsolve::DONE) {
-                    ssr[(size_t)e_cur * n + p] = s.ssr;
-                    total_fin += c0 - s.ssr * inv_den;
-                    --n_left;
-                } else {
-                    if (st == mmsolve::FAILED) n_fail++;
-                    else n_cut++;
-                    lk[p] = -INFINITY;
-                    p_valid = false;
-                }
             }
         }
     }
     flush_stats(stats, n_set, n_acc, n_rej, n_fail, 0u, mx);
+}
+
+// ------------------------------------------------------------------------------ collect
+// Ordered sum for the particles whose deferred solves the tail kernel has now finished.
+template <bool BOUNDED>
+__global__ void __launch_bounds__(256)
+mm_collect_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, int n_ex, int n_t,
+                  const double* __restrict__ ssr, double* __restrict__ lk, const unsigned* __restrict__ part_list,
+                  const unsigned* __restrict__ ctl, unsigned long long* __restrict__ stats) {
+    const unsigned count = ctl[2];
+    long long n_cut = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const unsigned p = part_list[i];
+        const double sigma = theta[2 * ld + p];
+        const double s2 = sigma * sigma;
+        const double c0 = -0.5 * n_t * log(2 * M_PI * s2);
+        const double inv_den = 1.0 / (2 * s2);
+        double total = 0.0;
+        for (int e = 0; e < n_ex; ++e) total += c0 - ssr[(size_t)e * n + p] * inv_den;
+        lk[p] = total;
+        n_cut += (BOUNDED && total == -INFINITY);
+    }
     if (BOUNDED) {
-        const unsigned long long w_cut = (unsigned long long)warp_sum_ll((long long)n_cut);
-        if (w_cut != 0 && threadIdx.x == 0) {
-            atomicAdd(&stats[8], w_cut);
-            atomicAdd(&stats[9], w_cut);
+        n_cut = warp_sum_ll(n_cut);
+        if (n_cut != 0 && (threadIdx.x & 31) == 0) {
+            atomicAdd(&stats[8], (unsigned long long)n_cut);
+            atomicAdd(&stats[9], (unsigned long long)n_cut);
         }
     }
 }
@@ -505,7 +502,7 @@ mm_rate_kernel_f32(const double* __restrict__ theta, int64_t ld, int64_t n,
 __global__ void mm_reset_kernel(unsigned long long* stats, unsigned* ctl) {
     if (threadIdx.x < 4) stats[threadIdx.x] = 0;
     if (threadIdx.x == 8 || threadIdx.x == 10 || threadIdx.x == 11 || threadIdx.x == 13) stats[threadIdx.x] = 0;
-    if (threadIdx.x < 2) ctl[threadIdx.x] = 0;
+    if (threadIdx.x < 3) ctl[threadIdx.x] = 0;
 }
 
 int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, int64_t n,
@@ -530,8 +527,7 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     if (smem > 48 * 1024 && !h->mm_smem_set) {
         CUDA_TRY(h, cudaFuncSetAttribute(mm_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(h, cudaFuncSetAttribute(mm_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(h, cudaFuncSetAttribute(mm_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(h, cudaFuncSetAttribute(mm_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(h, cudaFuncSetAttribute(mm_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->mm_smem_set = true;
     }
     if (h->mm_bulk_blocks_per_sm == 0) {
@@ -540,8 +536,7 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
         CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, mm_bulk_kernel<true>, BULK_BLOCK, smem));
         h->mm_bulk_blocks_per_sm = (a < b ? a : b) > 0 ? (a < b ? a : b) : 1;
     }
-    unsigned* queue = h->mm_ctl;
-    unsigned* defer_count = h->mm_ctl + 1;
+    unsigned* queue = h->mm_ctl;   // [0] solve queue head, [1] deferred solves, [2] deferred particles
     mm_reset_kernel<<<1, 32, 0, st>>>(h->stats, h->mm_ctl);
     LAUNCH_CHECK(h);
     if (bounded) {
@@ -560,21 +555,29 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
         mm_bulk_kernel<false><<<grid, BULK_BLOCK, smem, st>>>(theta, ld, un, active, nullptr, D.t, D.P, D.S0,
                                                             D.n_ex, D.n_t, budget, h->ssr, queue, h->stats);
     LAUNCH_CHECK(h);
-    // 12 warps per SM keep the latency-bound tail solves clear of each other on the FP64 pipe
-    const unsigned tail_grid = (unsigned)h->sm_count * 12;
-    if (bounded) {
+    unsigned* solve_list = h->mm_defer;                              // [n_ex * n_max]
+    unsigned* part_list = h->mm_defer + (size_t)h->ssr_rows * h->n_max;   // [n_max]
+    if (bounded)
         mm_finalize_kernel<true><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, active, lkmin, D.n_ex, D.n_t, h->ssr,
-                                                                  lk, h->mm_defer, defer_count, h->stats);
-        LAUNCH_CHECK(h);
-        mm_tail_kernel<true><<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, lkmin, D.t, D.P, D.S0, D.n_ex, D.n_t,
-                                                                 h->ssr, lk, h->mm_defer, defer_count, h->stats);
-    } else {
+                                                                  lk, h->mm_cutlim, solve_list, part_list, h->mm_ctl,
+                                                                  h->stats);
+    else
         mm_finalize_kernel<false><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, active, nullptr, D.n_ex, D.n_t,
-                                                                   h->ssr, lk, h->mm_defer, defer_count, h->stats);
-        LAUNCH_CHECK(h);
-        mm_tail_kernel<false><<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, nullptr, D.t, D.P, D.S0, D.n_ex,
-                                                                  D.n_t, h->ssr, lk, h->mm_defer, defer_count, h->stats);
-    }
+                                                                   h->ssr, lk, h->mm_cutlim, solve_list, part_list,
+                                                                   h->mm_ctl, h->stats);
+    LAUNCH_CHECK(h);
+    // 12 one-warp blocks per SM keep the latency-bound tail solves clear of each other on the FP64 pipe
+    const unsigned tail_grid = (unsigned)h->sm_count * 12;
+    mm_tail_kernel<<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, h->mm_cutlim, D.t, D.P, D.S0, D.n_ex, D.n_t,
+                                                       h->ssr, solve_list, h->mm_ctl, h->stats);
+    LAUNCH_CHECK(h);
+    const unsigned cgrid = (unsigned)h->sm_count * 8 < (un + 255) / 256 ? (unsigned)h->sm_count * 8 : (un + 255) / 256;
+    if (bounded)
+        mm_collect_kernel<true><<<cgrid, 256, 0, st>>>(theta, ld, un, D.n_ex, D.n_t, h->ssr, lk, part_list, h->mm_ctl,
+                                                      h->stats);
+    else
+        mm_collect_kernel<false><<<cgrid, 256, 0, st>>>(theta, ld, un, D.n_ex, D.n_t, h->ssr, lk, part_list, h->mm_ctl,
+                                                       h->stats);
     LAUNCH_CHECK(h);
     return SMCB_OK;
 }
