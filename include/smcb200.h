@@ -100,6 +100,12 @@ int smcb_loglik_bounded(smcb_handle* h, int model, const double* theta_dev, int6
 /* Tunables.  SMCB_PARAM_MM_BUDGET: attempted RK steps after which the bulk MM_PROGRESS kernel hands a
  * solve to the tail kernel (default 256; results do not depend on it). */
 #define SMCB_PARAM_MM_BUDGET 1
+/* SMCB_PARAM_MM_REFILL_MIN: free lanes a warp of the bulk kernel waits for before it sets up new solves
+ * (default 8, 1..32; results do not depend on it). */
+#define SMCB_PARAM_MM_REFILL_MIN 2
+/* SMCB_PARAM_MM_PATIENCE: ... and for how many attempted steps it waits (default 3); a warp whose lanes
+ * are all free refills at once. */
+#define SMCB_PARAM_MM_PATIENCE 3
 int smcb_set_param(smcb_handle* h, int key, double value);
 /* Model predictions for a few particles (the `C_l_` the reference returns for its parity plots,
  * EX/lik:74-77): pred_dev[i][n_ex][n_t].  MM_PROGRESS only. */

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Likelihood-kernel micro-run for profiling (ncu) and for quick timing while tuning K1.
 
-    python profiles/prof_loglik.py [log2_particles=20] [reps=3] [model=mm_progress|mm_rate32|mm_rate64|kinetic|kinetic32] [budget]
+    python profiles/prof_loglik.py [log2_particles=20] [reps=3] [model=mm_progress|mm_rate32|mm_rate64|kinetic|kinetic32] [budget] [refill_min] [patience]
 
 Evaluates (a) a prior cloud (Philox uniform box) and (b) a posterior-like cloud (for MM: a Gaussian
 around the reference posterior) and prints the CUDA-event time of each sweep and the device work
@@ -39,6 +39,10 @@ else:
 eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N))
 if len(sys.argv) > 4:   # deferral budget of the bulk MM_PROGRESS kernel
     eng._ck(eng.lib.smcb_set_param(eng.h, 1, float(sys.argv[4])))
+if len(sys.argv) > 5:   # lanes a bulk warp waits for before refilling
+    eng._ck(eng.lib.smcb_set_param(eng.h, 2, float(sys.argv[5])))
+if len(sys.argv) > 6:   # ... for how many attempted steps
+    eng._ck(eng.lib.smcb_set_param(eng.h, 3, float(sys.argv[6])))
 
 
 def sweep(tag):

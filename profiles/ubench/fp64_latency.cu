@@ -68,16 +68,16 @@ __global__ void thr_rcp(double* out, int iters) {
 }
 // one stiff solve, `lanes` active lanes of one warp all integrating the same problem
 __global__ void solve_steps(double* out, long long* cyc, unsigned* natt, double Vmax, double Km, double S0, int lanes) {
-    __shared__ double tt[40], pp[40];
-    for (int i = threadIdx.x; i < 40; i += blockDim.x) { tt[i] = 10.0 * i / 39.0; pp[i] = 0.05; }
+    __shared__ mmsolve::ObsPair obs[40];
+    for (int i = threadIdx.x; i < 40; i += blockDim.x) { obs[i].P = 0.05; obs[i].t_next = (i < 39) ? 10.0 * (i + 1) / 39.0 : INFINITY; }
     __syncthreads();
     if ((int)threadIdx.x >= lanes) return;
     mmsolve::Solve s;
     s.nVmax = -Vmax; s.Km = Km; s.S0 = S0; s.cut_lim = INFINITY;
     unsigned a = 0, r = 0;
     long long t0 = clock64();
-    int st = mmsolve::setup(s, tt, 40) ? mmsolve::RUNNING : mmsolve::FAILED;
-    while (st == mmsolve::RUNNING) st = mmsolve::attempt<false>(s, tt, pp, 40, nullptr, a, r);
+    int st = mmsolve::setup(s, 0.0, 10.0) ? mmsolve::RUNNING : mmsolve::FAILED;
+    while (st == mmsolve::RUNNING) st = mmsolve::attempt<false>(s, obs, nullptr, a, r);
     long long t1 = clock64();
     out[threadIdx.x] = s.ssr;
     if (threadIdx.x == 0) { cyc[0] = t1 - t0; natt[0] = a + r; }

@@ -218,6 +218,14 @@ extern "C" int smcb_set_param(smcb_handle* h, int key, double value) {
             REQUIRE(h, value >= 1 && value <= 1e9, SMCB_ERR_INVALID, "MM_BUDGET must be in [1, 1e9]");
             h->mm_budget = (int)value;
             return SMCB_OK;
+        case SMCB_PARAM_MM_REFILL_MIN:
+            REQUIRE(h, value >= 1 && value <= 32, SMCB_ERR_INVALID, "MM_REFILL_MIN must be in [1, 32]");
+            h->mm_refill_min = (int)value;
+            return SMCB_OK;
+        case SMCB_PARAM_MM_PATIENCE:
+            REQUIRE(h, value >= 0 && value <= 1e6, SMCB_ERR_INVALID, "MM_PATIENCE must be in [0, 1e6]");
+            h->mm_patience = (int)value;
+            return SMCB_OK;
         default:
             return smcb_fail(h, SMCB_ERR_INVALID, "smcb_set_param: unknown key %d", key);
     }

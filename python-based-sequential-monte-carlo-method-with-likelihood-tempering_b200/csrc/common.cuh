@@ -53,6 +53,8 @@ struct smcb_handle {
     unsigned* mm_defer = nullptr;    // [ssr_rows*n_max] deferred solves, then [n_max] their particles
     double* mm_cutlim = nullptr;     // [n_max] per-particle residual limit of a bounded sweep
     int mm_budget = 256;             // attempted steps after which the bulk kernel defers a solve
+    int mm_patience = 3;             // ... for this many attempted steps (unless the whole warp is free)
+    int mm_refill_min = 8;           // free lanes a warp of the bulk kernel waits for before setting up new solves
     int mm_bulk_blocks_per_sm = 0;   // occupancy of the bulk kernel (queried once)
     bool mm_smem_set = false;
     int32_t* floor_cnt = nullptr;    // [n_max]

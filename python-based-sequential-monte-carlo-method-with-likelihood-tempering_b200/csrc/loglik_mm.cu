@@ -43,18 +43,38 @@ using mmsolve::Solve;
 
 constexpr int BULK_BLOCK = 128;
 constexpr int BULK_CHUNK = 128;     // solves a warp takes from the queue at a time
-constexpr int REFILL_MIN = 8;       // free lanes needed before a warp stops to set up new solves
 constexpr int TAIL_BLOCK = 32;
 constexpr double DEFERRED = -1.0;   // marker in the per-solve result array (a residual sum is >= 0)
 
-__device__ __forceinline__ void stage_data(double* s_t, double* s_P, double* s_S0, const double* g_t,
-                                           const double* g_P, const double* g_S0, int n_ex, int n_t) {
-    for (int i = threadIdx.x; i < n_ex * n_t; i += blockDim.x) {
-        s_t[i] = g_t[i];
-        s_P[i] = g_P[i];
+// Shared-memory image of the data set: obs[n_ex][n_t] (P_obs[i], t[i+1]) pairs, then per experiment
+// (S0, t[0], t[n_t-1]).
+struct SharedData {
+    mmsolve::ObsPair* obs;
+    double* S0;
+    double* t0;
+    double* tb;
+};
+__host__ __device__ inline size_t shared_data_bytes(int n_ex, int n_t) {
+    return (size_t)n_ex * n_t * sizeof(mmsolve::ObsPair) + (size_t)3 * n_ex * sizeof(double);
+}
+__device__ __forceinline__ SharedData stage_data(void* smem, const double* g_t, const double* g_P,
+                                                 const double* g_S0, int n_ex, int n_t) {
+    SharedData D;
+    D.obs = reinterpret_cast<mmsolve::ObsPair*>(smem);
+    D.S0 = reinterpret_cast<double*>(D.obs + (size_t)n_ex * n_t);
+    D.t0 = D.S0 + n_ex;
+    D.tb = D.t0 + n_ex;
+    for (int k = threadIdx.x; k < n_ex * n_t; k += blockDim.x) {
+        const int e = k / n_t, i = k - e * n_t;
+        mmsolve::fill_pairs(D.obs + (size_t)e * n_t, g_t + (size_t)e * n_t, g_P + (size_t)e * n_t, n_t, i);
     }
-    for (int i = threadIdx.x; i < n_ex; i += blockDim.x) s_S0[i] = g_S0[i];
+    for (int e = threadIdx.x; e < n_ex; e += blockDim.x) {
+        D.S0[e] = g_S0[e];
+        D.t0[e] = g_t[(size_t)e * n_t];
+        D.tb[e] = g_t[(size_t)e * n_t + n_t - 1];
+    }
     __syncthreads();
+    return D;
 }
 
 // counters: see smcb_loglik_stats
@@ -103,13 +123,10 @@ template <bool BOUNDED>
 __global__ void __launch_bounds__(BULK_BLOCK)
 mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const uint8_t* __restrict__ active,
                const double* __restrict__ cutlim, const double* __restrict__ g_t, const double* __restrict__ g_P,
-               const double* __restrict__ g_S0, int n_ex, int n_t, unsigned budget, double* __restrict__ ssr_out,
-               unsigned* __restrict__ queue, unsigned long long* __restrict__ stats) {
-    extern __shared__ double smem[];
-    double* s_t = smem;
-    double* s_P = smem + (size_t)n_ex * n_t;
-    double* s_S0 = s_P + (size_t)n_ex * n_t;
-    stage_data(s_t, s_P, s_S0, g_t, g_P, g_S0, n_ex, n_t);
+               const double* __restrict__ g_S0, int n_ex, int n_t, unsigned budget, int refill_min,
+               int patience, double* __restrict__ ssr_out, unsigned* __restrict__ queue, unsigned long long* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SharedData D = stage_data(smem, g_t, g_P, g_S0, n_ex, n_t);
 
     const unsigned total = n * (unsigned)n_ex;
     const unsigned lane = threadIdx.x & 31;
@@ -119,19 +136,23 @@ mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const u
 
     Solve s;
     s.nVmax = -1.0; s.Km = 1.0; s.S0 = 0.0; s.t = 0.0; s.y = 0.0; s.f = 0.0; s.h_abs = 0.0; s.ssr = 0.0;
-    s.cut_lim = INFINITY; s.i_eval = 0;
+    s.cut_lim = INFINITY; s.i_eval = 0; s.t_next = 0.0; s.t_bound = 0.0;
     bool have = false;
     unsigned task = 0, n_att = 0;
-    const double* tt = s_t;
-    const double* pp = s_P;
+    const mmsolve::ObsPair* obs = D.obs;
     // work counters: a deferred solve is redone from scratch by the tail kernel, so its attempts here are
     // dropped again (acc0/rej0 = counters when the solve started) and every step is counted once
     unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, n_def = 0, mx = 0, acc0 = 0, rej0 = 0;
 
+    int waited = 0;   // attempted steps since a lane of this warp went free (warp-uniform)
     for (;;) {
         const unsigned busy = __ballot_sync(FULL_MASK, have);
         unsigned want = drained ? 0u : (~busy);
-        if (want != 0 && (__popc(want) >= REFILL_MIN || busy == 0)) {
+        // Refill when the whole warp is free, or when at least refill_min lanes have been waiting for
+        // `patience` steps: near the posterior the lanes of a warp finish within a step or two of each
+        // other and are set up together; in a prior cloud the stragglers are not waited for.
+        if (want != 0 && (busy == 0 || (__popc(want) >= refill_min && waited >= patience))) {
+            waited = 0;
             // ---- 1. hand out solves until every free lane holds a live one (or the queue is empty) ----
             bool got = false;
             unsigned e = 0, p = 0;
@@ -180,14 +201,13 @@ mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const u
             if (got) {
                 s.nVmax = -theta[p];
                 s.Km = theta[ld + p];
-                s.S0 = s_S0[e];
-                tt = s_t + (size_t)e * n_t;
-                pp = s_P + (size_t)e * n_t;
+                s.S0 = D.S0[e];
+                obs = D.obs + (size_t)e * n_t;
                 n_att = 0;
                 n_set++;
                 acc0 = n_acc;
                 rej0 = n_rej;
-                if (mmsolve::setup(s, tt, n_t)) {
+                if (mmsolve::setup(s, D.t0[e], D.tb[e])) {
                     have = true;
                 } else {
                     ssr_out[task] = INFINITY;
@@ -199,8 +219,9 @@ mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const u
             if (drained) break;
             continue;
         }
+        waited += (want != 0);
         if (have) {
-            const int st = mmsolve::attempt<false>(s, tt, pp, n_t, nullptr, n_acc, n_rej);
+            const int st = mmsolve::attempt<false>(s, obs, nullptr, n_acc, n_rej);
             ++n_att;
             if (st != mmsolve::RUNNING) {
                 ssr_out[task] = (st == mmsolve::DONE) ? s.ssr : INFINITY;
@@ -289,20 +310,16 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
         atomicAdd(&stats[14], (unsigned long long)ctl[2]);
     }
     if (blockIdx.x * TAIL_BLOCK >= count) return;   // nothing for this block: skip the staging too
-    extern __shared__ double smem[];
-    double* s_t = smem;
-    double* s_P = smem + (size_t)n_ex * n_t;
-    double* s_S0 = s_P + (size_t)n_ex * n_t;
-    stage_data(s_t, s_P, s_S0, g_t, g_P, g_S0, n_ex, n_t);
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SharedData D = stage_data(smem, g_t, g_P, g_S0, n_ex, n_t);
 
     Solve s;
     s.nVmax = -1.0; s.Km = 1.0; s.S0 = 0.0; s.t = 0.0; s.y = 0.0; s.f = 0.0; s.h_abs = 0.0; s.ssr = 0.0;
-    s.cut_lim = INFINITY; s.i_eval = 0;
+    s.cut_lim = INFINITY; s.i_eval = 0; s.t_next = 0.0; s.t_bound = 0.0;
     bool have = false;
     unsigned idx = blockIdx.x * TAIL_BLOCK + threadIdx.x, g = 0;
     const unsigned stride = gridDim.x * TAIL_BLOCK;
-    const double* tt = s_t;
-    const double* pp = s_P;
+    const mmsolve::ObsPair* obs = D.obs;
     unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, n_att = 0, mx = 0;
 
     for (;;) {
@@ -312,13 +329,12 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
             const unsigned e = g / n, p = g - e * n;
             s.nVmax = -theta[p];
             s.Km = theta[ld + p];
-            s.S0 = s_S0[e];
+            s.S0 = D.S0[e];
             s.cut_lim = cutlim[p];
-            tt = s_t + (size_t)e * n_t;
-            pp = s_P + (size_t)e * n_t;
+            obs = D.obs + (size_t)e * n_t;
             n_att = 0;
             n_set++;
-            if (mmsolve::setup(s, tt, n_t)) {
+            if (mmsolve::setup(s, D.t0[e], D.tb[e])) {
                 have = true;
             } else {
                 ssr[g] = INFINITY;
@@ -330,7 +346,7 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
             continue;
         }
         if (have) {
-            const int st = mmsolve::attempt<false>(s, tt, pp, n_t, nullptr, n_acc, n_rej);
+            const int st = mmsolve::attempt<false>(s, obs, nullptr, n_acc, n_rej);
             ++n_att;
             if (st != mmsolve::RUNNING) {
                 ssr[g] = (st == mmsolve::DONE) ? s.ssr : INFINITY;
@@ -376,21 +392,22 @@ mm_collect_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, int 
 // P_model of every (particle, experiment): pred[(p*n_ex + e)*n_t + i]  (the `C_l_` of sim_particle)
 __global__ void __launch_bounds__(128)
 mm_predict_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const double* __restrict__ g_t,
-                  const double* __restrict__ g_S0, int n_ex, int n_t, double* __restrict__ pred) {
+                  const double* __restrict__ g_P, const double* __restrict__ g_S0, int n_ex, int n_t,
+                  double* __restrict__ pred) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SharedData D = stage_data(smem, g_t, g_P, g_S0, n_ex, n_t);
     const unsigned g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n * (unsigned)n_ex) return;
     const unsigned p = g / n_ex, e = g - p * n_ex;
     Solve s;
     s.nVmax = -theta[p];
     s.Km = theta[ld + p];
-    s.S0 = g_S0[e];
+    s.S0 = D.S0[e];
     s.cut_lim = INFINITY;
-    const double* tt = g_t + (size_t)e * n_t;
     double* out = pred + (size_t)g * n_t;
     unsigned a = 0, r = 0;
-    int st = mmsolve::setup(s, tt, n_t) ? mmsolve::RUNNING : mmsolve::FAILED;
-    if (st == mmsolve::FAILED) s.i_eval = 0;
-    while (st == mmsolve::RUNNING) st = mmsolve::attempt<true>(s, tt, nullptr, n_t, out, a, r);
+    int st = mmsolve::setup(s, D.t0[e], D.tb[e]) ? mmsolve::RUNNING : mmsolve::FAILED;
+    while (st == mmsolve::RUNNING) st = mmsolve::attempt<true>(s, D.obs + (size_t)e * n_t, out, a, r);
     if (st == mmsolve::FAILED)   // scipy would return a short solution here
         for (int i = s.i_eval; i < n_t; ++i) out[i] = NAN;
 }
@@ -511,13 +528,15 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     const MmProgressData& D = h->mmp;
     REQUIRE(h, D.t != nullptr, SMCB_ERR_STATE, "smcb_set_data_mm_progress has not been called");
     if (n == 0) return SMCB_OK;
-    const size_t smem = ((size_t)2 * D.n_ex * D.n_t + D.n_ex) * sizeof(double);
+    const size_t smem = shared_data_bytes(D.n_ex, D.n_t);
     REQUIRE(h, smem <= 200 * 1024, SMCB_ERR_UNSUPPORTED, "data set too large for shared-memory staging");
     REQUIRE(h, n * (int64_t)D.n_ex < (1LL << 31), SMCB_ERR_UNSUPPORTED, "too many solves for one launch");
     const unsigned un = (unsigned)n;
     if (pred != nullptr) {
         const unsigned tasks = un * (unsigned)D.n_ex;
-        mm_predict_kernel<<<(tasks + 127) / 128, 128, 0, st>>>(theta, ld, un, D.t, D.S0, D.n_ex, D.n_t, pred);
+        if (smem > 48 * 1024)
+            CUDA_TRY(h, cudaFuncSetAttribute(mm_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mm_predict_kernel<<<(tasks + 127) / 128, 128, smem, st>>>(theta, ld, un, D.t, D.P, D.S0, D.n_ex, D.n_t, pred);
         LAUNCH_CHECK(h);
         return SMCB_OK;
     }
@@ -550,10 +569,10 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     const unsigned budget = (unsigned)h->mm_budget;
     if (bounded)
         mm_bulk_kernel<true><<<grid, BULK_BLOCK, smem, st>>>(theta, ld, un, active, h->mm_cutlim, D.t, D.P, D.S0,
-                                                           D.n_ex, D.n_t, budget, h->ssr, queue, h->stats);
+                                                           D.n_ex, D.n_t, budget, h->mm_refill_min, h->mm_patience, h->ssr, queue, h->stats);
     else
         mm_bulk_kernel<false><<<grid, BULK_BLOCK, smem, st>>>(theta, ld, un, active, nullptr, D.t, D.P, D.S0,
-                                                            D.n_ex, D.n_t, budget, h->ssr, queue, h->stats);
+                                                            D.n_ex, D.n_t, budget, h->mm_refill_min, h->mm_patience, h->ssr, queue, h->stats);
     LAUNCH_CHECK(h);
     unsigned* solve_list = h->mm_defer;                              // [n_ex * n_max]
     unsigned* part_list = h->mm_defer + (size_t)h->ssr_rows * h->n_max;   // [n_max]

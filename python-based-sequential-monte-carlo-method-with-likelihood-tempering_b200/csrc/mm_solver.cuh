@@ -136,11 +136,23 @@ MM_HD double ulp10(double t) {
 
 enum Status { RUNNING = 0, DONE = 1, FAILED = 2, CUT = 3 };
 
+// Observation grid of one experiment as the solver reads it: obs[i] = (P_obs[i], t[i+1]) with
+// t[n_t] = +inf, so emitting observation i and looking at the next time is one 16-byte load and the
+// end of the grid needs no index test.
+struct alignas(16) ObsPair {
+    double P, t_next;
+};
+MM_HD void fill_pairs(ObsPair* obs, const double* t, const double* P, int n_t, int i) {
+    obs[i].P = P[i];
+    obs[i].t_next = (i + 1 < n_t) ? t[i + 1] : INFINITY;
+}
+
 struct Solve {
     double nVmax, Km;   // -Vmax, Km of the particle
     double S0;          // initial substrate of the experiment
     double t, y, f;     // current time, state, f(t, y) (first-same-as-last)
-    double t_next;      // tt[i_eval], the next observation time (+inf after the last)
+    double t_next;      // t[i_eval], the next observation time (+inf after the last)
+    double t_bound;     // t[n_t-1]
     double h_abs;       // next step size; negative = retry of the same scipy step after a rejection
     double ssr;         // residual sum of squares so far
     double cut_lim;     // stop (CUT) as soon as ssr exceeds this; +inf = never
@@ -149,9 +161,9 @@ struct Solve {
 
 // select_initial_step (common.py:110-134) for n = 1, direction = +1, order 4.  Returns false when no
 // positive step size results (Km + S0 = 0 gives NaN, with which scipy would loop forever).
-MM_HD bool setup(Solve& s, const double* tt, int n_t) {
-    const double t0 = tt[0], t_bound = tt[n_t - 1];
+MM_HD bool setup(Solve& s, double t0, double t_bound) {
     s.t = t0;
+    s.t_bound = t_bound;
     s.y = s.S0;
     s.ssr = 0.0;
     s.i_eval = 0;
@@ -163,11 +175,11 @@ MM_HD bool setup(Solve& s, const double* tt, int n_t) {
     const double iscale = rcp64(fma(fabs(y), RTOL, ATOL));
     const double d0 = fabs(y * iscale);
     const double d1 = fabs(f * iscale);
-    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (0.01 * d0) * rcp64(d1);
     h0 = (interval < h0) ? interval : h0;
     const double y1 = fma(h0, f, y);
     const double f1 = mm_rate(s.nVmax, s.Km, y1);
-    const double d2 = fabs((f1 - f) * iscale) / h0;
+    const double d2 = fabs((f1 - f) * iscale) * rcp64(h0);
     double h1;
     if (d1 <= 1e-15 && d2 <= 1e-15) {
         h1 = h0 * 1e-3;
@@ -183,13 +195,13 @@ MM_HD bool setup(Solve& s, const double* tt, int n_t) {
     return hh > 0.0;   // false for NaN
 }
 
-// One attempted step (rk.py:111-176).  PRED: write P_model = S0 - S(t_eval) to pred[i] instead of
-// accumulating residuals.  n_acc / n_rej count accepted / rejected attempts.
+// One attempted step (rk.py:111-176).  obs: the experiment's observation grid (ObsPair).  PRED: write
+// P_model = S0 - S(t_eval) to pred[i] instead of accumulating residuals.  n_acc / n_rej count accepted /
+// rejected attempts.
 template <bool PRED>
-MM_HD int attempt(Solve& s, const double* tt, const double* pp, int n_t, double* pred, unsigned& n_acc,
-                  unsigned& n_rej) {
+MM_HD int attempt(Solve& s, const ObsPair* obs, double* pred, unsigned& n_acc, unsigned& n_rej) {
     const double t = s.t, y = s.y;
-    const double t_bound = tt[n_t - 1];
+    const double t_bound = s.t_bound;
     double ha = s.h_abs;
     bool rejected = false;
     if (ha < 0) {
@@ -241,16 +253,17 @@ MM_HD int attempt(Solve& s, const double* tt, const double* pp, int n_t, double*
             double ssr = s.ssr, te = s.t_next;
             do {
                 const double x = (te - t) * ih;
+                const ObsPair o = obs[i];
                 const double S = fma(x, fma(x, fma(x, fma(x, q4, q3), q2), K1), y);
                 const double Pm = s.S0 - S;   // Micmem_likelihood.py:32
                 if (PRED) {
                     pred[i] = Pm;
                 } else {
-                    const double r = pp[i] - Pm;   // :68
+                    const double r = o.P - Pm;   // :68
                     ssr = fma(r, r, ssr);
                 }
                 ++i;
-                te = (i < n_t) ? tt[i] : INFINITY;
+                te = o.t_next;
             } while (te <= t_new);
             s.i_eval = i;
             s.t_next = te;

@@ -7,11 +7,16 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../python-based-sequential-monte-carlo-method-with-likelihood-tempering_b200/csrc/mm_solver.cuh"
 
 extern "C" void twin_loglik(const double* theta, int64_t n, const double* t, const double* P, const double* S0,
                             int n_ex, int n_t, double* lk, int64_t* counters, int32_t* steps) {
     using namespace mmsolve;
+    std::vector<ObsPair> obs((size_t)n_ex * n_t);
+    for (int e = 0; e < n_ex; ++e)
+        for (int i = 0; i < n_t; ++i) fill_pairs(obs.data() + (size_t)e * n_t, t + e * n_t, P + e * n_t, n_t, i);
     for (int64_t p = 0; p < n; ++p) {
         const double Vmax = theta[3 * p], Km = theta[3 * p + 1], sigma = theta[3 * p + 2];
         if (sigma <= 0) {
@@ -29,8 +34,8 @@ extern "C" void twin_loglik(const double* theta, int64_t n, const double* t, con
             s.S0 = S0[e];
             s.cut_lim = INFINITY;
             unsigned n_acc = 0, n_rej = 0;
-            int st = setup(s, t + e * n_t, n_t) ? RUNNING : FAILED;
-            while (st == RUNNING) st = attempt<false>(s, t + e * n_t, P + e * n_t, n_t, nullptr, n_acc, n_rej);
+            int st = setup(s, t[e * n_t], t[e * n_t + n_t - 1]) ? RUNNING : FAILED;
+            while (st == RUNNING) st = attempt<false>(s, obs.data() + (size_t)e * n_t, nullptr, n_acc, n_rej);
             if (counters) {
                 counters[0] += 2 + 6 * (int64_t)(n_acc + n_rej);
                 counters[1] += n_acc;
@@ -47,6 +52,10 @@ extern "C" void twin_loglik(const double* theta, int64_t n, const double* t, con
 extern "C" void twin_predict(const double* theta, int64_t n, const double* t, const double* S0, int n_ex,
                              int n_t, double* pred) {
     using namespace mmsolve;
+    std::vector<ObsPair> obs((size_t)n_ex * n_t);
+    std::vector<double> zero((size_t)n_t, 0.0);
+    for (int e = 0; e < n_ex; ++e)
+        for (int i = 0; i < n_t; ++i) fill_pairs(obs.data() + (size_t)e * n_t, t + e * n_t, zero.data(), n_t, i);
     for (int64_t p = 0; p < n; ++p)
         for (int e = 0; e < n_ex; ++e) {
             Solve s;
@@ -55,7 +64,7 @@ extern "C" void twin_predict(const double* theta, int64_t n, const double* t, co
             s.S0 = S0[e];
             s.cut_lim = INFINITY;
             unsigned a = 0, r = 0;
-            int st = setup(s, t + e * n_t, n_t) ? RUNNING : FAILED;
-            while (st == RUNNING) st = attempt<true>(s, t + e * n_t, nullptr, n_t, pred + (p * n_ex + e) * n_t, a, r);
+            int st = setup(s, t[e * n_t], t[e * n_t + n_t - 1]) ? RUNNING : FAILED;
+            while (st == RUNNING) st = attempt<true>(s, obs.data() + (size_t)e * n_t, pred + (p * n_ex + e) * n_t, a, r);
         }
 }
