@@ -58,7 +58,7 @@ MODEL_MM_PROGRESS, MODEL_MM_RATE, MODEL_KINETIC_RK = 1, 2, 3
 SCAN_SEQUENTIAL, SCAN_FIXED = 0, 1
 MAX_DIM, MAX_CAND = 32, 16
 KIN_NCOND_FIELDS = 10
-PARAM_MM_BUDGET = 1
+PARAM_MM_BUDGET, PARAM_MM_REFILL_MIN, PARAM_MM_PATIENCE = 1, 2, 3
 N_STATS = 16
 
 

@@ -123,6 +123,15 @@ extern "C" int smcb_reserve(smcb_handle* h, int64_t n_max, int d_max) {
     int rows = 1;
     if (h->mmp.n_ex > rows) rows = h->mmp.n_ex;
     if (h->kin.n_cond > rows) rows = h->kin.n_cond;
+    // grow-only: scratch that is already large enough is kept (cudaMalloc/cudaFree of these buffers cost
+    // more than a whole sampler run at 2^20 particles)
+    if (n_max <= h->n_max && rows <= h->ssr_rows) {
+        if (d_max > h->d_max) h->d_max = d_max;
+        return SMCB_OK;
+    }
+    if (n_max < h->n_max) n_max = h->n_max;
+    if (rows < h->ssr_rows) rows = (int)h->ssr_rows;
+    if (d_max < h->d_max) d_max = h->d_max;
     int rc;
     if ((rc = dev_alloc(h, &h->ssr, (size_t)rows * n_max))) return rc;
     h->ssr_rows = rows;

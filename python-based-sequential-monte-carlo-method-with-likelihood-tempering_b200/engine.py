@@ -148,6 +148,41 @@ class Result:
     ancestors: list = field(default_factory=list)
 
 
+# ------------------------------------------------------------------------------------ handle pool
+# cudaMalloc / cudaFree of the library's scratch (a few hundred MB at 2^20 particles) cost more than a whole
+# sampler run, so a closed Engine parks its handle here and the next Engine on that device takes it over
+# (smcb_reserve only ever grows the scratch).  Handles are destroyed at interpreter exit.
+_POOL = {}
+
+
+def _acquire_handle(lib, device_index):
+    free = _POOL.get(device_index)
+    if free:
+        return free.pop()
+    h = _lib.p_void()
+    rc = lib.smcb_create(device_index, _lib.C.byref(h))
+    if rc != 0:
+        raise _lib.SmcbError(rc, lib.smcb_last_error(None).decode())
+    return h
+
+
+def _release_handle(device_index, h):
+    _POOL.setdefault(device_index, []).append(h)
+
+
+def release_pool():
+    """Destroy every parked handle (frees the device scratch)."""
+    lib = _lib.load()
+    for free in _POOL.values():
+        while free:
+            lib.smcb_destroy(free.pop())
+
+
+import atexit  # noqa: E402
+
+atexit.register(release_pool)
+
+
 # ------------------------------------------------------------------------------------ engine
 class Engine:
     def __init__(self, likelihood, prior, settings=None, device=None, comm=None):
@@ -164,11 +199,10 @@ class Engine:
             device = torch.cuda.current_device()
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
         torch.cuda.set_device(self.device)
-        h = _lib.p_void()
-        rc = self.lib.smcb_create(self.device.index, _lib.C.byref(h))
-        if rc != 0:
-            raise _lib.SmcbError(rc, self.lib.smcb_last_error(None).decode())
-        self.h = h
+        self.h = _acquire_handle(self.lib, self.device.index)
+        for key, val in ((_lib.PARAM_MM_BUDGET, self.cfg.mm_budget), (_lib.PARAM_MM_REFILL_MIN, self.cfg.mm_refill_min),
+                         (_lib.PARAM_MM_PATIENCE, self.cfg.mm_patience)):
+            self._ck(self.lib.smcb_set_param(self.h, key, float(val)))
         likelihood.upload(self.lib, self.h)
         N, W = self.cfg.n_particle, self.comm.world
         if N % W != 0:
@@ -207,8 +241,9 @@ class Engine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def close(self):
+        """Park the library handle (with its device scratch) for the next Engine on this device."""
         if getattr(self, "h", None):
-            self.lib.smcb_destroy(self.h)
+            _release_handle(self.device.index, self.h)
             self.h = None
 
     def __del__(self):

@@ -33,6 +33,9 @@ class Settings:
     cand_batch: int = 8                 # tempering candidates evaluated per pass (<=16)
     early_exit: bool = True             # stop sweeps when moved fraction exceeds r_threshold (reference)
     early_reject: bool = True           # let the likelihood stop once the MH rejection is certain (exact decisions)
+    mm_budget: int = 256                # MM_PROGRESS: attempted RK steps before a solve moves to the tail kernel
+    mm_refill_min: int = 8              # MM_PROGRESS: free lanes a warp waits for before setting up new solves ...
+    mm_patience: int = 3                # ... and for how many steps (results do not depend on these three)
     fused_sweeps: int = 0               # >0: run this many sweeps per launch with a frozen proposal factor
     bisect_iters: int = 60
 
