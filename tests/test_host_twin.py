@@ -1,0 +1,88 @@
+"""The DEVICE solver arithmetic, compiled for the host, against scipy (CPU only, no GPU needed).
+
+`csrc/mm_solver.cuh` is the header the CUDA kernels call for every attempted RK45 step.  It also compiles
+with plain g++ (`tests/host_twin.cpp`): same FMA chains, same reciprocal / root corrections, only the
+hardware seeds (MUFU.RCP64H, lg2/ex2) are replaced by truncated host values which the corrections make
+irrelevant.  These tests pin that arithmetic against the likelihoods the unmodified reference computed
+(golden fixture) and against the operation-for-operation C twin of scipy's RK45."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def twin(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("twin") / "libhost_twin.so")
+    subprocess.run(["g++", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC", "-o", so,
+                    os.path.join(HERE, "host_twin.cpp")], check=True)
+    lib = C.CDLL(so)
+
+    def loglik(theta, t, P, S0):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        t, P, S0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, P, S0))
+        n, (n_ex, n_t) = len(th), t.shape
+        lk, cnt, steps = np.empty(n), np.zeros(4, dtype=np.int64), np.zeros((n, n_ex), dtype=np.int32)
+        lib.twin_loglik(C.c_void_p(th.ctypes.data), C.c_int64(n), C.c_void_p(t.ctypes.data), C.c_void_p(P.ctypes.data),
+                        C.c_void_p(S0.ctypes.data), C.c_int(n_ex), C.c_int(n_t), C.c_void_p(lk.ctypes.data),
+                        C.c_void_p(cnt.ctypes.data), C.c_void_p(steps.ctypes.data))
+        return lk, cnt, steps
+
+    def predict(theta, t, S0):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        t, S0 = np.ascontiguousarray(t, dtype=np.float64), np.ascontiguousarray(S0, dtype=np.float64)
+        n, (n_ex, n_t) = len(th), t.shape
+        out = np.zeros((n, n_ex, n_t))
+        lib.twin_predict(C.c_void_p(th.ctypes.data), C.c_int64(n), C.c_void_p(t.ctypes.data), C.c_void_p(S0.ctypes.data),
+                         C.c_int(n_ex), C.c_int(n_t), C.c_void_p(out.ctypes.data))
+        return out
+
+    return loglik, predict
+
+
+def test_device_arithmetic_matches_every_reference_sweep(twin, golden):
+    """All 34 sweeps x 1000 particles the reference itself evaluated (prior cloud ... posterior)."""
+    loglik, _ = twin
+    d = (golden["data_t"], golden["data_P"], golden["data_S0"])
+    worst = 0.0
+    for sweep in range(golden["sweeps_in"].shape[0]):
+        got, cnt, _ = loglik(golden["sweeps_in"][sweep], *d)
+        want = golden["sweeps_out"][sweep]
+        worst = max(worst, float(np.max(np.abs(got - want) / np.abs(want))))
+        assert cnt[3] == 0
+    assert worst < 1e-9, worst            # bar: 1e-5 (BASELINE.json north_star)
+
+
+def test_device_arithmetic_takes_scipys_steps(twin, golden):
+    """Same accepted/rejected step counts as the strict-order C twin of scipy's RK45 on a prior cloud
+    (heavy-tailed: 10 ... >1e4 attempts per solve), solve by solve."""
+    from oracle import cmm
+    loglik, _ = twin
+    d = (golden["data_t"], golden["data_P"], golden["data_S0"])
+    th = np.random.RandomState(1).uniform(0, 10, (1 << 14, 3))
+    got, cnt, steps = loglik(th, *d)
+    want, info = cmm.loglik_progress(th, *d, want_steps=True)
+    assert np.array_equal(steps, info["steps"])
+    assert cnt[1] == info["accepted"] and cnt[2] == info["rejected"] and cnt[0] == info["nfev"]
+    assert steps.max() > 2000                                  # the cloud does contain stiff solves
+    assert np.max(np.abs(got - want) / np.abs(want)) < 1e-9
+
+
+def test_device_predictions_match_reference(twin, golden):
+    _, predict = twin
+    got = predict(golden["prior_particles"][:8], golden["data_t"], golden["data_S0"])
+    assert np.abs(got - golden["pmodel0"]).max() < 1e-11
+
+
+def test_known_answers_and_degenerate_parameters(twin, golden):
+    loglik, _ = twin
+    d = (golden["data_t"], golden["data_P"], golden["data_S0"])
+    th = np.array([[1.2, 0.5, 0.02], [1.0, 0.4, 0.05], [1.0, 0.4, 0.0], [1.0, 0.4, -1.0], [1.0, -2.0, 1.0]])
+    got, _, _ = loglik(th, *d)
+    assert abs(got[0] - 593.9635684697922) < 1e-7 and abs(got[1] - 424.5676547271564) < 1e-7
+    assert got[2] == -np.inf and got[3] == -np.inf             # sigma <= 0 (Micmem_likelihood.py:53-54)
+    assert got[4] == -np.inf                                   # Km + S0 = 0 for the S0 = 2 curves: no valid first step
