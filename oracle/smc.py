@@ -373,3 +373,49 @@ def resample_fixed(p_weight, u0, N=None):
         c_prev = c
     ancestors = np.repeat(np.arange(n, dtype=np.int64), counts)
     return ancestors, counts, dict(n_floor=int(fl.sum()), q_total=s, n_filled=int(counts.sum()))
+
+
+# --------------------------------------------------------------------------- shard twins (multi-GPU host logic tests)
+def resample_fixed_shard(w_shard, u0, N, carry_q, first):
+    """One shard of `resample_fixed`: counts of the particles in `w_shard` given the exact fixed-point
+    residual prefix `carry_q` of all lower ranks (mirrors smcb_resample_counts in FIXED mode with
+    carry_q / id_offset).  Returns (counts int64[n], floor_sum, q_total)."""
+    w = np.array(w_shard, dtype=np.float64)
+    inv_Np = 1 / N
+    fl = np.trunc(w * N)
+    resid = w - fl * inv_Np
+    q = np.rint(np.maximum(resid * float(TWO62), 0.0)).astype(np.uint64).astype(object)
+    u0q = int(np.rint(u0 * float(TWO62)))
+
+    def cross(s):
+        x = s * N
+        return 0 if x < u0q else ((x - u0q) >> 62) + 1
+
+    s = int(carry_q)
+    c_prev = 0 if first else cross(s)
+    counts = np.zeros(len(w), dtype=np.int64)
+    for j in range(len(w)):
+        s += int(q[j])
+        c = cross(s)
+        counts[j] = int(fl[j]) + (c - c_prev)
+        c_prev = c
+    return counts, int(fl.sum()), s - int(carry_q)
+
+
+def resample_sequential_shard(w_shard, carry, N):
+    """One shard of `resample_sequential`: carry = (running sum, next threshold) entering the shard.
+    Returns (counts, carry_out, floor_sum, crossings)."""
+    w = np.array(w_shard, dtype=np.float64)
+    inv_Np = 1 / N
+    p_is = np.trunc(w * N).astype(np.int64)
+    w = w - p_is * inv_Np
+    run, wrand = float(carry[0]), float(carry[1])
+    cnt = p_is.tolist()
+    n_cross = 0
+    for j, wj in enumerate(w.tolist()):
+        run += wj
+        if run >= wrand:
+            cnt[j] += 1
+            wrand += inv_Np
+            n_cross += 1
+    return np.array(cnt, dtype=np.int64), (run, wrand), int(p_is.sum()), n_cross

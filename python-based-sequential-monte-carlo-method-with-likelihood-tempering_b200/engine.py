@@ -115,6 +115,97 @@ def migration_plan(floor_tot, q_tot, N, n_local, u0, world):
     return plan
 
 
+# ------------------------------------------------------------------------------------ sharded resampling
+def sharded_resample(ops, comm, N, n_local, D1, u0, scan_mode, sendbuf, recvbuf, state_out):
+    """Cross-shard residual-systematic resampling: every rank ends up with slots
+    [rank*n_local, (rank+1)*n_local) of the globally resampled particle set in state_out[D1, n_local].
+
+    The arithmetic over particles is done by `ops` (the CUDA kernels behind the C-ABI in the engine; NumPy twins
+    of the oracle in the CPU/gloo tests), the exchanges by `comm`:
+        ops.totals() -> int64[2] tensor            (sum of floor counts, sum of fixed-point residuals)
+        ops.counts_fixed(carry_q) -> None          counts of this shard given the residual prefix of lower ranks
+        ops.counts_sequential(carry[2]) -> (carry_out[2], int64[2] tensor = (floor sum, crossings))
+        ops.expand_and_pack(m_loc, send, sendbuf)  ancestors of the first m_loc slots, gathered into one
+                                                   contiguous [D1][len] chunk per destination rank
+    Returns the number of slots filled before clamping to N."""
+    W, rank = comm.world, comm.rank
+    if scan_mode == "fixed":
+        allt = comm.all_gather_i64(ops.totals()).cpu().numpy()
+        plan = migration_plan(allt[:, 0], allt[:, 1], N, n_local, u0, W)
+        ops.counts_fixed(plan["carry_q"][rank])
+    else:
+        # the reference's running sum is inherently serial: shards take turns, passing the carry
+        carry = np.array([0.0, u0 * (1.0 / N)], dtype=np.float64)
+        carry_t = torch.zeros(2, dtype=torch.float64, device=sendbuf.device)
+        tot = None
+        for r in range(W):
+            if r == rank:
+                carry, tot = ops.counts_sequential(carry)
+                carry_t.copy_(torch.from_numpy(np.asarray(carry, dtype=np.float64)))
+            comm.broadcast(carry_t, src=r)
+            carry = carry_t.cpu().numpy().copy()
+        allt = comm.all_gather_i64(tot).cpu().numpy()   # [W, 2] = (floor sum, crossings)
+        O, M, pre = [], [], 0
+        for r in range(W):
+            O.append(pre)
+            M.append(int(allt[r, 0] + allt[r, 1]))
+            pre += M[-1]
+        plan = _plan_from_offsets(O, M, N, n_local, W)
+    m_loc = plan["M"][rank]
+    send = plan["send"][rank]
+    recv = [plan["send"][r][rank] for r in range(W)]
+    if m_loc > 0:
+        ops.expand_and_pack(m_loc, send, sendbuf)
+    comm.all_to_all(recvbuf[: D1 * sum(recv)], sendbuf[: D1 * sum(send)], [D1 * c for c in recv],
+                    [D1 * c for c in send])
+    off = 0
+    for r in range(W):
+        if recv[r]:
+            state_out[:, off:off + recv[r]].copy_(recvbuf[D1 * off: D1 * (off + recv[r])].view(D1, recv[r]))
+            off += recv[r]
+    return plan["filled"]
+
+
+class _DeviceShardOps:
+    """`ops` of sharded_resample on the GPU: the C-ABI kernels on the engine's buffers."""
+
+    def __init__(self, eng):
+        self.e = eng
+
+    def totals(self):
+        e = self.e
+        tot = e.icnt[4:6]
+        e._ck(e.lib.smcb_resample_totals(e.h, e.w.data_ptr(), e.n, e.N, tot.data_ptr(), e._stream))
+        return tot
+
+    def counts_fixed(self, carry_q):
+        e = self.e
+        e._ck(e.lib.smcb_resample_counts(e.h, e.w.data_ptr(), e.n, e.N, 0.0 if e._u0 is None else e._u0,
+                                         _lib.SCAN_FIXED, None, carry_q, e.id_offset, e.counts.data_ptr(),
+                                         e.icnt[4:6].data_ptr(), e._stream))
+
+    def counts_sequential(self, carry):
+        e = self.e
+        carry = np.ascontiguousarray(carry, dtype=np.float64)
+        tot = e.icnt[4:6]
+        e._ck(e.lib.smcb_resample_counts(e.h, e.w.data_ptr(), e.n, e.N, e._u0, _lib.SCAN_SEQUENTIAL,
+                                         carry.ctypes.data, 0, e.id_offset, e.counts.data_ptr(), tot.data_ptr(),
+                                         e._stream))
+        return carry, tot
+
+    def expand_and_pack(self, m_loc, send, sendbuf):
+        e = self.e
+        D1 = e.d + 1
+        e._ck(e.lib.smcb_ancestors(e.h, e.counts.data_ptr(), e.n, m_loc, e.anc.data_ptr(), e.icnt[6:7].data_ptr(),
+                                   e._stream))
+        off = 0
+        for q, cnt in enumerate(send):   # one contiguous [d+1][len] chunk per destination
+            if cnt:
+                e._ck(e.lib.smcb_gather(e.h, e.state.data_ptr(), e.n, e.anc[off:].data_ptr(), cnt, D1,
+                                        sendbuf[D1 * off:].data_ptr(), cnt, e._stream))
+                off += cnt
+
+
 # ------------------------------------------------------------------------------------ results
 @dataclass
 class StageRecord:
@@ -421,6 +512,7 @@ class Engine:
         Returns the number of slots filled before clamping; new state replaces the old."""
         st, lib, h = self._stream, self.lib, self.h
         mode = _SCAN[self.cfg.scan_mode]
+        self._u0 = float(u0)
         if weights is not None:
             self.w.copy_(torch.as_tensor(weights, dtype=torch.float64))
         else:
@@ -442,57 +534,14 @@ class Engine:
             self.state, self.state2 = self.state2, self.state
             return None   # filled count stays on the device (icnt[6]); read lazily
         # ---- sharded: cross-GPU exclusive scan of shard totals, then all-to-all migration ----
-        rank = self.comm.rank
-        if mode == _lib.SCAN_FIXED:
-            self._ck(lib.smcb_resample_totals(h, self.w.data_ptr(), self.n, self.N, tot.data_ptr(), st))
-            allt = self.comm.all_gather_i64(tot).cpu().numpy()
-            plan = migration_plan(allt[:, 0], allt[:, 1], self.N, self.n, u0, W)
-            self._ck(lib.smcb_resample_counts(h, self.w.data_ptr(), self.n, self.N, u0, mode, None,
-                                              plan["carry_q"][rank], self.id_offset, self.counts.data_ptr(),
-                                              tot.data_ptr(), st))
-        else:
-            # the reference's running sum is inherently serial: shards take turns, passing the carry
-            carry = np.array([0.0, u0 * (1.0 / self.N)], dtype=np.float64)
-            carry_t = torch.zeros(2, dtype=torch.float64, device=self.device)
-            for r in range(W):
-                if r == rank:
-                    self._ck(lib.smcb_resample_counts(h, self.w.data_ptr(), self.n, self.N, u0, mode,
-                                                      carry.ctypes.data, 0, self.id_offset, self.counts.data_ptr(),
-                                                      tot.data_ptr(), st))
-                    carry_t.copy_(torch.from_numpy(carry))
-                self.comm.broadcast(carry_t, src=r)
-                carry = carry_t.cpu().numpy().copy()
-            allt = self.comm.all_gather_i64(tot).cpu().numpy()   # [W, 2] = (floor sum, crossings)
-            O, M, pre = [], [], 0
-            for r in range(W):
-                O.append(pre)
-                M.append(int(allt[r, 0] + allt[r, 1]))
-                pre += M[-1]
-            plan = _plan_from_offsets(O, M, self.N, self.n, W)
-        m_loc = plan["M"][rank]
-        send = plan["send"][rank]
-        recv = [plan["send"][r][rank] for r in range(W)]
         if self.sendbuf is None:
             self.sendbuf = torch.empty(D1 * self.cap, dtype=torch.float64, device=self.device)
             self.recvbuf = torch.empty(D1 * self.n, dtype=torch.float64, device=self.device)
-        if m_loc > 0:
-            self._ck(lib.smcb_ancestors(h, self.counts.data_ptr(), self.n, m_loc, self.anc.data_ptr(),
-                                        filled_t.data_ptr(), st))
-            off = 0
-            for q in range(W):   # one contiguous [d+1][len] chunk per destination
-                if send[q]:
-                    self._ck(lib.smcb_gather(h, self.state.data_ptr(), self.n, self.anc[off:].data_ptr(), send[q],
-                                             D1, self.sendbuf[D1 * off:].data_ptr(), send[q], st))
-                    off += send[q]
-        self.comm.all_to_all(self.recvbuf[: D1 * sum(recv)], self.sendbuf[: D1 * sum(send)],
-                             [D1 * c for c in recv], [D1 * c for c in send])
-        off = 0
-        for r in range(W):
-            if recv[r]:
-                self.state2[:, off:off + recv[r]].copy_(self.recvbuf[D1 * off: D1 * (off + recv[r])].view(D1, recv[r]))
-                off += recv[r]
+        filled = sharded_resample(_DeviceShardOps(self), self.comm, self.N, self.n, D1, u0,
+                                  "fixed" if mode == _lib.SCAN_FIXED else "sequential",
+                                  self.sendbuf, self.recvbuf, self.state2)
         self.state, self.state2 = self.state2, self.state
-        return plan["filled"]
+        return filled
 
     # -------------------------------------------------------------------------------- K4
     def proposal_factor(self):
