@@ -106,7 +106,15 @@ int smcb_loglik_bounded(smcb_handle* h, int model, const double* theta_dev, int6
 /* SMCB_PARAM_MM_PATIENCE: ... and for how many attempted steps it waits (default 3); a warp whose lanes
  * are all free refills at once. */
 #define SMCB_PARAM_MM_PATIENCE 3
+/* SMCB_PARAM_PROFILE: non-zero = record CUDA events on the launching stream around the bulk and the tail
+ * kernel of every MM_PROGRESS sweep (at most 512 sweeps between two reads); see smcb_profile_read. */
+#define SMCB_PARAM_PROFILE 4
+/* SMCB_PARAM_MM_CHUNK: particles per work-queue item of the bulk kernel (default 32). */
+#define SMCB_PARAM_MM_CHUNK 5
 int smcb_set_param(smcb_handle* h, int key, double value);
+/* Device time of the MM_PROGRESS kernels since the last read (SMCB_PARAM_PROFILE): out_host[0] = ms inside
+ * mm_bulk_kernel, [1] = ms inside mm_tail_kernel, [2] = sweeps covered.  Synchronous; resets the record. */
+int smcb_profile_read(smcb_handle* h, double* out_host);
 /* Model predictions for a few particles (the `C_l_` the reference returns for its parity plots,
  * EX/lik:74-77): pred_dev[i][n_ex][n_t].  MM_PROGRESS only. */
 int smcb_predict_mm_progress(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n,
@@ -115,7 +123,8 @@ int smcb_predict_mm_progress(smcb_handle* h, const double* theta_dev, int64_t ld
  * [2]=rejected steps, [3]=failed solves of the last sweep; [4..7] the same four accumulated over every
  * sweep since smcb_create; [8]/[9] particles reported -inf by early rejection (last sweep / accumulated);
  * [10] largest number of attempted steps of one solve in the last sweep; [11]/[12] solves deferred to
- * the tail kernel; [13]/[14] particles the tail kernel processed; [15] unused.  Synchronous. */
+ * the tail kernel; [13]/[14] particles the tail kernel processed; [15] attempted steps taken inside the tail kernel
+ * (accumulated).  Synchronous. */
 int smcb_loglik_stats(smcb_handle* h, int64_t* out_host);
 
 /* ---- K2: tempering reductions (replaces EX/main:116-134) --------------------------------- */

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "smcb_loglik": [p_void, c_int, p_void, c_i64, c_i64, c_int, p_void, p_void, p_void],
     "smcb_loglik_bounded": [p_void, c_int, p_void, c_i64, c_i64, c_int, p_void, p_void, p_void, p_void],
     "smcb_set_param": [p_void, c_int, c_dbl],
+    "smcb_profile_read": [p_void, p_void],
     "smcb_predict_mm_progress": [p_void, p_void, c_i64, c_i64, p_void, p_void],
     "smcb_loglik_stats": [p_void, p_void],
     "smcb_lk_max": [p_void, p_void, c_i64, p_void, p_void],
@@ -58,7 +59,7 @@ MODEL_MM_PROGRESS, MODEL_MM_RATE, MODEL_KINETIC_RK = 1, 2, 3
 SCAN_SEQUENTIAL, SCAN_FIXED = 0, 1
 MAX_DIM, MAX_CAND = 32, 16
 KIN_NCOND_FIELDS = 10
-PARAM_MM_BUDGET, PARAM_MM_REFILL_MIN, PARAM_MM_PATIENCE = 1, 2, 3
+PARAM_MM_BUDGET, PARAM_MM_REFILL_MIN, PARAM_MM_PATIENCE, PARAM_PROFILE, PARAM_MM_CHUNK = 1, 2, 3, 4, 5
 N_STATS = 16
 
 

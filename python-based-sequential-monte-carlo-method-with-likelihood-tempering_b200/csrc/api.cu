@@ -94,6 +94,7 @@ extern "C" int smcb_create(int device, smcb_handle** out) {
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->seq_carry), 4 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mm_ctl), 4 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(h->mm_ctl, 0, 4 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mm_hist), 2 * 512 * sizeof(unsigned));
     if (e != cudaSuccess) {
         smcb_fail(nullptr, SMCB_ERR_CUDA, "smcb_create: cudaMalloc: %s", cudaGetErrorString(e));
         delete h;
@@ -107,6 +108,11 @@ extern "C" int smcb_destroy(smcb_handle* h) {
     if (!h) return SMCB_OK;
     cudaSetDevice(h->device);
     dev_free(&h->ssr); dev_free(&h->partial); dev_free(&h->stats); dev_free(&h->mm_ctl); dev_free(&h->mm_defer); dev_free(&h->mm_cutlim);
+    dev_free(&h->mm_bins); dev_free(&h->mm_perm); dev_free(&h->mm_hist);
+    if (h->prof_ev) {
+        for (int i = 0; i < SMCB_PROF_RING * 4; ++i) cudaEventDestroy(h->prof_ev[i]);
+        delete[] h->prof_ev;
+    }
     dev_free(&h->floor_cnt); dev_free(&h->resid_q); dev_free(&h->resid_f); dev_free(&h->tile_tot);
     dev_free(&h->tile_tot2); dev_free(&h->mark); dev_free(&h->seq_carry);
     dev_free(&h->mmp.t); dev_free(&h->mmp.P); dev_free(&h->mmp.S0);
@@ -143,6 +149,8 @@ extern "C" int smcb_reserve(smcb_handle* h, int64_t n_max, int d_max) {
     if ((rc = dev_alloc(h, &h->mark, (size_t)n_max))) return rc;
     if ((rc = dev_alloc(h, &h->mm_defer, (size_t)(rows + 1) * n_max))) return rc;   // deferred solves + particles
     if ((rc = dev_alloc(h, &h->mm_cutlim, (size_t)n_max))) return rc;
+    if ((rc = dev_alloc(h, &h->mm_bins, (size_t)n_max))) return rc;
+    if ((rc = dev_alloc(h, &h->mm_perm, (size_t)n_max))) return rc;
     const size_t tiles = (size_t)(n_max + 2047) / 2048 + 8;
     if ((rc = dev_alloc(h, &h->tile_tot, 2 * tiles))) return rc;
     if ((rc = dev_alloc(h, &h->tile_tot2, 2 * tiles))) return rc;
@@ -231,6 +239,19 @@ extern "C" int smcb_set_param(smcb_handle* h, int key, double value) {
             REQUIRE(h, value >= 1 && value <= 32, SMCB_ERR_INVALID, "MM_REFILL_MIN must be in [1, 32]");
             h->mm_refill_min = (int)value;
             return SMCB_OK;
+        case SMCB_PARAM_MM_CHUNK:
+            REQUIRE(h, value >= 1 && value <= 65536, SMCB_ERR_INVALID, "MM_CHUNK must be in [1, 65536]");
+            h->mm_chunk = (int)value;
+            return SMCB_OK;
+        case SMCB_PARAM_PROFILE:
+            if (value != 0 && h->prof_ev == nullptr) {
+                CUDA_TRY(h, cudaSetDevice(h->device));
+                h->prof_ev = new cudaEvent_t[SMCB_PROF_RING * 4];
+                for (int i = 0; i < SMCB_PROF_RING * 4; ++i) CUDA_TRY(h, cudaEventCreate(&h->prof_ev[i]));
+            }
+            h->prof_on = value != 0;
+            h->prof_sweeps = 0;
+            return SMCB_OK;
         case SMCB_PARAM_MM_PATIENCE:
             REQUIRE(h, value >= 0 && value <= 1e6, SMCB_ERR_INVALID, "MM_PATIENCE must be in [0, 1e6]");
             h->mm_patience = (int)value;
@@ -249,6 +270,24 @@ extern "C" int smcb_predict_mm_progress(smcb_handle* h, const double* theta_dev,
 extern "C" int smcb_loglik_stats(smcb_handle* h, int64_t* out_host) {
     REQUIRE(h, h && out_host, SMCB_ERR_INVALID, "null pointer");
     CUDA_TRY(h, cudaMemcpy(out_host, h->stats, SMCB_N_STATS * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return SMCB_OK;
+}
+
+extern "C" int smcb_profile_read(smcb_handle* h, double* out_host) {
+    REQUIRE(h, h && out_host, SMCB_ERR_INVALID, "null pointer");
+    out_host[0] = out_host[1] = out_host[2] = 0.0;
+    if (h->prof_ev == nullptr) return SMCB_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    for (int k = 0; k < h->prof_sweeps; ++k) {
+        float a = 0.f, b = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&a, h->prof_ev[k * 4 + 0], h->prof_ev[k * 4 + 1]));
+        CUDA_TRY(h, cudaEventElapsedTime(&b, h->prof_ev[k * 4 + 2], h->prof_ev[k * 4 + 3]));
+        out_host[0] += a;
+        out_host[1] += b;
+    }
+    out_host[2] = h->prof_sweeps;
+    h->prof_sweeps = 0;
     return SMCB_OK;
 }
 

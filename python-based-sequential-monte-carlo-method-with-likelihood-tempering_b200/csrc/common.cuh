@@ -10,6 +10,7 @@
 
 #define SMCB_VERSION 101
 #define SMCB_N_STATS 16
+#define SMCB_PROF_RING 512
 #define FULL_MASK 0xffffffffu
 
 struct MmProgressData {
@@ -52,7 +53,14 @@ struct smcb_handle {
     unsigned* mm_ctl = nullptr;      // [0] solve-queue head, [1] deferred solves, [2] deferred particles (MM_PROGRESS)
     unsigned* mm_defer = nullptr;    // [ssr_rows*n_max] deferred solves, then [n_max] their particles
     double* mm_cutlim = nullptr;     // [n_max] per-particle residual limit of a bounded sweep
+    unsigned short* mm_bins = nullptr;   // [n_max] cost bin of every particle (0xFFFF = no solve needed)
+    unsigned* mm_perm = nullptr;     // [n_max] particles to evaluate, heaviest cost bin first
+    unsigned* mm_hist = nullptr;     // [2*512] histogram and scatter cursors of the counting sort
+    bool prof_on = false;            // per-kernel CUDA-event timing of the MM_PROGRESS sweeps
+    int prof_sweeps = 0;
+    cudaEvent_t* prof_ev = nullptr;  // [SMCB_PROF_RING*4]
     int mm_budget = 256;             // attempted steps after which the bulk kernel defers a solve
+    int mm_chunk = 32;               // particles per queue item of the bulk kernel
     int mm_patience = 3;             // ... for this many attempted steps (unless the whole warp is free)
     int mm_refill_min = 8;           // free lanes a warp of the bulk kernel waits for before setting up new solves
     int mm_bulk_blocks_per_sm = 0;   // occupancy of the bulk kernel (queried once)

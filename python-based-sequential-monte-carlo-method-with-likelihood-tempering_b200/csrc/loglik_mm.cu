@@ -42,7 +42,6 @@ namespace {
 using mmsolve::Solve;
 
 constexpr int BULK_BLOCK = 128;
-constexpr int BULK_CHUNK = 128;     // solves a warp takes from the queue at a time
 constexpr int TAIL_BLOCK = 32;
 constexpr double DEFERRED = -1.0;   // marker in the per-solve result array (a residual sum is >= 0)
 
@@ -79,7 +78,8 @@ __device__ __forceinline__ SharedData stage_data(void* smem, const double* g_t, 
 
 // counters: see smcb_loglik_stats
 __device__ __forceinline__ void flush_stats(unsigned long long* stats, unsigned n_set, unsigned n_acc,
-                                            unsigned n_rej, unsigned n_fail, unsigned n_def, unsigned mx) {
+                                            unsigned n_rej, unsigned n_fail, unsigned n_def, unsigned mx,
+                                            bool is_tail = false) {
     if (stats == nullptr) return;
     const unsigned long long w_fev =
         (unsigned long long)warp_sum_ll(2LL * n_set + 6LL * ((long long)n_acc + n_rej));
@@ -96,6 +96,7 @@ __device__ __forceinline__ void flush_stats(unsigned long long* stats, unsigned 
         if (w_fail) { atomicAdd(&stats[3], w_fail); atomicAdd(&stats[7], w_fail); }
         if (w_def) { atomicAdd(&stats[11], w_def); atomicAdd(&stats[12], w_def); }
         if (mx) atomicMax(&stats[10], (unsigned long long)mx);
+        if (is_tail && (w_acc + w_rej)) atomicAdd(&stats[15], w_acc + w_rej);   // attempted steps of the tail kernel
     }
 }
 
@@ -118,17 +119,104 @@ __global__ void mm_prep_kernel(const double* __restrict__ theta, int64_t ld, int
     cutlim[p] = cl;
 }
 
-// ------------------------------------------------------------------------------ bulk
+// ------------------------------------------------------------------------------ ordering by cost
+// The number of steps scipy takes is, per experiment, almost a function of Vmax/Km alone (in a prior cloud
+// warps of consecutive particles run at 15% lane efficiency, warps of particles sorted by Vmax/Km at 93%:
+// DESIGN.md K1).  Every sweep therefore bins the particles it has to evaluate by Vmax/Km (8 bins per octave,
+// counting sort, heaviest first) and the bulk kernel walks that permutation.  Particles that need no solve
+// (inactive, sigma <= 0, hopeless before any residual) are left out, which also compacts the work list.
+constexpr int NBIN = 512;
+constexpr unsigned NOBIN = 0xFFFFu;
+
 template <bool BOUNDED>
+__device__ __forceinline__ unsigned cost_bin(const double* __restrict__ theta, int64_t ld, unsigned p,
+                                             const uint8_t* __restrict__ active,
+                                             const double* __restrict__ cutlim) {
+    if (active != nullptr && !active[p]) return NOBIN;
+    if (!(theta[2 * ld + p] > 0)) return NOBIN;           // sigma <= 0: finalize reports -inf
+    if (BOUNDED && cutlim[p] < 0) return NOBIN;           // hopeless before any residual: finalize reports -inf
+    const double r = theta[p] / theta[ld + p];            // Vmax / Km
+    // exponent and top 3 mantissa bits: 8 bins per octave over 2^-32 .. 2^32; heaviest (largest ratio) first
+    int b = (__double2hiint(r) >> 17) - ((1023 - 32) << 3);
+    if (!(r > 0)) b = 0;                                   // zero, negative, NaN: cheapest bin
+    b = b < 0 ? 0 : (b > NBIN - 1 ? NBIN - 1 : b);
+    return (unsigned)(NBIN - 1 - b);
+}
+
+template <bool BOUNDED>
+__global__ void __launch_bounds__(256)
+mm_bin_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const uint8_t* __restrict__ active,
+              const double* __restrict__ cutlim, unsigned short* __restrict__ bins, unsigned* __restrict__ hist) {
+    __shared__ unsigned s_hist[NBIN];
+    for (int i = threadIdx.x; i < NBIN; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) {
+        const unsigned b = cost_bin<BOUNDED>(theta, ld, p, active, cutlim);
+        bins[p] = (unsigned short)b;
+        if (b != NOBIN) atomicAdd(&s_hist[b], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NBIN; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+// exclusive scan of the histogram (one block of NBIN threads): cursor[b] = first slot of bin b, ctl[3] = total
+__global__ void __launch_bounds__(NBIN)
+mm_binscan_kernel(const unsigned* __restrict__ hist, unsigned* __restrict__ cursor, unsigned* __restrict__ ctl) {
+    __shared__ unsigned s[NBIN];
+    const int t = threadIdx.x;
+    s[t] = hist[t];
+    __syncthreads();
+    for (int o = 1; o < NBIN; o <<= 1) {
+        const unsigned v = (t >= o) ? s[t - o] : 0u;
+        __syncthreads();
+        s[t] += v;
+        __syncthreads();
+    }
+    cursor[t] = s[t] - hist[t];
+    if (t == NBIN - 1) ctl[3] = s[t];
+}
+
+__global__ void __launch_bounds__(256)
+mm_scatter_kernel(unsigned n, const unsigned short* __restrict__ bins, unsigned* __restrict__ cursor,
+                  unsigned* __restrict__ perm) {
+    __shared__ unsigned s_cnt[NBIN];
+    __shared__ unsigned s_base[NBIN];
+    for (int i = threadIdx.x; i < NBIN; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned b = NOBIN, rank = 0;
+    if (p < n) {
+        b = bins[p];
+        if (b != NOBIN) rank = atomicAdd(&s_cnt[b], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NBIN; i += blockDim.x)
+        if (s_cnt[i]) s_base[i] = atomicAdd(&cursor[i], s_cnt[i]);
+    __syncthreads();
+    if (b != NOBIN) perm[s_base[b] + rank] = p;
+}
+
+// ------------------------------------------------------------------------------ bulk
+// No early rejection inside this kernel: a solve that stopped at a random step would leave its lane idle
+// until the next refill, and with cost-ordered warps that costs more than the steps it saves (measured: sweeps
+// with a third of the solves cut ran at 40% of the attempt rate of uncut ones).  Hopeless particles never get
+// here (mm_bin_kernel), the bound is applied per particle in mm_finalize_kernel and per solve in mm_tail_kernel.
 __global__ void __launch_bounds__(BULK_BLOCK)
-mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const uint8_t* __restrict__ active,
-               const double* __restrict__ cutlim, const double* __restrict__ g_t, const double* __restrict__ g_P,
+mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const unsigned* __restrict__ perm,
+               const double* __restrict__ g_t, const double* __restrict__ g_P,
                const double* __restrict__ g_S0, int n_ex, int n_t, unsigned budget, int refill_min,
-               int patience, double* __restrict__ ssr_out, unsigned* __restrict__ queue, unsigned long long* __restrict__ stats) {
+               int patience, unsigned chunk, double* __restrict__ ssr_out, unsigned* __restrict__ queue, unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SharedData D = stage_data(smem, g_t, g_P, g_S0, n_ex, n_t);
 
-    const unsigned total = n * (unsigned)n_ex;
+    // Work list: the m particles of `perm` (heaviest cost bin first) in runs of `chunk`, each run once per
+    // experiment; queue item q = run (q / n_ex) of experiment (q % n_ex).  A warp's lanes thus hold consecutive
+    // particles of one experiment, and every experiment of the heavy bins is started early.
+    const unsigned m = queue[3];
+    const unsigned n_items = ((m + chunk - 1) / chunk) * (unsigned)n_ex;
+    unsigned w_base = 0, w_e = 0;    // first particle (index into perm) and experiment of the warp's current run
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned w_cur = 0, w_end = 0;   // the warp's current run of solves (warp-uniform)
@@ -153,49 +241,36 @@ mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const u
         // other and are set up together; in a prior cloud the stragglers are not waited for.
         if (want != 0 && (busy == 0 || (__popc(want) >= refill_min && waited >= patience))) {
             waited = 0;
-            // ---- 1. hand out solves until every free lane holds a live one (or the queue is empty) ----
+            // ---- 1. hand out the next solves of the queue to the free lanes ------------------------------
             bool got = false;
             unsigned e = 0, p = 0;
             while (want != 0) {
                 if (w_cur == w_end) {
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(queue, (unsigned)BULK_CHUNK);
-                    base = __shfl_sync(FULL_MASK, base, 0);
-                    if (base >= total) {
+                    unsigned q = 0;
+                    if (lane == 0) q = atomicAdd(queue, 1u);
+                    q = __shfl_sync(FULL_MASK, q, 0);
+                    if (q >= n_items) {
                         drained = true;
                         break;
                     }
-                    w_cur = base;
-                    w_end = (total - base < (unsigned)BULK_CHUNK) ? total : base + BULK_CHUNK;
+                    const unsigned run = q / (unsigned)n_ex;
+                    w_e = q - run * (unsigned)n_ex;
+                    w_base = run * chunk;
+                    w_cur = 0;
+                    w_end = (m - w_base < chunk) ? m - w_base : chunk;
                 }
                 const unsigned avail = w_end - w_cur;
                 const unsigned rank = __popc(want & lt_mask);
                 const bool mine = ((want >> lane) & 1u) && rank < avail;
-                const unsigned g = w_cur + rank;
+                if (mine) {
+                    e = w_e;
+                    p = perm[w_base + w_cur + rank];
+                    task = e * n + p;
+                    got = true;
+                }
                 const unsigned n_want = __popc(want);
                 w_cur += (n_want < avail) ? n_want : avail;
-                bool ok = false;
-                if (mine) {
-                    e = g / n;
-                    p = g - e * n;
-                    if (active == nullptr || active[p]) {
-                        if (theta[2 * ld + p] > 0) {   // sigma <= 0: finalize reports -inf
-                            ok = true;
-                            if (BOUNDED) {
-                                s.cut_lim = cutlim[p];
-                                if (s.cut_lim < 0) {   // hopeless before any residual
-                                    ssr_out[g] = INFINITY;
-                                    ok = false;
-                                }
-                            }
-                        }
-                    }
-                    if (ok) {
-                        got = true;
-                        task = g;
-                    }
-                }
-                want &= ~__ballot_sync(FULL_MASK, ok);
+                want &= ~__ballot_sync(FULL_MASK, mine);
             }
             // ---- 2. set the new solves up together ------------------------------------------------
             if (got) {
@@ -271,7 +346,10 @@ mm_finalize_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, con
                 else total += c0 - v * inv_den;   // logL_i, summed in experiment order (:70-73)
             }
             const double thr = BOUNDED ? lkmin[p] : -INFINITY;
-            if (n_def == 0 || total == -INFINITY) {
+            if (BOUNDED && cutlim[p] < 0) {   // n_ex*c0 < lkmin: no solve was run (mm_bin_kernel left it out)
+                lk[p] = -INFINITY;
+                cut = true;
+            } else if (n_def == 0 || total == -INFINITY) {
                 lk[p] = total;
                 cut = BOUNDED && total == -INFINITY;
             } else if (BOUNDED && total + n_def * c0 < thr) {
@@ -356,7 +434,7 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
             }
         }
     }
-    flush_stats(stats, n_set, n_acc, n_rej, n_fail, 0u, mx);
+    flush_stats(stats, n_set, n_acc, n_rej, n_fail, 0u, mx, true);
 }
 
 // ------------------------------------------------------------------------------ collect
@@ -515,11 +593,19 @@ mm_rate_kernel_f32(const double* __restrict__ theta, int64_t ld, int64_t n,
 
 }  // namespace
 
+// Optional per-kernel timing (SMCB_PARAM_PROFILE): CUDA events on the launching stream around the bulk and the
+// tail kernel of every sweep, read back by smcb_profile_read.
+static inline void prof_mark(smcb_handle* h, int which, cudaStream_t st) {
+    if (!h->prof_on || h->prof_sweeps >= SMCB_PROF_RING) return;
+    cudaEventRecord(h->prof_ev[h->prof_sweeps * 4 + which], st);
+}
+
 // sweep-local counters, the solve queue and the deferred-particle list head
-__global__ void mm_reset_kernel(unsigned long long* stats, unsigned* ctl) {
+__global__ void mm_reset_kernel(unsigned long long* stats, unsigned* ctl, unsigned* hist) {
     if (threadIdx.x < 4) stats[threadIdx.x] = 0;
     if (threadIdx.x == 8 || threadIdx.x == 10 || threadIdx.x == 11 || threadIdx.x == 13) stats[threadIdx.x] = 0;
-    if (threadIdx.x < 3) ctl[threadIdx.x] = 0;
+    if (threadIdx.x < 4) ctl[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < NBIN; i += blockDim.x) hist[i] = 0;
 }
 
 int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, int64_t n,
@@ -544,36 +630,41 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
             "smcb_reserve(n_max >= n) must be called before smcb_loglik");
     const bool bounded = lkmin != nullptr;
     if (smem > 48 * 1024 && !h->mm_smem_set) {
-        CUDA_TRY(h, cudaFuncSetAttribute(mm_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(h, cudaFuncSetAttribute(mm_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(h, cudaFuncSetAttribute(mm_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(h, cudaFuncSetAttribute(mm_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->mm_smem_set = true;
     }
     if (h->mm_bulk_blocks_per_sm == 0) {
-        int a = 0, b = 0;
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, mm_bulk_kernel<false>, BULK_BLOCK, smem));
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, mm_bulk_kernel<true>, BULK_BLOCK, smem));
-        h->mm_bulk_blocks_per_sm = (a < b ? a : b) > 0 ? (a < b ? a : b) : 1;
+        int a = 0;
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, mm_bulk_kernel, BULK_BLOCK, smem));
+        h->mm_bulk_blocks_per_sm = a > 0 ? a : 1;
     }
-    unsigned* queue = h->mm_ctl;   // [0] solve queue head, [1] deferred solves, [2] deferred particles
-    mm_reset_kernel<<<1, 32, 0, st>>>(h->stats, h->mm_ctl);
+    unsigned* queue = h->mm_ctl;   // [0] solve queue head, [1] deferred solves, [2] deferred particles, [3] particles to evaluate
+    unsigned* hist = h->mm_hist;   // [NBIN] histogram, then [NBIN] scatter cursors
+    mm_reset_kernel<<<1, 128, 0, st>>>(h->stats, h->mm_ctl, hist);
     LAUNCH_CHECK(h);
     if (bounded) {
         mm_prep_kernel<<<(un + 255) / 256, 256, 0, st>>>(theta, ld, n, active, lkmin, D.n_ex, D.n_t, h->mm_cutlim);
         LAUNCH_CHECK(h);
+        mm_bin_kernel<true><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, active, h->mm_cutlim, h->mm_bins, hist);
+    } else {
+        mm_bin_kernel<false><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, active, nullptr, h->mm_bins, hist);
     }
+    LAUNCH_CHECK(h);
+    mm_binscan_kernel<<<1, NBIN, 0, st>>>(hist, hist + NBIN, h->mm_ctl);
+    LAUNCH_CHECK(h);
+    mm_scatter_kernel<<<(un + 255) / 256, 256, 0, st>>>(un, h->mm_bins, hist + NBIN, h->mm_perm);
+    LAUNCH_CHECK(h);
     const unsigned tasks = un * (unsigned)D.n_ex;
     unsigned grid = (unsigned)(h->sm_count * h->mm_bulk_blocks_per_sm);
     const unsigned need = (tasks + BULK_BLOCK - 1) / BULK_BLOCK;
     if (need < grid) grid = need;
     const unsigned budget = (unsigned)h->mm_budget;
-    if (bounded)
-        mm_bulk_kernel<true><<<grid, BULK_BLOCK, smem, st>>>(theta, ld, un, active, h->mm_cutlim, D.t, D.P, D.S0,
-                                                           D.n_ex, D.n_t, budget, h->mm_refill_min, h->mm_patience, h->ssr, queue, h->stats);
-    else
-        mm_bulk_kernel<false><<<grid, BULK_BLOCK, smem, st>>>(theta, ld, un, active, nullptr, D.t, D.P, D.S0,
-                                                            D.n_ex, D.n_t, budget, h->mm_refill_min, h->mm_patience, h->ssr, queue, h->stats);
+    prof_mark(h, 0, st);
+    mm_bulk_kernel<<<grid, BULK_BLOCK, smem, st>>>(theta, ld, un, h->mm_perm, D.t, D.P, D.S0, D.n_ex, D.n_t, budget,
+                                                  h->mm_refill_min, h->mm_patience, (unsigned)h->mm_chunk, h->ssr, queue, h->stats);
     LAUNCH_CHECK(h);
+    prof_mark(h, 1, st);
     unsigned* solve_list = h->mm_defer;                              // [n_ex * n_max]
     unsigned* part_list = h->mm_defer + (size_t)h->ssr_rows * h->n_max;   // [n_max]
     if (bounded)
@@ -587,9 +678,11 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     LAUNCH_CHECK(h);
     // 12 one-warp blocks per SM keep the latency-bound tail solves clear of each other on the FP64 pipe
     const unsigned tail_grid = (unsigned)h->sm_count * 12;
+    prof_mark(h, 2, st);
     mm_tail_kernel<<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, h->mm_cutlim, D.t, D.P, D.S0, D.n_ex, D.n_t,
                                                        h->ssr, solve_list, h->mm_ctl, h->stats);
     LAUNCH_CHECK(h);
+    prof_mark(h, 3, st);
     const unsigned cgrid = (unsigned)h->sm_count * 8 < (un + 255) / 256 ? (unsigned)h->sm_count * 8 : (un + 255) / 256;
     if (bounded)
         mm_collect_kernel<true><<<cgrid, 256, 0, st>>>(theta, ld, un, D.n_ex, D.n_t, h->ssr, lk, part_list, h->mm_ctl,
@@ -598,6 +691,7 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
         mm_collect_kernel<false><<<cgrid, 256, 0, st>>>(theta, ld, un, D.n_ex, D.n_t, h->ssr, lk, part_list, h->mm_ctl,
                                                        h->stats);
     LAUNCH_CHECK(h);
+    if (h->prof_on) h->prof_sweeps++;
     return SMCB_OK;
 }
 

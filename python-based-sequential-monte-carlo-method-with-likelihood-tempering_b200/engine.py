@@ -292,7 +292,7 @@ class Engine:
         torch.cuda.set_device(self.device)
         self.h = _acquire_handle(self.lib, self.device.index)
         for key, val in ((_lib.PARAM_MM_BUDGET, self.cfg.mm_budget), (_lib.PARAM_MM_REFILL_MIN, self.cfg.mm_refill_min),
-                         (_lib.PARAM_MM_PATIENCE, self.cfg.mm_patience)):
+                         (_lib.PARAM_MM_PATIENCE, self.cfg.mm_patience), (_lib.PARAM_MM_CHUNK, self.cfg.mm_chunk)):
             self._ck(self.lib.smcb_set_param(self.h, key, float(val)))
         likelihood.upload(self.lib, self.h)
         N, W = self.cfg.n_particle, self.comm.world
@@ -351,6 +351,17 @@ class Engine:
         out = np.zeros(_lib.N_STATS, dtype=np.int64)
         self._ck(self.lib.smcb_loglik_stats(self.h, out.ctypes.data))
         return out
+
+    def kernel_profile(self, on=None):
+        """Per-kernel device time of the MM_PROGRESS sweeps (CUDA events inside the library).
+        on=True/False switches the recording; with on=None returns (bulk ms, tail ms, sweeps) since the
+        last read."""
+        if on is not None:
+            self._ck(self.lib.smcb_set_param(self.h, _lib.PARAM_PROFILE, 1.0 if on else 0.0))
+            return None
+        out = np.zeros(3, dtype=np.float64)
+        self._ck(self.lib.smcb_profile_read(self.h, out.ctypes.data))
+        return float(out[0]), float(out[1]), int(out[2])
 
     # -------------------------------------------------------------------------------- device timers
     def enable_profiling(self, on=True):
