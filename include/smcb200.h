@@ -111,6 +111,8 @@ int smcb_loglik_bounded(smcb_handle* h, int model, const double* theta_dev, int6
 #define SMCB_PARAM_PROFILE 4
 /* SMCB_PARAM_MM_CHUNK: particles per work-queue item of the bulk kernel (default 32). */
 #define SMCB_PARAM_MM_CHUNK 5
+/* SMCB_PARAM_MM_TAIL_WARPS: one-warp blocks per SM of the tail kernel (default 4). */
+#define SMCB_PARAM_MM_TAIL_WARPS 6
 int smcb_set_param(smcb_handle* h, int key, double value);
 /* Device time of the MM_PROGRESS kernels since the last read (SMCB_PARAM_PROFILE): out_host[0] = ms inside
  * mm_bulk_kernel, [1] = ms inside mm_tail_kernel, [2] = sweeps covered.  Synchronous; resets the record. */
@@ -119,12 +121,13 @@ int smcb_profile_read(smcb_handle* h, double* out_host);
  * EX/lik:74-77): pred_dev[i][n_ex][n_t].  MM_PROGRESS only. */
 int smcb_predict_mm_progress(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n,
                              double* pred_dev, void* stream);
-/* Work counters of MM_PROGRESS sweeps, out_host int64[16]: [0]=RHS evaluations, [1]=accepted steps,
+/* Work counters of MM_PROGRESS sweeps, out_host int64[24]: [0]=RHS evaluations, [1]=accepted steps,
  * [2]=rejected steps, [3]=failed solves of the last sweep; [4..7] the same four accumulated over every
  * sweep since smcb_create; [8]/[9] particles reported -inf by early rejection (last sweep / accumulated);
  * [10] largest number of attempted steps of one solve in the last sweep; [11]/[12] solves deferred to
  * the tail kernel; [13]/[14] particles the tail kernel processed; [15] attempted steps taken inside the tail kernel
- * (accumulated).  Synchronous. */
+ * (accumulated); [16] longest solve of the last sweep's tail kernel as (attempts << 32) | device clock cycles
+ * per attempted step of that solve; [17..23] unused.  Synchronous. */
 int smcb_loglik_stats(smcb_handle* h, int64_t* out_host);
 
 /* ---- K2: tempering reductions (replaces EX/main:116-134) --------------------------------- */

@@ -57,7 +57,8 @@ def sweep(tag):
         if model == "mm_progress":
             st = eng.loglik_stats()
             extra = (f" rhs/particle={st[0] / N:.1f} acc={st[1] / N:.1f} rej={st[2] / N:.1f} fail={st[3]}"
-                     f" max_attempts={st[10]} deferred_solves={st[11]} tail_particles={st[13]}")
+                     f" max_attempts={st[10]} deferred_solves={st[11]} tail_particles={st[13]}"
+                     f" longest_tail_solve={int(st[16]) >> 32}x{int(st[16]) & 0xffffffff}cyc")
         print(f"{model} {tag} N=2^{lg} rep{r}: {ms:.3f} ms  {N / ms * 1e3:.4g} evals/s{extra}", flush=True)
 
 

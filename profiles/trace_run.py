@@ -22,7 +22,8 @@ g = np.load(os.path.join(ROOT, "tests", "golden", "mm_reference_run.npz"))
 lik = pkg.MMProgress(g["data_t"], g["data_P"], g["data_S0"])
 prior = pkg.UniformBox([0, 0, 0], [10, 10, 10])
 chunk = int(sys.argv[4]) if len(sys.argv) > 4 else 32
-eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N, early_reject=er, mm_budget=int(budget), mm_chunk=chunk))
+tw = int(sys.argv[5]) if len(sys.argv) > 5 else 4
+eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N, early_reject=er, mm_budget=int(budget), mm_chunk=chunk, mm_tail_warps=tw))
 orig = eng.loglik_into
 rows = []
 
@@ -45,7 +46,7 @@ for rep in range(2):
     rows.clear()
     eng.sample_prior()
     res = eng.run()
-print(f"N=2^{lg} budget={budget:.0f} chunk={chunk} early_reject={er}: {res.seconds * 1e3:.1f} ms to beta=1, {len(res.betas)} stages, "
+print(f"N=2^{lg} budget={budget:.0f} chunk={chunk} tail_warps={tw} early_reject={er}: {res.seconds * 1e3:.1f} ms to beta=1, {len(res.betas)} stages, "
       f"sweeps {res.n_mh}, logZ {res.log_evidence:.4f}")
 print(" sweep      ms  bulk_ms  tail_ms   evaluated  rhs/eval  attempts/eval  cut_particles  max_attempts  deferred_solves  tail_particles")
 for i, r in enumerate(rows):

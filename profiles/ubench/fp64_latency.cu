@@ -67,13 +67,14 @@ __global__ void thr_rcp(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3;
 }
 // one stiff solve, `lanes` active lanes of one warp all integrating the same problem
-__global__ void solve_steps(double* out, long long* cyc, unsigned* natt, double Vmax, double Km, double S0, int lanes) {
+__global__ void solve_steps(double* out, long long* cyc, unsigned* natt, double Vmax, double Km, double S0, int lanes,
+                            double cut = INFINITY) {
     __shared__ mmsolve::ObsPair obs[40];
     for (int i = threadIdx.x; i < 40; i += blockDim.x) { obs[i].P = 0.05; obs[i].t_next = (i < 39) ? 10.0 * (i + 1) / 39.0 : INFINITY; }
     __syncthreads();
     if ((int)threadIdx.x >= lanes) return;
     mmsolve::Solve s;
-    s.nVmax = -Vmax; s.Km = Km; s.S0 = S0; s.cut_lim = INFINITY;
+    s.nVmax = -Vmax; s.Km = Km; s.S0 = S0; s.cut_lim = cut;
     unsigned a = 0, r = 0;
     long long t0 = clock64();
     int st = mmsolve::setup(s, 0.0, 10.0) ? mmsolve::RUNNING : mmsolve::FAILED;
@@ -81,6 +82,24 @@ __global__ void solve_steps(double* out, long long* cyc, unsigned* natt, double 
     long long t1 = clock64();
     out[threadIdx.x] = s.ssr;
     if (threadIdx.x == 0) { cyc[0] = t1 - t0; natt[0] = a + r; }
+}
+
+// the same solve in every lane of `grid` one-warp blocks: inter-warp contention without divergence
+__global__ void solve_many(double* out, long long* cyc, unsigned* natt, double Vmax, double Km, double S0, int active_lanes) {
+    __shared__ mmsolve::ObsPair obs[40];
+    for (int i = threadIdx.x; i < 40; i += blockDim.x) { obs[i].P = 0.05; obs[i].t_next = (i < 39) ? 10.0 * (i + 1) / 39.0 : INFINITY; }
+    __syncthreads();
+    if ((int)threadIdx.x >= active_lanes) return;
+    mmsolve::Solve s;
+    // lanes other than 0 integrate a neighbouring problem (slightly different Km): same length class, own path
+    s.nVmax = -Vmax; s.Km = Km * (1.0 + 0.01 * threadIdx.x); s.S0 = S0; s.cut_lim = INFINITY;
+    unsigned a = 0, r = 0;
+    long long t0 = clock64();
+    int st = mmsolve::setup(s, 0.0, 10.0) ? mmsolve::RUNNING : mmsolve::FAILED;
+    while (st == mmsolve::RUNNING) st = mmsolve::attempt<false>(s, obs, nullptr, a, r);
+    long long t1 = clock64();
+    out[blockIdx.x * 32 + threadIdx.x] = s.ssr;
+    if (threadIdx.x == 0 && blockIdx.x == 0) { cyc[0] = t1 - t0; natt[0] = a + r; }
 }
 
 int main() {
@@ -107,6 +126,20 @@ int main() {
         solve_steps<<<1, 32>>>(out, cyc, natt, 7.30644405, 4.35543917e-04, 0.1, lanes); cudaDeviceSynchronize();
         printf("stiff solve, %2d lane(s)    : %u attempts, %.1f cycles per attempt (%.3f us at 1.965 GHz)\n", lanes, natt[0],
                (double)cyc[0] / natt[0], (double)cyc[0] / natt[0] / 1965.0);
+    }
+    solve_steps<<<1, 32>>>(out, cyc, natt, 9.88869508e+00, 4.28267643e-04, 0.1, 1); cudaDeviceSynchronize();
+    printf("worst solve of the 2^20 bench prior, 1 lane: %u attempts, %.1f cycles per attempt, %.2f ms\n", natt[0],
+           (double)cyc[0] / natt[0], (double)cyc[0] / 1.965e6);
+    solve_steps<<<1, 32>>>(out, cyc, natt, 9.88869508e+00, 4.28267643e-04, 0.1, 1, 1e300); cudaDeviceSynchronize();
+    printf("worst solve, 1 lane, run-time residual limit: %.1f cycles per attempt\n", (double)cyc[0] / natt[0]);
+    for (int wps = 1; wps <= 12; wps *= 2) {
+        if (wps == 8) wps = 12;
+        solve_many<<<148 * wps, 32>>>(out, cyc, natt, 9.88869508e+00, 4.28267643e-04, 0.1, 1); cudaDeviceSynchronize();
+        printf("same solve, lane 0 of %2d warps per SM : %.1f cycles per attempt\n", wps, (double)cyc[0] / natt[0]);
+    }
+    for (int lanes = 2; lanes <= 32; lanes *= 4) {
+        solve_many<<<148 * 4, 32>>>(out, cyc, natt, 9.88869508e+00, 4.28267643e-04, 0.1, lanes); cudaDeviceSynchronize();
+        printf("4 warps per SM, %2d lanes with neighbouring stiff problems: %.1f cycles per attempt of lane 0 (%u attempts)\n", lanes, (double)cyc[0] / natt[0], natt[0]);
     }
     solve_steps<<<1, 32>>>(out, cyc, natt, 1.2, 0.5, 2.0, 1); cudaDeviceSynchronize();
     printf("posterior solve, 1 lane   : %u attempts, %.1f cycles per attempt\n", natt[0], (double)cyc[0] / natt[0]);

@@ -59,8 +59,8 @@ MODEL_MM_PROGRESS, MODEL_MM_RATE, MODEL_KINETIC_RK = 1, 2, 3
 SCAN_SEQUENTIAL, SCAN_FIXED = 0, 1
 MAX_DIM, MAX_CAND = 32, 16
 KIN_NCOND_FIELDS = 10
-PARAM_MM_BUDGET, PARAM_MM_REFILL_MIN, PARAM_MM_PATIENCE, PARAM_PROFILE, PARAM_MM_CHUNK = 1, 2, 3, 4, 5
-N_STATS = 16
+PARAM_MM_BUDGET, PARAM_MM_REFILL_MIN, PARAM_MM_PATIENCE, PARAM_PROFILE, PARAM_MM_CHUNK, PARAM_MM_TAIL_WARPS = 1, 2, 3, 4, 5, 6
+N_STATS = 24
 
 
 def library_path():

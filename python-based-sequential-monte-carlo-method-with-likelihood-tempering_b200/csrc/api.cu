@@ -92,8 +92,8 @@ extern "C" int smcb_create(int device, smcb_handle** out) {
     e = cudaMalloc(reinterpret_cast<void**>(&h->stats), SMCB_N_STATS * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(h->stats, 0, SMCB_N_STATS * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->seq_carry), 4 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mm_ctl), 4 * sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMemset(h->mm_ctl, 0, 4 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mm_ctl), 8 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(h->mm_ctl, 0, 8 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mm_hist), 2 * 512 * sizeof(unsigned));
     if (e != cudaSuccess) {
         smcb_fail(nullptr, SMCB_ERR_CUDA, "smcb_create: cudaMalloc: %s", cudaGetErrorString(e));
@@ -242,6 +242,10 @@ extern "C" int smcb_set_param(smcb_handle* h, int key, double value) {
         case SMCB_PARAM_MM_CHUNK:
             REQUIRE(h, value >= 1 && value <= 65536, SMCB_ERR_INVALID, "MM_CHUNK must be in [1, 65536]");
             h->mm_chunk = (int)value;
+            return SMCB_OK;
+        case SMCB_PARAM_MM_TAIL_WARPS:
+            REQUIRE(h, value >= 1 && value <= 32, SMCB_ERR_INVALID, "MM_TAIL_WARPS must be in [1, 32]");
+            h->mm_tail_warps = (int)value;
             return SMCB_OK;
         case SMCB_PARAM_PROFILE:
             if (value != 0 && h->prof_ev == nullptr) {

@@ -9,7 +9,7 @@
 #include "../../include/smcb200.h"
 
 #define SMCB_VERSION 101
-#define SMCB_N_STATS 16
+#define SMCB_N_STATS 24
 #define SMCB_PROF_RING 512
 #define FULL_MASK 0xffffffffu
 
@@ -50,7 +50,7 @@ struct smcb_handle {
     double* partial = nullptr;       // block partials for reductions
     int64_t partial_len = 0;
     unsigned long long* stats = nullptr;  // SMCB_N_STATS counters (device)
-    unsigned* mm_ctl = nullptr;      // [0] solve-queue head, [1] deferred solves, [2] deferred particles (MM_PROGRESS)
+    unsigned* mm_ctl = nullptr;      // [0] bulk queue head, [1] deferred solves, [2] deferred particles, [3] particles to evaluate, [4] tail queue head
     unsigned* mm_defer = nullptr;    // [ssr_rows*n_max] deferred solves, then [n_max] their particles
     double* mm_cutlim = nullptr;     // [n_max] per-particle residual limit of a bounded sweep
     unsigned short* mm_bins = nullptr;   // [n_max] cost bin of every particle (0xFFFF = no solve needed)
@@ -60,6 +60,7 @@ struct smcb_handle {
     int prof_sweeps = 0;
     cudaEvent_t* prof_ev = nullptr;  // [SMCB_PROF_RING*4]
     int mm_budget = 256;             // attempted steps after which the bulk kernel defers a solve
+    int mm_tail_warps = 4;           // one-warp blocks per SM of the tail kernel
     int mm_chunk = 32;               // particles per queue item of the bulk kernel
     int mm_patience = 3;             // ... for this many attempted steps (unless the whole warp is free)
     int mm_refill_min = 8;           // free lanes a warp of the bulk kernel waits for before setting up new solves

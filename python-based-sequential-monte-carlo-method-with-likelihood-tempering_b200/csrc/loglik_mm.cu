@@ -129,36 +129,45 @@ constexpr int NBIN = 512;
 constexpr unsigned NOBIN = 0xFFFFu;
 
 template <bool BOUNDED>
-__device__ __forceinline__ unsigned cost_bin(const double* __restrict__ theta, int64_t ld, unsigned p,
-                                             const uint8_t* __restrict__ active,
-                                             const double* __restrict__ cutlim) {
-    if (active != nullptr && !active[p]) return NOBIN;
-    if (!(theta[2 * ld + p] > 0)) return NOBIN;           // sigma <= 0: finalize reports -inf
-    if (BOUNDED && cutlim[p] < 0) return NOBIN;           // hopeless before any residual: finalize reports -inf
-    const double r = theta[p] / theta[ld + p];            // Vmax / Km
-    // exponent and top 3 mantissa bits: 8 bins per octave over 2^-32 .. 2^32; heaviest (largest ratio) first
-    int b = (__double2hiint(r) >> 17) - ((1023 - 32) << 3);
-    if (!(r > 0)) b = 0;                                   // zero, negative, NaN: cheapest bin
-    b = b < 0 ? 0 : (b > NBIN - 1 ? NBIN - 1 : b);
-    return (unsigned)(NBIN - 1 - b);
-}
-
-template <bool BOUNDED>
 __global__ void __launch_bounds__(256)
 mm_bin_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const uint8_t* __restrict__ active,
-              const double* __restrict__ cutlim, unsigned short* __restrict__ bins, unsigned* __restrict__ hist) {
+              const double* __restrict__ cutlim, unsigned short* __restrict__ bins, unsigned* __restrict__ hist,
+              double* __restrict__ lk, unsigned long long* __restrict__ stats) {
     __shared__ unsigned s_hist[NBIN];
     for (int i = threadIdx.x; i < NBIN; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool cut = false;
     if (p < n) {
-        const unsigned b = cost_bin<BOUNDED>(theta, ld, p, active, cutlim);
+        unsigned b = NOBIN;
+        if (active == nullptr || active[p]) {
+            if (!(theta[2 * ld + p] > 0)) {
+                lk[p] = -INFINITY;                        // sigma <= 0 (Micmem_likelihood.py:53-54)
+            } else if (BOUNDED && cutlim[p] < 0) {
+                lk[p] = -INFINITY;                        // n_ex*c0 < lkmin: hopeless before any residual
+                cut = true;
+            } else {
+                const double r = theta[p] / theta[ld + p];   // Vmax / Km
+                // exponent and top 3 mantissa bits: 8 bins per octave over 2^-32 .. 2^32; heaviest first
+                int k = (__double2hiint(r) >> 17) - ((1023 - 32) << 3);
+                if (!(r > 0)) k = 0;                      // zero, negative, NaN: cheapest bin
+                k = k < 0 ? 0 : (k > NBIN - 1 ? NBIN - 1 : k);
+                b = (unsigned)(NBIN - 1 - k);
+                atomicAdd(&s_hist[b], 1u);
+            }
+        }
         bins[p] = (unsigned short)b;
-        if (b != NOBIN) atomicAdd(&s_hist[b], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < NBIN; i += blockDim.x)
         if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+    if (BOUNDED) {
+        const unsigned mk = __ballot_sync(FULL_MASK, cut);
+        if (mk != 0 && (threadIdx.x & 31) == 0) {
+            atomicAdd(&stats[8], (unsigned long long)__popc(mk));
+            atomicAdd(&stats[9], (unsigned long long)__popc(mk));
+        }
+    }
 }
 
 // exclusive scan of the histogram (one block of NBIN threads): cursor[b] = first slot of bin b, ctl[3] = total
@@ -224,7 +233,7 @@ mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const u
 
     Solve s;
     s.nVmax = -1.0; s.Km = 1.0; s.S0 = 0.0; s.t = 0.0; s.y = 0.0; s.f = 0.0; s.h_abs = 0.0; s.ssr = 0.0;
-    s.cut_lim = INFINITY; s.i_eval = 0; s.t_next = 0.0; s.t_bound = 0.0;
+    s.cut_lim = INFINITY; s.i_eval = 0; s.rejected = 0; s.t_next = 0.0; s.t_bound = 0.0;
     bool have = false;
     unsigned task = 0, n_att = 0;
     const mmsolve::ObsPair* obs = D.obs;
@@ -317,58 +326,80 @@ mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const u
 }
 
 // ------------------------------------------------------------------------------ finalize
-// One thread per particle.  No deferred solve: ordered sum -> lk.  Otherwise, unless the bound already
-// decides it, every deferred solve goes to solve_list (for mm_tail_kernel), the particle to part_list
-// (for mm_collect_kernel) and cutlim[p] becomes the residual limit of ONE deferred solve given what the
-// finished ones contributed:  total_finished + n_deferred*c0 - ssr_e/(2 sigma^2) < lkmin.
+// One thread per evaluated particle, in cost order (thread i handles perm[i]).  No deferred solve: ordered
+// sum -> lk.  Otherwise, unless the bound already decides it, every deferred solve goes to solve_list (for
+// mm_tail_kernel), the particle to part_list (for mm_collect_kernel) and cutlim[p] becomes the residual limit
+// of ONE deferred solve given what the finished ones contributed:
+//     total_finished + n_deferred*c0 - ssr_e/(2 sigma^2) < lkmin.
+// Lists are appended warp by warp, so they stay (block-wise) in cost order: the lanes of a tail warp hold
+// solves of similar length.
 template <bool BOUNDED>
 __global__ void __launch_bounds__(256)
-mm_finalize_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const uint8_t* __restrict__ active,
+mm_finalize_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const unsigned* __restrict__ perm,
                    const double* __restrict__ lkmin, int n_ex, int n_t, const double* __restrict__ ssr,
                    double* __restrict__ lk, double* __restrict__ cutlim, unsigned* __restrict__ solve_list,
                    unsigned* __restrict__ part_list, unsigned* __restrict__ ctl,
                    unsigned long long* __restrict__ stats) {
-    const unsigned p = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned m = ctl[3];
+    const unsigned lane = threadIdx.x & 31;
     bool cut = false;
-    if (p < n && (active == nullptr || active[p])) {
+    int n_def = 0;
+    unsigned p = 0;
+    if (i < m) {
+        p = perm[i];
         const double sigma = theta[2 * ld + p];
-        if (sigma <= 0) {   // Micmem_likelihood.py:53-54
+        const double s2 = sigma * sigma;
+        const double c0 = -0.5 * n_t * log(2 * M_PI * s2);
+        const double inv_den = 1.0 / (2 * s2);
+        double total = 0.0;
+        for (int e = 0; e < n_ex; ++e) {
+            const double v = ssr[(size_t)e * n + p];
+            if (v < 0) ++n_def;
+            else total += c0 - v * inv_den;   // logL_i, summed in experiment order (Micmem_likelihood.py:70-73)
+        }
+        const double thr = BOUNDED ? lkmin[p] : -INFINITY;
+        if (n_def == 0 || total == -INFINITY) {
+            lk[p] = total;
+            cut = BOUNDED && total == -INFINITY;
+            n_def = 0;
+        } else if (BOUNDED && total + n_def * c0 < thr) {
             lk[p] = -INFINITY;
+            cut = true;
+            n_def = 0;
         } else {
-            const double s2 = sigma * sigma;
-            const double c0 = -0.5 * n_t * log(2 * M_PI * s2);
-            const double inv_den = 1.0 / (2 * s2);
-            double total = 0.0;
-            int n_def = 0;
-            for (int e = 0; e < n_ex; ++e) {
-                const double v = ssr[(size_t)e * n + p];
-                if (v < 0) ++n_def;
-                else total += c0 - v * inv_den;   // logL_i, summed in experiment order (:70-73)
-            }
-            const double thr = BOUNDED ? lkmin[p] : -INFINITY;
-            if (BOUNDED && cutlim[p] < 0) {   // n_ex*c0 < lkmin: no solve was run (mm_bin_kernel left it out)
-                lk[p] = -INFINITY;
-                cut = true;
-            } else if (n_def == 0 || total == -INFINITY) {
-                lk[p] = total;
-                cut = BOUNDED && total == -INFINITY;
-            } else if (BOUNDED && total + n_def * c0 < thr) {
-                lk[p] = -INFINITY;
-                cut = true;
-            } else {
-                cutlim[p] = (BOUNDED && thr > -INFINITY) ? (total + n_def * c0 - thr) * (2 * s2) : INFINITY;
-                part_list[atomicAdd(&ctl[2], 1u)] = p;
-                unsigned at = atomicAdd(&ctl[1], (unsigned)n_def);
-                for (int e = 0; e < n_ex; ++e)
-                    if (ssr[(size_t)e * n + p] < 0) solve_list[at++] = (unsigned)e * n + p;
-            }
+            cutlim[p] = (BOUNDED && thr > -INFINITY) ? (total + n_def * c0 - thr) * (2 * s2) : INFINITY;
+        }
+    }
+    // warp-aggregated append: lane order = cost order
+    const unsigned has = __ballot_sync(FULL_MASK, n_def > 0);
+    if (has != 0) {
+        int incl = n_def;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(FULL_MASK, incl, o);
+            if ((int)lane >= o) incl += up;
+        }
+        const int warp_total = __shfl_sync(FULL_MASK, incl, 31);
+        unsigned base_s = 0, base_p = 0;
+        if (lane == 0) {
+            base_s = atomicAdd(&ctl[1], (unsigned)warp_total);
+            base_p = atomicAdd(&ctl[2], (unsigned)__popc(has));
+        }
+        base_s = __shfl_sync(FULL_MASK, base_s, 0);
+        base_p = __shfl_sync(FULL_MASK, base_p, 0);
+        if (n_def > 0) {
+            part_list[base_p + __popc(has & ((1u << lane) - 1u))] = p;
+            unsigned at = base_s + (unsigned)(incl - n_def);
+            for (int e = 0; e < n_ex; ++e)
+                if (ssr[(size_t)e * n + p] < 0) solve_list[at++] = (unsigned)e * n + p;
         }
     }
     if (BOUNDED) {
-        const unsigned m = __ballot_sync(FULL_MASK, cut);
-        if (m != 0 && (threadIdx.x & 31) == 0) {
-            atomicAdd(&stats[8], (unsigned long long)__popc(m));
-            atomicAdd(&stats[9], (unsigned long long)__popc(m));
+        const unsigned mk = __ballot_sync(FULL_MASK, cut);
+        if (mk != 0 && lane == 0) {
+            atomicAdd(&stats[8], (unsigned long long)__popc(mk));
+            atomicAdd(&stats[9], (unsigned long long)__popc(mk));
         }
     }
 }
@@ -381,58 +412,47 @@ __global__ void __launch_bounds__(TAIL_BLOCK)
 mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const double* __restrict__ cutlim,
                const double* __restrict__ g_t, const double* __restrict__ g_P, const double* __restrict__ g_S0,
                int n_ex, int n_t, double* __restrict__ ssr, const unsigned* __restrict__ solve_list,
-               const unsigned* __restrict__ ctl, unsigned long long* __restrict__ stats) {
+               unsigned* __restrict__ ctl, unsigned long long* __restrict__ stats) {
     const unsigned count = ctl[1];
+    unsigned* tail_queue = ctl + 4;
     if (blockIdx.x == 0 && threadIdx.x == 0 && stats != nullptr) {
         stats[13] = ctl[2];
         atomicAdd(&stats[14], (unsigned long long)ctl[2]);
     }
-    if (blockIdx.x * TAIL_BLOCK >= count) return;   // nothing for this block: skip the staging too
+    if (blockIdx.x * TAIL_BLOCK >= count) return;   // more lanes than entries: skip the staging too
     extern __shared__ __align__(16) unsigned char smem[];
     const SharedData D = stage_data(smem, g_t, g_P, g_S0, n_ex, n_t);
 
-    Solve s;
-    s.nVmax = -1.0; s.Km = 1.0; s.S0 = 0.0; s.t = 0.0; s.y = 0.0; s.f = 0.0; s.h_abs = 0.0; s.ssr = 0.0;
-    s.cut_lim = INFINITY; s.i_eval = 0; s.t_next = 0.0; s.t_bound = 0.0;
-    bool have = false;
-    unsigned idx = blockIdx.x * TAIL_BLOCK + threadIdx.x, g = 0;
-    const unsigned stride = gridDim.x * TAIL_BLOCK;
-    const mmsolve::ObsPair* obs = D.obs;
-    unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, n_att = 0, mx = 0;
-
+    // Every lane pulls the next entry of the list when it is free (the list is only roughly heaviest first:
+    // mm_finalize_kernel's blocks append in whatever order they run).  All entries are started within the time
+    // the light solves take (~1 ms), so the kernel lasts about as long as its longest solve; that chain soon has
+    // its warp to itself.  Each lane runs a solve to its end in a plain loop - no warp-level bookkeeping on the
+    // critical chain.
+    unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, mx = 0;
     for (;;) {
-        if (!have && idx < count) {
-            g = solve_list[idx];
-            idx += stride;
-            const unsigned e = g / n, p = g - e * n;
-            s.nVmax = -theta[p];
-            s.Km = theta[ld + p];
-            s.S0 = D.S0[e];
-            s.cut_lim = cutlim[p];
-            obs = D.obs + (size_t)e * n_t;
-            n_att = 0;
-            n_set++;
-            if (mmsolve::setup(s, D.t0[e], D.tb[e])) {
-                have = true;
-            } else {
-                ssr[g] = INFINITY;
-                n_fail++;
-            }
-        }
-        if (__ballot_sync(FULL_MASK, have) == 0) {
-            if (__ballot_sync(FULL_MASK, idx < count) == 0) break;
-            continue;
-        }
-        if (have) {
-            const int st = mmsolve::attempt<false>(s, obs, nullptr, n_acc, n_rej);
-            ++n_att;
-            if (st != mmsolve::RUNNING) {
-                ssr[g] = (st == mmsolve::DONE) ? s.ssr : INFINITY;
-                if (st == mmsolve::FAILED) n_fail++;
-                mx = max(mx, n_att);
-                have = false;
-            }
-        }
+        const unsigned idx = atomicAdd(tail_queue, 1u);
+        if (idx >= count) break;
+        const unsigned g = solve_list[idx];
+        const unsigned e = g / n, p = g - e * n;
+        Solve s;
+        s.nVmax = -theta[p];
+        s.Km = theta[ld + p];
+        s.S0 = D.S0[e];
+        s.cut_lim = cutlim[p];
+        const mmsolve::ObsPair* obs = D.obs + (size_t)e * n_t;
+        const unsigned att0 = n_acc + n_rej;
+        n_set++;
+        const long long c0 = clock64();
+        int st = mmsolve::setup(s, D.t0[e], D.tb[e]) ? mmsolve::RUNNING : mmsolve::FAILED;
+        while (st == mmsolve::RUNNING) st = mmsolve::attempt<false>(s, obs, nullptr, n_acc, n_rej);
+        const long long c1 = clock64();
+        ssr[g] = (st == mmsolve::DONE) ? s.ssr : INFINITY;
+        if (st == mmsolve::FAILED) n_fail++;
+        const unsigned att = n_acc + n_rej - att0;
+        mx = max(mx, att);
+        // longest solve of the sweep and what one of its steps cost: (attempts << 32) | cycles per attempt
+        if (att > 1024 && stats != nullptr)
+            atomicMax(&stats[16], ((unsigned long long)att << 32) | (unsigned long long)((c1 - c0) / att));
     }
     flush_stats(stats, n_set, n_acc, n_rej, n_fail, 0u, mx, true);
 }
@@ -603,8 +623,9 @@ static inline void prof_mark(smcb_handle* h, int which, cudaStream_t st) {
 // sweep-local counters, the solve queue and the deferred-particle list head
 __global__ void mm_reset_kernel(unsigned long long* stats, unsigned* ctl, unsigned* hist) {
     if (threadIdx.x < 4) stats[threadIdx.x] = 0;
-    if (threadIdx.x == 8 || threadIdx.x == 10 || threadIdx.x == 11 || threadIdx.x == 13) stats[threadIdx.x] = 0;
-    if (threadIdx.x < 4) ctl[threadIdx.x] = 0;
+    if (threadIdx.x == 8 || threadIdx.x == 10 || threadIdx.x == 11 || threadIdx.x == 13 || threadIdx.x == 16)
+        stats[threadIdx.x] = 0;
+    if (threadIdx.x < 8) ctl[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < NBIN; i += blockDim.x) hist[i] = 0;
 }
 
@@ -646,9 +667,11 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     if (bounded) {
         mm_prep_kernel<<<(un + 255) / 256, 256, 0, st>>>(theta, ld, n, active, lkmin, D.n_ex, D.n_t, h->mm_cutlim);
         LAUNCH_CHECK(h);
-        mm_bin_kernel<true><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, active, h->mm_cutlim, h->mm_bins, hist);
+        mm_bin_kernel<true><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, active, h->mm_cutlim, h->mm_bins, hist, lk,
+                                                             h->stats);
     } else {
-        mm_bin_kernel<false><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, active, nullptr, h->mm_bins, hist);
+        mm_bin_kernel<false><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, active, nullptr, h->mm_bins, hist, lk,
+                                                              h->stats);
     }
     LAUNCH_CHECK(h);
     mm_binscan_kernel<<<1, NBIN, 0, st>>>(hist, hist + NBIN, h->mm_ctl);
@@ -668,16 +691,19 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     unsigned* solve_list = h->mm_defer;                              // [n_ex * n_max]
     unsigned* part_list = h->mm_defer + (size_t)h->ssr_rows * h->n_max;   // [n_max]
     if (bounded)
-        mm_finalize_kernel<true><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, active, lkmin, D.n_ex, D.n_t, h->ssr,
+        mm_finalize_kernel<true><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, h->mm_perm, lkmin, D.n_ex, D.n_t, h->ssr,
                                                                   lk, h->mm_cutlim, solve_list, part_list, h->mm_ctl,
                                                                   h->stats);
     else
-        mm_finalize_kernel<false><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, active, nullptr, D.n_ex, D.n_t,
+        mm_finalize_kernel<false><<<(un + 255) / 256, 256, 0, st>>>(theta, ld, un, h->mm_perm, nullptr, D.n_ex, D.n_t,
                                                                    h->ssr, lk, h->mm_cutlim, solve_list, part_list,
                                                                    h->mm_ctl, h->stats);
     LAUNCH_CHECK(h);
-    // 12 one-warp blocks per SM keep the latency-bound tail solves clear of each other on the FP64 pipe
-    const unsigned tail_grid = (unsigned)h->sm_count * 12;
+    // One-warp blocks, mm_tail_warps per SM (default 4 = one per SM sub-partition): a second warp on the
+    // scheduler of a long chain delays its instructions by a cycle here and there, which adds up to 20% over
+    // the 3e5 dependent instructions of a 1e5-step solve (measured: 40.8 ms with 12 warps per SM against
+    // 33.0 ms for the same solve alone on the GPU).
+    const unsigned tail_grid = (unsigned)h->sm_count * (unsigned)h->mm_tail_warps;
     prof_mark(h, 2, st);
     mm_tail_kernel<<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, h->mm_cutlim, D.t, D.P, D.S0, D.n_ex, D.n_t,
                                                        h->ssr, solve_list, h->mm_ctl, h->stats);

@@ -48,7 +48,7 @@ namespace mmsolve {
 
 MM_COEF RTOL = 1e-3, ATOL = 1e-6, SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;
 // 0.9*err^(-1/5) reaches MAX_FACTOR for err <= 0.09^5 and MIN_FACTOR for err >= 4.5^5
-MM_COEF ERR_LO = 5.9049e-6, ERR_HI = 1845.28125;
+MM_COEF ERR_LO = 5.9049e-6, ERR_HI = 1845.28125, ERR_ONE = 0.59049;   // 0.9*err^(-1/5) = 10, 0.2, 1
 
 // Dormand-Prince coefficients spelt as scipy spells them; the quotients are evaluated in FP64.
 MM_COEF A21 = 1.0 / 5;
@@ -94,7 +94,10 @@ MM_HD double rootm5_seed(double x) {
     // the F2F conversions cost ~40 cycles of latency each, these integer operations ~5.
     const unsigned hi = (unsigned)__double2hiint(x);
     const float xf = __uint_as_float(((hi - 0x38000000u) << 3) | ((unsigned)__double2loint(x) >> 29));
-    const unsigned rb = __float_as_uint(exp2f(-0.2f * __log2f(xf)));
+    float l, rf;   // plain MUFU.LG2 / MUFU.EX2: the range fix-ups of log2f()/exp2f() would sit on the critical chain
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(xf));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(-0.2f * l));
+    const unsigned rb = __float_as_uint(rf);
     return __hiloint2double((int)((rb >> 3) + 0x38000000u), (int)(rb << 29));
 #else
     return (double)powf((float)x, -0.2f);
@@ -125,6 +128,16 @@ MM_HD double rootm5(double x) {
     return fma(r, e * fma(C_ROOT_A, e, C_ROOT_B), r);
 }
 
+// SAFETY * x^(-1/5), the safety factor folded into the seed and the correction evaluated two operations deep
+// (r9*e and the polynomial in parallel).  Meaningful for x inside the FP32 range; callers only use it there.
+MM_HD double safety_rootm5(double x) {
+    const double r = rootm5_seed(x);
+    const double r9 = SAFETY * r;
+    const double r2 = r * r, r4 = r2 * r2;
+    const double e = fma(-x * r, r4, 1.0);
+    return fma(r9 * e, fma(C_ROOT_A, e, C_ROOT_B), r9);
+}
+
 MM_HD double ulp10(double t) {
     // 10 * |nextafter(t, +inf) - t|   (rk.py:113, direction = +1)
     union { double d; int64_t i; } v;
@@ -153,10 +166,11 @@ struct Solve {
     double t, y, f;     // current time, state, f(t, y) (first-same-as-last)
     double t_next;      // t[i_eval], the next observation time (+inf after the last)
     double t_bound;     // t[n_t-1]
-    double h_abs;       // next step size; negative = retry of the same scipy step after a rejection
+    double h_abs;       // next step size
     double ssr;         // residual sum of squares so far
     double cut_lim;     // stop (CUT) as soon as ssr exceeds this; +inf = never
     int i_eval;         // next observation time to emit
+    int rejected;       // the last attempt was rejected: this one retries the same scipy step (rk.py:150-170)
 };
 
 // select_initial_step (common.py:110-134) for n = 1, direction = +1, order 4.  Returns false when no
@@ -167,6 +181,7 @@ MM_HD bool setup(Solve& s, double t0, double t_bound) {
     s.y = s.S0;
     s.ssr = 0.0;
     s.i_eval = 0;
+    s.rejected = 0;
     s.t_next = t0;
     const double y = s.S0;
     const double f = mm_rate(s.nVmax, s.Km, y);
@@ -203,21 +218,23 @@ MM_HD int attempt(Solve& s, const ObsPair* obs, double* pred, unsigned& n_acc, u
     const double t = s.t, y = s.y;
     const double t_bound = s.t_bound;
     double ha = s.h_abs;
-    bool rejected = false;
-    if (ha < 0) {
-        rejected = true;
-        ha = -ha;
-    }
-    if (ha < fma(fabs(t), C_MINSTEP_REL, C_MINSTEP_ABS)) {   // only then can 10*ulp(t) matter
+    const bool rejected = s.rejected != 0;
+    // t_new = t + h_abs, clipped to t_bound; h = t_new - t   (rk.py:128-134), the two cases side by side
+    const double rem = t_bound - t;
+    double t_new = t + ha;
+    bool last = t_new - t_bound > 0;
+    double h = last ? rem : t_new - t;
+    if (ha < fma(fabs(t), C_MINSTEP_REL, C_MINSTEP_ABS)) {   // only then can min_step = 10*ulp(t) matter (rare)
         const double min_step = ulp10(t);
-        // scipy clamps h_abs up to min_step when it enters a step; an attempt shrunk below min_step by
-        // a rejection fails instead (TOO_SMALL_STEP: short solution, the reference would raise).
+        // scipy clamps h_abs up to min_step when it enters a step; an attempt shrunk below min_step by a
+        // rejection fails instead (TOO_SMALL_STEP: short solution, the reference would raise).
         if (!rejected && ha < min_step) ha = min_step;
         if (ha < min_step) return FAILED;
+        t_new = t + ha;
+        last = t_new - t_bound > 0;
+        h = last ? rem : t_new - t;
     }
-    double t_new = t + ha;
-    if (t_new - t_bound > 0) t_new = t_bound;
-    const double h = t_new - t;
+    if (last) t_new = t_bound;
     ha = fabs(h);
     const double hn = h * s.nVmax, Km = s.Km;
     const double K1 = h * s.f;
@@ -234,12 +251,14 @@ MM_HD int attempt(Solve& s, const ObsPair* obs, double* pred, unsigned& n_acc, u
     // error estimate sum_j E_j K_j; the last term as (E7*h)*k7 so that k7 enters by a single FMA
     const double ee = fma(E7 * h, k7, fma(E6, K6, fma(E5, K5, fma(E4, K4, fma(E3, K3, E1 * K1)))));
     const double err = fabs(ee * iscale);
-    // 0.9*err^(-1/5) where it is not clamped anyway
-    const double fr = SAFETY * rootm5(fmin(fmax(err, ERR_LO), ERR_HI));
+    // 0.9*err^(-1/5): used only for ERR_LO < err < ERR_HI, where it lies strictly inside (MIN_FACTOR, MAX_FACTOR);
+    // the clamps of rk.py:156-170 become selects on err, which are ready long before the root is
+    const double fr = safety_rootm5(err);
     if (err < 1.0) {
-        double factor = (err <= ERR_LO) ? MAX_FACTOR : fmin(MAX_FACTOR, fr);
-        if (rejected) factor = fmin(factor, 1.0);
+        double factor = (err <= ERR_LO) ? MAX_FACTOR : fr;
+        if (rejected && err < ERR_ONE) factor = 1.0;   // after a rejection the step may not grow (rk.py:158-159)
         s.h_abs = ha * factor;
+        s.rejected = 0;
         n_acc++;
         // dense output for every t_eval in (t_old, t_new] (ivp.py:712-728; t_eval[0] = t0 is emitted by
         // the first step with x = 0)
@@ -275,8 +294,9 @@ MM_HD int attempt(Solve& s, const ObsPair* obs, double* pred, unsigned& n_acc, u
         if (!PRED && s.ssr > s.cut_lim) return CUT;
         return (t_new - t_bound >= 0) ? DONE : RUNNING;
     }
-    double factor = (err < ERR_HI) ? fmax(MIN_FACTOR, fr) : MIN_FACTOR;   // NaN error: MIN_FACTOR, as Python's max()
-    s.h_abs = -(ha * factor);
+    const double factor = (err < ERR_HI) ? fr : MIN_FACTOR;   // NaN error: MIN_FACTOR, as Python's max()
+    s.h_abs = ha * factor;
+    s.rejected = 1;
     n_rej++;
     return RUNNING;
 }

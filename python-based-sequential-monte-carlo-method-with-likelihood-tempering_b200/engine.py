@@ -292,7 +292,8 @@ class Engine:
         torch.cuda.set_device(self.device)
         self.h = _acquire_handle(self.lib, self.device.index)
         for key, val in ((_lib.PARAM_MM_BUDGET, self.cfg.mm_budget), (_lib.PARAM_MM_REFILL_MIN, self.cfg.mm_refill_min),
-                         (_lib.PARAM_MM_PATIENCE, self.cfg.mm_patience), (_lib.PARAM_MM_CHUNK, self.cfg.mm_chunk)):
+                         (_lib.PARAM_MM_PATIENCE, self.cfg.mm_patience), (_lib.PARAM_MM_CHUNK, self.cfg.mm_chunk),
+                         (_lib.PARAM_MM_TAIL_WARPS, self.cfg.mm_tail_warps)):
             self._ck(self.lib.smcb_set_param(self.h, key, float(val)))
         likelihood.upload(self.lib, self.h)
         N, W = self.cfg.n_particle, self.comm.world

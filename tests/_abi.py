@@ -46,6 +46,6 @@ class Abi:
         return lk.cpu().numpy()
 
     def stats(self):
-        out = np.zeros(16, dtype=np.int64)
+        out = np.zeros(24, dtype=np.int64)
         self.ck(self.lib.smcb_loglik_stats(self.h, out.ctypes.data))
         return out
