@@ -111,7 +111,7 @@ int smcb_loglik_bounded(smcb_handle* h, int model, const double* theta_dev, int6
 #define SMCB_PARAM_PROFILE 4
 /* SMCB_PARAM_MM_CHUNK: particles per work-queue item of the bulk kernel (default 32). */
 #define SMCB_PARAM_MM_CHUNK 5
-/* SMCB_PARAM_MM_TAIL_WARPS: one-warp blocks per SM of the tail kernel (default 4). */
+/* SMCB_PARAM_MM_TAIL_WARPS: one-warp blocks per SM of the tail kernel (default 32, 1..32). */
 #define SMCB_PARAM_MM_TAIL_WARPS 6
 int smcb_set_param(smcb_handle* h, int key, double value);
 /* Device time of the MM_PROGRESS kernels since the last read (SMCB_PARAM_PROFILE): out_host[0] = ms inside

@@ -22,7 +22,7 @@ g = np.load(os.path.join(ROOT, "tests", "golden", "mm_reference_run.npz"))
 lik = pkg.MMProgress(g["data_t"], g["data_P"], g["data_S0"])
 prior = pkg.UniformBox([0, 0, 0], [10, 10, 10])
 chunk = int(sys.argv[4]) if len(sys.argv) > 4 else 32
-tw = int(sys.argv[5]) if len(sys.argv) > 5 else 4
+tw = int(sys.argv[5]) if len(sys.argv) > 5 else 32
 eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N, early_reject=er, mm_budget=int(budget), mm_chunk=chunk, mm_tail_warps=tw))
 orig = eng.loglik_into
 rows = []

@@ -95,6 +95,8 @@ extern "C" int smcb_create(int device, smcb_handle** out) {
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mm_ctl), 8 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(h->mm_ctl, 0, 8 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mm_hist), 2 * 512 * sizeof(unsigned));
+    if (e == cudaSuccess)   // tail kernel: at most 32 one-warp blocks per SM (SMCB_PARAM_MM_TAIL_WARPS)
+        e = cudaMalloc(reinterpret_cast<void**>(&h->mm_tailrec), (size_t)h->sm_count * (32 + 4) * 32 * 8 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         smcb_fail(nullptr, SMCB_ERR_CUDA, "smcb_create: cudaMalloc: %s", cudaGetErrorString(e));
         delete h;
@@ -108,7 +110,7 @@ extern "C" int smcb_destroy(smcb_handle* h) {
     if (!h) return SMCB_OK;
     cudaSetDevice(h->device);
     dev_free(&h->ssr); dev_free(&h->partial); dev_free(&h->stats); dev_free(&h->mm_ctl); dev_free(&h->mm_defer); dev_free(&h->mm_cutlim);
-    dev_free(&h->mm_bins); dev_free(&h->mm_perm); dev_free(&h->mm_hist);
+    dev_free(&h->mm_bins); dev_free(&h->mm_perm); dev_free(&h->mm_hist); dev_free(&h->mm_tailrec);
     if (h->prof_ev) {
         for (int i = 0; i < SMCB_PROF_RING * 4; ++i) cudaEventDestroy(h->prof_ev[i]);
         delete[] h->prof_ev;

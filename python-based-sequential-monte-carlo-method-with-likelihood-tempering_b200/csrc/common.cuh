@@ -55,12 +55,13 @@ struct smcb_handle {
     double* mm_cutlim = nullptr;     // [n_max] per-particle residual limit of a bounded sweep
     unsigned short* mm_bins = nullptr;   // [n_max] cost bin of every particle (0xFFFF = no solve needed)
     unsigned* mm_perm = nullptr;     // [n_max] particles to evaluate, heaviest cost bin first
+    unsigned long long* mm_tailrec = nullptr;   // [sm_count*32 warps*32 lanes][8] per-thread work record of the tail kernel
     unsigned* mm_hist = nullptr;     // [2*512] histogram and scatter cursors of the counting sort
     bool prof_on = false;            // per-kernel CUDA-event timing of the MM_PROGRESS sweeps
     int prof_sweeps = 0;
     cudaEvent_t* prof_ev = nullptr;  // [SMCB_PROF_RING*4]
     int mm_budget = 256;             // attempted steps after which the bulk kernel defers a solve
-    int mm_tail_warps = 4;           // one-warp blocks per SM of the tail kernel
+    int mm_tail_warps = 32;          // one-warp blocks per SM of the tail kernel
     int mm_chunk = 32;               // particles per queue item of the bulk kernel
     int mm_patience = 3;             // ... for this many attempted steps (unless the whole warp is free)
     int mm_refill_min = 8;           // free lanes a warp of the bulk kernel waits for before setting up new solves

@@ -405,33 +405,39 @@ mm_finalize_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, con
 }
 
 // ------------------------------------------------------------------------------ tail
-// One lane per deferred solve, restarted from t0 without a budget.  These are the 1e3 .. 1e5-step solves:
-// each is a strictly serial chain (~870 cycles per attempted step), so the kernel's duration is the
-// longest one; blocks of one warp spread them over all SM sub-partitions.
+// One lane per deferred solve, restarted from t0 without a budget.  These are the 1e3 .. 1e5-step solves: each
+// is a strictly serial chain (~680 cycles per attempted step), so the kernel lasts as long as its longest
+// solve.  Everything here serves that chain:
+//   * one-warp blocks, mm_tail_warps (4) per SM = one per scheduler;
+//   * entry k of the (roughly heaviest-first) list goes to lane k / n_blocks of block k % n_blocks, so the
+//     longest solves each lead a different warp and soon have it to themselves;
+//   * NO warp collective, __syncthreads or value-returning atomic after the data is staged: with any of those
+//     downstream the compiler fences every divergent region of the step with BSSY/BSYNC reconvergence
+//     barriers, which cost ~140 cycles per step (811 against 674 cycles, profiles/ubench_fp64_r01.log).  Work
+//     counters therefore go to a per-thread record that mm_collect_kernel adds up.
+constexpr int TAIL_REC = 8;   // per-thread record: set-ups, accepted, rejected, failed, max attempts, cycles/attempt of it
+
+template <bool LOOP>
 __global__ void __launch_bounds__(TAIL_BLOCK)
 mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const double* __restrict__ cutlim,
                const double* __restrict__ g_t, const double* __restrict__ g_P, const double* __restrict__ g_S0,
                int n_ex, int n_t, double* __restrict__ ssr, const unsigned* __restrict__ solve_list,
-               unsigned* __restrict__ ctl, unsigned long long* __restrict__ stats) {
+               const unsigned* __restrict__ ctl, unsigned long long* __restrict__ rec, unsigned first) {
     const unsigned count = ctl[1];
-    unsigned* tail_queue = ctl + 4;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && stats != nullptr) {
-        stats[13] = ctl[2];
-        atomicAdd(&stats[14], (unsigned long long)ctl[2]);
+    const unsigned tid = blockIdx.x * TAIL_BLOCK + threadIdx.x;
+    unsigned long long* my = rec + (size_t)tid * TAIL_REC;
+    if (first + blockIdx.x >= count) {   // no entry for any lane of this block
+        my[0] = 0;
+        return;
     }
-    if (blockIdx.x * TAIL_BLOCK >= count) return;   // more lanes than entries: skip the staging too
     extern __shared__ __align__(16) unsigned char smem[];
     const SharedData D = stage_data(smem, g_t, g_P, g_S0, n_ex, n_t);
 
-    // Every lane pulls the next entry of the list when it is free (the list is only roughly heaviest first:
-    // mm_finalize_kernel's blocks append in whatever order they run).  All entries are started within the time
-    // the light solves take (~1 ms), so the kernel lasts about as long as its longest solve; that chain soon has
-    // its warp to itself.  Each lane runs a solve to its end in a plain loop - no warp-level bookkeeping on the
-    // critical chain.
-    unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, mx = 0;
-    for (;;) {
-        const unsigned idx = atomicAdd(tail_queue, 1u);
-        if (idx >= count) break;
+    unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, mx = 0, mx_cyc = 0;
+    // LOOP = false: one entry per thread (the normal case; the launch has more threads than there are entries
+    // in any sweep seen so far).  LOOP = true: grid-stride over whatever lies beyond that launch's reach.
+    const unsigned stride = LOOP ? gridDim.x * TAIL_BLOCK : ~0u;
+    for (unsigned idx = first + threadIdx.x * gridDim.x + blockIdx.x; idx < count; idx += stride) {
         const unsigned g = solve_list[idx];
         const unsigned e = g / n, p = g - e * n;
         Solve s;
@@ -449,12 +455,13 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
         ssr[g] = (st == mmsolve::DONE) ? s.ssr : INFINITY;
         if (st == mmsolve::FAILED) n_fail++;
         const unsigned att = n_acc + n_rej - att0;
-        mx = max(mx, att);
-        // longest solve of the sweep and what one of its steps cost: (attempts << 32) | cycles per attempt
-        if (att > 1024 && stats != nullptr)
-            atomicMax(&stats[16], ((unsigned long long)att << 32) | (unsigned long long)((c1 - c0) / att));
+        if (att > mx) {
+            mx = att;
+            mx_cyc = (unsigned)((c1 - c0) / (att ? att : 1u));
+        }
+        if (!LOOP) break;
     }
-    flush_stats(stats, n_set, n_acc, n_rej, n_fail, 0u, mx, true);
+    my[0] = n_set; my[1] = n_acc; my[2] = n_rej; my[3] = n_fail; my[4] = mx; my[5] = mx_cyc;
 }
 
 // ------------------------------------------------------------------------------ collect
@@ -463,7 +470,25 @@ template <bool BOUNDED>
 __global__ void __launch_bounds__(256)
 mm_collect_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, int n_ex, int n_t,
                   const double* __restrict__ ssr, double* __restrict__ lk, const unsigned* __restrict__ part_list,
-                  const unsigned* __restrict__ ctl, unsigned long long* __restrict__ stats) {
+                  const unsigned* __restrict__ ctl, unsigned long long* __restrict__ stats,
+                  const unsigned long long* __restrict__ rec, unsigned n_rec) {
+    // work counters of the tail kernel's threads
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += gridDim.x * blockDim.x) {
+        const unsigned long long* r = rec + (size_t)i * TAIL_REC;
+        if (r[0] == 0) continue;
+        const unsigned long long att = r[1] + r[2], fev = 2ull * r[0] + 6ull * att;
+        atomicAdd(&stats[0], fev); atomicAdd(&stats[4], fev);
+        atomicAdd(&stats[1], r[1]); atomicAdd(&stats[5], r[1]);
+        atomicAdd(&stats[2], r[2]); atomicAdd(&stats[6], r[2]);
+        if (r[3]) { atomicAdd(&stats[3], r[3]); atomicAdd(&stats[7], r[3]); }
+        atomicMax(&stats[10], r[4]);
+        atomicAdd(&stats[15], att);
+        if (r[4] > 1024) atomicMax(&stats[16], (r[4] << 32) | r[5]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        stats[13] = ctl[2];
+        atomicAdd(&stats[14], (unsigned long long)ctl[2]);
+    }
     const unsigned count = ctl[2];
     long long n_cut = 0;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
@@ -652,7 +677,8 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     const bool bounded = lkmin != nullptr;
     if (smem > 48 * 1024 && !h->mm_smem_set) {
         CUDA_TRY(h, cudaFuncSetAttribute(mm_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(h, cudaFuncSetAttribute(mm_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(h, cudaFuncSetAttribute(mm_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(h, cudaFuncSetAttribute(mm_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->mm_smem_set = true;
     }
     if (h->mm_bulk_blocks_per_sm == 0) {
@@ -699,23 +725,27 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
                                                                    h->ssr, lk, h->mm_cutlim, solve_list, part_list,
                                                                    h->mm_ctl, h->stats);
     LAUNCH_CHECK(h);
-    // One-warp blocks, mm_tail_warps per SM (default 4 = one per SM sub-partition): a second warp on the
-    // scheduler of a long chain delays its instructions by a cycle here and there, which adds up to 20% over
-    // the 3e5 dependent instructions of a 1e5-step solve (measured: 40.8 ms with 12 warps per SM against
-    // 33.0 ms for the same solve alone on the GPU).
+    // One-warp blocks, one deferred solve per thread: mm_tail_warps (32) blocks per SM give every entry of the
+    // list its own lane in all sweeps seen so far (2^20 prior particles defer 33 618 solves; the launch holds
+    // 151 552); blocks without entries exit at once, so the long chains end up alone on their schedulers.
     const unsigned tail_grid = (unsigned)h->sm_count * (unsigned)h->mm_tail_warps;
     prof_mark(h, 2, st);
-    mm_tail_kernel<<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, h->mm_cutlim, D.t, D.P, D.S0, D.n_ex, D.n_t,
-                                                       h->ssr, solve_list, h->mm_ctl, h->stats);
+    mm_tail_kernel<false><<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, h->mm_cutlim, D.t, D.P, D.S0, D.n_ex, D.n_t,
+                                                              h->ssr, solve_list, h->mm_ctl, h->mm_tailrec, 0u);
+    LAUNCH_CHECK(h);
+    // entries beyond the reach of that launch (none in practice): grid-stride, records in the second half
+    mm_tail_kernel<true><<<(unsigned)h->sm_count * 4, TAIL_BLOCK, smem, st>>>(
+        theta, ld, un, h->mm_cutlim, D.t, D.P, D.S0, D.n_ex, D.n_t, h->ssr, solve_list, h->mm_ctl,
+        h->mm_tailrec + (size_t)tail_grid * TAIL_BLOCK * TAIL_REC, tail_grid * TAIL_BLOCK);
     LAUNCH_CHECK(h);
     prof_mark(h, 3, st);
-    const unsigned cgrid = (unsigned)h->sm_count * 8 < (un + 255) / 256 ? (unsigned)h->sm_count * 8 : (un + 255) / 256;
+    const unsigned cgrid = (unsigned)h->sm_count * 8;
     if (bounded)
         mm_collect_kernel<true><<<cgrid, 256, 0, st>>>(theta, ld, un, D.n_ex, D.n_t, h->ssr, lk, part_list, h->mm_ctl,
-                                                      h->stats);
+                                                      h->stats, h->mm_tailrec, (tail_grid + (unsigned)h->sm_count * 4) * TAIL_BLOCK);
     else
         mm_collect_kernel<false><<<cgrid, 256, 0, st>>>(theta, ld, un, D.n_ex, D.n_t, h->ssr, lk, part_list, h->mm_ctl,
-                                                       h->stats);
+                                                       h->stats, h->mm_tailrec, (tail_grid + (unsigned)h->sm_count * 4) * TAIL_BLOCK);
     LAUNCH_CHECK(h);
     if (h->prof_on) h->prof_sweeps++;
     return SMCB_OK;

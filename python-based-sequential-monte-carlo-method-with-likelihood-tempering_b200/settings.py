@@ -35,7 +35,7 @@ class Settings:
     early_reject: bool = True           # let the likelihood stop once the MH rejection is certain (exact decisions)
     mm_budget: int = 256                # MM_PROGRESS: attempted RK steps before a solve moves to the tail kernel
     mm_refill_min: int = 8              # MM_PROGRESS: free lanes a warp waits for before setting up new solves ...
-    mm_tail_warps: int = 4              # MM_PROGRESS: one-warp blocks per SM of the tail kernel
+    mm_tail_warps: int = 32             # MM_PROGRESS: one-warp blocks per SM of the tail kernel
     mm_chunk: int = 32                  # MM_PROGRESS: particles per work-queue item of the bulk kernel
     mm_patience: int = 3                # ... and for how many steps (results do not depend on these three)
     fused_sweeps: int = 0               # >0: run this many sweeps per launch with a frozen proposal factor
