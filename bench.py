@@ -303,6 +303,8 @@ def main():
         res = step()
     eng.enable_profiling(True)
     stats0 = eng.loglik_stats() if args.workload == "mm_progress" else None
+    if args.workload == "mm_progress":
+        eng.kernel_profile(True)          # CUDA events around the bulk and the tail kernel, on their stream
     launches0 = eng.launch_count()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -328,6 +330,9 @@ def main():
     launches = eng.launch_count() - launches0
     prof = eng.profile_summary()
     lik_ms = eng.profile_events("loglik")
+    kprof = eng.kernel_profile() if args.workload == "mm_progress" else None
+    if kprof is not None:
+        eng.kernel_profile(False)
     eng.enable_profiling(False)
     if world > 1:
         import torch.distributed as dist
@@ -355,16 +360,39 @@ def main():
                                "MEASURED_PEAKS.json has no FP64 figure",
                 "share_of_step": ms_lik / ms_total if ms_total else None,
                 "avg_launch_ms": ms_lik / max(n_lik, 1), "launches": n_lik}
+    roofline_tail = None
     if args.workload == "mm_progress":
-        d_stats = eng.loglik_stats()[4:8] - stats0[4:8]
+        st1 = eng.loglik_stats()
+        d_stats = st1[4:8] - stats0[4:8]
+        tail_attempts = int(st1[15] - stats0[15])
         local_evals = evals // world
-        flops = mm_progress_flops(d_stats, local_evals, lik.t.shape[0], lik.t.shape[1])
+        n_ex, n_t = lik.t.shape
+        flops_all = mm_progress_flops(d_stats, local_evals, n_ex, n_t)
         per = max(1, len(lik_ms) // max(args.steps, 1))
-        roofline["sweep_ms_last_step"] = [round(x, 3) for x in lik_ms[-per:]]
-        roofline.update(kernel="mm_bulk_kernel + mm_finalize_kernel + mm_tail_kernel (one likelihood sweep)", achieved=flops / (ms_lik * 1e-3) / 1e12,
-                        rhs_evals_per_particle_eval=float(d_stats[0]) / max(local_evals, 1),
-                        rejected_step_fraction=float(d_stats[2]) / max(float(d_stats[1] + d_stats[2]), 1.0))
+        bulk_ms, tail_ms, n_sw = kprof
+        # the bulk kernel's share of the algorithmic work: every step that was not taken inside the tail kernel
+        att_all = float(d_stats[1] + d_stats[2])
+        flops_bulk = flops_all * (1.0 - tail_attempts / max(att_all, 1.0))
+        roofline.update(
+            kernel="mm_bulk_kernel (one launch per likelihood sweep; all solves of up to 256 attempted steps)",
+            achieved=flops_bulk / (bulk_ms * 1e-3) / 1e12, launches=n_sw, avg_launch_ms=bulk_ms / max(n_sw, 1),
+            share_of_step=bulk_ms / ms_total if ms_total else None,
+            sweep_group_ms_last_step=[round(x, 3) for x in lik_ms[-per:]],
+            sweep_group_share_of_step=ms_lik / ms_total if ms_total else None,
+            rhs_evals_per_particle_eval=float(d_stats[0]) / max(local_evals, 1),
+            rejected_step_fraction=float(d_stats[2]) / max(att_all, 1.0),
+            flop_model="84/attempted step + 34/accepted step + 18/observation + 30/solve (DESIGN.md K1), step counts "
+                       "from the device counters; proposals rejected early are not counted")
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
+        longest = int(st1[16])
+        roofline_tail = {
+            "bound": "latency", "kernel": "mm_tail_kernel (deferred solves, one per lane; duration = longest solve)",
+            "launches": n_sw, "ms_per_step": tail_ms / args.steps, "share_of_step": tail_ms / ms_total if ms_total else None,
+            "attempted_steps_in_tail_per_step": tail_attempts / args.steps,
+            "longest_solve": {"attempts": longest >> 32, "cycles_per_attempt": longest & 0xffffffff},
+            "floor_cycles_per_attempt": 674,
+            "note": "a solve is a strictly serial chain of ~270 dependent FP64/MUFU instructions per attempted step; "
+                    "674 cycles is the same step measured alone on the GPU (profiles/ubench_fp64_r01.log)"}
     g_ms, g_bytes = gather_microbench(pkg, eng, torch, flush)
     roofline_hbm = {"bound": "hbm", "kernel": "gather_kernel (resampling gather of particle state)",
                     "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -423,7 +451,7 @@ def main():
                 "decisions_per_step": decided / args.steps,
                 "reference_evals_per_step": res.n_eval_reference,
                 "log_evidence": res.log_evidence, "posterior_mean": [float(x) for x in res.particles.mean(0)],
-                "roofline": roofline, "roofline_hbm": roofline_hbm,
+                "roofline": roofline, "roofline_tail": roofline_tail, "roofline_hbm": roofline_hbm,
                 "kernel_ms": {k: {"groups": v[0], "ms": v[1]} for k, v in prof.items()},
                 "fp32_fma_peak_tflops": fma[1] / 1e12,
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}

@@ -126,8 +126,8 @@ int smcb_predict_mm_progress(smcb_handle* h, const double* theta_dev, int64_t ld
  * sweep since smcb_create; [8]/[9] particles reported -inf by early rejection (last sweep / accumulated);
  * [10] largest number of attempted steps of one solve in the last sweep; [11]/[12] solves deferred to
  * the tail kernel; [13]/[14] particles the tail kernel processed; [15] attempted steps taken inside the tail kernel
- * (accumulated); [16] longest solve of the last sweep's tail kernel as (attempts << 32) | device clock cycles
- * per attempted step of that solve; [17..23] unused.  Synchronous. */
+ * (accumulated); [16] longest solve the tail kernel ran since the previous call of this function, as
+ * (attempts << 32) | device clock cycles per attempted step of that solve; [17..23] unused.  Synchronous. */
 int smcb_loglik_stats(smcb_handle* h, int64_t* out_host);
 
 /* ---- K2: tempering reductions (replaces EX/main:116-134) --------------------------------- */

@@ -276,6 +276,7 @@ extern "C" int smcb_predict_mm_progress(smcb_handle* h, const double* theta_dev,
 extern "C" int smcb_loglik_stats(smcb_handle* h, int64_t* out_host) {
     REQUIRE(h, h && out_host, SMCB_ERR_INVALID, "null pointer");
     CUDA_TRY(h, cudaMemcpy(out_host, h->stats, SMCB_N_STATS * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemset(h->stats + 16, 0, sizeof(unsigned long long)));   // [16] is "since the last read"
     return SMCB_OK;
 }
 

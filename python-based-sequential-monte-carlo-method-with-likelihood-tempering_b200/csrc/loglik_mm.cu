@@ -648,8 +648,7 @@ static inline void prof_mark(smcb_handle* h, int which, cudaStream_t st) {
 // sweep-local counters, the solve queue and the deferred-particle list head
 __global__ void mm_reset_kernel(unsigned long long* stats, unsigned* ctl, unsigned* hist) {
     if (threadIdx.x < 4) stats[threadIdx.x] = 0;
-    if (threadIdx.x == 8 || threadIdx.x == 10 || threadIdx.x == 11 || threadIdx.x == 13 || threadIdx.x == 16)
-        stats[threadIdx.x] = 0;
+    if (threadIdx.x == 8 || threadIdx.x == 10 || threadIdx.x == 11 || threadIdx.x == 13) stats[threadIdx.x] = 0;
     if (threadIdx.x < 8) ctl[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < NBIN; i += blockDim.x) hist[i] = 0;
 }
