@@ -537,39 +537,45 @@ mm_predict_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, cons
 
 // ------------------------------------------------------------------------------ MM_RATE
 // ll = -0.5*n*log(2 pi sigma^2) - sum_i (v_i - Vmax*S_i/(Km+S_i))^2 / (2 sigma^2)
-// One thread per particle; observations streamed through shared memory in tiles that every
-// thread of the block reads by broadcast.
+// Compute-bound: 10^4 observations per particle against 32 B of particle data.  Observations are streamed
+// through shared memory in tiles that every thread of the block reads by broadcast.
 constexpr int RATE_BLOCK = 128;
 constexpr int RATE_TILE = 2048;
 
+// FP64: one thread per particle.  Per observation DADD, MUFU.RCP64H + three DFMA (the reciprocal correction
+// folded into -Vmax*S/(Km+S), mmsolve::mm_rate), DADD, DFMA: 7 FP64-pipe operations (a true division costs ~20).
 __global__ void __launch_bounds__(RATE_BLOCK)
 mm_rate_kernel_f64(const double* __restrict__ theta, int64_t ld, int64_t n,
                    const uint8_t* __restrict__ active, const double* __restrict__ gS,
                    const double* __restrict__ gv, int64_t n_obs, double* __restrict__ lk) {
-    __shared__ double sS[RATE_TILE];
-    __shared__ double sv[RATE_TILE];
+    __shared__ double2 sSv[RATE_TILE];
     const int64_t p = (int64_t)blockIdx.x * RATE_BLOCK + threadIdx.x;
     const bool live = p < n && (active == nullptr || active[p]);
-    double Vmax = 1.0, Km = 1.0, sigma = 1.0;
+    double nVmax = -1.0, Km = 1.0, sigma = 1.0;
     if (live) {
-        Vmax = theta[p];
+        nVmax = -theta[p];
         Km = theta[ld + p];
         sigma = theta[2 * ld + p];
     }
-    double acc = 0.0;
+    double acc0 = 0.0, acc1 = 0.0;
     for (int64_t base = 0; base < n_obs; base += RATE_TILE) {
         const int m = (int)((n_obs - base < RATE_TILE) ? (n_obs - base) : RATE_TILE);
         __syncthreads();
-        for (int i = threadIdx.x; i < m; i += RATE_BLOCK) {
-            sS[i] = gS[base + i];
-            sv[i] = gv[base + i];
-        }
+        for (int i = threadIdx.x; i < m; i += RATE_BLOCK) sSv[i] = make_double2(gS[base + i], gv[base + i]);
         __syncthreads();
-#pragma unroll 4
-        for (int i = 0; i < m; ++i) {
-            const double S = sS[i];
-            const double r = sv[i] - Vmax * S / (Km + S);
-            acc = fma(r, r, acc);
+        int i = 0;
+#pragma unroll 2
+        for (; i + 1 < m; i += 2) {
+            const double2 o0 = sSv[i], o1 = sSv[i + 1];
+            const double r0 = o0.y + mmsolve::mm_rate(nVmax, Km, o0.x);
+            const double r1 = o1.y + mmsolve::mm_rate(nVmax, Km, o1.x);
+            acc0 = fma(r0, r0, acc0);
+            acc1 = fma(r1, r1, acc1);
+        }
+        if (i < m) {
+            const double2 o0 = sSv[i];
+            const double r0 = o0.y + mmsolve::mm_rate(nVmax, Km, o0.x);
+            acc0 = fma(r0, r0, acc0);
         }
     }
     if (live) {
@@ -577,63 +583,120 @@ mm_rate_kernel_f64(const double* __restrict__ theta, int64_t ld, int64_t n,
             lk[p] = -INFINITY;
         } else {
             const double s2 = sigma * sigma;
-            lk[p] = -0.5 * (double)n_obs * log(2 * M_PI * s2) - acc / (2 * s2);
+            lk[p] = -0.5 * (double)n_obs * log(2 * M_PI * s2) - (acc0 + acc1) / (2 * s2);
         }
     }
 }
 
-// FP32 arithmetic: per observation  g = S*rcp(Km+S);  r = v - Vmax*g;  acc += r*r  in FP32 over
-// 64-observation tiles, tile sums accumulated in FP64.
+// FP32 arithmetic, FP32 accumulation over 64-observation tiles, FP64 across tiles.  One thread evaluates two PAIRS
+// of particles; a pair so that (a) one MUFU.RCP serves two reciprocals, 1/a = b*rcp(a*b), 1/b = a*rcp(a*b) - the kernel was
+// MUFU-bound (73% of 16 rcp/clk/SM) with one reciprocal per term - and (b) the two particles form the halves of
+// packed fma.rn.f32x2 / mul.f32x2 / add.f32x2 operands, which halves the issue slots (the FMA pipe retires the same
+// 128 lanes/clk/SM either way: 71 vs 64 TFLOP/s measured, profiles/ubench/fp32x2.cu).  Per term and particle:
+// 5.5 FMA-pipe lanes + 0.5 MUFU; shared memory holds (S, S, v, v) so one LDS.128 feeds both packed operands.
+__device__ __forceinline__ unsigned long long pk(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+constexpr int RATE_PAIRS = 2;   // packed pairs per thread: 4 particles per thread
 __global__ void __launch_bounds__(RATE_BLOCK)
 mm_rate_kernel_f32(const double* __restrict__ theta, int64_t ld, int64_t n,
                    const uint8_t* __restrict__ active, const float2* __restrict__ gSv, int64_t n_obs,
                    double* __restrict__ lk) {
-    __shared__ float2 sSv[RATE_TILE];
-    const int64_t p = (int64_t)blockIdx.x * RATE_BLOCK + threadIdx.x;
-    const bool live = p < n && (active == nullptr || active[p]);
-    float Vmax = 1.f, Km = 1.f;
-    double sigma = 1.0;
-    if (live) {
-        Vmax = (float)theta[p];
-        Km = (float)theta[ld + p];
-        sigma = theta[2 * ld + p];
+    __shared__ float4 sObs[RATE_TILE];   // (S, S, v, v)
+    // thread t of block b owns particles base + t*2 + {0,1} (pair 0) and base + 2*RATE_BLOCK + t*2 + {0,1} (pair 1):
+    // one LDS.128 (512 B returned to the warp's registers, 4 clocks of the 128 B/clk path) now feeds four
+    // particles; with two it was that return path, not the FMA pipe, that bound the kernel.
+    const int64_t blk = (int64_t)blockIdx.x * RATE_BLOCK * 2 * RATE_PAIRS;
+    int64_t pid[RATE_PAIRS][2];
+    bool live[RATE_PAIRS][2];
+    unsigned long long KK[RATE_PAIRS], nVV[RATE_PAIRS];
+    double sg[RATE_PAIRS][2], acc[RATE_PAIRS][2];
+#pragma unroll
+    for (int q = 0; q < RATE_PAIRS; ++q) {
+        float V[2], K[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int64_t p = blk + (int64_t)q * 2 * RATE_BLOCK + threadIdx.x * 2 + j;
+            pid[q][j] = p;
+            live[q][j] = p < n && (active == nullptr || active[p]);
+            V[j] = 1.f; K[j] = 1.f; sg[q][j] = 1.0; acc[q][j] = 0.0;
+            if (live[q][j]) {
+                V[j] = (float)theta[p];
+                K[j] = (float)theta[ld + p];
+                sg[q][j] = theta[2 * ld + p];
+            }
+        }
+        KK[q] = pk(K[0], K[1]);
+        nVV[q] = pk(-V[0], -V[1]);
     }
-    double acc = 0.0;
     for (int64_t base = 0; base < n_obs; base += RATE_TILE) {
         const int m = (int)((n_obs - base < RATE_TILE) ? (n_obs - base) : RATE_TILE);
         __syncthreads();
-        for (int i = threadIdx.x; i < m; i += RATE_BLOCK) sSv[i] = gSv[base + i];
+        for (int i = threadIdx.x; i < m; i += RATE_BLOCK) {
+            const float2 o = gSv[base + i];
+            sObs[i] = make_float4(o.x, o.x, o.y, o.y);
+        }
         __syncthreads();
         for (int i0 = 0; i0 < m; i0 += 64) {
             const int i1 = (i0 + 64 < m) ? i0 + 64 : m;
-            float a0 = 0.f, a1 = 0.f;
-            int i = i0;
-            for (; i + 1 < i1; i += 2) {
-                const float2 o0 = sSv[i], o1 = sSv[i + 1];
-                const float g0 = __fdividef(o0.x, Km + o0.x);
-                const float g1 = __fdividef(o1.x, Km + o1.x);
-                const float r0 = fmaf(-Vmax, g0, o0.y);
-                const float r1 = fmaf(-Vmax, g1, o1.y);
-                a0 = fmaf(r0, r0, a0);
-                a1 = fmaf(r1, r1, a1);
+            unsigned long long a[RATE_PAIRS];
+#pragma unroll
+            for (int q = 0; q < RATE_PAIRS; ++q) a[q] = 0ull;   // (0.f, 0.f)
+#pragma unroll 4
+            for (int i = i0; i < i1; ++i) {
+                const float4 o = sObs[i];
+                const unsigned long long SS = pk(o.x, o.y), vv = pk(o.z, o.w);
+#pragma unroll
+                for (int q = 0; q < RATE_PAIRS; ++q) {
+                    const unsigned long long den = add2(KK[q], SS);       // (Km0+S, Km1+S)
+                    float d0, d1;
+                    upk(den, d0, d1);
+                    float r;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
+                    const unsigned long long g = mul2(SS, pk(r * d1, r * d0));   // S/(Km0+S), S/(Km1+S)
+                    const unsigned long long res = fma2(nVV[q], g, vv);          // v - Vmax*g
+                    a[q] = fma2(res, res, a[q]);
+                }
             }
-            if (i < i1) {
-                const float2 o0 = sSv[i];
-                const float g0 = __fdividef(o0.x, Km + o0.x);
-                const float r0 = fmaf(-Vmax, g0, o0.y);
-                a0 = fmaf(r0, r0, a0);
+#pragma unroll
+            for (int q = 0; q < RATE_PAIRS; ++q) {
+                float a0, a1;
+                upk(a[q], a0, a1);
+                acc[q][0] += (double)a0;
+                acc[q][1] += (double)a1;
             }
-            acc += (double)(a0 + a1);
         }
     }
-    if (live) {
-        if (sigma <= 0) {
-            lk[p] = -INFINITY;
-        } else {
-            const double s2 = sigma * sigma;
-            lk[p] = -0.5 * (double)n_obs * log(2 * M_PI * s2) - acc / (2 * s2);
-        }
-    }
+#pragma unroll
+    for (int q = 0; q < RATE_PAIRS; ++q)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (live[q][j]) {
+                const double s2 = sg[q][j] * sg[q][j];
+                lk[pid[q][j]] = (sg[q][j] <= 0) ? -INFINITY
+                                               : -0.5 * (double)n_obs * log(2 * M_PI * s2) - acc[q][j] / (2 * s2);
+            }
 }
 
 }  // namespace
@@ -756,8 +819,10 @@ int launch_loglik_mm_rate(smcb_handle* h, const double* theta, int64_t ld, int64
     REQUIRE(h, D.S != nullptr, SMCB_ERR_STATE, "smcb_set_data_mm_rate has not been called");
     if (n == 0) return SMCB_OK;
     const int64_t grid = (n + RATE_BLOCK - 1) / RATE_BLOCK;
-    if (D.precision == 32)
-        mm_rate_kernel_f32<<<(unsigned)grid, RATE_BLOCK, 0, st>>>(theta, ld, n, active, D.Sv32, D.n_obs, lk);
+    const int64_t per_block = (int64_t)RATE_BLOCK * 2 * RATE_PAIRS;
+    if (D.precision == 32)   // four particles per thread
+        mm_rate_kernel_f32<<<(unsigned)((n + per_block - 1) / per_block), RATE_BLOCK, 0, st>>>(
+            theta, ld, n, active, D.Sv32, D.n_obs, lk);
     else
         mm_rate_kernel_f64<<<(unsigned)grid, RATE_BLOCK, 0, st>>>(theta, ld, n, active, D.S, D.v, D.n_obs, lk);
     LAUNCH_CHECK(h);
