@@ -393,6 +393,17 @@ def main():
             "floor_cycles_per_attempt": 674,
             "note": "a solve is a strictly serial chain of ~270 dependent FP64/MUFU instructions per attempted step; "
                     "674 cycles is the same step measured alone on the GPU (profiles/ubench_fp64_r01.log)"}
+    if args.workload == "mm_rate":
+        # SURVEY 8(d) form A: 6 flop per (particle, observation) with the reciprocal counted as one; the kernel
+        # spends 5.5 FMA-pipe lane slots + 0.5 MUFU per term, so lane-slot occupancy is the tighter figure
+        terms = float(evals // world) * lik.n_obs
+        lane_peak = fma[1] / 2.0                      # FMA-pipe lane slots per second (an FFMA is 2 flop)
+        roofline.update(bound="fp32", kernel="mm_rate_kernel_f32 (4 particles per thread, paired reciprocals, f32x2)",
+                        achieved=6.0 * terms / (ms_lik * 1e-3) / 1e12, peak=fma[1] / 1e12,
+                        peak_source="FP32 FFMA micro-benchmark run in this process (smcb_measure_fma_peak)",
+                        fma_pipe_lane_slot_frac=5.5 * terms / (ms_lik * 1e-3) / lane_peak,
+                        terms_per_s=terms / (ms_lik * 1e-3))
+        roofline["frac"] = roofline["achieved"] / roofline["peak"]
     g_ms, g_bytes = gather_microbench(pkg, eng, torch, flush)
     roofline_hbm = {"bound": "hbm", "kernel": "gather_kernel (resampling gather of particle state)",
                     "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
