@@ -316,10 +316,14 @@ class Engine:
         self.moved = torch.zeros(self.n, dtype=torch.uint8, device=dev)
         self.counts = torch.zeros(self.n, dtype=torch.int32, device=dev)
         self.anc = torch.zeros(self.cap, dtype=torch.int32, device=dev)
-        self.scal = torch.zeros(64, dtype=f64, device=dev)       # [0]=max, [2:34]=tempering sums
+        self.scal = torch.zeros(128, dtype=f64, device=dev)      # [0]=max, [1]=accepted sum_w, [2:]=tempering sums
+        self.filled_hist = torch.zeros(max(self.cfg.itr_max, 1) + 1, dtype=torch.int64, device=dev)
+        self._h_mom = torch.zeros(self.d + self.d * self.d, dtype=f64).pin_memory()
+        self._h_cnt = torch.zeros(4, dtype=torch.int64).pin_memory()
         self.mom = torch.zeros(self.d + self.d * self.d, dtype=f64, device=dev)
         self.icnt = torch.zeros(8, dtype=torch.int64, device=dev)  # [0:4] MH counters, [4:6] totals, [6] filled
         self.sendbuf = None
+        self._w_cov = None
         self.prof = None          # name -> list of (start, end) CUDA events when profiling is on
         self._low = np.ascontiguousarray(prior.low)
         self._high = np.ascontiguousarray(prior.high)
@@ -448,11 +452,15 @@ class Engine:
         sums = self.scal[2:2 + 2 * _lib.MAX_CAND]
 
         def eval_batch(gms):
+            """Sums for up to 3*MAX_CAND increments: launches of <= MAX_CAND candidates back to back, ONE D2H."""
             g = np.ascontiguousarray(gms, dtype=np.float64)
-            with self._timed("temper"):
-                self._ck(self.lib.smcb_temper_sums(self.h, self.lk.data_ptr(), self.n, self.scal.data_ptr(),
-                                                   g.ctypes.data, len(g), sums.data_ptr(), st))
-            self.comm.all_reduce_sum(sums[: 2 * len(g)])
+            for o in range(0, len(g), _lib.MAX_CAND):
+                part = g[o:o + _lib.MAX_CAND]
+                dst = self.scal[2 + 2 * o: 2 + 2 * (o + len(part))]
+                with self._timed("temper"):
+                    self._ck(self.lib.smcb_temper_sums(self.h, self.lk.data_ptr(), self.n, self.scal.data_ptr(),
+                                                       part.ctypes.data, len(part), dst.data_ptr(), st))
+            self.comm.all_reduce_sum(self.scal[2: 2 + 2 * len(g)])
             host = self.scal[: 2 + 2 * len(g)].cpu().numpy()   # one D2H: max + sums
             return float(host[0]), host[2:]
 
@@ -467,8 +475,9 @@ class Engine:
                 g_new = (g_new - gamma_old) * cfg.gm_reduction_rate + gamma_old
             g_after_last = g_new
             k_acc, max_lk = None, None
-            for b0 in range(0, len(cands), cfg.cand_batch):
-                batch = cands[b0:b0 + cfg.cand_batch]
+            per_round = 3 * cfg.cand_batch     # the reference's run needs 0..17 back-offs: one rendezvous per stage
+            for b0 in range(0, len(cands), per_round):
+                batch = cands[b0:b0 + per_round]
                 max_lk, s = eval_batch([g - gamma_old for g in batch])
                 for k in range(len(batch)):
                     s1, s2 = float(s[2 * k]), float(s[2 * k + 1])
@@ -488,7 +497,7 @@ class Engine:
             gm = cands[k_acc] - gamma_old
             s1, s2 = float(s[2 * k]), float(s[2 * k + 1])
             ess = 1.0 / (s2 / (s1 * s1)) / N
-            self.scal[1:2].copy_(sums[2 * k:2 * k + 1])
+            self.scal[1:2].copy_(self.scal[2 + 2 * k: 3 + 2 * k])
             return dict(gamma_new=gamma_new, gm=gm, ess=ess, sum_w=s1, max_lk=max_lk, n_backoff=n_back)
 
         # bisection on ESS/N = ess_limit (north_star's alternative rule)
@@ -556,9 +565,8 @@ class Engine:
         return filled
 
     # -------------------------------------------------------------------------------- K4
-    def proposal_factor(self):
-        """cov = np.cov(p_filt.T, bias=True) * w_cov, factorised the way NumPy's legacy
-        multivariate_normal does (SVD): x = z @ (sqrt(s)[:,None] * Vt)."""
+    def _launch_moments(self):
+        """Enqueue column sums and centred second moments of the current particles (device + collectives only)."""
         st, d = self._stream, self.d
         with self._timed("moments"):
             self._ck(self.lib.smcb_colsum(self.h, self.state.data_ptr(), self.n, self.n, d, self.mom.data_ptr(), st))
@@ -570,10 +578,23 @@ class Engine:
             self._ck(self.lib.smcb_centered_moments(self.h, self.state.data_ptr(), self.n, self.n, d,
                                                     mean.data_ptr(), cov_t.data_ptr(), st))
         self.comm.all_reduce_sum(cov_t)
-        cov = cov_t.cpu().numpy().reshape(d, d) / float(self.N)
-        cov = cov * self.cfg.w_cov(d)
-        (u, s, v) = np.linalg.svd(cov)
-        return np.ascontiguousarray(np.sqrt(s)[:, None] * v), cov
+
+    def _factor_from_moments(self, cov_sum):
+        """cov = np.cov(p_filt.T, bias=True) * w_cov, factorised the way NumPy's legacy multivariate_normal
+        does (SVD): x = z @ (sqrt(s)[:,None] * Vt)."""
+        d = self.d
+        cov = np.array(cov_sum, dtype=np.float64).reshape(d, d) / float(self.N)
+        if self._w_cov is None:
+            self._w_cov = self.cfg.w_cov(d)
+        cov = cov * self._w_cov
+        (u, sv, v) = np.linalg.svd(cov)
+        return np.ascontiguousarray(np.sqrt(sv)[:, None] * v), cov
+
+    def proposal_factor(self):
+        """Moments of the current particles -> (F, cov) (`Micmem_SMC_main.py:212-215` + the factor of :220)."""
+        self._launch_moments()
+        d = self.d
+        return self._factor_from_moments(self.mom[d:d + d * d].cpu().numpy())
 
     def mh_sweep(self, gamma, F, ratio, stage, sweep, Z=None, U=None):
         """One sweep: propose, evaluate in-box proposals, accept.  MH counters accumulate in icnt[0:2]."""
@@ -668,8 +689,15 @@ class Engine:
                     if done < n_mh:
                         F, _ = self.proposal_factor()
             else:
+                # One host<->device rendezvous per sweep: after a sweep has been enqueued, the moments the NEXT
+                # sweep would need are enqueued speculatively, and the sweep's counters come back together with
+                # them (if the early-exit rule then stops the stage the moment kernels were wasted: ~20 us).
+                dd = d + d * d
+                self._launch_moments()
+                self._h_mom.copy_(self.mom, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
                 for j in range(n_mh):
-                    F, cov = self.proposal_factor()
+                    F, cov = self._factor_from_moments(self._h_mom[d:dd].numpy())
                     Z = stream.normals(N, d) if stream is not None else None
                     U = stream.uniforms(N) if stream is not None else None
                     if Z is not None and self.comm.world > 1:
@@ -679,9 +707,16 @@ class Engine:
                         hook("sweep", step=step, j=j, engine=self, F=F, cov=cov, gamma=gamma_new, ratio=ratio)
                     self.mh_sweep(gamma_new, F, ratio, step, j, Z, U)
                     n_run += 1
-                    cnt = self.icnt[:4].clone()
-                    self.comm.all_reduce_sum(cnt)
-                    c = cnt.cpu().numpy()
+                    cnt = self.icnt[:4]
+                    if self.comm.world > 1:
+                        cnt = cnt.clone()
+                        self.comm.all_reduce_sum(cnt)
+                    self._h_cnt.copy_(cnt, non_blocking=True)
+                    if j + 1 < n_mh:
+                        self._launch_moments()
+                        self._h_mom.copy_(self.mom, non_blocking=True)
+                    torch.cuda.current_stream(self.device).synchronize()
+                    c = self._h_cnt.numpy()
                     moved, stage_evals, stage_cut = int(c[1]), int(c[2]), int(c[3])
                     if cfg.early_exit and moved > r_th * N:
                         break
@@ -691,7 +726,8 @@ class Engine:
             n_cut += stage_cut
             n_sweeps_total += n_run
             if filled is None:
-                filled = int(self.icnt[6].item())
+                self.filled_hist[step].copy_(self.icnt[6])   # read once, after the run
+                filled = -1
             stages.append(StageRecord(step, gamma_new, t["ess"], t["max_lk"], t["n_backoff"], n_run, moved, logZ,
                                       ratio, filled))
             if hook is not None:
@@ -702,6 +738,11 @@ class Engine:
             gamma_old = gamma_new
         ev1.record()
         ev1.synchronize()
+        if any(sr.filled < 0 for sr in stages):
+            fh = self.filled_hist.cpu().numpy()
+            for sr in stages:
+                if sr.filled < 0:
+                    sr.filled = int(fh[sr.step])
         secs = ev0.elapsed_time(ev1) * 1e-3
         return Result(particles=self.particles().cpu().numpy(), lk=self.lk.cpu().numpy().copy(),
                       betas=[s.gamma for s in stages], ess=[s.ess for s in stages], log_evidence=logZ,
