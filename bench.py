@@ -175,6 +175,26 @@ def cpu_baseline_mm_progress(target_s=15.0):
                       f"(every {stride}th, all 34 sweeps), scipy solve_ivp RK45 via oracle.mm, {dt:.1f} s"}
 
 
+def cpu_config1_run():
+    """BASELINE config 1 on the CPU: the reference's own run (N=1000, its seed, its random stream) through the
+    oracle's restatement of the loop, likelihood sweeps fanned out over all host cores.  Returns seconds."""
+    import multiprocessing as mp
+    from oracle import smc
+    g = np.load(GOLDEN)
+    data = (g["data_t"], g["data_P"], g["data_S0"])
+    cores = os.cpu_count() or 1
+    st = smc.ReferenceStream(int(g["seed"]))
+    p0 = st.prior_uniform([0, 0, 0], [10, 10, 10], 1000)
+    with mp.get_context("fork").Pool(cores) as pool:
+        cpu_sweep(pool, cores, p0[: cores * 4], data)          # warm the workers
+        t0 = time.perf_counter()
+        p, lk, tr = smc.run(lambda th: cpu_sweep(pool, cores, th, data), p0, np.zeros(3), np.full(3, 10.0),
+                            smc.Settings(), st)
+        dt = time.perf_counter() - t0
+    return {"seconds": dt, "stages": len(tr.gamma), "sweeps": int(sum(tr.n_mh)) + 1, "cores": cores,
+            "log_evidence": tr.log_evidence[-1], "posterior_mean": [float(x) for x in p.mean(0)]}
+
+
 def run_reference_arm(args):
     """CPU implementation of the hot path (oracle restatement of the reference) on a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -255,7 +275,9 @@ def gather_microbench(pkg, eng, torch, flush):
 def main():
     args = parse()
     if args.cpu_baseline_only:
-        print(json.dumps(cpu_baseline_mm_progress()), flush=True)
+        out = cpu_baseline_mm_progress()
+        out["config1_run"] = cpu_config1_run()
+        print(json.dumps(out), flush=True)
         return
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -418,6 +440,23 @@ def main():
                     "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
                     "launch_ms": g_ms, "bytes": g_bytes}
 
+    # ---- BASELINE config 1: the reference's own problem size (N = 1000, its seed and random stream) -----------
+    config1 = None
+    if args.workload == "mm_progress" and world == 1:
+        from oracle import smc as osmc          # only the reference's random stream is taken from the checker
+        g1 = np.load(GOLDEN)
+        eng1 = pkg.Engine(lik, prior, pkg.Settings(n_particle=1000, scan_mode="sequential"))
+        t1 = []
+        for it in range(3):
+            st_ref = osmc.ReferenceStream(int(g1["seed"]))
+            p0 = st_ref.prior_uniform([0, 0, 0], [10, 10, 10], 1000)
+            r1 = eng1.run(p0, stream=st_ref)
+            t1.append(r1.seconds)
+        config1 = {"workload": "reference MM run: N=1000, seed 20250205, NumPy legacy stream (same draws as the reference)",
+                   "time_to_beta1_s": float(np.median(t1[1:])), "stages": len(r1.betas), "sweeps": int(sum(r1.n_mh)) + 1,
+                   "log_evidence": r1.log_evidence, "posterior_mean": [float(x) for x in r1.particles.mean(0)]}
+        eng1.close()
+
     # ---- end to end through the public API, host buffers ----------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -474,7 +513,7 @@ def main():
                 "kernel_ms_per_step": {k: {"groups": v[0], "ms": v[1]} for k, v in prof.items()},
                 "kernel_ms_note": "device time of each kernel group in one extra, untimed step",
                 "fp32_fma_peak_tflops": fma[1] / 1e12,
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+                "config1": config1, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
