@@ -295,6 +295,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL announces its version on stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line here
+        os.environ["NCCL_DEBUG"] = os.environ.get("SMCB_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         comm = pkg.TorchComm()
     n_gpus = world

@@ -260,6 +260,11 @@ MM_HD int attempt(Solve& s, const ObsPair* obs, double* pred, unsigned& n_acc, u
         s.h_abs = ha * factor;
         s.rejected = 0;
         n_acc++;
+        // the step ends the solve iff t_new reached t_bound: clipped (last), or t + h_abs hit it exactly
+        const bool done = last || t_new == t_bound;
+        s.t = t_new;
+        s.y = y_new;
+        s.f = k7;
         // dense output for every t_eval in (t_old, t_new] (ivp.py:712-728; t_eval[0] = t0 is emitted by
         // the first step with x = 0)
         if (s.t_next <= t_new) {
@@ -287,12 +292,9 @@ MM_HD int attempt(Solve& s, const ObsPair* obs, double* pred, unsigned& n_acc, u
             s.i_eval = i;
             s.t_next = te;
             s.ssr = ssr;
+            if (!PRED && ssr > s.cut_lim) return CUT;   // residuals only change here
         }
-        s.t = t_new;
-        s.y = y_new;
-        s.f = k7;
-        if (!PRED && s.ssr > s.cut_lim) return CUT;
-        return (t_new - t_bound >= 0) ? DONE : RUNNING;
+        return done ? DONE : RUNNING;
     }
     const double factor = (err < ERR_HI) ? fr : MIN_FACTOR;   // NaN error: MIN_FACTOR, as Python's max()
     s.h_abs = ha * factor;
