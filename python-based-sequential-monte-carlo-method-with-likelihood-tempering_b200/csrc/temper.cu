@@ -10,14 +10,16 @@ namespace {
 
 constexpr int RB = 256;   // reduction block
 
+// vec: lk is 16-byte aligned and pairs are read with one 128-bit load; otherwise (odd leading dimension) the same
+// pairs are read with two 64-bit loads - the element-to-thread mapping, hence every sum, is the same either way.
 __global__ void __launch_bounds__(RB) max_partial_kernel(const double* __restrict__ lk, int64_t n,
-                                                         double* __restrict__ partial) {
+                                                         double* __restrict__ partial, bool vec) {
     __shared__ double sm[32];
     double m = -INFINITY;
     const int64_t stride = (int64_t)gridDim.x * RB * 2;
     for (int64_t i = ((int64_t)blockIdx.x * RB + threadIdx.x) * 2; i < n; i += stride) {
         if (i + 1 < n) {
-            const double2 v = *reinterpret_cast<const double2*>(lk + i);
+            const double2 v = vec ? *reinterpret_cast<const double2*>(lk + i) : make_double2(lk[i], lk[i + 1]);
             m = fmax(m, fmax(v.x, v.y));
         } else {
             m = fmax(m, lk[i]);
@@ -55,7 +57,7 @@ struct GmList {
 template <int K>
 __global__ void __launch_bounds__(RB)
 temper_partial_kernel(const double* __restrict__ lk, int64_t n, const double* __restrict__ max_dev,
-                      const GmList gms, double* __restrict__ partial) {
+                      const GmList gms, double* __restrict__ partial, bool vec) {
     __shared__ double sm[2 * K * 32];
     const double mx = max_dev[0];
     double acc[2 * K];
@@ -66,7 +68,7 @@ temper_partial_kernel(const double* __restrict__ lk, int64_t n, const double* __
         double d0, d1;
         bool two = i + 1 < n;
         if (two) {
-            const double2 v = *reinterpret_cast<const double2*>(lk + i);
+            const double2 v = vec ? *reinterpret_cast<const double2*>(lk + i) : make_double2(lk[i], lk[i + 1]);
             d0 = v.x - mx;
             d1 = v.y - mx;
         } else {
@@ -132,10 +134,10 @@ int final_colsum(smcb_handle* h, const double* partial, int nb, int ncol, double
 extern "C" int smcb_lk_max(smcb_handle* h, const double* lk_dev, int64_t n, double* out_dev, void* stream) {
     REQUIRE(h, h && lk_dev && out_dev && n > 0, SMCB_ERR_INVALID, "null pointer or n<=0");
     REQUIRE(h, h->partial != nullptr, SMCB_ERR_STATE, "smcb_reserve has not been called");
-    REQUIRE(h, (reinterpret_cast<uintptr_t>(lk_dev) & 15) == 0, SMCB_ERR_INVALID, "lk_dev must be 16-byte aligned");
+    const bool vec = (reinterpret_cast<uintptr_t>(lk_dev) & 15) == 0;
     const int nb = reduce_grid(h, n);
     cudaStream_t st = as_stream(stream);
-    max_partial_kernel<<<nb, RB, 0, st>>>(lk_dev, n, h->partial);
+    max_partial_kernel<<<nb, RB, 0, st>>>(lk_dev, n, h->partial, vec);
     LAUNCH_CHECK(h);
     max_final_kernel<<<1, RB, 0, st>>>(h->partial, nb, out_dev);
     LAUNCH_CHECK(h);
@@ -147,7 +149,7 @@ extern "C" int smcb_temper_sums(smcb_handle* h, const double* lk_dev, int64_t n,
     REQUIRE(h, h && lk_dev && max_dev && gm_host && out_dev && n > 0, SMCB_ERR_INVALID, "null pointer or n<=0");
     REQUIRE(h, n_cand >= 1 && n_cand <= SMCB_MAX_CAND, SMCB_ERR_INVALID, "n_cand out of range");
     REQUIRE(h, h->partial != nullptr, SMCB_ERR_STATE, "smcb_reserve has not been called");
-    REQUIRE(h, (reinterpret_cast<uintptr_t>(lk_dev) & 15) == 0, SMCB_ERR_INVALID, "lk_dev must be 16-byte aligned");
+    const bool vec = (reinterpret_cast<uintptr_t>(lk_dev) & 15) == 0;
     GmList g;
     for (int k = 0; k < SMCB_MAX_CAND; ++k) g.gm[k] = (k < n_cand) ? gm_host[k] : 0.0;
     const int nb = reduce_grid(h, n);
@@ -155,19 +157,19 @@ extern "C" int smcb_temper_sums(smcb_handle* h, const double* lk_dev, int64_t n,
     int K;
     if (n_cand <= 1) {
         K = 1;
-        temper_partial_kernel<1><<<nb, RB, 0, st>>>(lk_dev, n, max_dev, g, h->partial);
+        temper_partial_kernel<1><<<nb, RB, 0, st>>>(lk_dev, n, max_dev, g, h->partial, vec);
     } else if (n_cand <= 2) {
         K = 2;
-        temper_partial_kernel<2><<<nb, RB, 0, st>>>(lk_dev, n, max_dev, g, h->partial);
+        temper_partial_kernel<2><<<nb, RB, 0, st>>>(lk_dev, n, max_dev, g, h->partial, vec);
     } else if (n_cand <= 4) {
         K = 4;
-        temper_partial_kernel<4><<<nb, RB, 0, st>>>(lk_dev, n, max_dev, g, h->partial);
+        temper_partial_kernel<4><<<nb, RB, 0, st>>>(lk_dev, n, max_dev, g, h->partial, vec);
     } else if (n_cand <= 8) {
         K = 8;
-        temper_partial_kernel<8><<<nb, RB, 0, st>>>(lk_dev, n, max_dev, g, h->partial);
+        temper_partial_kernel<8><<<nb, RB, 0, st>>>(lk_dev, n, max_dev, g, h->partial, vec);
     } else {
         K = 16;
-        temper_partial_kernel<16><<<nb, RB, 0, st>>>(lk_dev, n, max_dev, g, h->partial);
+        temper_partial_kernel<16><<<nb, RB, 0, st>>>(lk_dev, n, max_dev, g, h->partial, vec);
     }
     LAUNCH_CHECK(h);
     // partial is [nb][2K]; only the first 2*n_cand columns are wanted, but they are the leading

@@ -110,6 +110,50 @@ def test_philox_run_matches_oracle_loop_mm_rate(pkg, scan_mode):
     eng.close()
 
 
+@pytest.mark.parametrize("N", [1, 2, 37, 999, 4099])
+def test_odd_and_tiny_particle_counts(pkg, N):
+    """Ragged sizes through the whole loop (odd leading dimensions: rows of the state are then only 8-byte
+    aligned; N below a warp, N not a multiple of any block size): same run as the oracle loop."""
+    seed = 7
+    lik, prior = _rate_problem(pkg, 120)
+    eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N, seed=seed))
+    eng.sample_prior()
+    p0 = eng.particles().cpu().numpy()
+    res = eng.run(keep_ancestors=True)
+    p, lk, tr = smc.run(lambda th: mm.loglik_rate(th, lik.S, lik.v), p0, prior.low, prior.high,
+                        smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed)
+    assert np.array_equal(np.array(res.betas), np.array(tr.gamma))
+    assert res.n_mh == tr.n_mh and res.n_moved == tr.moved
+    for a, b in zip(res.ancestors, tr.ancestors):
+        assert np.array_equal(a, b)
+    assert np.abs(res.particles - p).max() < 1e-9 and np.abs(res.lk / lk - 1).max() < 1e-9
+    eng.close()
+
+
+def test_mm_progress_small_odd_run(pkg, golden):
+    """The progress-curve path (cost ordering, bulk / tail kernels, early rejection) at N = 37 against the oracle
+    loop driven by the C twin of scipy's RK45."""
+    from oracle import cmm
+    N, seed = 37, 11
+    d = (golden["data_t"], golden["data_P"], golden["data_S0"])
+    lik = pkg.MMProgress(*d)
+    prior = pkg.UniformBox([0, 0, 0], [10, 10, 10])
+    for early in (True, False):
+        eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N, seed=seed, early_reject=early, mm_budget=8))
+        eng.sample_prior()
+        p0 = eng.particles().cpu().numpy()
+        res = eng.run(keep_ancestors=True)
+        p, lk, tr = smc.run(lambda th: cmm.loglik_progress(th, *d)[0], p0, prior.low, prior.high,
+                            smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed)
+        assert np.array_equal(np.array(res.betas), np.array(tr.gamma))
+        assert res.n_mh == tr.n_mh and res.n_moved == tr.moved
+        for a, b in zip(res.ancestors, tr.ancestors):
+            assert np.array_equal(a, b)
+        assert np.abs(res.particles - p).max() < 1e-9 and np.abs(res.lk / lk - 1).max() < 1e-8
+        assert (res.n_eval_cut > 0) == early
+        eng.close()
+
+
 def test_bisection_rule_matches_oracle(pkg):
     N = 2048
     lik, prior = _rate_problem(pkg, 200)
