@@ -14,8 +14,9 @@ from . import _lib
 from .settings import Settings
 from .prior import UniformBox
 from .likelihood import MMProgress, MMRate, KineticRK
+from .artefacts import RunWriter
 
-__all__ = ["Settings", "UniformBox", "MMProgress", "MMRate", "KineticRK", "Engine", "run", "build",
+__all__ = ["Settings", "UniformBox", "MMProgress", "MMRate", "KineticRK", "RunWriter", "Engine", "run", "build",
            "LocalComm", "TorchComm", "migration_plan"]
 
 
