@@ -421,6 +421,25 @@ class Engine:
         """[n_local, d] tensor (AoS copy of the current shard)."""
         return self.state[: self.d].t().contiguous()
 
+    # -------------------------------------------------------------------------------- checkpoint
+    def state_dict(self):
+        """Everything needed to continue the last `run(max_stages=...)` of this shard: particles, their
+        log-likelihoods, gamma, stage counter, log-evidence, counters and the host RNG state (the device RNG is
+        Philox keyed by (seed, particle id, stage, sweep): it has no state to save)."""
+        if getattr(self, "_ckpt", None) is None:
+            raise RuntimeError("state_dict() is available after run()")
+        out = dict(self._ckpt)
+        out["particles"] = self.particles().cpu().numpy()
+        out["lk"] = self.lk.cpu().numpy().copy()
+        out["n_particle"], out["rank"], out["world"], out["seed"] = self.N, self.comm.rank, self.comm.world, self.cfg.seed
+        return out
+
+    def load_state_dict(self, sd):
+        if sd["n_particle"] != self.N or sd["world"] != self.comm.world or sd["rank"] != self.comm.rank:
+            raise ValueError("checkpoint was taken with a different particle count or sharding")
+        self.set_particles(sd["particles"])
+        self.lk.copy_(torch.as_tensor(sd["lk"], dtype=torch.float64))
+
     # -------------------------------------------------------------------------------- K1
     def loglik_into(self, theta, lk_out, active=None, lkmin=None):
         """lk_out[i] = log-likelihood of theta[:, i] (active: byte mask of the particles to evaluate;
@@ -636,13 +655,16 @@ class Engine:
                                             self.icnt.data_ptr(), self._stream))
 
     # -------------------------------------------------------------------------------- the loop
-    def run(self, particles=None, stream=None, keep_ancestors=False, hook=None):
+    def run(self, particles=None, stream=None, keep_ancestors=False, hook=None, max_stages=None, resume=None):
         """Tempered SMC from gamma=0 to gamma=1.
 
-        particles: [n_local, d] initial (prior) particles, or None to use what `set_particles` /
-                   `sample_prior` left on the device.
-        stream:    optional object with u0(), normals(N, d), uniforms(N) supplying the random inputs
-                   (parity mode); default is one seeded host draw for u0 and Philox on the device.
+        particles:  [n_local, d] initial (prior) particles, or None to use what `set_particles` /
+                    `sample_prior` left on the device.
+        stream:     optional object with u0(), normals(N, d), uniforms(N) supplying the random inputs
+                    (parity mode); default is one seeded host draw for u0 and Philox on the device.
+        max_stages: stop after this many stages (the state can then be saved with `state_dict`).
+        resume:     a `state_dict()` of this shard taken at a stage boundary: the run continues from there and
+                    ends exactly where the uninterrupted run would have.
         """
         cfg, N, d = self.cfg, self.N, self.d
         if particles is not None:
@@ -650,13 +672,22 @@ class Engine:
         host_rng = np.random.RandomState(cfg.seed)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        self.sim_particle()
-        n_eval, n_sweeps_total = N, 0    # evaluations requested (global): N + in-box proposals of every sweep
-        n_cut = 0                        # of those, proposals rejected early (reported -inf before all observations)
-        gamma_old, logZ = 0.0, 0.0
+        gamma_old, logZ, first_step = 0.0, 0.0, 1
         stages, ancestors = [], []
+        if resume is None:
+            self.sim_particle()
+            n_eval, n_sweeps_total = N, 0    # evaluations requested (global): N + in-box proposals of every sweep
+            n_cut = 0                        # of those, proposals rejected early (reported -inf before all observations)
+        else:
+            self.load_state_dict(resume)
+            host_rng.set_state(resume["host_rng_state"])
+            gamma_old, logZ, first_step = float(resume["gamma"]), float(resume["log_evidence"]), int(resume["step"]) + 1
+            n_eval, n_cut, n_sweeps_total = int(resume["n_eval"]), int(resume["n_eval_cut"]), int(resume["n_sweeps"])
+            stages = list(resume["stages"])
         reached = False
-        for step in range(1, cfg.itr_max):
+        for step in range(first_step, cfg.itr_max):
+            if max_stages is not None and step - first_step >= max_stages:
+                break
             t = self.temper(gamma_old)
             gamma_new, gm = t["gamma_new"], t["gm"]
             logZ += math.log(t["sum_w"] / N) + gm * t["max_lk"]
@@ -744,6 +775,9 @@ class Engine:
                 if sr.filled < 0:
                     sr.filled = int(fh[sr.step])
         secs = ev0.elapsed_time(ev1) * 1e-3
+        self._ckpt = dict(gamma=gamma_old if not reached else 1.0, log_evidence=logZ,
+                          step=stages[-1].step if stages else 0, n_eval=n_eval, n_eval_cut=n_cut,
+                          n_sweeps=n_sweeps_total, stages=list(stages), host_rng_state=host_rng.get_state())
         return Result(particles=self.particles().cpu().numpy(), lk=self.lk.cpu().numpy().copy(),
                       betas=[s.gamma for s in stages], ess=[s.ess for s in stages], log_evidence=logZ,
                       n_moved=[s.moved for s in stages], n_mh=[s.n_mh for s in stages], stages=stages,

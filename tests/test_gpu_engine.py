@@ -154,6 +154,29 @@ def test_mm_progress_small_odd_run(pkg, golden):
         eng.close()
 
 
+def test_checkpoint_resume_is_exact(pkg, tmp_path):
+    """stop after 3 stages, save, resume in a fresh engine -> the uninterrupted run, bit for bit."""
+    import pickle
+    N = 3000
+    lik, prior = _rate_problem(pkg, 150)
+    cfg = pkg.Settings(n_particle=N, seed=5)
+    eng = pkg.Engine(lik, prior, cfg)
+    eng.sample_prior()
+    full = eng.run()
+    eng.sample_prior()
+    part = eng.run(max_stages=3)
+    assert len(part.betas) == 3 and not part.reached_one and part.betas == full.betas[:3]
+    with open(tmp_path / "ckpt.pkl", "wb") as f:
+        pickle.dump(eng.state_dict(), f)
+    eng.close()
+    eng2 = pkg.Engine(lik, prior, cfg)
+    rest = eng2.run(resume=pickle.load(open(tmp_path / "ckpt.pkl", "rb")))
+    assert rest.reached_one and rest.betas == full.betas and rest.n_mh == full.n_mh and rest.n_moved == full.n_moved
+    assert rest.log_evidence == full.log_evidence and rest.n_eval == full.n_eval
+    assert np.array_equal(rest.particles, full.particles) and np.array_equal(rest.lk, full.lk)
+    eng2.close()
+
+
 def test_bisection_rule_matches_oracle(pkg):
     N = 2048
     lik, prior = _rate_problem(pkg, 200)
