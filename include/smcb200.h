@@ -189,23 +189,31 @@ int smcb_mh_propose(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t
                     const double* F_host, double ratio, const double* low_host, const double* high_host,
                     const double* z_dev, uint64_t seed, uint64_t id_offset, uint32_t stage, uint32_t sweep,
                     double* prop_dev, int64_t ld_prop, uint8_t* inbox_dev, void* stream);
-/* Accept step (EX/main:231-241): r = exp((lk2-lk1)*gamma)*inbox >= u; theta/lk updated in place;
+/* Accept step (EX/main:231-241): r = exp((lk2-lk1)*gamma)*inbox [* exp(dlp)] >= u; theta/lk updated in place;
  * moved_dev[i] |= r; counts_dev int64[4] += {accepted this sweep, newly moved, in-box proposals
  * (= likelihood evaluations this sweep requested), in-box proposals whose lk2 is -inf (= rejected early
  * by smcb_loglik_bounded before every observation was integrated)}.
  *   u_dev: external uniforms [n] or NULL = Philox (same key, separate stream id). */
 int smcb_mh_accept(smcb_handle* h, double* theta_dev, int64_t ld, double* lk_dev, const double* prop_dev,
                    int64_t ld_prop, const double* lk2_dev, const uint8_t* inbox_dev, int64_t n, int d,
-                   double gamma, const double* u_dev, uint64_t seed, uint64_t id_offset, uint32_t stage,
-                   uint32_t sweep, uint8_t* moved_dev, int64_t* counts_dev, void* stream);
+                   double gamma, const double* u_dev, const double* dlp_dev, uint64_t seed, uint64_t id_offset,
+                   uint32_t stage, uint32_t sweep, uint8_t* moved_dev, int64_t* counts_dev, void* stream);
 /* Early-rejection threshold for smcb_loglik_bounded: with u the uniform smcb_mh_accept will draw for
  * particle i (same u_dev / Philox key), the proposal is certainly rejected if
  *     lk2 < lkmin[i] = lk1[i] + log(u)/gamma - margin,   margin = 1e-9*(1 + |lk1| + |log u|/gamma),
  * because then exp((lk2-lk1)*gamma) < u even after rounding.  u == 0, gamma <= 0 or a non-finite lk1 give
  * -inf (never reject early).  Out-of-box particles (inbox == 0) get -inf as well; they are not evaluated. */
 int smcb_mh_threshold(smcb_handle* h, const double* lk_dev, const uint8_t* inbox_dev, int64_t n, double gamma,
-                      const double* u_dev, uint64_t seed, uint64_t id_offset, uint32_t stage, uint32_t sweep,
-                      double* lkmin_dev, void* stream);
+                      const double* u_dev, const double* dlp_dev, uint64_t seed, uint64_t id_offset, uint32_t stage,
+                      uint32_t sweep, double* lkmin_dev, void* stream);
+/* Mixed normal / uniform priors (the reference's `pp = exp(px*gamma) * (p0_2/p0_1)`, SMC_methanation_main.py:359-375,
+ * cal_prior SMC_example/Micmem_SMC_main.py:60-90): out_dev[i] = log p(prop_i) - log p(theta_i) over the normally
+ * distributed parameters, sum_k inv2var_k*((theta_k-mu_k)^2 - (prop_k-mu_k)^2) with inv2var_k = 1/(2 sigma_k^2), 0 for a
+ * uniform parameter (those enter through the box test of smcb_mh_propose; give them low/high, and -inf/+inf to the
+ * normal ones).  Pass the result as dlp_dev to smcb_mh_threshold and smcb_mh_accept (NULL = uniform priors only). */
+int smcb_prior_logratio(smcb_handle* h, const double* theta_dev, int64_t ld, const double* prop_dev, int64_t ld_prop,
+                        int64_t n, int d, const double* mu_host, const double* inv2var_host, const uint8_t* inbox_dev,
+                        double* out_dev, void* stream);
 /* Several MH sweeps fused in one launch with a frozen proposal factor (documented deviation from
  * the per-sweep covariance refresh of EX/main:212): propose + box + likelihood + accept, particle
  * state held in registers.  KINETIC_RK.  counts_dev int64[3] as for smcb_mh_accept. */

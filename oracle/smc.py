@@ -180,8 +180,11 @@ def in_box(theta, low, high):
     return np.all((theta >= low) & (theta <= high), axis=1)
 
 
-def mh_sweep(p_filt, lk1, gamma_new, F, Z, U, mhstep_ratio, loglik, low, high):
+def mh_sweep(p_filt, lk1, gamma_new, F, Z, U, mhstep_ratio, loglik, low, high, log_prior_ratio=None):
     """One sweep.  Z: f64[N,d] standard normals, U: f64[N] uniforms.
+    log_prior_ratio(theta_new, theta_old) -> log p(new) - log p(old) for priors with normal components: the
+    reference's `pp = np.exp(px * gamma_new) * (p0_2/p0_1)` (`SMC_methanation_main.py:359-375`; never reached
+    in its shipped configuration), written with the log ratio so that far-out particles do not give 0/0.
     Returns (p_filt', lk1', r int32[N], n_eval)."""
     step = np.dot(Z, F)
     p_pred = p_filt + step * mhstep_ratio
@@ -190,6 +193,8 @@ def mh_sweep(p_filt, lk1, gamma_new, F, Z, U, mhstep_ratio, loglik, low, high):
     lk2 = np.asarray(loglik(p_pred), dtype=np.float64)
     with np.errstate(over="ignore", invalid="ignore"):
         pp = np.exp((lk2 - lk1) * gamma_new) * p0
+        if log_prior_ratio is not None:
+            pp = pp * np.exp(np.where(p0 > 0, log_prior_ratio(p_pred, p_filt), 0.0))
     r = (pp >= U).astype(np.int32)
     sel = r.astype(bool)
     p_new = np.where(sel[:, None], p_pred, p_filt)
@@ -273,7 +278,8 @@ class Trace:
     n_eval: int = 0
 
 
-def run(loglik, p_pred, low, high, cfg: Settings, stream, lk0=None, hook=None, resampler=None, early_exit=True):
+def run(loglik, p_pred, low, high, cfg: Settings, stream, lk0=None, hook=None, resampler=None, early_exit=True,
+        log_prior_ratio=None):
     """Whole tempered-SMC run.  Returns (particles, lk, Trace).
 
     resampler: `resample_sequential` (the reference, default) or `resample_fixed` (the engine's
@@ -312,7 +318,7 @@ def run(loglik, p_pred, low, high, cfg: Settings, stream, lk0=None, hook=None, r
                 hook("sweep", step=step, j=j, p_filt=p_filt, lk1=lk1, cov=cov_m, F=F, Z=Z, U=U,
                      gamma=gamma_new, ratio=mhstep_ratio)
             p_filt, lk1, r, ne = mh_sweep(p_filt, lk1, gamma_new, F, Z, U, mhstep_ratio,
-                                          loglik, low, high)
+                                          loglik, low, high, log_prior_ratio)
             tr.n_eval += N          # the reference evaluates all N (out-of-box ones at the old point)
             r_ac = np.maximum(r_ac, r)
             n_run += 1

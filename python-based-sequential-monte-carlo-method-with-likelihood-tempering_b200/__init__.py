@@ -12,11 +12,11 @@ or through the `smcb200` alias module at the repository root.
 """
 from . import _lib
 from .settings import Settings
-from .prior import UniformBox
+from .prior import UniformBox, IndependentPrior
 from .likelihood import MMProgress, MMRate, KineticRK
 from .artefacts import RunWriter
 
-__all__ = ["Settings", "UniformBox", "MMProgress", "MMRate", "KineticRK", "RunWriter", "Engine", "run", "build",
+__all__ = ["Settings", "UniformBox", "IndependentPrior", "MMProgress", "MMRate", "KineticRK", "RunWriter", "Engine", "run", "build",
            "LocalComm", "TorchComm", "migration_plan"]
 
 

@@ -43,8 +43,10 @@ _SIGNATURES = {
     "smcb_mh_propose": [p_void, p_void, c_i64, c_i64, c_int, p_void, c_dbl, p_void, p_void, p_void, c_u64, c_u64,
                         c_u32, c_u32, p_void, c_i64, p_void, p_void],
     "smcb_mh_accept": [p_void, p_void, c_i64, p_void, p_void, c_i64, p_void, p_void, c_i64, c_int, c_dbl, p_void,
-                       c_u64, c_u64, c_u32, c_u32, p_void, p_void, p_void],
-    "smcb_mh_threshold": [p_void, p_void, p_void, c_i64, c_dbl, p_void, c_u64, c_u64, c_u32, c_u32, p_void, p_void],
+                       p_void, c_u64, c_u64, c_u32, c_u32, p_void, p_void, p_void],
+    "smcb_prior_logratio": [p_void, p_void, c_i64, p_void, c_i64, c_i64, c_int, p_void, p_void, p_void, p_void, p_void],
+    "smcb_mh_threshold": [p_void, p_void, p_void, c_i64, c_dbl, p_void, p_void, c_u64, c_u64, c_u32, c_u32, p_void,
+                          p_void],
     "smcb_mh_fused": [p_void, c_int, p_void, c_i64, p_void, c_i64, c_int, p_void, c_dbl, p_void, p_void, c_dbl,
                       c_int, c_u64, c_u64, c_u32, c_u32, p_void, p_void, p_void],
     "smcb_philox_draws": [p_void, c_i64, c_int, c_u64, c_u64, c_u32, c_u32, p_void, p_void, p_void],

@@ -169,8 +169,9 @@ propose_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, int d_rt
 __global__ void __launch_bounds__(MB)
 accept_kernel(double* __restrict__ theta, int64_t ld, double* __restrict__ lk, const double* __restrict__ prop,
               int64_t ld_prop, const double* __restrict__ lk2, const uint8_t* __restrict__ inbox, int64_t n, int d,
-              double gamma, const double* __restrict__ u_ext, uint64_t seed, uint64_t id_offset, uint32_t stage,
-              uint32_t sweep, uint8_t* __restrict__ moved, unsigned long long* __restrict__ counts) {
+              double gamma, const double* __restrict__ u_ext, const double* __restrict__ dlp, uint64_t seed,
+              uint64_t id_offset, uint32_t stage, uint32_t sweep, uint8_t* __restrict__ moved,
+              unsigned long long* __restrict__ counts) {
     __shared__ long long sm[4][32];
     const int64_t i = (int64_t)blockIdx.x * MB + threadIdx.x;
     long long acc = 0, newly = 0, evald = 0, ninf = 0;
@@ -185,6 +186,7 @@ accept_kernel(double* __restrict__ theta, int64_t ld, double* __restrict__ lk, c
             l2 = lk2[i];
             ninf = (l2 == -INFINITY);   // rejected early by smcb_loglik_bounded (or a genuinely impossible proposal)
             pp = exp(__dmul_rn(__dsub_rn(l2, lk[i]), gamma));   // exp(px*gamma_new)*p0
+            if (dlp != nullptr) pp *= exp(dlp[i]);              // * p(theta')/p(theta)  (methanation main:369)
         }
         const bool r = pp >= u;   // NaN compares false, as in NumPy
         if (r) {
@@ -235,8 +237,8 @@ accept_kernel(double* __restrict__ theta, int64_t ld, double* __restrict__ lk, c
 // subtraction, the product and exp(), so the test fails for certain.
 __global__ void __launch_bounds__(MB)
 threshold_kernel(const double* __restrict__ lk, const uint8_t* __restrict__ inbox, int64_t n, double gamma,
-                 const double* __restrict__ u_ext, uint64_t seed, uint64_t id_offset, uint32_t stage, uint32_t sweep,
-                 double* __restrict__ lkmin) {
+                 const double* __restrict__ u_ext, const double* __restrict__ dlp, uint64_t seed, uint64_t id_offset,
+                 uint32_t stage, uint32_t sweep, double* __restrict__ lkmin) {
     const int64_t i = (int64_t)blockIdx.x * MB + threadIdx.x;
     if (i >= n) return;
     double thr = -INFINITY;
@@ -246,12 +248,35 @@ threshold_kernel(const double* __restrict__ lk, const uint8_t* __restrict__ inbo
                              : philox_uniform(seed, id_offset + (uint64_t)i, stage, sweep, SMCB_SLOT_UNIFORM);
         const double l1 = lk[i];
         if (u > 0.0 && gamma > 0.0 && isfinite(l1)) {
-            const double lu = log(u) / gamma;   // <= 0 (u < 1); u >= 1 gives lu >= 0: any finite lk2 might still pass
+            // with a prior ratio the test is exp((lk2-lk1)*gamma + dlp) >= u: log(u) - dlp takes the place of log(u)
+            const double lu = (log(u) - (dlp != nullptr ? dlp[i] : 0.0)) / gamma;
             thr = l1 + lu - 1e-9 * (1.0 + fabs(l1) + fabs(lu));
             if (!(thr == thr)) thr = -INFINITY;
         }
     }
     lkmin[i] = thr;
+}
+
+// ---- log prior ratio of independent normal components ----------------------------------------------
+// out[i] = sum_k inv2var_k * ((theta_k - mu_k)^2 - (prop_k - mu_k)^2) = log p(prop) - log p(theta) over the
+// normally distributed parameters (inv2var_k = 1/(2 sigma_k^2); 0 marks a uniform one, whose ratio is 1 in-box).
+__global__ void __launch_bounds__(MB)
+prior_logratio_kernel(const double* __restrict__ theta, int64_t ld, const double* __restrict__ prop, int64_t ld_prop,
+                      int64_t n, int d, const __grid_constant__ MhParams prm, const uint8_t* __restrict__ inbox,
+                      double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * MB + threadIdx.x;
+    if (i >= n) return;
+    double acc = 0.0;
+    if (inbox == nullptr || inbox[i]) {
+        for (int k = 0; k < d; ++k) {
+            const double iv = prm.high[k];            // inv2var
+            if (iv > 0.0) {
+                const double a = theta[(int64_t)k * ld + i] - prm.low[k], b = prop[(int64_t)k * ld_prop + i] - prm.low[k];
+                acc += iv * (a * a - b * b);
+            }
+        }
+    }
+    out[i] = acc;
 }
 
 __global__ void philox_draws_kernel(int64_t n, int d, uint64_t seed, uint64_t id_offset, uint32_t stage,
@@ -369,26 +394,44 @@ extern "C" int smcb_mh_propose(smcb_handle* h, const double* theta_dev, int64_t 
     return SMCB_OK;
 }
 
+extern "C" int smcb_prior_logratio(smcb_handle* h, const double* theta_dev, int64_t ld, const double* prop_dev,
+                                   int64_t ld_prop, int64_t n, int d, const double* mu_host, const double* inv2var_host,
+                                   const uint8_t* inbox_dev, double* out_dev, void* stream) {
+    REQUIRE(h, h && theta_dev && prop_dev && mu_host && inv2var_host && out_dev, SMCB_ERR_INVALID, "null pointer");
+    REQUIRE(h, n > 0 && d >= 1 && d <= SMCB_MAX_DIM && ld >= n && ld_prop >= n, SMCB_ERR_INVALID, "bad size");
+    MhParams prm;
+    memset(&prm, 0, sizeof(prm));
+    for (int k = 0; k < d; ++k) {
+        prm.low[k] = mu_host[k];
+        prm.high[k] = inv2var_host[k];
+    }
+    prior_logratio_kernel<<<(unsigned)((n + MB - 1) / MB), MB, 0, as_stream(stream)>>>(theta_dev, ld, prop_dev, ld_prop, n,
+                                                                                   d, prm, inbox_dev, out_dev);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
 extern "C" int smcb_mh_threshold(smcb_handle* h, const double* lk_dev, const uint8_t* inbox_dev, int64_t n, double gamma,
-                                 const double* u_dev, uint64_t seed, uint64_t id_offset, uint32_t stage,
-                                 uint32_t sweep, double* lkmin_dev, void* stream) {
+                                 const double* u_dev, const double* dlp_dev, uint64_t seed, uint64_t id_offset,
+                                 uint32_t stage, uint32_t sweep, double* lkmin_dev, void* stream) {
     REQUIRE(h, h && lk_dev && lkmin_dev && n > 0, SMCB_ERR_INVALID, "bad argument");
-    threshold_kernel<<<(unsigned)((n + MB - 1) / MB), MB, 0, as_stream(stream)>>>(lk_dev, inbox_dev, n, gamma, u_dev, seed,
-                                                                              id_offset, stage, sweep, lkmin_dev);
+    threshold_kernel<<<(unsigned)((n + MB - 1) / MB), MB, 0, as_stream(stream)>>>(
+        lk_dev, inbox_dev, n, gamma, u_dev, dlp_dev, seed, id_offset, stage, sweep, lkmin_dev);
     LAUNCH_CHECK(h);
     return SMCB_OK;
 }
 
 extern "C" int smcb_mh_accept(smcb_handle* h, double* theta_dev, int64_t ld, double* lk_dev, const double* prop_dev,
                               int64_t ld_prop, const double* lk2_dev, const uint8_t* inbox_dev, int64_t n, int d,
-                              double gamma, const double* u_dev, uint64_t seed, uint64_t id_offset, uint32_t stage,
-                              uint32_t sweep, uint8_t* moved_dev, int64_t* counts_dev, void* stream) {
+                              double gamma, const double* u_dev, const double* dlp_dev, uint64_t seed,
+                              uint64_t id_offset, uint32_t stage, uint32_t sweep, uint8_t* moved_dev,
+                              int64_t* counts_dev, void* stream) {
     REQUIRE(h, h && theta_dev && lk_dev && prop_dev && lk2_dev && inbox_dev && moved_dev && counts_dev,
             SMCB_ERR_INVALID, "null pointer");
     REQUIRE(h, n > 0 && d >= 1 && d <= SMCB_MAX_DIM && ld >= n && ld_prop >= n, SMCB_ERR_INVALID, "bad size");
     accept_kernel<<<(unsigned)((n + MB - 1) / MB), MB, 0, as_stream(stream)>>>(
-        theta_dev, ld, lk_dev, prop_dev, ld_prop, lk2_dev, inbox_dev, n, d, gamma, u_dev, seed, id_offset, stage,
-        sweep, moved_dev, reinterpret_cast<unsigned long long*>(counts_dev));
+        theta_dev, ld, lk_dev, prop_dev, ld_prop, lk2_dev, inbox_dev, n, d, gamma, u_dev, dlp_dev, seed, id_offset,
+        stage, sweep, moved_dev, reinterpret_cast<unsigned long long*>(counts_dev));
     LAUNCH_CHECK(h);
     return SMCB_OK;
 }

@@ -327,6 +327,11 @@ class Engine:
         self.prof = None          # name -> list of (start, end) CUDA events when profiling is on
         self._low = np.ascontiguousarray(prior.low)
         self._high = np.ascontiguousarray(prior.high)
+        self.dlp = None           # log prior ratio of the current proposals (priors with normal components only)
+        if getattr(prior, "has_normal", False):
+            if self.cfg.fused_sweeps > 0:
+                raise NotImplementedError("fused sweeps support uniform priors only")
+            self.dlp = torch.zeros(self.n, dtype=f64, device=dev)
 
     # -------------------------------------------------------------------------------- helpers
     def _ck(self, rc):
@@ -411,11 +416,23 @@ class Engine:
         self.state[: self.d].copy_(p.to(self.device, non_blocking=True).t())
 
     def sample_prior(self, seed=None):
-        """Uniform box prior drawn on the device with Philox (keyed by global particle id)."""
+        """Prior sample drawn on the device with Philox (keyed by global particle id): uniform components by
+        smcb_sample_uniform_box, normal ones as mu + sigma*z with the z of smcb_philox_draws (stage 0xFFFFFFFE)."""
         seed = self.cfg.seed if seed is None else seed
+        low, high = self._low, self._high
+        if self.dlp is not None:        # finite stand-ins for the unbounded components; overwritten below
+            low = np.where(np.isfinite(low), low, 0.0)
+            high = np.where(np.isfinite(high), high, 1.0)
         self._ck(self.lib.smcb_sample_uniform_box(self.h, self.state.data_ptr(), self.n, self.n, self.d,
-                                                  self._low.ctypes.data, self._high.ctypes.data, seed,
+                                                  low.ctypes.data, high.ctypes.data, seed,
                                                   self.id_offset, self._stream))
+        if self.dlp is not None:
+            z = torch.empty((self.n, self.d), dtype=torch.float64, device=self.device)
+            self._ck(self.lib.smcb_philox_draws(self.h, self.n, self.d, seed, self.id_offset, 0xFFFFFFFE, 0,
+                                                z.data_ptr(), None, self._stream))
+            for k, (kind, a, b) in enumerate(self.prior.dists):
+                if kind == "normal":
+                    self.state[k].copy_(a + b * z[:, k])
 
     def particles(self):
         """[n_local, d] tensor (AoS copy of the current shard)."""
@@ -631,18 +648,25 @@ class Engine:
             self._ck(lib.smcb_mh_propose(h, self.state.data_ptr(), self.n, self.n, d, F.ctypes.data, ratio,
                                          self._low.ctypes.data, self._high.ctypes.data, z_ptr, seed, self.id_offset,
                                          stage, sweep, self.prop.data_ptr(), self.n, self.inbox.data_ptr(), st))
+        dlp_ptr = None
+        if self.dlp is not None:
+            # log p(theta') - log p(theta) over the normal components: pp = exp(px*gamma) * p0_2/p0_1 (main:369)
+            self._ck(lib.smcb_prior_logratio(h, self.state.data_ptr(), self.n, self.prop.data_ptr(), self.n, self.n, d,
+                                             self.prior.mu.ctypes.data, self.prior.inv2var.ctypes.data,
+                                             self.inbox.data_ptr(), self.dlp.data_ptr(), st))
+            dlp_ptr = self.dlp.data_ptr()
         lkmin = None
         if self.cfg.early_reject:
             # value below which the accept test below is certain to fail: the likelihood kernel may stop there
             lkmin = self.lkmin
             with self._timed("propose"):
-                self._ck(lib.smcb_mh_threshold(h, self.lk.data_ptr(), self.inbox.data_ptr(), self.n, gamma, u_ptr, seed,
-                                               self.id_offset, stage, sweep, lkmin.data_ptr(), st))
+                self._ck(lib.smcb_mh_threshold(h, self.lk.data_ptr(), self.inbox.data_ptr(), self.n, gamma, u_ptr,
+                                               dlp_ptr, seed, self.id_offset, stage, sweep, lkmin.data_ptr(), st))
         self.loglik_into(self.prop, self.lk2, active=self.inbox, lkmin=lkmin)
         with self._timed("accept"):
             self._ck(lib.smcb_mh_accept(h, self.state.data_ptr(), self.n, self.lk.data_ptr(), self.prop.data_ptr(),
                                         self.n, self.lk2.data_ptr(), self.inbox.data_ptr(), self.n, d, gamma, u_ptr,
-                                        seed, self.id_offset, stage, sweep, self.moved.data_ptr(),
+                                        dlp_ptr, seed, self.id_offset, stage, sweep, self.moved.data_ptr(),
                                         self.icnt.data_ptr(), st))
 
     def mh_fused(self, gamma, F, ratio, stage, sweep0, n_sweeps):

@@ -154,6 +154,40 @@ def test_mm_progress_small_odd_run(pkg, golden):
         eng.close()
 
 
+def test_mixed_normal_uniform_prior_matches_oracle_loop(pkg):
+    """normal + uniform components, density ratio in the MH test, against the oracle loop."""
+    from oracle import philox
+    N, seed = 4096, 3
+    lik = pkg.MMRate.synthetic(150)
+    prior = pkg.IndependentPrior.from_priors({"Vmax": {"dist": "normal", "mu": 1.0, "sigma": 0.5},
+                                             "Km": {"dist": "uniform", "low": 0, "high": 10},
+                                             "sigma": {"dist": "uniform", "low": 0, "high": 10}})
+    eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N, seed=seed))
+    eng.sample_prior()
+    p0 = eng.particles().cpu().numpy()
+    ids = np.arange(N, dtype=np.uint64)
+    z = philox.normals(seed, ids, 0xFFFFFFFE, 0, 3)
+    ub = philox.uniform_box(seed, ids, np.array([0.0, 0.0, 0.0]), np.array([1.0, 10.0, 10.0]))
+    assert np.abs(p0[:, 0] - (1.0 + 0.5 * z[:, 0])).max() < 1e-12 and np.array_equal(p0[:, 1:], ub[:, 1:])
+    res = eng.run(keep_ancestors=True)
+    p, lk, tr = smc.run(lambda th: mm.loglik_rate(th, lik.S, lik.v), p0, prior.low, prior.high,
+                        smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed,
+                        log_prior_ratio=prior.log_ratio)
+    assert np.array_equal(np.array(res.betas), np.array(tr.gamma))
+    assert res.n_mh == tr.n_mh and res.n_moved == tr.moved
+    for a, b in zip(res.ancestors, tr.ancestors):
+        assert np.array_equal(a, b)
+    assert np.abs(res.particles - p).max() < 1e-9 and np.abs(res.lk / lk - 1).max() < 1e-9
+    # the ratio does matter here: the same run with the uniform box alone ends elsewhere
+    p_u, _, tr_u = smc.run(lambda th: mm.loglik_rate(th, lik.S, lik.v), p0, prior.low, prior.high,
+                           smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed)
+    assert tr_u.moved != tr.moved
+    # log-ratio form == the reference's pdf-ratio form where the pdfs are representable
+    th_a, th_b = p[:100], p0[:100]
+    assert np.allclose(np.exp(prior.log_ratio(th_a, th_b)), prior.pdf(th_a) / prior.pdf(th_b), rtol=1e-10)
+    eng.close()
+
+
 def test_checkpoint_resume_is_exact(pkg, tmp_path):
     """stop after 3 stages, save, resume in a fresh engine -> the uninterrupted run, bit for bit."""
     import pickle

@@ -121,7 +121,7 @@ def test_mh_threshold_is_conservative(abi):
     for gamma in (0.0023263051398720674, 0.37, 1.0):
         out = abi.zeros(n)
         lt, ut, it = abi.t(lk1), abi.t(u), abi.t(inbox, torch.uint8)
-        abi.ck(abi.lib.smcb_mh_threshold(abi.h, lt.data_ptr(), it.data_ptr(), n, gamma, ut.data_ptr(), 0, 0, 0, 0,
+        abi.ck(abi.lib.smcb_mh_threshold(abi.h, lt.data_ptr(), it.data_ptr(), n, gamma, ut.data_ptr(), None, 0, 0, 0, 0,
                                          out.data_ptr(), None))
         thr = out.cpu().numpy()
         assert np.all(np.isneginf(thr[inbox == 0])) and np.isneginf(thr[0]) and np.all(np.isneginf(thr[4:7]))
@@ -454,7 +454,7 @@ def test_propose_and_accept_match_oracle(abi, d):
     # z @ F is accumulated in the same order as np.dot for d<=8 up to FMA contraction
     assert np.abs(got_prop - prop_ref).max() < 1e-13 * 10
     abi.ck(abi.lib.smcb_mh_accept(abi.h, th.data_ptr(), n, lk.data_ptr(), prop.data_ptr(), n, lk2t.data_ptr(),
-                                  inbox.data_ptr(), n, d, gamma, Ut.data_ptr(), 1, 0, 1, 0, moved.data_ptr(),
+                                  inbox.data_ptr(), n, d, gamma, Ut.data_ptr(), None, 1, 0, 1, 0, moved.data_ptr(),
                                   cnt.data_ptr(), None))
     torch.cuda.synchronize()
     assert np.array_equal(moved.cpu().numpy(), r.astype(np.uint8))
