@@ -471,7 +471,8 @@ def main():
         for it in range(1 + max(1, min(args.steps, 2))):
             barrier()
             t0 = time.perf_counter()
-            r = pkg.run(lik, prior, particles=host_p, settings=cfg, comm=comm)     # H2D + run + D2H inside
+            r = pkg.run(lik, prior, particles=host_p, settings=cfg, comm=comm)     # H2D + run inside
+            post, post_lk = r.particles, r.lk                                      # D2H of the result
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if world > 1:

@@ -221,22 +221,63 @@ class StageRecord:
     filled: int
 
 
-@dataclass
+_PINNED = {}
+
+
+def _to_host(t):
+    """Device tensor -> fresh NumPy array through a cached pinned staging buffer (a pageable D2H runs at a fifth
+    of the pinned rate; the staging buffer is reused, the returned array is the caller's own)."""
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    buf = _PINNED.get(t.dtype)
+    if buf is None or buf.numel() < t.numel():
+        buf = torch.empty(max(t.numel(), 1), dtype=t.dtype).pin_memory()
+        _PINNED[t.dtype] = buf
+    stage = buf[: t.numel()].view(t.shape)
+    stage.copy_(t)
+    return stage.numpy().copy()
+
+
 class Result:
-    particles: np.ndarray            # [N, d] posterior particles (this rank's shard when sharded)
-    lk: np.ndarray                   # [N]
-    betas: list
-    ess: list
-    log_evidence: float
-    n_moved: list
-    n_mh: list
-    stages: list
-    n_eval: int                      # particle log-likelihood evaluations requested on the device (global)
-    n_eval_cut: int                  # of those, proposals whose rejection was proven before the last observation
-    n_eval_reference: int            # what the reference would have evaluated: N * (1 + sweeps)
-    seconds: float                   # device time first sweep -> end of gamma=1 block
-    reached_one: bool
-    ancestors: list = field(default_factory=list)
+    """What a run returns.  Scalars and per-stage records are host values; the posterior particles and their
+    log-likelihoods stay on the device (a snapshot of this shard's state) and are copied to the host the first
+    time `particles` / `lk` is read."""
+
+    def __init__(self, state_dev, d, betas, ess, log_evidence, n_moved, n_mh, stages, n_eval, n_eval_cut,
+                 n_eval_reference, seconds, reached_one, ancestors=None):
+        self._state, self._d = state_dev, d
+        self._particles = self._lk = None
+        self.betas, self.ess, self.log_evidence = betas, ess, log_evidence
+        self.n_moved, self.n_mh, self.stages = n_moved, n_mh, stages
+        self.n_eval = n_eval                      # particle log-likelihood evaluations requested on the device (global)
+        self.n_eval_cut = n_eval_cut              # of those, proposals whose rejection was proven before the last observation
+        self.n_eval_reference = n_eval_reference  # what the reference would have evaluated: N * (1 + sweeps)
+        self.seconds = seconds                    # device time first sweep -> end of gamma=1 block
+        self.reached_one = reached_one
+        self.ancestors = ancestors if ancestors is not None else []
+
+    @property
+    def particles_device(self):
+        """[d, n_local] device tensor (SoA) of this shard's posterior particles."""
+        return self._state[: self._d]
+
+    @property
+    def particles(self):
+        """[n_local, d] posterior particles on the host (this rank's shard when sharded)."""
+        if self._particles is None:
+            self._particles = _to_host(self._state[: self._d].t())
+        return self._particles
+
+    @property
+    def lk(self):
+        """[n_local] log-likelihoods of the posterior particles on the host."""
+        if self._lk is None:
+            self._lk = _to_host(self._state[self._d])
+        return self._lk
+
+    def __repr__(self):
+        return (f"Result(stages={len(self.betas)}, reached_one={self.reached_one}, log_evidence={self.log_evidence!r}, "
+                f"n_eval={self.n_eval}, n_eval_cut={self.n_eval_cut}, seconds={self.seconds!r})")
 
 
 # ------------------------------------------------------------------------------------ handle pool
@@ -802,7 +843,7 @@ class Engine:
         self._ckpt = dict(gamma=gamma_old if not reached else 1.0, log_evidence=logZ,
                           step=stages[-1].step if stages else 0, n_eval=n_eval, n_eval_cut=n_cut,
                           n_sweeps=n_sweeps_total, stages=list(stages), host_rng_state=host_rng.get_state())
-        return Result(particles=self.particles().cpu().numpy(), lk=self.lk.cpu().numpy().copy(),
+        return Result(state_dev=self.state.clone(), d=d,
                       betas=[s.gamma for s in stages], ess=[s.ess for s in stages], log_evidence=logZ,
                       n_moved=[s.moved for s in stages], n_mh=[s.n_mh for s in stages], stages=stages,
                       n_eval=n_eval, n_eval_cut=n_cut, n_eval_reference=N * (1 + n_sweeps_total),
