@@ -445,12 +445,13 @@ def main():
     # ---- BASELINE config 1: the reference's own problem size (N = 1000, its seed and random stream) -----------
     config1 = None
     if args.workload == "mm_progress" and world == 1:
-        from oracle import smc as osmc          # only the reference's random stream is taken from the checker
+        from importlib import import_module
+        LegacyNumpyStream = import_module(pkg.__name__ + ".reference_api").LegacyNumpyStream
         g1 = np.load(GOLDEN)
         eng1 = pkg.Engine(lik, prior, pkg.Settings(n_particle=1000, scan_mode="sequential"))
         t1 = []
         for it in range(3):
-            st_ref = osmc.ReferenceStream(int(g1["seed"]))
+            st_ref = LegacyNumpyStream(int(g1["seed"]))
             p0 = st_ref.prior_uniform([0, 0, 0], [10, 10, 10], 1000)
             r1 = eng1.run(p0, stream=st_ref)
             t1.append(r1.seconds)

@@ -36,3 +36,26 @@ class ReferenceSurface:
         inside = pr.contains(np.asarray(theta))
         dens = 1.0 / np.prod(np.where(pr.high > pr.low, pr.high - pr.low, 1.0))
         return inside * dens
+
+
+class LegacyNumpyStream:
+    """The random inputs of a run drawn from NumPy's legacy global generator in the order the reference driver
+    consumes it: `np.random.seed(seed)` and the prior draws at import (`Micmem_settings.py:47,69-87`), then per
+    stage `rand()` (`Micmem_SMC_main.py:156`) and per sweep `multivariate_normal(...)` - i.e.
+    `standard_normal(N*d).reshape(N, d)` through the SVD factor - followed by `uniform(0, 1, N)` (`:220,235`).
+    Pass it as `Engine.run(particles, stream=...)` to reproduce a run of the reference draw for draw."""
+
+    def __init__(self, seed=20250205):
+        self.rs = np.random.RandomState(seed)
+
+    def prior_uniform(self, low, high, N):
+        return np.stack([self.rs.uniform(l, h, N) for l, h in zip(low, high)], axis=1)
+
+    def u0(self):
+        return self.rs.rand()
+
+    def normals(self, N, d):
+        return self.rs.standard_normal(N * d).reshape(N, d)
+
+    def uniforms(self, N):
+        return self.rs.uniform(0, 1, N)
