@@ -5,35 +5,36 @@
 // scipy's adaptive RK45 taken step for step - lives in mm_solver.cuh; this file is the mapping onto the
 // machine.
 //
-// Work is a list of n_ex*n solves (experiment-major: solve g = e*n + p), each 10 .. 1e5 attempted steps
-// depending on (Vmax, Km): in a prior cloud the median solve takes 12 attempts, one in a thousand takes
-// more than 800 and the worst of 2^20 particles takes ~1e5 strictly sequential ones.  Three kernels:
+// Work is n_ex solves per particle, each 10 .. 1e5 attempted steps depending on (Vmax, Km): in a prior cloud
+// the median solve takes 12 attempts, one in a thousand takes more than 800 and the worst of 2^20 particles
+// takes 8e4 strictly sequential ones; near the posterior every solve takes ~19.  One sweep is these launches:
 //
-//   mm_bulk_kernel      persistent warps, one solve per lane.  A warp draws runs of consecutive solves
-//                       from a global queue; a lane whose solve ends waits until REFILL_MIN lanes of its
-//                       warp are free (or none is busy) and they are then set up together, so neither
-//                       the set-up code nor the step code runs for a handful of lanes.  Consecutive solves
-//                       belong to consecutive particles of the same experiment: coalesced parameter
-//                       loads, broadcast reads of the observation grid in shared memory, and (near the
-//                       posterior) the same accept/reject sequence in every lane.  A solve that needs
-//                       more than `budget` attempts is abandoned and marked DEFERRED, which bounds the
-//                       drain time of the kernel.
-//   mm_finalize_kernel  one thread per particle: sums the experiments in the reference's order
-//                       (Micmem_likelihood.py:70-73), or lists its deferred solves for the tail kernel.
-//   mm_tail_kernel      one lane per deferred solve, restarted without a budget.  These few thousand
-//                       solves are latency-bound (~0.45 us per step, measured); the grid is sized so that
-//                       they do not compete for the FP64 pipe.  mm_collect_kernel then sums their particles.
+//   mm_prep_kernel      (bounded sweeps) residual limit per particle from its early-rejection threshold.
+//   mm_bin / mm_binscan / mm_scatter_kernel
+//                       counting sort of the particles that need solves by Vmax/Km (heaviest first); inactive,
+//                       sigma <= 0 and hopeless particles get their -inf here and leave the work list.
+//   mm_bulk_kernel      persistent warps, one solve per lane.  A warp draws runs of 32 cost-ordered particles of
+//                       one experiment from a global queue (all experiments of the heavy bins come first), so
+//                       its lanes take nearly the same steps; a lane whose solve ends waits until a few lanes
+//                       of its warp have been free for a few steps (or none is busy) and they are then set up
+//                       together.  A solve that needs more than `budget` attempts is marked DEFERRED, which
+//                       bounds the drain time of the kernel.
+//   mm_finalize_kernel  one thread per evaluated particle: sums the experiments in the reference's order
+//                       (Micmem_likelihood.py:70-73), applies the particle-level bound, or lists the particle's
+//                       deferred solves for the tail kernel.
+//   mm_tail_kernel      one deferred solve per thread, restarted without a budget.  These few thousand solves
+//                       are latency-bound (~0.37 us per step); the kernel lasts as long as its longest solve.
+//   mm_collect_kernel   ordered sum for the particles the tail kernel finished.
 //
 // Early rejection (MH sweeps).  Residuals only accumulate, so with c0 = -n_t/2 log(2 pi sigma^2)
-//     n_ex*c0 - ssr_e/(2 sigma^2)                                   (one solve alone)
-//     sum_finished (c0 - ssr_e/(2 sigma^2)) + n_deferred*c0         (finalize; minus one deferred solve's
-//                                                                    own term in the tail kernel)
+//     n_ex*c0                                                        (before any solve: mm_bin_kernel)
+//     sum_finished (c0 - ssr_e/(2 sigma^2)) + n_deferred*c0          (mm_finalize_kernel; minus one deferred
+//                                                                     solve's running term in mm_tail_kernel)
 // are upper bounds of the particle's log-likelihood.  Given lkmin[p] (smcb_mh_threshold: the value below
 // which the Metropolis test of Micmem_SMC_main.py:231-236 is certain to reject, with a safety margin) a
-// solve stops as soon as a bound falls below it and the particle reports -inf: the accept/reject
-// decision, hence the whole run, is exactly what it would have been.  Stiff proposals are almost always
-// hopeless ones, so this removes the serial tail from MH sweeps; the first sweep has no threshold and
-// keeps it.
+// particle whose bound falls below it reports -inf: the accept/reject decision, hence the whole run, is
+// exactly what it would have been.  Stiff proposals are almost always hopeless ones, so this removes most of
+// the serial tail from MH sweeps; the first sweep has no threshold and keeps it.
 #include "common.cuh"
 #include "mm_solver.cuh"
 
