@@ -462,3 +462,38 @@ def test_propose_and_accept_match_oracle(abi, d):
     assert c[0] == r.sum() and c[1] == r.sum() and c[2] == n_in
     assert np.array_equal(lk.cpu().numpy(), lk_new)
     assert np.abs(th.cpu().numpy().T - p_new).max() < 1e-12
+
+
+# ------------------------------------------------------------------------------------ error behaviour
+def test_error_codes_and_messages(mm_abi):
+    """Every entry point returns a negative SMCB_ERR_* code with a message instead of raising or crashing
+    (the counterpart of the reference's blanket try/except, Micmem_SMC_main.py:305-314)."""
+    import ctypes as C
+    lib, h = mm_abi.lib, mm_abi.h
+    n = 64
+    th, lk = mm_abi.zeros(3, n), mm_abi.zeros(n)
+    th += 1.0
+
+    def msg():
+        return lib.smcb_last_error(h).decode()
+
+    assert lib.smcb_loglik(h, 99, th.data_ptr(), n, n, 3, None, lk.data_ptr(), None) == -1 and "unknown model" in msg()
+    assert lib.smcb_loglik(h, 1, th.data_ptr(), n, n, 5, None, lk.data_ptr(), None) == -1 and "d=3" in msg()
+    assert lib.smcb_loglik(h, 1, None, n, n, 3, None, lk.data_ptr(), None) == -1 and "null" in msg()
+    assert lib.smcb_loglik(h, 1, th.data_ptr(), n - 1, n, 3, None, lk.data_ptr(), None) == -1      # ld < n
+    assert lib.smcb_loglik(h, 1, th.data_ptr(), 1 << 22, 1 << 22, 3, None, lk.data_ptr(), None) == -3 \
+        and "smcb_reserve" in msg()                                                              # beyond the reserve
+    assert lib.smcb_set_param(h, 12345, 1.0) == -1 and "unknown key" in msg()
+    assert lib.smcb_set_param(h, 1, 0.0) == -1                                                    # budget < 1
+    t = np.array([[0.0, 1.0, 1.0]])
+    assert lib.smcb_set_data_mm_progress(h, t.ctypes.data, t.ctypes.data, t.ctypes.data, 1, 3) == -1 \
+        and "strictly increasing" in msg()
+    out = mm_abi.zeros(4)
+    assert lib.smcb_temper_sums(h, lk.data_ptr(), n, out.data_ptr(), t.ctypes.data, 99, out.data_ptr(), None) == -1
+    bad = C.c_void_p()
+    assert lib.smcb_create(4096, C.byref(bad)) == -1 and not bad.value                            # no such device
+    assert b"out of range" in lib.smcb_last_error(None)
+    # the handle is still usable after errors
+    assert lib.smcb_loglik(h, 1, th.data_ptr(), n, n, 3, None, lk.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert np.all(np.isfinite(lk.cpu().numpy()))
