@@ -324,10 +324,20 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL announces its version on stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line here
-        os.environ["NCCL_DEBUG"] = os.environ.get("SMCB_NCCL_DEBUG", "WARN")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        comm = pkg.TorchComm()
+        # NCCL announces its version on stdout when the first communicator is created; stdout carries exactly one
+        # JSON line here, so file descriptor 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            comm = pkg.TorchComm()
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     n_gpus = world
 
     lik, prior, n_loc, cfg_kw, desc = make_workload(pkg, args.workload, args.particles)
