@@ -95,8 +95,6 @@ extern "C" int smcb_create(int device, smcb_handle** out) {
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mm_ctl), 8 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(h->mm_ctl, 0, 8 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mm_hist), 2 * 512 * sizeof(unsigned));
-    if (e == cudaSuccess)   // tail kernel: at most 32 one-warp blocks per SM (SMCB_PARAM_MM_TAIL_WARPS)
-        e = cudaMalloc(reinterpret_cast<void**>(&h->mm_tailrec), (size_t)h->sm_count * (32 + 4) * 32 * 8 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         smcb_fail(nullptr, SMCB_ERR_CUDA, "smcb_create: cudaMalloc: %s", cudaGetErrorString(e));
         delete h;
@@ -153,6 +151,12 @@ extern "C" int smcb_reserve(smcb_handle* h, int64_t n_max, int d_max) {
     if ((rc = dev_alloc(h, &h->mm_cutlim, (size_t)n_max))) return rc;
     if ((rc = dev_alloc(h, &h->mm_bins, (size_t)n_max))) return rc;
     if ((rc = dev_alloc(h, &h->mm_perm, (size_t)n_max))) return rc;
+    {   // tail kernel: one 4-word record per thread of max(32 warps per SM, one lane per 32 solves) + the loop launch
+        size_t lanes = (size_t)h->sm_count * 32 * 32;
+        if ((size_t)rows * n_max / 32 > lanes) lanes = (size_t)rows * n_max / 32 + 32;
+        lanes += (size_t)h->sm_count * 4 * 32;
+        if ((rc = dev_alloc(h, &h->mm_tailrec, lanes * 4))) return rc;
+    }
     const size_t tiles = (size_t)(n_max + 2047) / 2048 + 8;
     if ((rc = dev_alloc(h, &h->tile_tot, 2 * tiles))) return rc;
     if ((rc = dev_alloc(h, &h->tile_tot2, 2 * tiles))) return rc;

@@ -55,7 +55,7 @@ struct smcb_handle {
     double* mm_cutlim = nullptr;     // [n_max] per-particle residual limit of a bounded sweep
     unsigned short* mm_bins = nullptr;   // [n_max] cost bin of every particle (0xFFFF = no solve needed)
     unsigned* mm_perm = nullptr;     // [n_max] particles to evaluate, heaviest cost bin first
-    unsigned long long* mm_tailrec = nullptr;   // [sm_count*32 warps*32 lanes][8] per-thread work record of the tail kernel
+    unsigned long long* mm_tailrec = nullptr;   // [lanes of the tail launches][4] per-thread work record of the tail kernel (sized in smcb_reserve)
     unsigned* mm_hist = nullptr;     // [2*512] histogram and scatter cursors of the counting sort
     bool prof_on = false;            // per-kernel CUDA-event timing of the MM_PROGRESS sweeps
     int prof_sweeps = 0;

@@ -416,7 +416,7 @@ mm_finalize_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, con
 //     downstream the compiler fences every divergent region of the step with BSSY/BSYNC reconvergence
 //     barriers, which cost ~140 cycles per step (811 against 674 cycles, profiles/ubench_fp64_r01.log).  Work
 //     counters therefore go to a per-thread record that mm_collect_kernel adds up.
-constexpr int TAIL_REC = 8;   // per-thread record: set-ups, accepted, rejected, failed, max attempts, cycles/attempt of it
+constexpr int TAIL_REC = 4;   // per-thread record: set-ups | failed << 32, accepted, rejected, max attempts << 32 | its cycles/attempt
 
 template <bool LOOP>
 __global__ void __launch_bounds__(TAIL_BLOCK)
@@ -462,7 +462,10 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
         }
         if (!LOOP) break;
     }
-    my[0] = n_set; my[1] = n_acc; my[2] = n_rej; my[3] = n_fail; my[4] = mx; my[5] = mx_cyc;
+    my[0] = (unsigned long long)n_set | ((unsigned long long)n_fail << 32);
+    my[1] = n_acc;
+    my[2] = n_rej;
+    my[3] = ((unsigned long long)mx << 32) | mx_cyc;
 }
 
 // ------------------------------------------------------------------------------ collect
@@ -477,14 +480,15 @@ mm_collect_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, int 
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rec; i += gridDim.x * blockDim.x) {
         const unsigned long long* r = rec + (size_t)i * TAIL_REC;
         if (r[0] == 0) continue;
-        const unsigned long long att = r[1] + r[2], fev = 2ull * r[0] + 6ull * att;
+        const unsigned long long n_set = r[0] & 0xffffffffull, n_fail = r[0] >> 32, mx = r[3] >> 32;
+        const unsigned long long att = r[1] + r[2], fev = 2ull * n_set + 6ull * att;
         atomicAdd(&stats[0], fev); atomicAdd(&stats[4], fev);
         atomicAdd(&stats[1], r[1]); atomicAdd(&stats[5], r[1]);
         atomicAdd(&stats[2], r[2]); atomicAdd(&stats[6], r[2]);
-        if (r[3]) { atomicAdd(&stats[3], r[3]); atomicAdd(&stats[7], r[3]); }
-        atomicMax(&stats[10], r[4]);
+        if (n_fail) { atomicAdd(&stats[3], n_fail); atomicAdd(&stats[7], n_fail); }
+        atomicMax(&stats[10], mx);
         atomicAdd(&stats[15], att);
-        if (r[4] > 1024) atomicMax(&stats[16], (r[4] << 32) | r[5]);
+        if (mx > 1024) atomicMax(&stats[16], r[3]);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         stats[13] = ctl[2];
@@ -788,10 +792,11 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
                                                                    h->ssr, lk, h->mm_cutlim, solve_list, part_list,
                                                                    h->mm_ctl, h->stats);
     LAUNCH_CHECK(h);
-    // One-warp blocks, one deferred solve per thread: mm_tail_warps (32) blocks per SM give every entry of the
-    // list its own lane in all sweeps seen so far (2^20 prior particles defer 33 618 solves; the launch holds
-    // 151 552); blocks without entries exit at once, so the long chains end up alone on their schedulers.
-    const unsigned tail_grid = (unsigned)h->sm_count * (unsigned)h->mm_tail_warps;
+    // One-warp blocks, one deferred solve per thread.  The grid holds the larger of mm_tail_warps (32) blocks per
+    // SM and one lane per 32 solves of the sweep (a prior cloud defers 0.5% of its solves: 33 618 of 6.3e6 at 2^20
+    // particles); blocks without entries exit at once, so the long chains end up alone on their schedulers.
+    unsigned tail_grid = (unsigned)h->sm_count * (unsigned)h->mm_tail_warps;
+    if (tasks / 32 / TAIL_BLOCK > tail_grid) tail_grid = tasks / 32 / TAIL_BLOCK;
     prof_mark(h, 2, st);
     mm_tail_kernel<false><<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, h->mm_cutlim, D.t, D.P, D.S0, D.n_ex, D.n_t,
                                                               h->ssr, solve_list, h->mm_ctl, h->mm_tailrec, 0u);
