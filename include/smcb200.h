@@ -214,9 +214,10 @@ int smcb_mh_threshold(smcb_handle* h, const double* lk_dev, const uint8_t* inbox
 int smcb_prior_logratio(smcb_handle* h, const double* theta_dev, int64_t ld, const double* prop_dev, int64_t ld_prop,
                         int64_t n, int d, const double* mu_host, const double* inv2var_host, const uint8_t* inbox_dev,
                         double* out_dev, void* stream);
-/* Several MH sweeps fused in one launch with a frozen proposal factor (documented deviation from
- * the per-sweep covariance refresh of EX/main:212): propose + box + likelihood + accept, particle
- * state held in registers.  KINETIC_RK.  counts_dev int64[3] as for smcb_mh_accept. */
+/* Several MH sweeps in one call with a frozen proposal factor (documented deviation from the per-sweep covariance
+ * refresh of EX/main:212) and no host round trip in between: per sweep a propose kernel (Philox normals, factor
+ * mat-vec, box test; survivors packed into a list), the reactor marches of the survivors in full warps, and an
+ * accept kernel.  At most 64 sweeps per call.  KINETIC_RK.  counts_dev int64[3] as for smcb_mh_accept. */
 int smcb_mh_fused(smcb_handle* h, int model, double* theta_dev, int64_t ld, double* lk_dev, int64_t n, int d,
                   const double* F_host, double ratio, const double* low_host, const double* high_host,
                   double gamma, int n_sweeps, uint64_t seed, uint64_t id_offset, uint32_t stage,

@@ -109,6 +109,8 @@ extern "C" int smcb_destroy(smcb_handle* h) {
     cudaSetDevice(h->device);
     dev_free(&h->ssr); dev_free(&h->partial); dev_free(&h->stats); dev_free(&h->mm_ctl); dev_free(&h->mm_defer); dev_free(&h->mm_cutlim);
     dev_free(&h->mm_bins); dev_free(&h->mm_perm); dev_free(&h->mm_hist); dev_free(&h->mm_tailrec);
+    dev_free(&h->fused_plist); dev_free(&h->fused_owner);
+    if (h->fused_ctl) cudaFree(h->fused_ctl);
     if (h->prof_ev) {
         for (int i = 0; i < SMCB_PROF_RING * 4; ++i) cudaEventDestroy(h->prof_ev[i]);
         delete[] h->prof_ev;

@@ -57,6 +57,10 @@ struct smcb_handle {
     unsigned* mm_perm = nullptr;     // [n_max] particles to evaluate, heaviest cost bin first
     unsigned long long* mm_tailrec = nullptr;   // [lanes of the tail launches][4] per-thread work record of the tail kernel (sized in smcb_reserve)
     unsigned* mm_hist = nullptr;     // [2*512] histogram and scatter cursors of the counting sort
+    double* fused_plist = nullptr;   // smcb_mh_fused: surviving proposals of a sweep [d][n_max]
+    unsigned* fused_owner = nullptr; // ... their particles
+    void* fused_ctl = nullptr;       // ... per-sweep counts of surviving proposals
+    int64_t fused_cap = 0;
     bool prof_on = false;            // per-kernel CUDA-event timing of the MM_PROGRESS sweeps
     int prof_sweeps = 0;
     cudaEvent_t* prof_ev = nullptr;  // [SMCB_PROF_RING*4]

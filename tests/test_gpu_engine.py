@@ -249,14 +249,22 @@ def test_kinetic_run_matches_oracle_loop(pkg):
     eng.close()
 
 
-def test_fused_sweeps_match_oracle_with_frozen_factor(pkg):
-    """smcb_mh_fused: k sweeps in one launch, proposal factor frozen (documented deviation)."""
+@pytest.mark.parametrize("n_pairs", [4, 16])
+def test_fused_sweeps_match_oracle_with_frozen_factor(pkg, n_pairs):
+    """smcb_mh_fused: k sweeps in one call, proposal factor frozen (documented deviation); d = 5 (reference
+    methanation parameters) and d = 32 (config 5 family)."""
     N, seed, k = 512, 11, 3
     cond = kinetic.synthetic_conditions(6)
-    base = kinetic.base_vector(4)
+    base = kinetic.base_vector(n_pairs)
     obs = kinetic.synthetic_observations(cond, base, n_steps=10)
-    low, high = kinetic.reference_box()
-    lik = pkg.KineticRK(cond, obs, base, kinetic.EST_POSITION, n_steps=10)
+    if n_pairs == 4:
+        est = kinetic.EST_POSITION
+        low, high = kinetic.reference_box()
+    else:
+        est = np.arange(32, dtype=np.int32)
+        low, high = np.minimum(base[:32] * 0.8, base[:32] * 1.2), np.maximum(base[:32] * 0.8, base[:32] * 1.2)
+    d = len(est)
+    lik = pkg.KineticRK(cond, obs, base, est, n_steps=10)
     eng = pkg.Engine(lik, pkg.UniformBox(low, high), pkg.Settings(n_particle=N, seed=seed))
     eng.sample_prior()
     eng.sim_particle()
@@ -271,11 +279,12 @@ def test_fused_sweeps_match_oracle_with_frozen_factor(pkg):
     r_ac = np.zeros(N, dtype=np.int32)
     n_in = 0
     for s in range(k):
-        Z, U = philox.normals(seed, ids, stage, s, 5), philox.uniforms(seed, ids, stage, s)
+        Z, U = philox.normals(seed, ids, stage, s, d), philox.uniforms(seed, ids, stage, s)
         X, lk1, r, ne = smc.mh_sweep(X, lk1, gamma, F, Z, U, ratio,
-                                     lambda th: kinetic.loglik(th, cond, obs, base, kinetic.EST_POSITION, 10), low, high)
+                                     lambda th: kinetic.loglik(th, cond, obs, base, est, 10), low, high)
         r_ac = np.maximum(r_ac, r)
         n_in += ne
+    assert n_in > 0 and r_ac.sum() > 0
     assert np.array_equal(eng.moved.cpu().numpy(), r_ac.astype(np.uint8))
     c = eng.icnt.cpu().numpy()
     assert c[1] == r_ac.sum() and c[2] == n_in

@@ -234,6 +234,28 @@ def test_kinetic_fixture_known_answers(abi):
         assert np.median(rel) < 1e-12 and (rel < 1e-9).mean() > 0.9, (np.median(rel), rel.max())
 
 
+@pytest.mark.parametrize("n_pairs", [4, 16])
+def test_kinetic_masked_sweep_is_packed_not_changed(abi, n_pairs):
+    """A masked sweep packs the active particles into full warps first; values equal the unmasked sweep's
+    bit for bit, inactive slots are left alone, ragged sizes and empty / sparse / full masks included."""
+    import os
+    kf = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kinetic_synth.npz"))
+    tag = str(n_pairs)
+    est = np.ascontiguousarray(kf["est4"] if n_pairs == 4 else np.arange(32), dtype=np.int32)
+    cond, base, obs = (np.ascontiguousarray(kf[k]) for k in ("cond", "base" + tag, "obs" + tag))
+    abi.ck(abi.lib.smcb_set_data_kinetic(abi.h, cond.ctypes.data, obs.ctypes.data, 30, base.ctypes.data, n_pairs,
+                                         est.ctypes.data, len(est), 50))
+    th = np.tile(kf["theta" + tag], (16, 1))[:1001]
+    n = len(th)
+    full = abi.loglik(3, th)
+    rs = np.random.RandomState(5)
+    for n_sub, p_on in ((n, 0.02), (n, 0.5), (n, 1.0), (n, 0.0), (min(n, 131), 0.3), (1, 1.0)):
+        act = (rs.uniform(size=n_sub) < p_on).astype(np.uint8)
+        part = abi.loglik(3, th[:n_sub], active=act)
+        assert np.array_equal(part[act == 1], full[:n_sub][act == 1])
+        assert np.all(part[act == 0] == 0.0)
+
+
 # ------------------------------------------------------------------------------------ K2 tempering
 @pytest.mark.parametrize("n", [1, 2, 777, 1000, (1 << 20) + 3])
 def test_temper_reductions(abi, n):
