@@ -54,6 +54,9 @@ kinetic_ssr_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, cons
                    const double* __restrict__ obs, int n_cond, int n_steps, const double* __restrict__ base,
                    const int* __restrict__ inv_pos, double* __restrict__ ssr) {
     const int c = blockIdx.y;
+    __shared__ double etab[expt::TAB_N];
+    expt::load_table(etab);
+    __syncthreads();
     if (!PACKED) {
         const int64_t p = (int64_t)blockIdx.x * KB + threadIdx.x;
         if (p >= n) return;
@@ -61,7 +64,7 @@ kinetic_ssr_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, cons
         double sigma;
         load_kin<M>(theta, ld, p, base, inv_pos, K, &sigma);
         ssr[(int64_t)c * n + p] =
-            kin::condition_ssr<M>(K, cond + (int64_t)c * SMCB_KIN_NCOND_FIELDS, n_steps, obs, n_cond, c);
+            kin::condition_ssr<M>(K, cond + (int64_t)c * SMCB_KIN_NCOND_FIELDS, n_steps, obs, n_cond, c, etab);
     } else {
         const unsigned m = *count, stride = gridDim.x * KB;
 #pragma unroll 1
@@ -71,7 +74,7 @@ kinetic_ssr_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, cons
             double sigma;
             load_kin<M>(theta, ld, p, base, inv_pos, K, &sigma);
             ssr[(int64_t)c * n + p] =
-                kin::condition_ssr<M>(K, cond + (int64_t)c * SMCB_KIN_NCOND_FIELDS, n_steps, obs, n_cond, c);
+                kin::condition_ssr<M>(K, cond + (int64_t)c * SMCB_KIN_NCOND_FIELDS, n_steps, obs, n_cond, c, etab);
         }
     }
 }

@@ -19,6 +19,7 @@
 // pairs (kf, ks, kCO2, kH2O); M=1 is exactly func_rCH4, M=4 gives the 32-parameter family.
 #pragma once
 #include "common.cuh"
+#include "exp_table.cuh"
 
 namespace kin {
 
@@ -54,6 +55,7 @@ __device__ __forceinline__ double sqrt_fast(double x) {
     return fma(xy, e * fma(0.375, e, 0.5), xy);             // x*y0*(1 + e/2 + 3e^2/8)
 }
 
+
 struct Cond {
     double N0[5];     // inlet molar fluxes u_in*C_k_in
     double P0;        // total pressure (sum C_in) R T_in
@@ -88,7 +90,8 @@ struct Kin {
 };
 
 template <int M>
-__device__ __forceinline__ double rate(const Kin<M>& K, double T, double Ca, double Cb, double Cc, double Cd) {
+__device__ __forceinline__ double rate(const Kin<M>& K, double T, double Ca, double Cb, double Cc, double Cd,
+                                       const double* __restrict__ etab) {
     const double RT6 = R_GAS * T * 1e-6;
     const double PH2 = Ca * RT6, PCO2 = Cb * RT6, PCH4 = Cc * RT6, PH2O = Cd * RT6;
     const double sH2 = sqrt_fast(fmax(0.001, PH2));
@@ -96,10 +99,10 @@ __device__ __forceinline__ double rate(const Kin<M>& K, double T, double Ca, dou
     double r = 0.0;
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        const double kf = K.A[4 * m + 0] * exp(K.nEoR[4 * m + 0] * invT);
-        const double ks = K.A[4 * m + 1] * exp(K.nEoR[4 * m + 1] * invT);
-        const double kC = K.A[4 * m + 2] * exp(K.nEoR[4 * m + 2] * invT);
-        const double kW = K.A[4 * m + 3] * exp(K.nEoR[4 * m + 3] * invT);
+        const double kf = K.A[4 * m + 0] * expt::exp_fast(K.nEoR[4 * m + 0] * invT, etab);
+        const double ks = K.A[4 * m + 1] * expt::exp_fast(K.nEoR[4 * m + 1] * invT, etab);
+        const double kC = K.A[4 * m + 2] * expt::exp_fast(K.nEoR[4 * m + 2] * invT, etab);
+        const double kW = K.A[4 * m + 3] * expt::exp_fast(K.nEoR[4 * m + 3] * invT, etab);
         const double dC = 1.0 + kC * PCO2, dW = 1.0 + kW * PH2O;
         const double rf = 5075e3 * kf * kC * PCO2 * sH2 * rcp(dC * dC);
         const double rr = 5075e3 * ks * kW * PH2O * (PCH4 * PCH4) * rcp(dW * dW);
@@ -126,9 +129,10 @@ __device__ __forceinline__ Local local_state(const Cond& c, double xi, double G)
 }
 
 template <int M>
-__device__ __forceinline__ void rhs(const Kin<M>& K, const Cond& c, double xi, double G, double* dxi, double* dG) {
+__device__ __forceinline__ void rhs(const Kin<M>& K, const Cond& c, double xi, double G, double* dxi, double* dG,
+                                    const double* __restrict__ etab) {
     const Local s = local_state(c, xi, G);
-    const double r = rate<M>(K, s.T, s.C[0], s.C[1], s.C[2], s.C[3]);
+    const double r = rate<M>(K, s.T, s.C[0], s.C[1], s.C[2], s.C[3], etab);
     const double csum = s.C[0] + s.C[1] + s.C[2] + s.C[3] + s.C[4];
     const double rho = c.P0 / R_GAS * rcp(s.T) *
                        (s.C[0] * 2 + s.C[1] * 44 + s.C[2] * 16 + s.C[3] * 18 + s.C[4] * 40) * rcp(csum) * 0.001;
@@ -139,16 +143,17 @@ __device__ __forceinline__ void rhs(const Kin<M>& K, const Cond& c, double xi, d
 // integrate one operating condition; returns sum_k (F_k - obs_k)^2 over the five species
 template <int M>
 __device__ __forceinline__ double condition_ssr(const Kin<M>& K, const double* __restrict__ cond_row, int n_steps,
-                                                const double* __restrict__ obs, int n_cond, int ci) {
+                                                const double* __restrict__ obs, int n_cond, int ci,
+                                                const double* __restrict__ etab) {
     const Cond c = load_cond(cond_row, n_steps);
     double xi = 0.0, G = c.G0;
     const double h = c.dz;
     for (int s = 0; s < n_steps; ++s) {
         double a1, b1, a2, b2, a3, b3, a4, b4;
-        rhs<M>(K, c, xi, G, &a1, &b1);
-        rhs<M>(K, c, xi + 0.5 * h * a1, G + 0.5 * h * b1, &a2, &b2);
-        rhs<M>(K, c, xi + 0.5 * h * a2, G + 0.5 * h * b2, &a3, &b3);
-        rhs<M>(K, c, xi + h * a3, G + h * b3, &a4, &b4);
+        rhs<M>(K, c, xi, G, &a1, &b1, etab);
+        rhs<M>(K, c, xi + 0.5 * h * a1, G + 0.5 * h * b1, &a2, &b2, etab);
+        rhs<M>(K, c, xi + 0.5 * h * a2, G + 0.5 * h * b2, &a3, &b3, etab);
+        rhs<M>(K, c, xi + h * a3, G + h * b3, &a4, &b4, etab);
         xi += h / 6.0 * (a1 + 2.0 * a2 + 2.0 * a3 + a4);
         G += h / 6.0 * (b1 + 2.0 * b2 + 2.0 * b3 + b4);
     }

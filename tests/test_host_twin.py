@@ -86,3 +86,28 @@ def test_known_answers_and_degenerate_parameters(twin, golden):
     assert abs(got[0] - 593.9635684697922) < 1e-7 and abs(got[1] - 424.5676547271564) < 1e-7
     assert got[2] == -np.inf and got[3] == -np.inf             # sigma <= 0 (Micmem_likelihood.py:53-54)
     assert got[4] == -np.inf                                   # Km + S0 = 0 for the S0 = 2 curves: no valid first step
+
+
+def test_arrhenius_exp_is_within_an_ulp_of_libm(tmp_path):
+    """csrc/exp_table.cuh (table + degree-5 polynomial, used by the kinetic reactor march) against NumPy's exp."""
+    so = str(tmp_path / "libhost_exp.so")
+    subprocess.run(["g++", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC", "-o", so,
+                    os.path.join(HERE, "host_exp.cpp")], check=True)
+    lib = C.CDLL(so)
+    rs = np.random.RandomState(0)
+    x = np.concatenate([rs.uniform(-700, 700, 400000), rs.uniform(-60, 5, 400000), rs.normal(0, 1e-3, 1000),
+                        np.array([0.0, -0.0, 1e-300, -1e-300, 699.999, -699.999, 707.999, -707.999, 708.0, -708.0, 709.7, -745.0, 800.0, 1e300, -1e300,
+                                  -800.0, np.inf, -np.inf, np.nan]),
+                        np.arange(-3000, 3000) * (np.log(2) / 128)])          # the reduction's break points
+    y = np.empty_like(x)
+    lib.exp_fast_host(C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), C.c_long(len(x)))
+    with np.errstate(over="ignore", under="ignore"):
+        want = np.exp(x)
+    want[x >= 708.0] = np.inf                      # the device function's documented range
+    want[x <= -708.0] = 0.0
+    assert np.array_equal(np.isnan(y), np.isnan(want))
+    fin = np.isfinite(want) & (want > 0)
+    assert np.array_equal(y[~fin & ~np.isnan(want)], want[~fin & ~np.isnan(want)])
+    ulp = np.abs(y[fin] - want[fin]) / np.spacing(want[fin])
+    assert ulp.max() <= 1.0, ulp.max()             # never more than one ulp away from libm
+    assert np.mean(ulp == 0) > 0.7                 # and identical to it three times out of four
