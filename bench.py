@@ -16,7 +16,8 @@ Workloads (BASELINE.json configs):
                 observations), 2^20 particles per GPU, FP64, scipy-RK45-twin arithmetic.  DEFAULT.
   mm_rate       config 4 shape: 10 000 rate-law observations, 2^22 particles per GPU (--particles)
   kinetic       config 3: methanation-style reactor, d=5, 30 conditions, RK4 x 50, 2^18 particles
-  kinetic32     config 5: 32-parameter kinetic family, 10 fused MH sweeps per stage, 2^20 particles
+  kinetic32     config 5: 32-parameter kinetic family, 10 fused MH sweeps per stage, 2^21 particles per GPU
+                (2^24 over 8 GPUs; --total-particles 16777216 for the strong-scaling series)
 With N > 1 (torchrun) particles are sharded, per-GPU count fixed => "scaling": "weak".
 
 `--impl reference` times the reference's CPU implementation of the same path (the oracle's
@@ -51,6 +52,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="mm_progress", choices=["mm_progress", "mm_rate", "kinetic", "kinetic32"])
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (0 = workload default)")
+    ap.add_argument("--total-particles", type=int, default=0,
+                    help="strong scaling: this many particles in total, split evenly over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
@@ -88,7 +91,7 @@ def make_workload(pkg, name, n_per_gpu):
         lo, hi = base[:32] * 0.8, base[:32] * 1.2
         lik = pkg.KineticRK(cond, obs, base, est, n_steps=50)
         prior = pkg.UniformBox(np.minimum(lo, hi), np.maximum(lo, hi))
-        n = n_per_gpu or (1 << 20)
+        n = n_per_gpu or (1 << 21)
         cfg = dict(fused_sweeps=10, mhstep_num=10, ad_mhstep_num=10, early_exit=False)
         desc = "32-parameter kinetic family (4 LH channels), 30 conditions, RK4 x 50, 10 fused MH sweeps/stage"
     return lik, prior, n, cfg, desc
@@ -340,6 +343,9 @@ def main():
             os.close(saved_fd)
     n_gpus = world
 
+    if args.total_particles:
+        assert args.total_particles % world == 0, "--total-particles must be a multiple of the number of GPUs"
+        args.particles = args.total_particles // world
     lik, prior, n_loc, cfg_kw, desc = make_workload(pkg, args.workload, args.particles)
     N = n_loc * world
     cfg = pkg.Settings(n_particle=N, **cfg_kw)
@@ -541,7 +547,8 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.workload != "mm_rate" else "f32",
+                "scaling": "strong" if args.total_particles else "weak", "vs_baseline": None,
+                "dtype": "f64" if args.workload != "mm_rate" else "f32",
                 "data": "synthetic",
                 "config": {"workload": f"{args.workload}: {desc}", "particles_total": N, "particles_per_gpu": n_loc,
                            "d": prior.d, "observations": int(lik.n_obs), "temper_rule": cfg.temper_rule,

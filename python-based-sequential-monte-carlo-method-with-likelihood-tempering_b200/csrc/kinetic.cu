@@ -127,6 +127,10 @@ fused_propose_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, in
     long long n_acc = 0, n_new = 0;
     double pr[DMAX];   // compile-time loop bounds below keep the proposal in registers
     if (i < n) {
+        // the particle is only needed after the mat-vec: start its rows on their way now, without holding registers
+#pragma unroll
+        for (int k = 0; k < DMAX; ++k)
+            if (k < d) asm volatile("prefetch.global.L2 [%0];" ::"l"(theta + (int64_t)k * ld + i));
 #pragma unroll
         for (int k = 0; k < DMAX; ++k) pr[k] = 0.0;
 #pragma unroll
