@@ -44,6 +44,8 @@ extern "C" {
 #define SMCB_MODEL_MM_PROGRESS 1 /* EX/lik:35-77: six progress curves, scipy-RK45 twin */
 #define SMCB_MODEL_MM_RATE 2     /* synthetic rate-law observations (S_i, v_i)         */
 #define SMCB_MODEL_KINETIC_RK 3  /* methanation-style plug-flow reactor, fixed-step RK4 */
+#define SMCB_MODEL_KINETIC_DAE 4 /* ME/lik:69-277: the reference's transient 357-unknown reactor DAE, implicit Euler to
+                                    75 s (data as for KINETIC_RK with the reference's 8 kinetic parameters; n_steps unused) */
 
 /* resampling prefix-sum arithmetic */
 #define SMCB_SCAN_SEQUENTIAL 0 /* the reference's sequentially rounded FP64 sum (EX/main:165-174), bit-exact */

@@ -13,10 +13,10 @@ or through the `smcb200` alias module at the repository root.
 from . import _lib
 from .settings import Settings
 from .prior import UniformBox, IndependentPrior
-from .likelihood import MMProgress, MMRate, KineticRK
+from .likelihood import MMProgress, MMRate, KineticRK, KineticDAE
 from .artefacts import RunWriter
 
-__all__ = ["Settings", "UniformBox", "IndependentPrior", "MMProgress", "MMRate", "KineticRK", "RunWriter", "Engine", "run", "build",
+__all__ = ["Settings", "UniformBox", "IndependentPrior", "MMProgress", "MMRate", "KineticRK", "KineticDAE", "RunWriter", "Engine", "run", "build",
            "LocalComm", "TorchComm", "migration_plan"]
 
 

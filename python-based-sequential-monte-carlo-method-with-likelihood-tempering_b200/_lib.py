@@ -57,7 +57,7 @@ _RESTYPE = {"smcb_last_error": C.c_char_p, "smcb_launch_count": c_i64}
 
 EXPORTS = tuple(_SIGNATURES)
 
-MODEL_MM_PROGRESS, MODEL_MM_RATE, MODEL_KINETIC_RK = 1, 2, 3
+MODEL_MM_PROGRESS, MODEL_MM_RATE, MODEL_KINETIC_RK, MODEL_KINETIC_DAE = 1, 2, 3, 4
 SCAN_SEQUENTIAL, SCAN_FIXED = 0, 1
 MAX_DIM, MAX_CAND = 32, 16
 KIN_NCOND_FIELDS = 10

@@ -111,6 +111,7 @@ extern "C" int smcb_destroy(smcb_handle* h) {
     dev_free(&h->mm_bins); dev_free(&h->mm_perm); dev_free(&h->mm_hist); dev_free(&h->mm_tailrec);
     dev_free(&h->fused_plist); dev_free(&h->fused_owner);
     if (h->fused_ctl) cudaFree(h->fused_ctl);
+    dev_free(&h->dae_dts);
     if (h->prof_ev) {
         for (int i = 0; i < SMCB_PROF_RING * 4; ++i) cudaEventDestroy(h->prof_ev[i]);
         delete[] h->prof_ev;
@@ -231,6 +232,8 @@ extern "C" int smcb_loglik_bounded(smcb_handle* h, int model, const double* thet
             return launch_loglik_mm_rate(h, theta_dev, ld, n, active_dev, lk_dev, st);
         case SMCB_MODEL_KINETIC_RK:
             return launch_loglik_kinetic(h, theta_dev, ld, n, d, active_dev, lk_dev, st);
+        case SMCB_MODEL_KINETIC_DAE:
+            return launch_loglik_dae(h, theta_dev, ld, n, d, active_dev, lk_dev, st);
         default:
             return smcb_fail(h, SMCB_ERR_INVALID, "smcb_loglik: unknown model %d", model);
     }

@@ -61,6 +61,8 @@ struct smcb_handle {
     unsigned* fused_owner = nullptr; // ... their particles
     void* fused_ctl = nullptr;       // ... per-sweep counts of surviving proposals
     int64_t fused_cap = 0;
+    double* dae_dts = nullptr;       // transient reactor model: time steps of the fixed grid
+    int dae_n_dt = 0;
     bool prof_on = false;            // per-kernel CUDA-event timing of the MM_PROGRESS sweeps
     int prof_sweeps = 0;
     cudaEvent_t* prof_ev = nullptr;  // [SMCB_PROF_RING*4]
@@ -157,3 +159,9 @@ int launch_loglik_mm_rate(smcb_handle* h, const double* theta, int64_t ld, int64
                           const uint8_t* active, double* lk, cudaStream_t st);
 int launch_loglik_kinetic(smcb_handle* h, const double* theta, int64_t ld, int64_t n, int d,
                           const uint8_t* active, double* lk, cudaStream_t st);
+int launch_loglik_dae(smcb_handle* h, const double* theta, int64_t ld, int64_t n, int d,
+                      const uint8_t* active, double* lk, cudaStream_t st);
+int kinetic_pack_active(smcb_handle* h, const uint8_t* active, int64_t n, cudaStream_t st, unsigned** list,
+                        unsigned** count);
+int kinetic_finalize(smcb_handle* h, const double* theta, int64_t ld, int64_t n, const uint8_t* active, double* lk,
+                     cudaStream_t st);

@@ -1,0 +1,388 @@
+// K1'' (SURVEY.md 8(f) N3): the reference's transient fixed-bed reactor model, one thread block per
+// (particle, operating condition).
+//
+// Replaces the body of my_model (SMC_methanation/methanation_set_likelihood.py:144-277): 7 x 51 = 357 unknowns
+// (five concentrations, temperature, velocity on 51 axial nodes), residual `reaction` (:69-139) restated node by
+// node below and pinned against the reference's own function (tests/golden/methanation_dae_residual.npz through
+// oracle/methanation_dae.py, which this file twins).  The reference integrates with SUNDIALS IDA (variable-order
+// BDF, absent here); the integrator is builder-defined: implicit Euler on a fixed geometric time grid from 0 to
+// 75 s (host-supplied), full Newton, finite-difference Jacobian.  Node j's equations involve nodes j-1, j, j+1
+// only, so with the unknowns ordered node by node the Jacobian is block tridiagonal with 7x7 blocks:
+//   * residuals and the 3 x 7 perturbed residuals per node are independent tasks spread over the block's threads
+//     (the reaction rate, the expensive part, is reused when a neighbour is perturbed);
+//   * the linear solve is a block Thomas sweep, each node's 7 x 15 system [D' | C | rhs] reduced by Gauss-Jordan
+//     with row pivoting in shared memory, 105 threads on one element each.
+// Everything lives in shared memory (68 KB per block, three blocks per SM).  Cost: ~35 steps x ~4 Newton
+// iterations per march; this is the like-for-like physics mode for reference-sized particle counts, the plug-flow
+// RK4 march of kinetic.cu is the throughput mode.
+#include <vector>
+
+#include "common.cuh"
+#include "kinetic.cuh"
+
+namespace {
+
+constexpr int NX = 51;        // methanation_set_conditon.py:44
+constexpr int NV = 7;         // C_H2, C_CO2, C_CH4, C_H2O, C_Ar, T, u
+constexpr int NB = NV * NV;
+constexpr int DAE_THREADS = 128;
+constexpr int MROW = 16;      // row stride of the 7 x 15 elimination scratch
+constexpr int NEWTON_MAX = 25;
+
+constexpr double DZ_DISP = 0.95e-5;   // Dz   set_conditon.py:76
+constexpr double RHOS = 5075.0;       //      :77
+constexpr double CPS = 698.0;         //      :83
+constexpr double KEFF = 0.72;         //      :84
+constexpr double T_BED0 = 400.0;      // SMC_methanation.py:421
+constexpr double NEWTON_TOL = 1e-10, FD_REL = 1e-7;
+
+struct Case {
+    double Cin[5], T_in, T_j, u_in, voidf, dz, P0;
+    double k8[8];
+};
+
+__device__ __forceinline__ double floor_of(int v) { return v < 5 ? 1e-3 : (v == 5 ? 1.0 : 1e-4); }
+
+// func_rCH4 (set_likelihood.py:44-58)
+__device__ __forceinline__ double rate_ch4(const Case& c, double T, double Ca, double Cb, double Cc, double Cd) {
+    const double RT6 = kin::R_GAS * T * 1e-6;
+    const double PH2 = Ca * RT6, PCO2 = Cb * RT6, PCH4 = Cc * RT6, PH2O = Cd * RT6;
+    const double kf = c.k8[0] * exp(-c.k8[1] / kin::R_GAS / T);
+    const double ks = c.k8[2] * exp(-c.k8[3] / kin::R_GAS / T);
+    const double kC = c.k8[4] * exp(-c.k8[5] / kin::R_GAS / T);
+    const double kW = c.k8[6] * exp(-c.k8[7] / kin::R_GAS / T);
+    const double dC = 1.0 + kC * PCO2, dW = 1.0 + kW * PH2O;
+    const double rf = 5075e3 * kf * kC * PCO2 * sqrt(fmax(0.001, PH2)) / (dC * dC);
+    const double rr = 5075e3 * ks * kW * PH2O * (PCH4 * PCH4) / (dW * dW);
+    return rf - rr;
+}
+
+// func_rohg (:61-66)
+__device__ __forceinline__ double density(const Case& c, const double* y) {
+    return c.P0 / kin::R_GAS / y[5] * (y[0] * 2 + y[1] * 44 + y[2] * 16 + y[3] * 18 + y[4] * 40) /
+           (y[0] + y[1] + y[2] + y[3] + y[4]) * 0.001;
+}
+
+// Equations of node j (`reaction` :69-139) given the unknowns of nodes j-1 (yl), j (yc), j+1 (yr), the previous
+// time level of node j and 1/dt.  out[0..4] species balances, out[5] the equation the reference keeps in the T slot
+// (continuity; u condition at the outlet), out[6] the one in the u slot (energy; u = u_in at the inlet, T condition
+// at the outlet).  r, rho: rate and gas density of node j.
+__device__ __forceinline__ void node_equations(const Case& c, int j, const double* yl, const double* yc,
+                                               const double* yr, const double* yold, double inv_dt, double r,
+                                               double rho, double* out) {
+    const double sc[5] = {-4.0, -1.0, 1.0, 2.0, 0.0};
+    if (j == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) out[k] = (yc[k] - yold[k]) * inv_dt;
+        out[6] = yc[6] - c.u_in;
+        return;
+    }
+    if (j == NX - 1) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) out[k] = yc[k] - yl[k];
+        out[5] = yc[6] - yl[6];
+        out[6] = yc[5] - yl[5];
+        return;
+    }
+    const double dz = c.dz, vd = c.voidf, dz2 = dz * dz;
+    const double T = yc[5], u = yc[6], Tl = yl[5], ul = yl[6], Tr = yr[5];
+    const double dT = (T - yold[5]) * inv_dt;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const double lap = (j == 1) ? (yr[k] - yc[k]) : (yr[k] - 2 * yc[k] + yl[k]);
+        out[k] = -vd * ((yc[k] - yold[k]) * inv_dt) - (u * yc[k] - ul * yl[k]) / dz + vd * DZ_DISP * lap / dz2 +
+                 (1 - vd) * sc[k] * r;
+    }
+    double cont = -u * c.P0 * (1 / T - 1 / Tl) / dz - c.P0 / T * (u - ul) / dz +
+                  vd * DZ_DISP * c.P0 * (1 / Tr - 2 / T + 1 / Tl) / dz2 + (1 - vd) * kin::R_GAS * (-2) * r;
+    if (j == 1) cont += c.P0 * vd / (T * T) * dT;
+    out[5] = cont;
+    const double store = (j == 1) ? 1.0 : 0.1;
+    out[6] = -store * (vd * rho * kin::CPG + (1 - vd) * RHOS * CPS) * dT - rho * kin::CPG * (T * u - Tl * ul) / dz +
+             KEFF * (Tr - 2 * T + Tl) / dz2 + (1 - vd) * (-kin::HR) * r - 2 * kin::U_WALL / kin::DINT * (T - c.T_j);
+}
+
+struct Smem {
+    double Y[NX * NV];      // unknowns, node by node
+    double Yold[NX * NV];
+    double F[NX * NV];      // residual, then right-hand side / Thomas g / Newton update
+    double A[NX * NB];      // dF_j/dY_{j-1}
+    double D[NX * NB];      // dF_j/dY_j
+    double C[NX * NB];      // dF_j/dY_{j+1}, then the Thomas W
+    double M[NV * MROW];
+    double rr[NX], rho[NX];
+    double red[DAE_THREADS / 32];
+    Case cs;
+    int fail;
+};
+
+__global__ void __launch_bounds__(DAE_THREADS)
+dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const unsigned* __restrict__ list,
+                 const unsigned* __restrict__ count, const double* __restrict__ cond,
+                 const double* __restrict__ obs, int n_cond, const double* __restrict__ base,
+                 const int* __restrict__ inv_pos, const double* __restrict__ dts, int n_dt,
+                 double* __restrict__ ssr) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int64_t m = (count != nullptr) ? (int64_t)*count : n;
+    for (int64_t item = blockIdx.x; item < m * n_cond; item += gridDim.x) {
+        const int ci = (int)(item / m);
+        const int64_t q = item - (int64_t)ci * m;
+        const int64_t p = (list != nullptr) ? (int64_t)list[q] : q;
+        __syncthreads();   // previous item's readers of shared memory are done
+        if (tid == 0) {
+            const double* row = cond + (int64_t)ci * SMCB_KIN_NCOND_FIELDS;
+            double csum = 0.0;
+            for (int k = 0; k < 5; ++k) {
+                s.cs.Cin[k] = row[k];
+                csum += row[k] * kin::R_GAS * row[5];
+            }
+            s.cs.T_in = row[5];
+            s.cs.T_j = row[6];
+            s.cs.u_in = row[7];
+            s.cs.voidf = row[8];
+            s.cs.dz = row[9] / (NX - 1);
+            s.cs.P0 = csum;
+            for (int k = 0; k < 8; ++k) {
+                const int ip = inv_pos[k];
+                s.cs.k8[k] = (ip >= 0) ? theta[(int64_t)ip * ld + p] : base[k];
+            }
+            s.fail = 0;
+        }
+        __syncthreads();
+        const Case& c = s.cs;
+        for (int e = tid; e < NX * NV; e += DAE_THREADS) {   // start state (SMC_methanation.py:412-423)
+            const int j = e / NV, v = e - j * NV;
+            s.Y[e] = (v < 5) ? c.Cin[v] : (v == 5 ? (j == 0 ? c.T_in : T_BED0) : c.u_in);
+        }
+        __syncthreads();
+        bool failed = false;
+        for (int step = 0; step < n_dt && !failed; ++step) {
+            const double inv_dt = 1.0 / dts[step];
+            for (int e = tid; e < NX * NV; e += DAE_THREADS) s.Yold[e] = s.Y[e];
+            __syncthreads();
+            bool converged = false;
+            for (int it = 0; it < NEWTON_MAX && !converged && !failed; ++it) {
+                // ---- residual of every node, rate and density kept for the Jacobian
+                if (tid < NX) {
+                    const int j = tid;
+                    const double* yc = s.Y + j * NV;
+                    const double* yl = s.Y + (j > 0 ? j - 1 : j) * NV;
+                    const double* yr = s.Y + (j < NX - 1 ? j + 1 : j) * NV;
+                    double r = 0.0, rho = 0.0, out[NV];
+                    if (j > 0 && j < NX - 1) {
+                        r = rate_ch4(c, yc[5], yc[0], yc[1], yc[2], yc[3]);
+                        rho = density(c, yc);
+                    }
+                    s.rr[j] = r;
+                    s.rho[j] = rho;
+                    node_equations(c, j, yl, yc, yr, s.Yold + j * NV, inv_dt, r, rho, out);
+                    bool fin = true;
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        s.F[j * NV + k] = out[k];
+                        fin = fin && isfinite(out[k]);
+                    }
+                    if (!fin) s.fail = 1;
+                }
+                __syncthreads();
+                if (s.fail) {
+                    failed = true;
+                    break;
+                }
+                // ---- finite-difference blocks: task = (node j, neighbour nb, variable v)
+                for (int t = tid; t < NX * 3 * NV; t += DAE_THREADS) {
+                    const int j = t / (3 * NV), rem = t - j * 3 * NV, nb = rem / NV, v = rem - nb * NV;
+                    const int jn = j - 1 + nb;
+                    double* blk = (nb == 0 ? s.A : (nb == 1 ? s.D : s.C)) + j * NB;
+                    if (jn < 0 || jn >= NX) {
+#pragma unroll
+                        for (int k = 0; k < NV; ++k) blk[k * NV + v] = 0.0;
+                        continue;
+                    }
+                    double yl[NV], yc[NV], yr[NV];
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        yc[k] = s.Y[j * NV + k];
+                        yl[k] = s.Y[(j > 0 ? j - 1 : j) * NV + k];
+                        yr[k] = s.Y[(j < NX - 1 ? j + 1 : j) * NV + k];
+                    }
+                    const double y0 = s.Y[jn * NV + v];
+                    const double yp = y0 + FD_REL * fmax(fabs(y0), floor_of(v));
+                    const double delta = yp - y0;
+                    double r = s.rr[j], rho = s.rho[j];
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {   // compile-time indices keep the copies in registers
+                        if (k == v) {
+                            if (nb == 0) yl[k] = yp;
+                            else if (nb == 1) yc[k] = yp;
+                            else yr[k] = yp;
+                        }
+                    }
+                    if (nb == 1 && j > 0 && j < NX - 1) {
+                        r = rate_ch4(c, yc[5], yc[0], yc[1], yc[2], yc[3]);
+                        rho = density(c, yc);
+                    }
+                    double out[NV];
+                    node_equations(c, j, yl, yc, yr, s.Yold + j * NV, inv_dt, r, rho, out);
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) blk[k * NV + v] = (out[k] - s.F[j * NV + k]) / delta;
+                }
+                __syncthreads();
+                // ---- block Thomas, forward: M = [D_j - A_j W_{j-1} | C_j | -F_j - A_j g_{j-1}], Gauss-Jordan
+                const int row = tid / 15, col = tid - row * 15;
+                const bool elem = tid < NV * 15;
+                for (int j = 0; j < NX; ++j) {
+                    if (elem) {
+                        const double* Aj = s.A + j * NB + row * NV;
+                        double val;
+                        if (col < NV) {
+                            val = s.D[j * NB + row * NV + col];
+                            if (j > 0)
+                                for (int k = 0; k < NV; ++k) val -= Aj[k] * s.C[(j - 1) * NB + k * NV + col];
+                        } else if (col < 2 * NV) {
+                            val = s.C[j * NB + row * NV + (col - NV)];
+                        } else {
+                            val = -s.F[j * NV + row];
+                            if (j > 0)
+                                for (int k = 0; k < NV; ++k) val -= Aj[k] * s.F[(j - 1) * NV + k];
+                        }
+                        s.M[row * MROW + col] = val;
+                    }
+                    __syncthreads();
+                    unsigned used = 0, rowof = 0;   // every thread tracks the same pivot choices
+                    for (int pv = 0; pv < NV; ++pv) {
+                        int piv = -1;
+                        double best = -1.0;
+                        for (int rr_ = 0; rr_ < NV; ++rr_) {
+                            const double a = fabs(s.M[rr_ * MROW + pv]);
+                            if (!((used >> rr_) & 1u) && a > best) {
+                                best = a;
+                                piv = rr_;
+                            }
+                        }
+                        if (piv < 0 || !(best > 0.0)) {   // singular or NaN block
+                            piv = 0;
+                            while ((used >> piv) & 1u) ++piv;
+                            if (tid == 0) s.fail = 1;
+                        }
+                        used |= 1u << piv;
+                        rowof |= (unsigned)piv << (3 * pv);
+                        double a = 0.0, b = 0.0, pvv = 1.0, mine = 0.0;
+                        if (elem) {
+                            a = s.M[row * MROW + pv];
+                            b = s.M[piv * MROW + col];
+                            pvv = s.M[piv * MROW + pv];
+                            mine = s.M[row * MROW + col];
+                        }
+                        __syncthreads();
+                        if (elem) {
+                            const double bn = b / pvv;
+                            s.M[row * MROW + col] = (row == piv) ? bn : mine - a * bn;
+                        }
+                        __syncthreads();
+                    }
+                    if (tid < NV * 8) {   // unknown pu of node j sits in row rowof[pu]
+                        const int pu = tid >> 3, cc = tid & 7, src = (rowof >> (3 * pu)) & 7u;
+                        if (cc < NV) s.C[j * NB + pu * NV + cc] = s.M[src * MROW + NV + cc];
+                        else s.F[j * NV + pu] = s.M[src * MROW + 2 * NV];
+                    }
+                    __syncthreads();
+                }
+                // ---- backward: x_j = g_j - W_j x_{j+1}
+                for (int j = NX - 2; j >= 0; --j) {
+                    double x = 0.0;
+                    if (tid < NV) {
+                        x = s.F[j * NV + tid];
+                        for (int k = 0; k < NV; ++k) x -= s.C[j * NB + tid * NV + k] * s.F[(j + 1) * NV + k];
+                    }
+                    __syncthreads();
+                    if (tid < NV) s.F[j * NV + tid] = x;
+                    __syncthreads();
+                }
+                if (s.fail) {
+                    failed = true;
+                    break;
+                }
+                // ---- update and convergence test
+                double worst = 0.0;
+                bool fin = true;
+                for (int e = tid; e < NX * NV; e += DAE_THREADS) {
+                    const int v = e % NV;
+                    const double dy = s.F[e], y = s.Y[e] + dy;
+                    s.Y[e] = y;
+                    fin = fin && isfinite(y);
+                    worst = fmax(worst, fabs(dy) / (fabs(y) + floor_of(v)));
+                }
+                if (!fin) worst = INFINITY;
+                worst = warp_max(worst);
+                if ((tid & 31) == 0) s.red[tid >> 5] = worst;
+                __syncthreads();
+                worst = 0.0;
+                for (int w = 0; w < DAE_THREADS / 32; ++w) worst = fmax(worst, s.red[w]);
+                __syncthreads();
+                if (!(worst < INFINITY)) failed = true;
+                else if (worst < NEWTON_TOL) converged = true;
+            }
+            if (!converged) failed = true;
+        }
+        if (tid == 0) {
+            // outlet flows (set_likelihood.py:204-208), -10000 on failure (:244), squared residuals of the five species
+            const double* yo = s.Y + (NX - 1) * NV;
+            const double T = yo[5], u = yo[6];
+            double F[5];
+            bool ok = !failed;
+            for (int k = 0; k < 5; ++k) {
+                F[k] = yo[k] * kin::S_TUBE * u * 60 * kin::R_GAS * T / c.P0 * 1e6 * c.P0 / kin::P_STP * 298 / T;
+                ok = ok && isfinite(F[k]);
+            }
+            double acc = 0.0;
+            for (int k = 0; k < 5; ++k) {
+                const double f = ok ? F[k] : kin::FAIL_FLOW;
+                const double rsd = f - obs[(int64_t)k * n_cond + ci];
+                acc += rsd * rsd;
+            }
+            ssr[(int64_t)ci * n + p] = acc;
+        }
+    }
+}
+
+}  // namespace
+
+int launch_loglik_dae(smcb_handle* h, const double* theta, int64_t ld, int64_t n, int d, const uint8_t* active,
+                      double* lk, cudaStream_t st) {
+    const KineticData& D = h->kin;
+    REQUIRE(h, D.cond != nullptr, SMCB_ERR_STATE, "smcb_set_data_kinetic has not been called");
+    REQUIRE(h, D.n_pairs == 4, SMCB_ERR_UNSUPPORTED, "the transient reactor model has the reference's 8 kinetic parameters");
+    REQUIRE(h, d == D.d, SMCB_ERR_INVALID, "d differs from the d given to smcb_set_data_kinetic");
+    if (n == 0) return SMCB_OK;
+    REQUIRE(h, h->ssr != nullptr && n <= h->n_max && D.n_cond <= h->ssr_rows, SMCB_ERR_STATE,
+            "smcb_reserve too small for this sweep");
+    if (!h->dae_dts) {   // fixed time grid: 1 ms growing by 1.5x up to 5 s, last step clipped at 75 s
+        std::vector<double> dts;
+        double t = 0.0, dt = 1e-3;
+        while (t < 75.0) {
+            const double k = dt < 75.0 - t ? dt : 75.0 - t;
+            dts.push_back(k);
+            t += k;
+            dt = dt * 1.5 < 5.0 ? dt * 1.5 : 5.0;
+        }
+        CUDA_TRY(h, cudaMalloc((void**)&h->dae_dts, sizeof(double) * dts.size()));
+        CUDA_TRY(h, cudaMemcpy(h->dae_dts, dts.data(), sizeof(double) * dts.size(), cudaMemcpyHostToDevice));
+        h->dae_n_dt = (int)dts.size();
+        CUDA_TRY(h, cudaFuncSetAttribute(dae_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(Smem)));
+    }
+    unsigned* list = nullptr;
+    unsigned* count = nullptr;
+    int rc = kinetic_pack_active(h, active, n, st, &list, &count);
+    if (rc != SMCB_OK) return rc;
+    int64_t blocks = n * (int64_t)D.n_cond;
+    if (blocks > (int64_t)h->sm_count * 3) blocks = (int64_t)h->sm_count * 3;
+    dae_march_kernel<<<(unsigned)blocks, DAE_THREADS, sizeof(Smem), st>>>(theta, ld, n, list, count, D.cond, D.obs,
+                                                                         D.n_cond, D.base, D.est_pos, h->dae_dts,
+                                                                         h->dae_n_dt, h->ssr);
+    LAUNCH_CHECK(h);
+    return kinetic_finalize(h, theta, ld, n, active, lk, st);
+}

@@ -264,6 +264,30 @@ extern "C" int smcb_set_data_kinetic(smcb_handle* h, const double* cond_host, co
     return SMCB_OK;
 }
 
+// work list of a masked sweep (null pointers when there is no mask)
+int kinetic_pack_active(smcb_handle* h, const uint8_t* active, int64_t n, cudaStream_t st, unsigned** list,
+                        unsigned** count) {
+    *list = nullptr;
+    *count = nullptr;
+    if (active == nullptr) return SMCB_OK;
+    *list = h->mm_perm;
+    *count = reinterpret_cast<unsigned*>(h->mm_ctl);
+    CUDA_TRY(h, cudaMemsetAsync(*count, 0, sizeof(unsigned), st));
+    kinetic_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(active, n, *list, *count);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+// lk from the per-condition residual sums in h->ssr
+int kinetic_finalize(smcb_handle* h, const double* theta, int64_t ld, int64_t n, const uint8_t* active, double* lk,
+                     cudaStream_t st) {
+    const KineticData& D = h->kin;
+    kinetic_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(theta, ld, n, active, h->ssr, D.n_cond,
+                                                                       D.base, D.est_pos, 2 * D.n_pairs, lk);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
 int launch_loglik_kinetic(smcb_handle* h, const double* theta, int64_t ld, int64_t n, int d, const uint8_t* active,
                           double* lk, cudaStream_t st) {
     const KineticData& D = h->kin;
@@ -275,14 +299,9 @@ int launch_loglik_kinetic(smcb_handle* h, const double* theta, int64_t ld, int64
     dim3 grid((unsigned)((n + KB - 1) / KB), (unsigned)D.n_cond);
     unsigned* list = nullptr;
     unsigned* count = nullptr;
-    if (active != nullptr) {
-        count = reinterpret_cast<unsigned*>(h->mm_ctl);
-        if (grid.x > (unsigned)h->sm_count * 4) grid.x = (unsigned)h->sm_count * 4;
-        list = h->mm_perm;
-        CUDA_TRY(h, cudaMemsetAsync(count, 0, sizeof(unsigned), st));
-        kinetic_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(active, n, list, count);
-        LAUNCH_CHECK(h);
-    }
+    const int rc = kinetic_pack_active(h, active, n, st, &list, &count);
+    if (rc != SMCB_OK) return rc;
+    if (active != nullptr && grid.x > (unsigned)h->sm_count * 4) grid.x = (unsigned)h->sm_count * 4;
 #define SSR_ARGS theta, ld, n, list, count, D.cond, D.obs, D.n_cond, D.n_steps, D.base, D.est_pos, h->ssr
     if (D.n_pairs == 4 && !active) kinetic_ssr_kernel<1, false><<<grid, KB, 0, st>>>(SSR_ARGS);
     else if (D.n_pairs == 4) kinetic_ssr_kernel<1, true><<<grid, KB, 0, st>>>(SSR_ARGS);
@@ -290,10 +309,7 @@ int launch_loglik_kinetic(smcb_handle* h, const double* theta, int64_t ld, int64
     else kinetic_ssr_kernel<4, true><<<grid, KB, 0, st>>>(SSR_ARGS);
 #undef SSR_ARGS
     LAUNCH_CHECK(h);
-    kinetic_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(theta, ld, n, active, h->ssr, D.n_cond,
-                                                                       D.base, D.est_pos, 2 * D.n_pairs, lk);
-    LAUNCH_CHECK(h);
-    return SMCB_OK;
+    return kinetic_finalize(h, theta, ld, n, active, lk, st);
 }
 
 extern "C" int smcb_mh_fused(smcb_handle* h, int model, double* theta_dev, int64_t ld, double* lk_dev, int64_t n,

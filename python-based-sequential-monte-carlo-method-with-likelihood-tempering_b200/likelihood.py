@@ -104,3 +104,17 @@ class KineticRK:
         _lib.check(handle, lib.smcb_set_data_kinetic(
             handle, self.cond.ctypes.data, self.obs.ctypes.data, self.cond.shape[0], self.base.ctypes.data,
             self.n_pairs, self.est_pos.ctypes.data, self.d, self.n_steps))
+
+
+class KineticDAE(KineticRK):
+    """The reference's transient fixed-bed reactor (`reaction`, methanation_set_likelihood.py:69-139: 7 unknowns on 51
+    axial nodes, start-up from a 400 K bed to 75 s) instead of the plug-flow march: like-for-like physics for
+    reference-sized particle counts.  Same operating-condition rows, observations and parameter
+    vector as `KineticRK` with the reference's 8 kinetic parameters; implicit Euler on a fixed time grid, one thread
+    block per (particle, condition) (`csrc/dae.cu`).  Fused sweeps are not available for this model."""
+    model_id = _lib.MODEL_KINETIC_DAE
+
+    def __init__(self, cond, obs, base, est_pos, names=None):
+        super().__init__(cond, obs, base, est_pos, n_steps=1, names=names)
+        if self.n_pairs != 4:
+            raise ValueError("the transient reactor model takes the reference's 8 kinetic parameters + sigma")

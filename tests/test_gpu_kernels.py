@@ -256,6 +256,33 @@ def test_kinetic_masked_sweep_is_packed_not_changed(abi, n_pairs):
         assert np.all(part[act == 0] == 0.0)
 
 
+def test_transient_reactor_matches_oracle_march(abi):
+    """SURVEY.md 8(f) N3, model KINETIC_DAE: one thread block per (particle, condition) marches the reference's
+    357-unknown reactor DAE to 75 s; same implicit-Euler grid and Newton tolerance as oracle/methanation_dae.py."""
+    from oracle import methanation_dae as dae
+    cond = kinetic.synthetic_conditions(3)
+    base = kinetic.base_vector(4)
+    est = np.array(kinetic.EST_POSITION, dtype=np.int32)
+    obs = kinetic.synthetic_observations(cond, base)
+    low, high = kinetic.reference_box()
+    abi.ck(abi.lib.smcb_set_data_kinetic(abi.h, cond.ctypes.data, obs.ctypes.data, 3, base.ctypes.data, 4,
+                                         est.ctypes.data, 5, 1))
+    rs = np.random.RandomState(2)
+    th = np.vstack([base[est], base[est] * rs.uniform(0.8, 1.25, (5, 5))])
+    want = dae.loglik(th, cond, obs, base, est)
+    got = abi.loglik(4, th)
+    assert np.all(np.isfinite(got)) and np.all(want > -1e7)       # none of these marches fails
+    assert _rel(got, want).max() < 1e-7, _rel(got, want).max()    # Newton tolerance 1e-10 on both sides; bar 1e-5
+    act = np.array([1, 0, 1, 1, 0, 1], dtype=np.uint8)            # masked sweep: packed work list
+    part = abi.loglik(4, th, active=act)
+    assert np.array_equal(part[act == 1], got[act == 1]) and np.all(part[act == 0] == 0.0)
+    # a particle whose kinetics make Newton diverge gets the reference's failure penalty, not an error
+    bad = th[:1].copy()
+    bad[0, 0] *= 1e12
+    lk_bad = abi.loglik(4, bad)
+    assert np.isfinite(lk_bad[0]) and lk_bad[0] < got[0] - 1e3
+
+
 # ------------------------------------------------------------------------------------ K2 tempering
 @pytest.mark.parametrize("n", [1, 2, 777, 1000, (1 << 20) + 3])
 def test_temper_reductions(abi, n):
