@@ -13,8 +13,9 @@ index-1 DAE with SUNDIALS IDA through `assimulo` (`SMC_methanation/methanation_s
 
 PARITY OF THE TIME INTEGRATION IS UNPINNED: assimulo / IDA (variable-order BDF) is not installed and the
 reference stores no trajectories.  The integrator below is builder-defined and is what the device kernel
-(`csrc/dae.cu`) twins: implicit Euler (BDF1) on a fixed geometric time grid from 0 to 75 s, full Newton with a
-finite-difference block-tridiagonal Jacobian per iteration.  The bed's thermal time constant is ~8 s
+(`csrc/dae.cu`) twins: implicit Euler (BDF1) on a fixed geometric time grid from 0 to 75 s, modified Newton (a
+finite-difference block-tridiagonal Jacobian kept while the update shrinks by 0.3x per iteration); a step whose Newton
+iteration does not converge fails the march (-10000 flows, the reference's own penalty for IDA failures).  The bed's thermal time constant is ~8 s
 ((1-void) rho_s Cps 0.1 / (2U/dint)), so at 75 s the state is the steady state of the reference's discretised
 balances to ~1e-4, which is what both integrators converge to.
 
@@ -42,7 +43,7 @@ T_FINAL = 75.0               # set_likelihood.py:198
 
 # builder-defined time grid and Newton controls (twinned by csrc/dae.cu)
 DT0, DT_GROW, DT_MAX = 1e-3, 1.5, 5.0
-NEWTON_MAX, NEWTON_TOL = 25, 1e-10
+NEWTON_MAX, NEWTON_TOL = 40, 1e-10
 FLOOR = np.array([1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1.0, 1e-4])     # scale floors of (C x5, T, u)
 FD_REL = 1e-7
 
@@ -156,18 +157,28 @@ def _jacobian_banded(Y, Y_old, dt, cond_row, k8, F0):
 
 
 def integrate(cond_row, k8, return_history=False):
-    """Implicit-Euler march of one operating condition to 75 s.  Returns (Y, ok)."""
+    """Implicit-Euler march of one operating condition to 75 s with the device kernel's modified Newton: the Jacobian
+    of an iteration is kept for the following ones until the update stops shrinking by 0.3x.  Returns (Y, ok)."""
     Y = start_state(cond_row)
     hist = []
     with np.errstate(all="ignore"):
+        dt_prev, ab, steady = 0.0, None, False
         for dt in time_grid():
+            if steady:                       # nothing moved over a repeated step: the remaining steps are no-ops
+                if return_history:
+                    hist.append(Y.copy())
+                continue
             Y_old = Y.copy()
-            ok = False
-            for _ in range(NEWTON_MAX):
+            same_dt = dt == dt_prev          # the previous step's Jacobian serves a step of the same size
+            dt_prev = dt
+            ok, need_jac, prev_worst = False, not same_dt, np.inf
+            for it in range(NEWTON_MAX):
                 F0 = residual(Y, (Y - Y_old) / dt, cond_row, k8)
                 if not np.all(np.isfinite(F0)):
                     break
-                ab, kl, ku = _jacobian_banded(Y, Y_old, dt, cond_row, k8, F0)
+                if need_jac:
+                    need_jac = False
+                    ab, kl, ku = _jacobian_banded(Y, Y_old, dt, cond_row, k8, F0)
                 try:
                     dx = solve_banded((kl, ku), ab, -F0.T.reshape(-1), check_finite=True)
                 except (ValueError, np.linalg.LinAlgError):
@@ -176,11 +187,16 @@ def integrate(cond_row, k8, return_history=False):
                 Y = Y + dY
                 if not np.all(np.isfinite(Y)):
                     break
-                if np.max(np.abs(dY) / (np.abs(Y) + FLOOR[:, None])) < NEWTON_TOL:
+                worst = np.max(np.abs(dY) / (np.abs(Y) + FLOOR[:, None]))
+                if worst < NEWTON_TOL:
                     ok = True
+                    steady = it == 0 and same_dt
                     break
+                if worst > 0.3 * prev_worst:
+                    need_jac = True
+                prev_worst = worst
             if not ok:
-                return Y, False
+                return (Y, False, hist) if return_history else (Y, False)
             if return_history:
                 hist.append(Y.copy())
     return (Y, True, hist) if return_history else (Y, True)

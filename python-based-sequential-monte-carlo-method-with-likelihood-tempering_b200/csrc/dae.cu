@@ -10,10 +10,12 @@
 // only, so with the unknowns ordered node by node the Jacobian is block tridiagonal with 7x7 blocks:
 //   * residuals and the 3 x 7 perturbed residuals per node are independent tasks spread over the block's threads
 //     (the reaction rate, the expensive part, is reused when a neighbour is perturbed);
-//   * the linear solve is a block Thomas sweep, each node's 7 x 15 system [D' | C | rhs] reduced by Gauss-Jordan
-//     with row pivoting in shared memory, 105 threads on one element each.
-// Everything lives in shared memory (68 KB per block, three blocks per SM).  Cost: ~35 steps x ~4 Newton
-// iterations per march; this is the like-for-like physics mode for reference-sized particle counts, the plug-flow
+//   * the linear solve is a block Thomas sweep: each node's 7 x 21 system [D' | C | I] is reduced by Gauss-Jordan
+//     with row pivoting in shared memory, 147 threads on one element each, and the factors (inv D', W) are kept;
+//   * Newton is the modified kind: the factors serve the following iterations (one residual pass and one
+//     substitution by a single warp each) until the update stops shrinking by 0.3x, then they are refreshed.
+// Everything lives in shared memory (69 KB per block, three blocks per SM).  Cost: 35 steps x (1-2 Jacobians +
+// ~6 substitutions) per march; this is the like-for-like physics mode for reference-sized particle counts, the plug-flow
 // RK4 march of kinetic.cu is the throughput mode.
 #include <vector>
 
@@ -25,9 +27,10 @@ namespace {
 constexpr int NX = 51;        // methanation_set_conditon.py:44
 constexpr int NV = 7;         // C_H2, C_CO2, C_CH4, C_H2O, C_Ar, T, u
 constexpr int NB = NV * NV;
-constexpr int DAE_THREADS = 128;
-constexpr int MROW = 16;      // row stride of the 7 x 15 elimination scratch
-constexpr int NEWTON_MAX = 25;
+constexpr int DAE_THREADS = 160;
+constexpr int MCOLS = 3 * NV; // elimination scratch [D' | C | I]: 7 x 21, one thread per element
+constexpr int MROW = 22;      // its row stride
+constexpr int NEWTON_MAX = 40;
 
 constexpr double DZ_DISP = 0.95e-5;   // Dz   set_conditon.py:76
 constexpr double RHOS = 5075.0;       //      :77
@@ -107,8 +110,8 @@ struct Smem {
     double Yold[NX * NV];
     double F[NX * NV];      // residual, then right-hand side / Thomas g / Newton update
     double A[NX * NB];      // dF_j/dY_{j-1}
-    double D[NX * NB];      // dF_j/dY_j
-    double C[NX * NB];      // dF_j/dY_{j+1}, then the Thomas W
+    double D[NX * NB];      // dF_j/dY_j, then inv D'_j of the block factorisation
+    double C[NX * NB];      // dF_j/dY_{j+1}, then W_j = inv D'_j C_j
     double M[NV * MROW];
     double rr[NX], rho[NX];
     double red[DAE_THREADS / 32];
@@ -157,12 +160,18 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
             s.Y[e] = (v < 5) ? c.Cin[v] : (v == 5 ? (j == 0 ? c.T_in : T_BED0) : c.u_in);
         }
         __syncthreads();
-        bool failed = false;
-        for (int step = 0; step < n_dt && !failed; ++step) {
-            const double inv_dt = 1.0 / dts[step];
+        bool failed = false, steady = false;
+        double dt_prev = 0.0;
+        for (int step = 0; step < n_dt && !failed && !steady; ++step) {
+            const double dt = dts[step], inv_dt = 1.0 / dt;
+            // the factors of the previous step serve this one when the step size is the same (the 5 s steps of the
+            // second half of the march, where the bed is close to its steady state)
+            const bool same_dt = dt == dt_prev;
+            dt_prev = dt;
             for (int e = tid; e < NX * NV; e += DAE_THREADS) s.Yold[e] = s.Y[e];
             __syncthreads();
-            bool converged = false;
+            bool converged = false, need_jac = !same_dt;
+            double prev_worst = INFINITY;
             for (int it = 0; it < NEWTON_MAX && !converged && !failed; ++it) {
                 // ---- residual of every node, rate and density kept for the Jacobian
                 if (tid < NX) {
@@ -191,120 +200,144 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
                     failed = true;
                     break;
                 }
-                // ---- finite-difference blocks: task = (node j, neighbour nb, variable v)
-                for (int t = tid; t < NX * 3 * NV; t += DAE_THREADS) {
-                    const int j = t / (3 * NV), rem = t - j * 3 * NV, nb = rem / NV, v = rem - nb * NV;
-                    const int jn = j - 1 + nb;
-                    double* blk = (nb == 0 ? s.A : (nb == 1 ? s.D : s.C)) + j * NB;
-                    if (jn < 0 || jn >= NX) {
+                if (need_jac) {
+                    need_jac = false;
+                    // ---- finite-difference blocks: task = (node j, neighbour nb, variable v)
+                    for (int t = tid; t < NX * 3 * NV; t += DAE_THREADS) {
+                        const int j = t / (3 * NV), rem = t - j * 3 * NV, nb = rem / NV, v = rem - nb * NV;
+                        const int jn = j - 1 + nb;
+                        double* blk = (nb == 0 ? s.A : (nb == 1 ? s.D : s.C)) + j * NB;
+                        if (jn < 0 || jn >= NX) {
 #pragma unroll
-                        for (int k = 0; k < NV; ++k) blk[k * NV + v] = 0.0;
-                        continue;
-                    }
-                    double yl[NV], yc[NV], yr[NV];
-#pragma unroll
-                    for (int k = 0; k < NV; ++k) {
-                        yc[k] = s.Y[j * NV + k];
-                        yl[k] = s.Y[(j > 0 ? j - 1 : j) * NV + k];
-                        yr[k] = s.Y[(j < NX - 1 ? j + 1 : j) * NV + k];
-                    }
-                    const double y0 = s.Y[jn * NV + v];
-                    const double yp = y0 + FD_REL * fmax(fabs(y0), floor_of(v));
-                    const double delta = yp - y0;
-                    double r = s.rr[j], rho = s.rho[j];
-#pragma unroll
-                    for (int k = 0; k < NV; ++k) {   // compile-time indices keep the copies in registers
-                        if (k == v) {
-                            if (nb == 0) yl[k] = yp;
-                            else if (nb == 1) yc[k] = yp;
-                            else yr[k] = yp;
+                            for (int k = 0; k < NV; ++k) blk[k * NV + v] = 0.0;
+                            continue;
                         }
-                    }
-                    if (nb == 1 && j > 0 && j < NX - 1) {
-                        r = rate_ch4(c, yc[5], yc[0], yc[1], yc[2], yc[3]);
-                        rho = density(c, yc);
-                    }
-                    double out[NV];
-                    node_equations(c, j, yl, yc, yr, s.Yold + j * NV, inv_dt, r, rho, out);
+                        double yl[NV], yc[NV], yr[NV];
 #pragma unroll
-                    for (int k = 0; k < NV; ++k) blk[k * NV + v] = (out[k] - s.F[j * NV + k]) / delta;
-                }
-                __syncthreads();
-                // ---- block Thomas, forward: M = [D_j - A_j W_{j-1} | C_j | -F_j - A_j g_{j-1}], Gauss-Jordan
-                const int row = tid / 15, col = tid - row * 15;
-                const bool elem = tid < NV * 15;
-                for (int j = 0; j < NX; ++j) {
-                    if (elem) {
-                        const double* Aj = s.A + j * NB + row * NV;
-                        double val;
-                        if (col < NV) {
-                            val = s.D[j * NB + row * NV + col];
-                            if (j > 0)
-                                for (int k = 0; k < NV; ++k) val -= Aj[k] * s.C[(j - 1) * NB + k * NV + col];
-                        } else if (col < 2 * NV) {
-                            val = s.C[j * NB + row * NV + (col - NV)];
-                        } else {
-                            val = -s.F[j * NV + row];
-                            if (j > 0)
-                                for (int k = 0; k < NV; ++k) val -= Aj[k] * s.F[(j - 1) * NV + k];
+                        for (int k = 0; k < NV; ++k) {
+                            yc[k] = s.Y[j * NV + k];
+                            yl[k] = s.Y[(j > 0 ? j - 1 : j) * NV + k];
+                            yr[k] = s.Y[(j < NX - 1 ? j + 1 : j) * NV + k];
                         }
-                        s.M[row * MROW + col] = val;
-                    }
-                    __syncthreads();
-                    unsigned used = 0, rowof = 0;   // every thread tracks the same pivot choices
-                    for (int pv = 0; pv < NV; ++pv) {
-                        int piv = -1;
-                        double best = -1.0;
-                        for (int rr_ = 0; rr_ < NV; ++rr_) {
-                            const double a = fabs(s.M[rr_ * MROW + pv]);
-                            if (!((used >> rr_) & 1u) && a > best) {
-                                best = a;
-                                piv = rr_;
+                        const double y0 = s.Y[jn * NV + v];
+                        const double yp = y0 + FD_REL * fmax(fabs(y0), floor_of(v));
+                        const double delta = yp - y0;
+                        double r = s.rr[j], rho = s.rho[j];
+#pragma unroll
+                        for (int k = 0; k < NV; ++k) {   // compile-time indices keep the copies in registers
+                            if (k == v) {
+                                if (nb == 0) yl[k] = yp;
+                                else if (nb == 1) yc[k] = yp;
+                                else yr[k] = yp;
                             }
                         }
-                        if (piv < 0 || !(best > 0.0)) {   // singular or NaN block
-                            piv = 0;
-                            while ((used >> piv) & 1u) ++piv;
-                            if (tid == 0) s.fail = 1;
+                        if (nb == 1 && j > 0 && j < NX - 1) {
+                            r = rate_ch4(c, yc[5], yc[0], yc[1], yc[2], yc[3]);
+                            rho = density(c, yc);
                         }
-                        used |= 1u << piv;
-                        rowof |= (unsigned)piv << (3 * pv);
-                        double a = 0.0, b = 0.0, pvv = 1.0, mine = 0.0;
+                        double out[NV];
+                        node_equations(c, j, yl, yc, yr, s.Yold + j * NV, inv_dt, r, rho, out);
+                        const double inv_delta = 1.0 / delta;
+#pragma unroll
+                        for (int k = 0; k < NV; ++k) blk[k * NV + v] = (out[k] - s.F[j * NV + k]) * inv_delta;
+                    }
+                    __syncthreads();
+                    // ---- block Thomas factorisation: M = [D_j - A_j W_{j-1} | C_j | I] -> [I | W_j | inv D'_j]
+                    // by Gauss-Jordan with row pivoting, one thread per element; W_j replaces C_j, inv D'_j replaces D_j
+                    const int row = tid / MCOLS, col = tid - row * MCOLS;
+                    const bool elem = tid < NV * MCOLS;
+                    for (int j = 0; j < NX; ++j) {
                         if (elem) {
-                            a = s.M[row * MROW + pv];
-                            b = s.M[piv * MROW + col];
-                            pvv = s.M[piv * MROW + pv];
-                            mine = s.M[row * MROW + col];
+                            double val;
+                            if (col < NV) {
+                                const double* Aj = s.A + j * NB + row * NV;
+                                val = s.D[j * NB + row * NV + col];
+                                if (j > 0)
+                                    for (int k = 0; k < NV; ++k) val -= Aj[k] * s.C[(j - 1) * NB + k * NV + col];
+                            } else if (col < 2 * NV) {
+                                val = s.C[j * NB + row * NV + (col - NV)];
+                            } else {
+                                val = (col - 2 * NV == row) ? 1.0 : 0.0;
+                            }
+                            s.M[row * MROW + col] = val;
                         }
                         __syncthreads();
-                        if (elem) {
-                            const double bn = b / pvv;
-                            s.M[row * MROW + col] = (row == piv) ? bn : mine - a * bn;
+                        unsigned used = 0, rowof = 0;   // every thread tracks the same pivot choices
+                        for (int pv = 0; pv < NV; ++pv) {
+                            int piv = -1;
+                            double best = -1.0;
+                            for (int rr_ = 0; rr_ < NV; ++rr_) {
+                                const double a = fabs(s.M[rr_ * MROW + pv]);
+                                if (!((used >> rr_) & 1u) && a > best) {
+                                    best = a;
+                                    piv = rr_;
+                                }
+                            }
+                            if (piv < 0 || !(best > 0.0)) {   // singular or NaN block
+                                piv = 0;
+                                while ((used >> piv) & 1u) ++piv;
+                                if (tid == 0) s.fail = 1;
+                            }
+                            used |= 1u << piv;
+                            rowof |= (unsigned)piv << (3 * pv);
+                            double a = 0.0, b = 0.0, pvv = 1.0, mine = 0.0;
+                            if (elem) {
+                                a = s.M[row * MROW + pv];
+                                b = s.M[piv * MROW + col];
+                                pvv = s.M[piv * MROW + pv];
+                                mine = s.M[row * MROW + col];
+                            }
+                            __syncthreads();
+                            if (elem) {
+                                const double bn = b * kin::rcp(pvv);
+                                s.M[row * MROW + col] = (row == piv) ? bn : mine - a * bn;
+                            }
+                            __syncthreads();
+                        }
+                        if (tid < NV * 14) {   // unknown pu of node j sits in row rowof[pu]
+                            const int pu = tid / 14, cc = tid - pu * 14, src = (rowof >> (3 * pu)) & 7u;
+                            const double val = s.M[src * MROW + NV + cc];
+                            if (cc < NV) s.C[j * NB + pu * NV + cc] = val;
+                            else s.D[j * NB + pu * NV + (cc - NV)] = val;
                         }
                         __syncthreads();
                     }
-                    if (tid < NV * 8) {   // unknown pu of node j sits in row rowof[pu]
-                        const int pu = tid >> 3, cc = tid & 7, src = (rowof >> (3 * pu)) & 7u;
-                        if (cc < NV) s.C[j * NB + pu * NV + cc] = s.M[src * MROW + NV + cc];
-                        else s.F[j * NV + pu] = s.M[src * MROW + 2 * NV];
+                    if (s.fail) {
+                        failed = true;
+                        break;
                     }
-                    __syncthreads();
                 }
-                // ---- backward: x_j = g_j - W_j x_{j+1}
-                for (int j = NX - 2; j >= 0; --j) {
-                    double x = 0.0;
-                    if (tid < NV) {
-                        x = s.F[j * NV + tid];
-                        for (int k = 0; k < NV; ++k) x -= s.C[j * NB + tid * NV + k] * s.F[(j + 1) * NV + k];
+                // ---- substitution with the stored factors (warp 0): g_j = inv D'_j (-F_j - A_j g_{j-1}), then
+                // x_j = g_j - W_j x_{j+1}; F ends up holding the Newton update
+                if (tid < 32) {
+                    for (int j = 0; j < NX; ++j) {
+                        double tmp = 0.0;
+                        if (tid < NV) {
+                            tmp = -s.F[j * NV + tid];
+                            if (j > 0)
+                                for (int k = 0; k < NV; ++k) tmp -= s.A[j * NB + tid * NV + k] * s.F[(j - 1) * NV + k];
+                            s.M[tid] = tmp;
+                        }
+                        __syncwarp();
+                        if (tid < NV) {
+                            double g = 0.0;
+                            for (int k = 0; k < NV; ++k) g += s.D[j * NB + tid * NV + k] * s.M[k];
+                            s.F[j * NV + tid] = g;
+                        }
+                        __syncwarp();
                     }
-                    __syncthreads();
-                    if (tid < NV) s.F[j * NV + tid] = x;
-                    __syncthreads();
+                    for (int j = NX - 2; j >= 0; --j) {
+                        double x = 0.0;
+                        if (tid < NV) {
+                            x = s.F[j * NV + tid];
+                            for (int k = 0; k < NV; ++k) x -= s.C[j * NB + tid * NV + k] * s.F[(j + 1) * NV + k];
+                        }
+                        __syncwarp();
+                        if (tid < NV) s.F[j * NV + tid] = x;
+                        __syncwarp();
+                    }
                 }
-                if (s.fail) {
-                    failed = true;
-                    break;
-                }
+                __syncthreads();
                 // ---- update and convergence test
                 double worst = 0.0;
                 bool fin = true;
@@ -323,7 +356,14 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
                 for (int w = 0; w < DAE_THREADS / 32; ++w) worst = fmax(worst, s.red[w]);
                 __syncthreads();
                 if (!(worst < INFINITY)) failed = true;
-                else if (worst < NEWTON_TOL) converged = true;
+                else if (worst < NEWTON_TOL) {
+                    converged = true;
+                    // nothing moved over a repeated step: the state is steady and the remaining steps are no-ops
+                    if (it == 0 && same_dt) steady = true;
+                }
+                // the factors are kept for the next iteration unless the update stopped shrinking (modified Newton)
+                else if (worst > 0.3 * prev_worst) need_jac = true;
+                prev_worst = worst;
             }
             if (!converged) failed = true;
         }

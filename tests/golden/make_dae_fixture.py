@@ -68,3 +68,15 @@ for case in range(12):
 np.savez_compressed(os.path.join(HERE, "methanation_dae_residual.npz"), X=np.array(X), dX=np.array(dX), P=np.array(P),
                     RES=np.array(RES))
 print("wrote methanation_dae_residual.npz", np.array(RES).shape)
+
+# ---- synthetic observations of the transient model for the 30 builder-chosen operating conditions:
+# data = model(baseparams) + N(0, sigma^2) as in SMC_methanation_main.py:89-95, with the oracle's implicit-Euler march
+from oracle import methanation_dae as dae  # noqa: E402
+
+cond30 = kinetic.synthetic_conditions(30)
+base4 = kinetic.base_vector(4)
+F = dae.outlet_flows(base4[None, :], cond30)[0]
+obs = F + kinetic.SIGMA_TRUE * np.random.RandomState(20250206).standard_normal(F.shape)
+np.savez_compressed(os.path.join(HERE, "dae_synth.npz"), cond=cond30, base4=base4, flows=F, obs=obs,
+                    est4=np.array(kinetic.EST_POSITION, dtype=np.int32))
+print("wrote dae_synth.npz", F.shape, "failed marches:", int(np.sum(F == kinetic.FAIL_FLOW)))
