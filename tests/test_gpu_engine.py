@@ -294,6 +294,32 @@ def test_fused_sweeps_match_oracle_with_frozen_factor(pkg, n_pairs):
     eng.close()
 
 
+def test_transient_reactor_run_is_self_consistent(pkg):
+    """SURVEY.md 8(f) N3 through the engine: tempered run with the reference's transient reactor model (the oracle
+    needs ~1.4 s per march, so the checks are the run's own invariants; the likelihood itself is pinned against the
+    oracle in test_gpu_kernels.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dae_synth.npz"))
+    cond, obs = g["cond"][:4], np.ascontiguousarray(g["obs"][:, :4])
+    low, high = kinetic.reference_box()
+    N = 256
+    lik = pkg.KineticDAE(cond, obs, g["base4"], g["est4"])
+    eng = pkg.Engine(lik, pkg.UniformBox(low, high), pkg.Settings(n_particle=N, seed=3))
+    eng.sample_prior()
+    res = eng.run(keep_ancestors=True)
+    b = np.array(res.betas)
+    assert res.reached_one and b[-1] == 1.0 and np.all(np.diff(b) > 0)
+    assert all(np.all(np.diff(a) >= 0) for a in res.ancestors)
+    # the stored likelihoods are those of the stored particles
+    lk_run = res.lk.copy()
+    eng.sim_particle()
+    assert np.array_equal(eng.lk.cpu().numpy(), lk_run)
+    # no surviving particle carries a failed march, and the noise level is recovered (truth 5, data of 4 conditions)
+    assert lk_run.min() > -1e4
+    assert 2.0 < res.particles[:, 4].mean() < 12.0
+    eng.close()
+
+
 def test_full_size_run_properties(pkg, golden):
     """BASELINE config 2: MM progress curves, 2^20 particles, FP64.  The oracle cannot follow 3.6e7
     scipy solves, so check what must hold at any size: schedule monotone to exactly 1, ESS above the
