@@ -108,8 +108,9 @@ __device__ __forceinline__ void node_equations(const Case& c, int j, const doubl
 struct Smem {
     double Y[NX * NV];      // unknowns, node by node
     double Yold[NX * NV];
-    double F[NX * NV];      // residual, then right-hand side / Thomas g / Newton update
-    double A[NX * NB];      // dF_j/dY_{j-1}
+    double F[NX * NV];      // residual, then Thomas g / Newton update
+    double H[NX * NV];      // -inv D' F
+    double A[NX * NB];      // dF_j/dY_{j-1}, then L_j = inv D'_j A_j
     double D[NX * NB];      // dF_j/dY_j, then inv D'_j of the block factorisation
     double C[NX * NB];      // dF_j/dY_{j+1}, then W_j = inv D'_j C_j
     double M[NV * MROW];
@@ -119,7 +120,7 @@ struct Smem {
     int fail;
 };
 
-__global__ void __launch_bounds__(DAE_THREADS)
+__global__ void __launch_bounds__(DAE_THREADS, 3)
 dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const unsigned* __restrict__ list,
                  const unsigned* __restrict__ count, const double* __restrict__ cond,
                  const double* __restrict__ obs, int n_cond, const double* __restrict__ base,
@@ -264,16 +265,15 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
                         __syncthreads();
                         unsigned used = 0, rowof = 0;   // every thread tracks the same pivot choices
                         for (int pv = 0; pv < NV; ++pv) {
-                            int piv = -1;
-                            double best = -1.0;
-                            for (int rr_ = 0; rr_ < NV; ++rr_) {
-                                const double a = fabs(s.M[rr_ * MROW + pv]);
-                                if (!((used >> rr_) & 1u) && a > best) {
-                                    best = a;
-                                    piv = rr_;
-                                }
-                            }
-                            if (piv < 0 || !(best > 0.0)) {   // singular or NaN block
+                            // pivot row: largest magnitude among the unused rows, found by every warp for itself from
+                            // the high words of the seven candidates (29 bits of magnitude are plenty for a pivot choice)
+                            const int lane = tid & 31;
+                            unsigned key = 0;
+                            if (lane < NV && !((used >> lane) & 1u))
+                                key = ((unsigned)__double2hiint(s.M[lane * MROW + pv]) & 0x7ffffff8u) | (unsigned)lane;
+                            key = __reduce_max_sync(0xffffffffu, key);
+                            int piv = (int)(key & 7u);
+                            if (key < 8u || key >= 0x7ff00000u) {   // singular or non-finite block
                                 piv = 0;
                                 while ((used >> piv) & 1u) ++piv;
                                 if (tid == 0) s.fail = 1;
@@ -306,35 +306,59 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
                         failed = true;
                         break;
                     }
-                }
-                // ---- substitution with the stored factors (warp 0): g_j = inv D'_j (-F_j - A_j g_{j-1}), then
-                // x_j = g_j - W_j x_{j+1}; F ends up holding the Newton update
-                if (tid < 32) {
-                    for (int j = 0; j < NX; ++j) {
-                        double tmp = 0.0;
-                        if (tid < NV) {
-                            tmp = -s.F[j * NV + tid];
-                            if (j > 0)
-                                for (int k = 0; k < NV; ++k) tmp -= s.A[j * NB + tid * NV + k] * s.F[(j - 1) * NV + k];
-                            s.M[tid] = tmp;
+                    // L_j = inv D'_j A_j replaces A_j: the forward recurrence is then one 7x7 product per node
+                    for (int j0 = 0; j0 < NX; j0 += 13) {   // 13 whole nodes (637 products) per pass, four per thread
+                        const int e_end = (j0 + 13 < NX ? j0 + 13 : NX) * NB;
+                        double lv[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int e = j0 * NB + tid + i * DAE_THREADS;
+                            double acc = 0.0;
+                            if (e < e_end) {
+                                const int j = e / NB, rc = e - j * NB, pu = rc / NV, cc = rc - pu * NV;
+                                for (int k = 0; k < NV; ++k) acc += s.D[j * NB + pu * NV + k] * s.A[j * NB + k * NV + cc];
+                            }
+                            lv[i] = acc;
                         }
-                        __syncwarp();
-                        if (tid < NV) {
-                            double g = 0.0;
-                            for (int k = 0; k < NV; ++k) g += s.D[j * NB + tid * NV + k] * s.M[k];
-                            s.F[j * NV + tid] = g;
+                        __syncthreads();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int e = j0 * NB + tid + i * DAE_THREADS;
+                            if (e < e_end) s.A[e] = lv[i];
                         }
-                        __syncwarp();
+                        __syncthreads();
                     }
+                }
+                // ---- substitution with the stored factors: h_j = -inv D'_j F_j for all nodes at once, then the two
+                // serial recurrences g_j = h_j - L_j g_{j-1} and x_j = g_j - W_j x_{j+1} by seven lanes of warp 0, the
+                // running vector in registers and exchanged by shuffles; F ends up holding the Newton update
+                for (int e = tid; e < NX * NV; e += DAE_THREADS) {
+                    const int j = e / NV, pu = e - j * NV;
+                    double acc = 0.0;
+                    for (int k = 0; k < NV; ++k) acc -= s.D[j * NB + pu * NV + k] * s.F[j * NV + k];
+                    s.H[e] = acc;
+                }
+                __syncthreads();
+                if (tid < 32) {
+                    const int ln = tid < NV ? tid : 0;
+                    double g = s.H[ln];
+                    if (tid < NV) s.F[ln] = g;
+                    for (int j = 1; j < NX; ++j) {
+                        const double* Lr = s.A + j * NB + ln * NV;
+                        double acc = s.H[j * NV + ln];
+#pragma unroll
+                        for (int k = 0; k < NV; ++k) acc -= Lr[k] * __shfl_sync(0xffffffffu, g, k);
+                        g = acc;
+                        if (tid < NV) s.F[j * NV + ln] = g;
+                    }
+                    double x = g;   // x_{NX-1} = g_{NX-1}
                     for (int j = NX - 2; j >= 0; --j) {
-                        double x = 0.0;
-                        if (tid < NV) {
-                            x = s.F[j * NV + tid];
-                            for (int k = 0; k < NV; ++k) x -= s.C[j * NB + tid * NV + k] * s.F[(j + 1) * NV + k];
-                        }
-                        __syncwarp();
-                        if (tid < NV) s.F[j * NV + tid] = x;
-                        __syncwarp();
+                        const double* Wr = s.C + j * NB + ln * NV;
+                        double acc = s.F[j * NV + ln];
+#pragma unroll
+                        for (int k = 0; k < NV; ++k) acc -= Wr[k] * __shfl_sync(0xffffffffu, x, k);
+                        x = acc;
+                        if (tid < NV) s.F[j * NV + ln] = x;
                     }
                 }
                 __syncthreads();
