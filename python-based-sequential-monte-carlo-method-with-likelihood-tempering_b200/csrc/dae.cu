@@ -14,7 +14,7 @@
 //     with row pivoting in shared memory, 147 threads on one element each, and the factors (inv D', W) are kept;
 //   * Newton is the modified kind: the factors serve the following iterations (one residual pass and one
 //     substitution by a single warp each) until the update stops shrinking by 0.3x, then they are refreshed.
-// Everything lives in shared memory (69 KB per block, three blocks per SM).  Cost: 35 steps x (1-2 Jacobians +
+// Everything lives in shared memory (73 KB per block, three blocks per SM).  Cost: 35 steps x (1-2 Jacobians +
 // ~6 substitutions) per march; this is the like-for-like physics mode for reference-sized particle counts, the plug-flow
 // RK4 march of kinetic.cu is the throughput mode.
 #include <vector>
@@ -113,7 +113,7 @@ struct Smem {
     double A[NX * NB];      // dF_j/dY_{j-1}, then L_j = inv D'_j A_j
     double D[NX * NB];      // dF_j/dY_j, then inv D'_j of the block factorisation
     double C[NX * NB];      // dF_j/dY_{j+1}, then W_j = inv D'_j C_j
-    double M[NV * MROW];
+    double M[NV * MROW], M2[NV * MROW];   // elimination scratch, double-buffered
     double rr[NX], rho[NX];
     double red[DAE_THREADS / 32];
     Case cs;
@@ -247,22 +247,18 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
                     // by Gauss-Jordan with row pivoting, one thread per element; W_j replaces C_j, inv D'_j replaces D_j
                     const int row = tid / MCOLS, col = tid - row * MCOLS;
                     const bool elem = tid < NV * MCOLS;
+                    // The scratch is double-buffered: a pivot step reads one copy and writes the other (one barrier per
+                    // step), and the last barrier of a node covers both the write-back of its factors and the
+                    // assembly of the next node's system, which takes W_j straight from the scratch.
+                    double* Mc = s.M;
+                    double* Mn = s.M2;
+                    if (elem) {   // node 0: [D_0 | C_0 | I]
+                        Mc[row * MROW + col] = col < NV ? s.D[row * NV + col]
+                                                        : (col < 2 * NV ? s.C[row * NV + (col - NV)]
+                                                                        : (col - 2 * NV == row ? 1.0 : 0.0));
+                    }
+                    __syncthreads();
                     for (int j = 0; j < NX; ++j) {
-                        if (elem) {
-                            double val;
-                            if (col < NV) {
-                                const double* Aj = s.A + j * NB + row * NV;
-                                val = s.D[j * NB + row * NV + col];
-                                if (j > 0)
-                                    for (int k = 0; k < NV; ++k) val -= Aj[k] * s.C[(j - 1) * NB + k * NV + col];
-                            } else if (col < 2 * NV) {
-                                val = s.C[j * NB + row * NV + (col - NV)];
-                            } else {
-                                val = (col - 2 * NV == row) ? 1.0 : 0.0;
-                            }
-                            s.M[row * MROW + col] = val;
-                        }
-                        __syncthreads();
                         unsigned used = 0, rowof = 0;   // every thread tracks the same pivot choices
                         for (int pv = 0; pv < NV; ++pv) {
                             // pivot row: largest magnitude among the unused rows, found by every warp for itself from
@@ -270,7 +266,7 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
                             const int lane = tid & 31;
                             unsigned key = 0;
                             if (lane < NV && !((used >> lane) & 1u))
-                                key = ((unsigned)__double2hiint(s.M[lane * MROW + pv]) & 0x7ffffff8u) | (unsigned)lane;
+                                key = ((unsigned)__double2hiint(Mc[lane * MROW + pv]) & 0x7ffffff8u) | (unsigned)lane;
                             key = __reduce_max_sync(0xffffffffu, key);
                             int piv = (int)(key & 7u);
                             if (key < 8u || key >= 0x7ff00000u) {   // singular or non-finite block
@@ -280,27 +276,44 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
                             }
                             used |= 1u << piv;
                             rowof |= (unsigned)piv << (3 * pv);
-                            double a = 0.0, b = 0.0, pvv = 1.0, mine = 0.0;
                             if (elem) {
-                                a = s.M[row * MROW + pv];
-                                b = s.M[piv * MROW + col];
-                                pvv = s.M[piv * MROW + pv];
-                                mine = s.M[row * MROW + col];
-                            }
-                            __syncthreads();
-                            if (elem) {
+                                const double a = Mc[row * MROW + pv], b = Mc[piv * MROW + col], pvv = Mc[piv * MROW + pv],
+                                             mine = Mc[row * MROW + col];
                                 const double bn = b * kin::rcp(pvv);
-                                s.M[row * MROW + col] = (row == piv) ? bn : mine - a * bn;
+                                Mn[row * MROW + col] = (row == piv) ? bn : mine - a * bn;
                             }
                             __syncthreads();
+                            double* t = Mc;
+                            Mc = Mn;
+                            Mn = t;
                         }
-                        if (tid < NV * 14) {   // unknown pu of node j sits in row rowof[pu]
+                        // Mc = [I | W_j | inv D'_j] with unknown pu in row rowof[pu]
+                        if (tid < NV * 14) {
                             const int pu = tid / 14, cc = tid - pu * 14, src = (rowof >> (3 * pu)) & 7u;
-                            const double val = s.M[src * MROW + NV + cc];
+                            const double val = Mc[src * MROW + NV + cc];
                             if (cc < NV) s.C[j * NB + pu * NV + cc] = val;
                             else s.D[j * NB + pu * NV + (cc - NV)] = val;
                         }
+                        if (elem && j + 1 < NX) {   // [D_{j+1} - A_{j+1} W_j | C_{j+1} | I]
+                            const int jn = j + 1;
+                            double val;
+                            if (col < NV) {
+                                const double* Aj = s.A + jn * NB + row * NV;
+                                val = s.D[jn * NB + row * NV + col];
+#pragma unroll
+                                for (int k = 0; k < NV; ++k)
+                                    val -= Aj[k] * Mc[((rowof >> (3 * k)) & 7u) * MROW + NV + col];
+                            } else if (col < 2 * NV) {
+                                val = s.C[jn * NB + row * NV + (col - NV)];
+                            } else {
+                                val = (col - 2 * NV == row) ? 1.0 : 0.0;
+                            }
+                            Mn[row * MROW + col] = val;
+                        }
                         __syncthreads();
+                        double* t = Mc;
+                        Mc = Mn;
+                        Mn = t;
                     }
                     if (s.fail) {
                         failed = true;
