@@ -41,29 +41,31 @@ constexpr double NEWTON_TOL = 1e-10, FD_REL = 1e-7;
 
 struct Case {
     double Cin[5], T_in, T_j, u_in, voidf, dz, P0;
-    double k8[8];
+    double inv_dz, inv_dz2;   // 1/dz, 1/dz^2
+    double kA[4], nEoR[4];    // prefactors and -E/R of (kf, ks, kCO2, kH2O)
 };
 
 __device__ __forceinline__ double floor_of(int v) { return v < 5 ? 1e-3 : (v == 5 ? 1.0 : 1e-4); }
 
-// func_rCH4 (set_likelihood.py:44-58)
+// func_rCH4 (set_likelihood.py:44-58); quotients as MUFU-seeded reciprocals (kin::rcp, < 1 ulp)
 __device__ __forceinline__ double rate_ch4(const Case& c, double T, double Ca, double Cb, double Cc, double Cd) {
     const double RT6 = kin::R_GAS * T * 1e-6;
     const double PH2 = Ca * RT6, PCO2 = Cb * RT6, PCH4 = Cc * RT6, PH2O = Cd * RT6;
-    const double kf = c.k8[0] * exp(-c.k8[1] / kin::R_GAS / T);
-    const double ks = c.k8[2] * exp(-c.k8[3] / kin::R_GAS / T);
-    const double kC = c.k8[4] * exp(-c.k8[5] / kin::R_GAS / T);
-    const double kW = c.k8[6] * exp(-c.k8[7] / kin::R_GAS / T);
+    const double iT = kin::rcp(T);
+    const double kf = c.kA[0] * exp(c.nEoR[0] * iT);
+    const double ks = c.kA[1] * exp(c.nEoR[1] * iT);
+    const double kC = c.kA[2] * exp(c.nEoR[2] * iT);
+    const double kW = c.kA[3] * exp(c.nEoR[3] * iT);
     const double dC = 1.0 + kC * PCO2, dW = 1.0 + kW * PH2O;
-    const double rf = 5075e3 * kf * kC * PCO2 * sqrt(fmax(0.001, PH2)) / (dC * dC);
-    const double rr = 5075e3 * ks * kW * PH2O * (PCH4 * PCH4) / (dW * dW);
+    const double rf = 5075e3 * kf * kC * PCO2 * kin::sqrt_fast(fmax(0.001, PH2)) * kin::rcp(dC * dC);
+    const double rr = 5075e3 * ks * kW * PH2O * (PCH4 * PCH4) * kin::rcp(dW * dW);
     return rf - rr;
 }
 
 // func_rohg (:61-66)
 __device__ __forceinline__ double density(const Case& c, const double* y) {
-    return c.P0 / kin::R_GAS / y[5] * (y[0] * 2 + y[1] * 44 + y[2] * 16 + y[3] * 18 + y[4] * 40) /
-           (y[0] + y[1] + y[2] + y[3] + y[4]) * 0.001;
+    return c.P0 / kin::R_GAS * kin::rcp(y[5]) * (y[0] * 2 + y[1] * 44 + y[2] * 16 + y[3] * 18 + y[4] * 40) *
+           kin::rcp(y[0] + y[1] + y[2] + y[3] + y[4]) * 0.001;
 }
 
 // Equations of node j (`reaction` :69-139) given the unknowns of nodes j-1 (yl), j (yc), j+1 (yr), the previous
@@ -87,22 +89,23 @@ __device__ __forceinline__ void node_equations(const Case& c, int j, const doubl
         out[6] = yc[5] - yl[5];
         return;
     }
-    const double dz = c.dz, vd = c.voidf, dz2 = dz * dz;
+    const double idz = c.inv_dz, idz2 = c.inv_dz2, vd = c.voidf;
     const double T = yc[5], u = yc[6], Tl = yl[5], ul = yl[6], Tr = yr[5];
+    const double iT = kin::rcp(T), iTl = kin::rcp(Tl), iTr = kin::rcp(Tr);
     const double dT = (T - yold[5]) * inv_dt;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         const double lap = (j == 1) ? (yr[k] - yc[k]) : (yr[k] - 2 * yc[k] + yl[k]);
-        out[k] = -vd * ((yc[k] - yold[k]) * inv_dt) - (u * yc[k] - ul * yl[k]) / dz + vd * DZ_DISP * lap / dz2 +
+        out[k] = -vd * ((yc[k] - yold[k]) * inv_dt) - (u * yc[k] - ul * yl[k]) * idz + vd * DZ_DISP * lap * idz2 +
                  (1 - vd) * sc[k] * r;
     }
-    double cont = -u * c.P0 * (1 / T - 1 / Tl) / dz - c.P0 / T * (u - ul) / dz +
-                  vd * DZ_DISP * c.P0 * (1 / Tr - 2 / T + 1 / Tl) / dz2 + (1 - vd) * kin::R_GAS * (-2) * r;
-    if (j == 1) cont += c.P0 * vd / (T * T) * dT;
+    double cont = -u * c.P0 * (iT - iTl) * idz - c.P0 * iT * (u - ul) * idz +
+                  vd * DZ_DISP * c.P0 * (iTr - 2 * iT + iTl) * idz2 + (1 - vd) * kin::R_GAS * (-2) * r;
+    if (j == 1) cont += c.P0 * vd * (iT * iT) * dT;
     out[5] = cont;
     const double store = (j == 1) ? 1.0 : 0.1;
-    out[6] = -store * (vd * rho * kin::CPG + (1 - vd) * RHOS * CPS) * dT - rho * kin::CPG * (T * u - Tl * ul) / dz +
-             KEFF * (Tr - 2 * T + Tl) / dz2 + (1 - vd) * (-kin::HR) * r - 2 * kin::U_WALL / kin::DINT * (T - c.T_j);
+    out[6] = -store * (vd * rho * kin::CPG + (1 - vd) * RHOS * CPS) * dT - rho * kin::CPG * (T * u - Tl * ul) * idz +
+             KEFF * (Tr - 2 * T + Tl) * idz2 + (1 - vd) * (-kin::HR) * r - 2 * kin::U_WALL / kin::DINT * (T - c.T_j);
 }
 
 struct Smem {
@@ -147,10 +150,14 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
             s.cs.u_in = row[7];
             s.cs.voidf = row[8];
             s.cs.dz = row[9] / (NX - 1);
+            s.cs.inv_dz = 1.0 / s.cs.dz;
+            s.cs.inv_dz2 = s.cs.inv_dz * s.cs.inv_dz;
             s.cs.P0 = csum;
             for (int k = 0; k < 8; ++k) {
                 const int ip = inv_pos[k];
-                s.cs.k8[k] = (ip >= 0) ? theta[(int64_t)ip * ld + p] : base[k];
+                const double val = (ip >= 0) ? theta[(int64_t)ip * ld + p] : base[k];
+                if (k & 1) s.cs.nEoR[k >> 1] = -val / kin::R_GAS;
+                else s.cs.kA[k >> 1] = val;
             }
             s.fail = 0;
         }
