@@ -16,6 +16,7 @@ Workloads (BASELINE.json configs):
                 observations), 2^20 particles per GPU, FP64, scipy-RK45-twin arithmetic.  DEFAULT.
   mm_rate       config 4 shape: 10 000 rate-law observations, 2^22 particles per GPU (--particles)
   kinetic       config 3: methanation-style reactor, d=5, 30 conditions, RK4 x 50, 2^18 particles
+  kinetic_dae   SURVEY 8(f) N3: the reference's transient reactor DAE, 30 conditions, the reference's N = 1000
   kinetic32     config 5: 32-parameter kinetic family, 10 fused MH sweeps per stage, 2^21 particles per GPU
                 (2^24 over 8 GPUs; --total-particles 16777216 for the strong-scaling series)
 With N > 1 (torchrun) particles are sharded, per-GPU count fixed => "scaling": "weak".
@@ -50,7 +51,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="mm_progress", choices=["mm_progress", "mm_rate", "kinetic", "kinetic32"])
+    ap.add_argument("--workload", default="mm_progress", choices=["mm_progress", "mm_rate", "kinetic", "kinetic32", "kinetic_dae"])
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (0 = workload default)")
     ap.add_argument("--total-particles", type=int, default=0,
                     help="strong scaling: this many particles in total, split evenly over the GPUs")
@@ -85,6 +86,14 @@ def make_workload(pkg, name, n_per_gpu):
         n = n_per_gpu or (1 << 18)
         cfg = dict()
         desc = "methanation-style plug-flow reactor, d=5, 30 conditions, RK4 x 50 steps, FP64"
+    elif name == "kinetic_dae":
+        g = np.load(os.path.join(ROOT, "tests", "golden", "dae_synth.npz"))
+        lik = pkg.KineticDAE(g["cond"], g["obs"], g["base4"], g["est4"])
+        prior = pkg.UniformBox(kf["low4"], kf["high4"], names=["Af", "Eaf", "Ar", "Ear", "sigma"])
+        n = n_per_gpu or 1000
+        cfg = dict()
+        desc = ("the reference's transient fixed-bed reactor (357-unknown DAE, 30 conditions, start-up to 75 s), "
+                "implicit Euler + modified Newton, FP64")
     else:
         cond, base, obs = kf["cond"], kf["base16"], kf["obs16"]
         est = np.arange(32, dtype=np.int32)
@@ -224,6 +233,31 @@ def cpu_baseline_kinetic(target_n=65536):
                       f"vectorised over the particles of a chunk), multiprocessing over all cores, {dt:.1f} s"}
 
 
+def _cpu_dae_chunk(args):
+    from oracle import methanation_dae as dae
+    th, cond, obs, base, est = args
+    return dae.loglik(th, cond, obs, base, est)
+
+
+def cpu_baseline_dae(per_core=2):
+    """The transient reactor likelihood on the host cores: oracle/methanation_dae.py (NumPy residual, banded LAPACK
+    solves; the reference's assimulo / IDA is not installed), particles around the data-generating parameters."""
+    import multiprocessing as mp
+    g = np.load(os.path.join(ROOT, "tests", "golden", "dae_synth.npz"))
+    cond, base, obs, est = g["cond"], g["base4"], g["obs"], g["est4"]
+    cores = os.cpu_count() or 1
+    n = per_core * cores
+    th = base[est] * np.random.RandomState(1).uniform(0.8, 1.25, (n, len(est)))
+    chunks = [c for c in np.array_split(th, cores) if len(c)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        pool.map(_cpu_dae_chunk, [(c, cond, obs, base, est) for c in chunks])
+        dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} particles x 30 conditions (={n * 30} marches), oracle.methanation_dae (same implicit-Euler "
+                      f"grid and Newton policy as the device kernel), multiprocessing over all cores, {dt:.1f} s"}
+
+
 def run_reference_arm(args):
     """CPU implementation of the hot path (oracle restatement of the reference) on a bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -306,6 +340,9 @@ def main():
     if args.cpu_baseline_only:
         if args.workload == "kinetic":
             print(json.dumps(cpu_baseline_kinetic()), flush=True)
+            return
+        if args.workload == "kinetic_dae":
+            print(json.dumps(cpu_baseline_dae()), flush=True)
             return
         out = cpu_baseline_mm_progress()
         out["config1_run"] = cpu_config1_run()
@@ -536,12 +573,12 @@ def main():
                "api": "smcb200.run(likelihood, prior, pinned host particles, settings) -> Result (host arrays)"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload in ("mm_progress", "kinetic"):
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload in ("mm_progress", "kinetic", "kinetic_dae"):
         # separate process: the worker pool forks, which must not happen under a live CUDA context
         out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline-only", "--workload",
                               args.workload], capture_output=True, text=True, timeout=600)
         cpu = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {"error": out.stderr[-300:]}
-        if args.workload == "kinetic" and "value" in cpu:
+        if args.workload in ("kinetic", "kinetic_dae") and "value" in cpu:
             # the CPU cannot run 1e7 evaluations in the bench's time budget: the figure below is the measured CPU
             # likelihood rate applied to the evaluations the GPU run needed - an extrapolation, labelled as such
             cpu["time_to_beta1_s_extrapolated"] = (evals / args.steps) / cpu["value"]
