@@ -75,6 +75,24 @@ inline double from_bits(int hi, int lo) {
 }
 #endif
 
+// exp(x) for |x| < 708 (the caller has checked): no range handling at all
+EXPT_HD double exp_core(double x, const double* tab) {
+    const double t = fma(x, C[0], C[1]);
+    const int k = lo_bits(t);
+    const double kf = t - C[1];
+    double r = fma(kf, C[2], x);
+    r = fma(kf, C[3], r);
+    double q = fma(r, C[4], C[5]);
+    q = fma(q, r, C[6]);
+    q = fma(q, r, C[7]);
+    const double p = fma(q, r * r, r);
+    const double tj = tab[k & 63];
+    const double y = fma(tj, p, tj);
+    return from_bits(hi_bits(y) + ((k >> 6) << 20), lo_bits(y));
+}
+
+// exp(x) for any x: out-of-range and non-finite arguments replaced by integer selects on the bits of x (written out
+// rather than wrapped around exp_core: through a repacked double the compiler turns the selects into branches)
 EXPT_HD double exp_fast(double x, const double* tab) {
     const double t = fma(x, C[0], C[1]);
     const int k = lo_bits(t);
@@ -87,7 +105,6 @@ EXPT_HD double exp_fast(double x, const double* tab) {
     const double p = fma(q, r * r, r);
     const double tj = tab[k & 63];
     const double y = fma(tj, p, tj);
-    // 2^e into the exponent field; out-of-range and non-finite arguments replaced by integer selects
     const int hx = hi_bits(x), lx = lo_bits(x);
     const unsigned ax = (unsigned)hx & 0x7fffffffu;
     int hi = hi_bits(y) + ((k >> 6) << 20), lo = lo_bits(y);

@@ -23,6 +23,7 @@ __device__ __forceinline__ void load_kin(const double* __restrict__ theta, int64
         const double E = (ie >= 0) ? theta[(int64_t)ie * ld + p] : base[2 * j + 1];
         K.nEoR[j] = -E / kin::R_GAS;
     }
+    K.set_limit();
     const int is = inv_pos[8 * M];
     *sigma = (is >= 0) ? theta[(int64_t)is * ld + p] : base[8 * M];
 }
