@@ -10,8 +10,9 @@
 // only, so with the unknowns ordered node by node the Jacobian is block tridiagonal with 7x7 blocks:
 //   * residuals and the 3 x 7 perturbed residuals per node are independent tasks spread over the block's threads
 //     (the reaction rate, the expensive part, is reused when a neighbour is perturbed);
-//   * the linear solve is a block Thomas sweep: each node's 7 x 21 system [D' | C | I] is reduced by Gauss-Jordan
-//     with row pivoting in shared memory, 147 threads on one element each, and the factors (inv D', W) are kept;
+//   * the linear solve is a twisted block Thomas sweep (from both ends to the middle node): each node's 7 x 21
+//     system [D' | C | I] is reduced by Gauss-Jordan with row pivoting in shared memory, 147 threads on one element
+//     of each of the two chains, and the factors are kept;
 //   * Newton is the modified kind: the factors serve the following iterations (one residual pass and one
 //     substitution by a single warp each) until the update stops shrinking by 0.3x, then they are refreshed.
 // Everything lives in shared memory (73 KB per block, three blocks per SM).  Cost: 35 steps x (1-2 Jacobians +
@@ -31,6 +32,7 @@ constexpr int DAE_THREADS = 160;
 constexpr int MCOLS = 3 * NV; // elimination scratch [D' | C | I]: 7 x 21, one thread per element
 constexpr int MROW = 22;      // its row stride
 constexpr int NEWTON_MAX = 40;
+constexpr int MID = NX / 2;   // node where the two elimination chains meet
 
 constexpr double DZ_DISP = 0.95e-5;   // Dz   set_conditon.py:76
 constexpr double RHOS = 5075.0;       //      :77
@@ -112,11 +114,11 @@ struct Smem {
     double Y[NX * NV];      // unknowns, node by node
     double Yold[NX * NV];
     double F[NX * NV];      // residual, then Thomas g / Newton update
-    double H[NX * NV];      // -inv D' F
     double A[NX * NB];      // dF_j/dY_{j-1}, then L_j = inv D'_j A_j
     double D[NX * NB];      // dF_j/dY_j, then inv D'_j of the block factorisation
     double C[NX * NB];      // dF_j/dY_{j+1}, then W_j = inv D'_j C_j
-    double M[NV * MROW], M2[NV * MROW];   // elimination scratch, double-buffered
+    double M[4 * NV * MROW];              // elimination scratch: two systems, double-buffered; between
+                                          // factorisations its first NX*NV words hold h = -inv D F
     double rr[NX], rho[NX];
     double red[DAE_THREADS / 32];
     Case cs;
@@ -250,83 +252,128 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
                         for (int k = 0; k < NV; ++k) blk[k * NV + v] = (out[k] - s.F[j * NV + k]) * inv_delta;
                     }
                     __syncthreads();
-                    // ---- block Thomas factorisation: M = [D_j - A_j W_{j-1} | C_j | I] -> [I | W_j | inv D'_j]
-                    // by Gauss-Jordan with row pivoting, one thread per element; W_j replaces C_j, inv D'_j replaces D_j
+                    // ---- twisted block factorisation: the elimination runs from both ends towards the middle node MID,
+                    // two independent chains of half the length.  Step t reduces, by Gauss-Jordan with row pivoting
+                    // and one thread per element (of both systems),
+                    //   top    node t:       [D - A W_{t-1} | C | I] -> [I | W | inv D']    (W replaces C, inv D' replaces D)
+                    //   bottom node NX-1-t:  [D - C V_{b+1} | A | I] -> [I | V | inv D'']   (V replaces A, inv D'' replaces D)
+                    // The scratch is double-buffered (one barrier per pivot step); the last barrier of a step covers
+                    // the write-back of the factors and the assembly of the next two systems, which take W and V
+                    // straight from the scratch.  The middle node closes with inv(D - A W_{MID-1} - C V_{MID+1}).
                     const int row = tid / MCOLS, col = tid - row * MCOLS;
                     const bool elem = tid < NV * MCOLS;
-                    // The scratch is double-buffered: a pivot step reads one copy and writes the other (one barrier per
-                    // step), and the last barrier of a node covers both the write-back of its factors and the
-                    // assembly of the next node's system, which takes W_j straight from the scratch.
-                    double* Mc = s.M;
-                    double* Mn = s.M2;
-                    if (elem) {   // node 0: [D_0 | C_0 | I]
-                        Mc[row * MROW + col] = col < NV ? s.D[row * NV + col]
-                                                        : (col < 2 * NV ? s.C[row * NV + (col - NV)]
-                                                                        : (col - 2 * NV == row ? 1.0 : 0.0));
+                    const int lane = tid & 31;
+                    double* Mc[2] = {s.M, s.M + 2 * NV * MROW};
+                    double* Mn[2] = {s.M + NV * MROW, s.M + 3 * NV * MROW};
+                    if (elem) {
+                        const int jb = NX - 1;
+                        Mc[0][row * MROW + col] = col < NV ? s.D[row * NV + col]
+                                                           : (col < 2 * NV ? s.C[row * NV + (col - NV)]
+                                                                           : (col - 2 * NV == row ? 1.0 : 0.0));
+                        Mc[1][row * MROW + col] = col < NV ? s.D[jb * NB + row * NV + col]
+                                                           : (col < 2 * NV ? s.A[jb * NB + row * NV + (col - NV)]
+                                                                           : (col - 2 * NV == row ? 1.0 : 0.0));
                     }
                     __syncthreads();
-                    for (int j = 0; j < NX; ++j) {
-                        unsigned used = 0, rowof = 0;   // every thread tracks the same pivot choices
+                    for (int t = 0; t <= MID; ++t) {
+                        const bool last = t == MID;          // middle node: one system only
+                        const int nsys = last ? 1 : 2;
+                        const int jt = t, jb = NX - 1 - t;
+                        unsigned used[2] = {0, 0}, rowof[2] = {0, 0};   // every thread tracks the same pivot choices
                         for (int pv = 0; pv < NV; ++pv) {
-                            // pivot row: largest magnitude among the unused rows, found by every warp for itself from
-                            // the high words of the seven candidates (29 bits of magnitude are plenty for a pivot choice)
-                            const int lane = tid & 31;
-                            unsigned key = 0;
-                            if (lane < NV && !((used >> lane) & 1u))
-                                key = ((unsigned)__double2hiint(Mc[lane * MROW + pv]) & 0x7ffffff8u) | (unsigned)lane;
-                            key = __reduce_max_sync(0xffffffffu, key);
-                            int piv = (int)(key & 7u);
-                            if (key < 8u || key >= 0x7ff00000u) {   // singular or non-finite block
-                                piv = 0;
-                                while ((used >> piv) & 1u) ++piv;
-                                if (tid == 0) s.fail = 1;
-                            }
-                            used |= 1u << piv;
-                            rowof |= (unsigned)piv << (3 * pv);
-                            if (elem) {
-                                const double a = Mc[row * MROW + pv], b = Mc[piv * MROW + col], pvv = Mc[piv * MROW + pv],
-                                             mine = Mc[row * MROW + col];
-                                const double bn = b * kin::rcp(pvv);
-                                Mn[row * MROW + col] = (row == piv) ? bn : mine - a * bn;
+#pragma unroll
+                            for (int y = 0; y < 2; ++y) {
+                                if (y < nsys) {
+                                    // pivot row: largest magnitude among the unused rows, found by every warp for
+                                    // itself from the high words of the seven candidates
+                                    unsigned key = 0;
+                                    if (lane < NV && !((used[y] >> lane) & 1u))
+                                        key = ((unsigned)__double2hiint(Mc[y][lane * MROW + pv]) & 0x7ffffff8u) | (unsigned)lane;
+                                    key = __reduce_max_sync(0xffffffffu, key);
+                                    int piv = (int)(key & 7u);
+                                    if (key < 8u || key >= 0x7ff00000u) {   // singular or non-finite block
+                                        piv = 0;
+                                        while ((used[y] >> piv) & 1u) ++piv;
+                                        if (tid == 0) s.fail = 1;
+                                    }
+                                    used[y] |= 1u << piv;
+                                    rowof[y] |= (unsigned)piv << (3 * pv);
+                                    if (elem) {
+                                        const double* M0 = Mc[y];
+                                        const double a = M0[row * MROW + pv], b2 = M0[piv * MROW + col],
+                                                     pvv = M0[piv * MROW + pv], mine = M0[row * MROW + col];
+                                        const double bn = b2 * kin::rcp(pvv);
+                                        Mn[y][row * MROW + col] = (row == piv) ? bn : mine - a * bn;
+                                    }
+                                }
                             }
                             __syncthreads();
-                            double* t = Mc;
-                            Mc = Mn;
-                            Mn = t;
+#pragma unroll
+                            for (int y = 0; y < 2; ++y) {
+                                double* tmp = Mc[y];
+                                Mc[y] = Mn[y];
+                                Mn[y] = tmp;
+                            }
                         }
-                        // Mc = [I | W_j | inv D'_j] with unknown pu in row rowof[pu]
+                        // Mc[y] = [I | W or V | inverse] with unknown pu in row rowof[y][pu]
                         if (tid < NV * 14) {
-                            const int pu = tid / 14, cc = tid - pu * 14, src = (rowof >> (3 * pu)) & 7u;
-                            const double val = Mc[src * MROW + NV + cc];
-                            if (cc < NV) s.C[j * NB + pu * NV + cc] = val;
-                            else s.D[j * NB + pu * NV + (cc - NV)] = val;
+                            const int pu = tid / 14, cc = tid - pu * 14;
+                            const double vt = Mc[0][((rowof[0] >> (3 * pu)) & 7u) * MROW + NV + cc];
+                            if (last) {
+                                if (cc >= NV) s.D[MID * NB + pu * NV + (cc - NV)] = vt;
+                            } else {
+                                const double vb = Mc[1][((rowof[1] >> (3 * pu)) & 7u) * MROW + NV + cc];
+                                if (cc < NV) {
+                                    s.C[jt * NB + pu * NV + cc] = vt;
+                                    s.A[jb * NB + pu * NV + cc] = vb;
+                                } else {
+                                    s.D[jt * NB + pu * NV + (cc - NV)] = vt;
+                                    s.D[jb * NB + pu * NV + (cc - NV)] = vb;
+                                }
+                            }
                         }
-                        if (elem && j + 1 < NX) {   // [D_{j+1} - A_{j+1} W_j | C_{j+1} | I]
-                            const int jn = j + 1;
-                            double val;
+                        if (elem && !last) {
+                            const int nt = jt + 1, nbm = jb - 1;   // next top / bottom nodes; they coincide at MID
+                            const bool mid_next = nt == MID;
+                            double vt, vb = 0.0;
                             if (col < NV) {
-                                const double* Aj = s.A + jn * NB + row * NV;
-                                val = s.D[jn * NB + row * NV + col];
+                                vt = s.D[nt * NB + row * NV + col];
 #pragma unroll
                                 for (int k = 0; k < NV; ++k)
-                                    val -= Aj[k] * Mc[((rowof >> (3 * k)) & 7u) * MROW + NV + col];
+                                    vt -= s.A[nt * NB + row * NV + k] * Mc[0][((rowof[0] >> (3 * k)) & 7u) * MROW + NV + col];
+                                if (mid_next) {
+#pragma unroll
+                                    for (int k = 0; k < NV; ++k)
+                                        vt -= s.C[nt * NB + row * NV + k] * Mc[1][((rowof[1] >> (3 * k)) & 7u) * MROW + NV + col];
+                                } else {
+                                    vb = s.D[nbm * NB + row * NV + col];
+#pragma unroll
+                                    for (int k = 0; k < NV; ++k)
+                                        vb -= s.C[nbm * NB + row * NV + k] * Mc[1][((rowof[1] >> (3 * k)) & 7u) * MROW + NV + col];
+                                }
                             } else if (col < 2 * NV) {
-                                val = s.C[jn * NB + row * NV + (col - NV)];
+                                vt = mid_next ? 0.0 : s.C[nt * NB + row * NV + (col - NV)];
+                                vb = mid_next ? 0.0 : s.A[nbm * NB + row * NV + (col - NV)];
                             } else {
-                                val = (col - 2 * NV == row) ? 1.0 : 0.0;
+                                vt = vb = (col - 2 * NV == row) ? 1.0 : 0.0;
                             }
-                            Mn[row * MROW + col] = val;
+                            Mn[0][row * MROW + col] = vt;
+                            Mn[1][row * MROW + col] = vb;
                         }
                         __syncthreads();
-                        double* t = Mc;
-                        Mc = Mn;
-                        Mn = t;
+#pragma unroll
+                        for (int y = 0; y < 2; ++y) {
+                            double* tmp = Mc[y];
+                            Mc[y] = Mn[y];
+                            Mn[y] = tmp;
+                        }
                     }
                     if (s.fail) {
                         failed = true;
                         break;
                     }
-                    // L_j = inv D'_j A_j replaces A_j: the forward recurrence is then one 7x7 product per node
+                    // L_j = inv D'_j A_j replaces A_j above the middle, U_j = inv D''_j C_j replaces C_j below it: each
+                    // forward recurrence is then one 7x7 product per node
                     for (int j0 = 0; j0 < NX; j0 += 13) {   // 13 whole nodes (637 products) per pass, four per thread
                         const int e_end = (j0 + 13 < NX ? j0 + 13 : NX) * NB;
                         double lv[4];
@@ -336,7 +383,8 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
                             double acc = 0.0;
                             if (e < e_end) {
                                 const int j = e / NB, rc = e - j * NB, pu = rc / NV, cc = rc - pu * NV;
-                                for (int k = 0; k < NV; ++k) acc += s.D[j * NB + pu * NV + k] * s.A[j * NB + k * NV + cc];
+                                const double* src = (j < MID ? s.A : s.C) + j * NB;
+                                for (int k = 0; k < NV; ++k) acc += s.D[j * NB + pu * NV + k] * src[k * NV + cc];
                             }
                             lv[i] = acc;
                         }
@@ -344,41 +392,91 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int e = j0 * NB + tid + i * DAE_THREADS;
-                            if (e < e_end) s.A[e] = lv[i];
+                            if (e < e_end) {
+                                const int j = e / NB;
+                                if (j < MID) s.A[e] = lv[i];
+                                else if (j > MID) s.C[e] = lv[i];
+                            }
                         }
                         __syncthreads();
                     }
                 }
-                // ---- substitution with the stored factors: h_j = -inv D'_j F_j for all nodes at once, then the two
-                // serial recurrences g_j = h_j - L_j g_{j-1} and x_j = g_j - W_j x_{j+1} by seven lanes of warp 0, the
-                // running vector in registers and exchanged by shuffles; F ends up holding the Newton update
+                // ---- substitution with the stored factors.  h_j = -inv D_j F_j for all nodes at once (the raw -F at
+                // the middle); then warp 0 runs g_j = h_j - L_j g_{j-1} down from node 0 while warp 1 runs
+                // q_j = h_j - U_j q_{j+1} up from node NX-1, seven lanes each, the running vector in registers and
+                // exchanged by shuffles; the middle node closes the system; then x_j = g_j - W_j x_{j+1} and
+                // x_j = q_j - V_j x_{j-1} run back outwards.  F ends up holding the Newton update.
+                double* const H = s.M;
+                static_assert(4 * NV * MROW >= NX * NV, "h does not fit the elimination scratch");
                 for (int e = tid; e < NX * NV; e += DAE_THREADS) {
                     const int j = e / NV, pu = e - j * NV;
                     double acc = 0.0;
-                    for (int k = 0; k < NV; ++k) acc -= s.D[j * NB + pu * NV + k] * s.F[j * NV + k];
-                    s.H[e] = acc;
+                    if (j == MID) acc = -s.F[e];
+                    else
+                        for (int k = 0; k < NV; ++k) acc -= s.D[j * NB + pu * NV + k] * s.F[j * NV + k];
+                    H[e] = acc;
                 }
                 __syncthreads();
-                if (tid < 32) {
-                    const int ln = tid < NV ? tid : 0;
-                    double g = s.H[ln];
-                    if (tid < NV) s.F[ln] = g;
-                    for (int j = 1; j < NX; ++j) {
-                        const double* Lr = s.A + j * NB + ln * NV;
-                        double acc = s.H[j * NV + ln];
+                {
+                    const int lane = tid & 31, ln = lane < NV ? lane : 0, w = tid >> 5;
+                    if (w == 0) {
+                        double g = H[ln];
+                        if (lane < NV) s.F[ln] = g;
+                        for (int j = 1; j < MID; ++j) {
+                            const double* Lr = s.A + j * NB + ln * NV;
+                            double acc = H[j * NV + ln];
 #pragma unroll
-                        for (int k = 0; k < NV; ++k) acc -= Lr[k] * __shfl_sync(0xffffffffu, g, k);
-                        g = acc;
-                        if (tid < NV) s.F[j * NV + ln] = g;
+                            for (int k = 0; k < NV; ++k) acc -= Lr[k] * __shfl_sync(0xffffffffu, g, k);
+                            g = acc;
+                            if (lane < NV) s.F[j * NV + ln] = g;
+                        }
+                    } else if (w == 1) {
+                        double q = H[(NX - 1) * NV + ln];
+                        if (lane < NV) s.F[(NX - 1) * NV + ln] = q;
+                        for (int j = NX - 2; j > MID; --j) {
+                            const double* Ur = s.C + j * NB + ln * NV;
+                            double acc = H[j * NV + ln];
+#pragma unroll
+                            for (int k = 0; k < NV; ++k) acc -= Ur[k] * __shfl_sync(0xffffffffu, q, k);
+                            q = acc;
+                            if (lane < NV) s.F[j * NV + ln] = q;
+                        }
                     }
-                    double x = g;   // x_{NX-1} = g_{NX-1}
-                    for (int j = NX - 2; j >= 0; --j) {
-                        const double* Wr = s.C + j * NB + ln * NV;
-                        double acc = s.F[j * NV + ln];
+                    __syncthreads();
+                    if (w == 0) {   // middle node: x = inv(Dm) (b - A g_{MID-1} - C q_{MID+1})
+                        double tmpv = 0.0;
+                        if (lane < NV) {
+                            tmpv = H[MID * NV + ln];
+                            for (int k = 0; k < NV; ++k)
+                                tmpv -= s.A[MID * NB + ln * NV + k] * s.F[(MID - 1) * NV + k] +
+                                        s.C[MID * NB + ln * NV + k] * s.F[(MID + 1) * NV + k];
+                        }
+                        double xm = 0.0;
 #pragma unroll
-                        for (int k = 0; k < NV; ++k) acc -= Wr[k] * __shfl_sync(0xffffffffu, x, k);
-                        x = acc;
-                        if (tid < NV) s.F[j * NV + ln] = x;
+                        for (int k = 0; k < NV; ++k) xm += s.D[MID * NB + ln * NV + k] * __shfl_sync(0xffffffffu, tmpv, k);
+                        if (lane < NV) s.F[MID * NV + ln] = xm;
+                    }
+                    __syncthreads();
+                    if (w == 0) {
+                        double x = s.F[MID * NV + ln];
+                        for (int j = MID - 1; j >= 0; --j) {
+                            const double* Wr = s.C + j * NB + ln * NV;
+                            double acc = s.F[j * NV + ln];
+#pragma unroll
+                            for (int k = 0; k < NV; ++k) acc -= Wr[k] * __shfl_sync(0xffffffffu, x, k);
+                            x = acc;
+                            if (lane < NV) s.F[j * NV + ln] = x;
+                        }
+                    } else if (w == 1) {
+                        double x = s.F[MID * NV + ln];
+                        for (int j = MID + 1; j < NX; ++j) {
+                            const double* Vr = s.A + j * NB + ln * NV;
+                            double acc = s.F[j * NV + ln];
+#pragma unroll
+                            for (int k = 0; k < NV; ++k) acc -= Vr[k] * __shfl_sync(0xffffffffu, x, k);
+                            x = acc;
+                            if (lane < NV) s.F[j * NV + ln] = x;
+                        }
                     }
                 }
                 __syncthreads();
