@@ -50,3 +50,22 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_model_ids_and_likelihood_specs_match_the_header(pkg):
+    """The Python likelihood classes carry the header's model ids; the transient reactor model accepts only the
+    reference's 8 kinetic parameters."""
+    import numpy as np
+    text = open(os.path.join(ROOT, "include", "smcb200.h")).read()
+    ids = {k: int(v) for k, v in re.findall(r"#define\s+SMCB_MODEL_([A-Z_]+)\s+(\d+)", text)}
+    assert ids == {"MM_PROGRESS": 1, "MM_RATE": 2, "KINETIC_RK": 3, "KINETIC_DAE": 4}
+    assert (pkg.MMProgress.model_id, pkg.MMRate.model_id, pkg.KineticRK.model_id, pkg.KineticDAE.model_id) == (1, 2, 3, 4)
+    cond = np.ones((3, pkg._lib.KIN_NCOND_FIELDS))
+    obs = np.zeros((5, 3))
+    base9 = np.arange(1.0, 10.0)
+    lik = pkg.KineticDAE(cond, obs, base9, [0, 1, 2, 3, 8])
+    assert (lik.n_pairs, lik.d, lik.n_obs) == (4, 5, 15)
+    with pytest.raises(ValueError):
+        pkg.KineticDAE(cond, obs, np.arange(1.0, 34.0), np.arange(32))       # 32-parameter family: plug-flow model only
+    with pytest.raises(ValueError):
+        pkg.KineticRK(cond, np.zeros((4, 3)), base9, [0, 1, 2, 3, 8])         # observations must be [5, n_cond]
