@@ -496,7 +496,12 @@ def main():
             rhs_evals_per_particle_eval=float(d_stats[0]) / max(local_evals, 1),
             rejected_step_fraction=float(d_stats[2]) / max(att_all, 1.0),
             flop_model="84/attempted step + 34/accepted step + 18/observation + 30/solve (DESIGN.md K1), step counts "
-                       "from the device counters; proposals rejected early are not counted")
+                       "from the device counters; proposals rejected early are not counted",
+            # DRAM bytes of one launch from the ncu --set full capture of a posterior-cloud sweep at 2^20 particles
+            # (profiles/ncu_full_r01_bulk_posterior_v2.md: 41.8 MB read + 21.9 MB written), scaled to this shard's
+            # particle count - not re-measured here; the kernel moves 61 B per particle and is nowhere near HBM-bound
+            traffic=(63.72e6 / (1 << 20)) * eng.n,
+            traffic_source="ncu capture profiles/ncu_full_r01_bulk_posterior_v2.md, per particle x particles of a sweep")
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
         longest = int(st1[16])
         roofline_tail = {
@@ -521,8 +526,13 @@ def main():
     g_ms, g_bytes = gather_microbench(pkg, eng, torch, flush)
     roofline_hbm = {"bound": "hbm", "kernel": "gather_kernel (resampling gather of particle state)",
                     "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
-                    "launch_ms": g_ms, "bytes": g_bytes}
+                    "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak,
+                    # DRAM bytes of one launch from the ncu --set full capture (profiles/ncu_stage_kernels_r01.md: 151.0 MB
+                    # read + 91.1 MB written for 2^22 particles, d = 3; the writes lag the kernel in the 126 MB L2),
+                    # scaled to this launch's particle count - not re-measured here
+                    "traffic": (242.1e6 / (1 << 22)) * eng.n if eng.d == 3 else None,
+                    "traffic_source": "ncu capture profiles/ncu_stage_kernels_r01.md, per particle x particles of this launch",
+                    "peak_source": hbm_src, "launch_ms": g_ms, "bytes": g_bytes}
 
     # ---- BASELINE config 1: the reference's own problem size (N = 1000, its seed and random stream) -----------
     config1 = None
