@@ -14,8 +14,9 @@ index-1 DAE with SUNDIALS IDA through `assimulo` (`SMC_methanation/methanation_s
 PARITY OF THE TIME INTEGRATION IS UNPINNED: assimulo / IDA (variable-order BDF) is not installed and the
 reference stores no trajectories.  The integrator below is builder-defined and is what the device kernel
 (`csrc/dae.cu`) twins: implicit Euler (BDF1) on a fixed geometric time grid from 0 to 75 s, modified Newton (a
-finite-difference block-tridiagonal Jacobian kept while the update shrinks by 0.3x per iteration); a step whose Newton
-iteration does not converge fails the march (-10000 flows, the reference's own penalty for IDA failures).  The bed's thermal time constant is ~8 s
+finite-difference block-tridiagonal Jacobian kept while the update shrinks by 0.3x per iteration); a grid step whose
+Newton iteration does not converge is retried in smaller pieces, and a march that still cannot advance fails
+(-10000 flows, the reference's own penalty for IDA failures).  The bed's thermal time constant is ~8 s
 ((1-void) rho_s Cps 0.1 / (2U/dint)), so at 75 s the state is the steady state of the reference's discretised
 balances to ~1e-4, which is what both integrators converge to.
 
@@ -44,6 +45,7 @@ T_FINAL = 75.0               # set_likelihood.py:198
 # builder-defined time grid and Newton controls (twinned by csrc/dae.cu)
 DT0, DT_GROW, DT_MAX = 1e-3, 1.5, 5.0
 NEWTON_MAX, NEWTON_TOL = 40, 1e-10
+MAX_RETRY = 8                # failed pieces allowed within one grid step
 FLOOR = np.array([1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 1.0, 1e-4])     # scale floors of (C x5, T, u)
 FD_REL = 1e-7
 
@@ -156,47 +158,60 @@ def _jacobian_banded(Y, Y_old, dt, cond_row, k8, F0):
     return ab, kl, ku
 
 
+def _attempt(Y, Y_old, dt, cond_row, k8, fac):
+    """One implicit-Euler step of size dt from Y_old by modified Newton (start iterate Y): the Jacobian of an
+    iteration is kept for the following ones, and for later steps of the same size (fac["dt"]), until the update
+    stops shrinking by 0.3x.  Returns (Y, converged, iterations)."""
+    need_jac, prev_worst = fac.get("dt") != dt, np.inf
+    for it in range(NEWTON_MAX):
+        F0 = residual(Y, (Y - Y_old) / dt, cond_row, k8)
+        if not np.all(np.isfinite(F0)):
+            break
+        if need_jac:
+            need_jac = False
+            fac["ab"], fac["dt"] = _jacobian_banded(Y, Y_old, dt, cond_row, k8, F0), dt
+        ab, kl, ku = fac["ab"]
+        try:
+            dx = solve_banded((kl, ku), ab, -F0.T.reshape(-1), check_finite=True)
+        except (ValueError, np.linalg.LinAlgError):
+            break
+        dY = dx.reshape(NX, 7).T
+        Y = Y + dY
+        if not np.all(np.isfinite(Y)):
+            break
+        worst = np.max(np.abs(dY) / (np.abs(Y) + FLOOR[:, None]))
+        if worst < NEWTON_TOL:
+            return Y, True, it + 1
+        if worst > 0.3 * prev_worst:
+            need_jac = True
+        prev_worst = worst
+    fac["dt"] = None
+    return Y, False, NEWTON_MAX
+
+
 def integrate(cond_row, k8, return_history=False):
-    """Implicit-Euler march of one operating condition to 75 s with the device kernel's modified Newton: the Jacobian
-    of an iteration is kept for the following ones until the update stops shrinking by 0.3x.  Returns (Y, ok)."""
+    """Implicit-Euler march of one operating condition to 75 s (twinned by csrc/dae.cu).  A grid step whose Newton
+    iteration fails is retried from the same state in pieces: the piece is quartered after a failure and doubled after
+    a success; more than MAX_RETRY failures within one grid step fail the march.  Once a whole grid step of the same
+    size as the previous one converges at its first iteration the state is steady and the remaining steps are
+    skipped.  Returns (Y, ok) or (Y, ok, history of the grid points)."""
     Y = start_state(cond_row)
-    hist = []
+    hist, fac, steady, H_prev = [], {}, False, 0.0
     with np.errstate(all="ignore"):
-        dt_prev, ab, steady = 0.0, None, False
-        for dt in time_grid():
-            if steady:                       # nothing moved over a repeated step: the remaining steps are no-ops
-                if return_history:
-                    hist.append(Y.copy())
-                continue
-            Y_old = Y.copy()
-            same_dt = dt == dt_prev          # the previous step's Jacobian serves a step of the same size
-            dt_prev = dt
-            ok, need_jac, prev_worst = False, not same_dt, np.inf
-            for it in range(NEWTON_MAX):
-                F0 = residual(Y, (Y - Y_old) / dt, cond_row, k8)
-                if not np.all(np.isfinite(F0)):
-                    break
-                if need_jac:
-                    need_jac = False
-                    ab, kl, ku = _jacobian_banded(Y, Y_old, dt, cond_row, k8, F0)
-                try:
-                    dx = solve_banded((kl, ku), ab, -F0.T.reshape(-1), check_finite=True)
-                except (ValueError, np.linalg.LinAlgError):
-                    break
-                dY = dx.reshape(NX, 7).T
-                Y = Y + dY
-                if not np.all(np.isfinite(Y)):
-                    break
-                worst = np.max(np.abs(dY) / (np.abs(Y) + FLOOR[:, None]))
-                if worst < NEWTON_TOL:
-                    ok = True
-                    steady = it == 0 and same_dt
-                    break
-                if worst > 0.3 * prev_worst:
-                    need_jac = True
-                prev_worst = worst
-            if not ok:
-                return (Y, False, hist) if return_history else (Y, False)
+        for H in time_grid():
+            if not steady:
+                t_left, dt, n_fail = H, H, 0
+                while t_left > 1e-12 * H and not steady:
+                    dt = min(dt, t_left)
+                    Y_new, ok, its = _attempt(Y.copy(), Y, dt, cond_row, k8, fac)
+                    if ok:
+                        steady = its == 1 and dt == H and H == H_prev
+                        Y, t_left, dt = Y_new, t_left - dt, dt * 2
+                    else:
+                        dt, n_fail = dt * 0.25, n_fail + 1
+                        if n_fail > MAX_RETRY:
+                            return (Y, False, hist) if return_history else (Y, False)
+                H_prev = H
             if return_history:
                 hist.append(Y.copy())
     return (Y, True, hist) if return_history else (Y, True)

@@ -28,7 +28,8 @@ for rep in range(2):
     ms = e0.elapsed_time(e1)
     lk = eng.lk.cpu().numpy()
     print(f"prior sweep N={N} x 30 conditions: {ms:.1f} ms, {N * 30 / ms * 1e3:.0f} marches/s, "
-          f"{N / ms * 1e3:.0f} evals/s; lk finite {np.isfinite(lk).mean():.3f}, median {np.median(lk):.1f}", flush=True)
+          f"{N / ms * 1e3:.0f} evals/s; lk finite {np.isfinite(lk).mean():.3f}, median {np.median(lk):.1f}, "
+          f"particles with a failed march {np.mean(lk < -1e6):.3f}", flush=True)
 if do_run:
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -5,8 +5,8 @@
 // (five concentrations, temperature, velocity on 51 axial nodes), residual `reaction` (:69-139) restated node by
 // node below and pinned against the reference's own function (tests/golden/methanation_dae_residual.npz through
 // oracle/methanation_dae.py, which this file twins).  The reference integrates with SUNDIALS IDA (variable-order
-// BDF, absent here); the integrator is builder-defined: implicit Euler on a fixed geometric time grid from 0 to
-// 75 s (host-supplied), full Newton, finite-difference Jacobian.  Node j's equations involve nodes j-1, j, j+1
+// BDF, absent here); the integrator is builder-defined: implicit Euler on a geometric time grid from 0 to 75 s
+// (host-supplied; a grid step whose Newton iteration fails is retried in smaller pieces), finite-difference Jacobian.  Node j's equations involve nodes j-1, j, j+1
 // only, so with the unknowns ordered node by node the Jacobian is block tridiagonal with 7x7 blocks:
 //   * residuals and the 3 x 7 perturbed residuals per node are independent tasks spread over the block's threads
 //     (the reaction rate, the expensive part, is reused when a neighbour is perturbed);
@@ -32,6 +32,7 @@ constexpr int DAE_THREADS = 160;
 constexpr int MCOLS = 3 * NV; // elimination scratch [D' | C | I]: 7 x 21, one thread per element
 constexpr int MROW = 22;      // its row stride
 constexpr int NEWTON_MAX = 40;
+constexpr int MAX_RETRY = 8;  // failed pieces allowed within one grid step
 constexpr int MID = NX / 2;   // node where the two elimination chains meet
 
 constexpr double DZ_DISP = 0.95e-5;   // Dz   set_conditon.py:76
@@ -170,19 +171,24 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
             s.Y[e] = (v < 5) ? c.Cin[v] : (v == 5 ? (j == 0 ? c.T_in : T_BED0) : c.u_in);
         }
         __syncthreads();
+        // Time stepping.  One pass of the loop below is one attempted implicit-Euler piece.  A grid step H whose Newton
+        // iteration fails is retried from the same state in pieces: the piece is quartered after a failure and doubled
+        // after a success; more than MAX_RETRY failures within one grid step fail the march.
         bool failed = false, steady = false;
-        double dt_prev = 0.0;
-        for (int step = 0; step < n_dt && !failed && !steady; ++step) {
-            const double dt = dts[step], inv_dt = 1.0 / dt;
-            // the factors of the previous step serve this one when the step size is the same (the 5 s steps of the
-            // second half of the march, where the bed is close to its steady state)
-            const bool same_dt = dt == dt_prev;
-            dt_prev = dt;
+        double dt_fac = 0.0, H_prev = 0.0;   // step size the stored factors belong to; previous grid step
+        int step = 0, n_retry = 0;
+        double H = dts[0], t_left = H, dt = H;
+        while (!failed && !steady) {
+            dt = fmin(dt, t_left);
+            const double inv_dt = 1.0 / dt;
+            const bool whole_repeat = dt == H && H == H_prev;
             for (int e = tid; e < NX * NV; e += DAE_THREADS) s.Yold[e] = s.Y[e];
             __syncthreads();
-            bool converged = false, need_jac = !same_dt;
+            // the factors of the previous piece serve this one when the step size is the same (the 5 s steps of the
+            // second half of the march, where the bed is close to its steady state)
+            bool converged = false, bad = false, need_jac = !(dt == dt_fac);
             double prev_worst = INFINITY;
-            for (int it = 0; it < NEWTON_MAX && !converged && !failed; ++it) {
+            for (int it = 0; it < NEWTON_MAX && !converged && !bad; ++it) {
                 // ---- residual of every node, rate and density kept for the Jacobian
                 if (tid < NX) {
                     const int j = tid;
@@ -207,11 +213,12 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
                 }
                 __syncthreads();
                 if (s.fail) {
-                    failed = true;
+                    bad = true;
                     break;
                 }
                 if (need_jac) {
                     need_jac = false;
+                    dt_fac = dt;
                     // ---- finite-difference blocks: task = (node j, neighbour nb, variable v)
                     for (int t = tid; t < NX * 3 * NV; t += DAE_THREADS) {
                         const int j = t / (3 * NV), rem = t - j * 3 * NV, nb = rem / NV, v = rem - nb * NV;
@@ -369,7 +376,7 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
                         }
                     }
                     if (s.fail) {
-                        failed = true;
+                        bad = true;
                         break;
                     }
                     // L_j = inv D'_j A_j replaces A_j above the middle, U_j = inv D''_j C_j replaces C_j below it: each
@@ -497,17 +504,36 @@ dae_march_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const 
                 worst = 0.0;
                 for (int w = 0; w < DAE_THREADS / 32; ++w) worst = fmax(worst, s.red[w]);
                 __syncthreads();
-                if (!(worst < INFINITY)) failed = true;
+                if (!(worst < INFINITY)) bad = true;
                 else if (worst < NEWTON_TOL) {
                     converged = true;
-                    // nothing moved over a repeated step: the state is steady and the remaining steps are no-ops
-                    if (it == 0 && same_dt) steady = true;
+                    // nothing moved over a whole, repeated grid step: the state is steady, the rest are no-ops
+                    if (it == 0 && whole_repeat) steady = true;
                 }
                 // the factors are kept for the next iteration unless the update stopped shrinking (modified Newton)
                 else if (worst > 0.3 * prev_worst) need_jac = true;
                 prev_worst = worst;
             }
-            if (!converged) failed = true;
+            if (converged) {
+                t_left -= dt;
+                dt *= 2.0;
+                if (!(t_left > 1e-12 * H)) {   // grid step complete
+                    H_prev = H;
+                    n_retry = 0;
+                    if (++step >= n_dt) break;
+                    H = dts[step];
+                    t_left = H;
+                    dt = H;
+                }
+            } else {   // back to the state before the piece, smaller piece, fresh factors
+                __syncthreads();
+                for (int e = tid; e < NX * NV; e += DAE_THREADS) s.Y[e] = s.Yold[e];
+                if (tid == 0) s.fail = 0;
+                __syncthreads();
+                dt_fac = 0.0;
+                dt *= 0.25;
+                if (++n_retry > MAX_RETRY) failed = true;
+            }
         }
         if (tid == 0) {
             // outlet flows (set_likelihood.py:204-208), -10000 on failure (:244), squared residuals of the five species
