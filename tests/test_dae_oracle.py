@@ -51,3 +51,24 @@ def test_transient_and_plug_flow_models_agree_on_conversion():
     assert np.all(Fd > -1)
     assert np.max(np.abs(Fd[2] / Fp[2] - 1)) < 0.05
     assert np.max(np.abs(Fd[4] / Fp[4] - 1)) < 1e-6               # argon passes through
+
+
+def test_a_failed_grid_step_is_retried_in_pieces():
+    """Fast kinetics (A_f 14x the data-generating value, E_f halved): Newton diverges on the bare grid during ignition;
+    with the retry rule the march goes through and lands on a steady state of the same balances."""
+    g = np.load(os.path.join(HERE, "golden", "dae_synth.npz"))
+    row = g["cond"][0]
+    k8 = kinetic.BASEPARAMS.copy()
+    k8[:4] = [1.87749225e+02, 2.77515159e+04, 7.66117997e+05, 7.35659385e+04]
+    Y, fac, bare_ok = dae.start_state(row), {}, True
+    with np.errstate(all="ignore"):
+        for H in dae.time_grid():
+            Y, ok, _ = dae._attempt(Y.copy(), Y, H, row, k8, fac)
+            if not ok:
+                bare_ok = False
+                break
+    assert not bare_ok
+    Y, ok = dae.integrate(row, k8)
+    assert ok and np.all(np.isfinite(Y))
+    F = dae.residual(Y, np.zeros_like(Y), row, k8)
+    assert np.max(np.abs(F[:5, 1:-1])) < 1e-5 * np.max(np.abs(row[7] * row[:5] / (row[9] / 50)))
