@@ -6,18 +6,20 @@
 // node below and pinned against the reference's own function (tests/golden/methanation_dae_residual.npz through
 // oracle/methanation_dae.py, which this file twins).  The reference integrates with SUNDIALS IDA (variable-order
 // BDF, absent here); the integrator is builder-defined: implicit Euler on a geometric time grid from 0 to 75 s
-// (host-supplied; a grid step whose Newton iteration fails is retried in smaller pieces), finite-difference Jacobian.  Node j's equations involve nodes j-1, j, j+1
-// only, so with the unknowns ordered node by node the Jacobian is block tridiagonal with 7x7 blocks:
+// (host-supplied; a grid step whose Newton iteration fails is retried in smaller pieces), finite-difference
+// Jacobian.  Node j's equations involve nodes j-1, j, j+1 only, so with the unknowns ordered node by node the
+// Jacobian is block tridiagonal with 7x7 blocks:
 //   * residuals and the 3 x 7 perturbed residuals per node are independent tasks spread over the block's threads
 //     (the reaction rate, the expensive part, is reused when a neighbour is perturbed);
 //   * the linear solve is a twisted block Thomas sweep (from both ends to the middle node): each node's 7 x 21
 //     system [D' | C | I] is reduced by Gauss-Jordan with row pivoting in shared memory, 147 threads on one element
 //     of each of the two chains, and the factors are kept;
-//   * Newton is the modified kind: the factors serve the following iterations (one residual pass and one
-//     substitution by a single warp each) until the update stops shrinking by 0.3x, then they are refreshed.
+//   * Newton is the modified kind: the factors serve the following iterations and the following pieces of the
+//     same size (one residual pass, one parallel product and two register recurrences run by two warps) until the
+//     update stops shrinking by 0.3x, then they are refreshed.
 // Everything lives in shared memory (73 KB per block, three blocks per SM).  Cost: 35 steps x (1-2 Jacobians +
-// ~6 substitutions) per march; this is the like-for-like physics mode for reference-sized particle counts, the plug-flow
-// RK4 march of kinetic.cu is the throughput mode.
+// ~6 substitutions) per march; this is the like-for-like physics mode for reference-sized particle counts, the
+// plug-flow RK4 march of kinetic.cu is the throughput mode.
 #include <vector>
 
 #include "common.cuh"
