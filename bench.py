@@ -161,8 +161,8 @@ def _cpu_chunk(args):
     return mm.sweep_progress(P, t, Pobs, S0, which="scipy")
 
 
-def cpu_sweep(pool, cores, P, data):
-    chunks = [c for c in np.array_split(P, cores * 4) if len(c)]
+def cpu_sweep(pool, cores, P, data, per_core=4):
+    chunks = [c for c in np.array_split(P, cores * per_core) if len(c)]
     return np.concatenate(pool.map(_cpu_chunk, [(c, *data) for c in chunks]))
 
 
@@ -258,8 +258,17 @@ def cpu_baseline_dae(per_core=2):
                       f"grid and Newton policy as the device kernel), multiprocessing over all cores, {dt:.1f} s"}
 
 
+REF_PARTICLES = 128      # particles of one reference-arm step (fixed: the same sample on every box)
+DATA_LABEL = {"mm_progress": "observations: the reference's own six CSVs (SMC_example/data/mm_pseudo_data_0..5.csv, 6x40 "
+                             "points, carried in tests/golden/mm_reference_run.npz); prior particles: synthetic, U[0,10]^3",
+              "mm_rate": "synthetic", "kinetic": "synthetic", "kinetic32": "synthetic", "kinetic_dae": "synthetic"}
+
+
 def run_reference_arm(args):
-    """CPU implementation of the hot path (oracle restatement of the reference) on a bounded sample."""
+    """The reference's CPU implementation of the hot path (the oracle's restatement of Micmem_SMC_main.py:98-262 with
+    scipy RK45 as the likelihood, fanned out over all host cores) on a bounded sample.  One step is what a step of
+    the main arm is - one complete tempered-SMC run, prior -> beta = 1 - with REF_PARTICLES particles instead of
+    2^20 (the reference evaluates all N particles in every sweep, out-of-box proposals at the old point)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -268,38 +277,39 @@ def run_reference_arm(args):
     g = np.load(GOLDEN)
     data = (g["data_t"], g["data_P"], g["data_S0"])
     cores = os.cpu_count() or 1
-    M = min(1000, max(64, 40 * cores))         # particles per step: ~0.3-3 s of work per step on all cores
-    # particle cloud: a mid-run cloud of the reference's own run, so the RK step counts are representative
+    M = REF_PARTICLES
     cfg = smc.Settings(n_particle=M)
-    times = []
+    times, evals, sweeps, stages = [], 0, 0, 0
     with mp.get_context("fork").Pool(cores) as pool:
-        loglik = lambda th: cpu_sweep(pool, cores, th, data)
-        rs = np.random.RandomState(1)
-        sweeps = g["sweeps_in"]
+        loglik = lambda th: cpu_sweep(pool, cores, th, data, per_core=1)
         for it in range(args.warmup + args.steps):
-            cloud = sweeps[(it * 5) % len(sweeps)][:M]
+            st = smc.ReferenceStream(int(g["seed"]) + it)          # legacy NumPy stream, the reference's draw order
+            p0 = st.prior_uniform([0, 0, 0], [10, 10, 10], M)
             t0 = time.perf_counter()
-            lk = loglik(cloud)                                                        # sim_particle
-            t = smc.temper_backoff(lk, 0.0, cfg)                                      # tempering
-            anc = smc.fit_ancestors(smc.resample_sequential(t["p_weight"], rs.rand())[0], M)   # resampling
-            p_filt, lk1 = cloud[anc], lk[anc]
-            F = smc.proposal_factor(smc.particle_cov(p_filt) * cfg.w_cov(3))
-            smc.mh_sweep(p_filt, lk1, t["gamma_new"], F, rs.standard_normal((M, 3)), rs.uniform(0, 1, M), 1.0,
-                         loglik, np.zeros(3), np.full(3, 10.0))                       # one MH sweep
+            _, _, tr = smc.run(loglik, p0, np.zeros(3), np.full(3, 10.0), cfg, st)
             dt = time.perf_counter() - t0
             if it >= args.warmup:
                 times.append(dt)
+                evals += tr.n_eval
+                sweeps += int(sum(tr.n_mh)) + 1
+                stages += len(tr.gamma)
     total = sum(times)
-    val = 2 * M * len(times) / total
+    val = evals / total
+    k = len(times)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "mm_progress: Michaelis-Menten tempered SMC, reference CSV data, FP64",
-                       "particles_per_step": M, "evals_per_step": 2 * M},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / k,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": DATA_LABEL["mm_progress"],
+            "config": {"workload": "mm_progress: Michaelis-Menten tempered SMC, 6x40 progress-curve observations "
+                                   "(reference CSVs), FP64",
+                       "particles_total": M, "step": "one full tempered-SMC run, prior -> beta=1",
+                       "evals_per_step": evals / k, "stages_per_step": stages / k, "sweeps_per_step": sweeps / k},
+            "time_to_beta1_s": total / k,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"per step: likelihood sweep + tempering + resampling + one MH sweep (2 "
-                                       f"likelihood sweeps) over {M} particles of the reference run's clouds; "
-                                       "oracle restatement (scipy RK45), multiprocessing over all cores"},
+                             "sample": f"{k} complete tempered-SMC runs of {M} prior particles each (the main arm's step "
+                                       f"at {M} instead of 2^20 particles; N evaluations per sweep as in the reference); "
+                                       "oracle restatement of the loop, scipy solve_ivp RK45 likelihood, "
+                                       "multiprocessing over all cores, one chunk of particles per core"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -598,13 +608,14 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "strong" if args.total_particles else "weak", "vs_baseline": None,
                 "dtype": "f64" if args.workload != "mm_rate" else "f32",
-                "data": "synthetic",
+                "data": DATA_LABEL[args.workload],
                 "config": {"workload": f"{args.workload}: {desc}", "particles_total": N, "particles_per_gpu": n_loc,
                            "d": prior.d, "observations": int(lik.n_obs), "temper_rule": cfg.temper_rule,
                            "scan_mode": cfg.scan_mode, "l2": "256 MiB flush between timed steps",
                            "step": "one full tempered-SMC run, prior -> beta=1"},
                 "time_to_beta1_s": secs / args.steps, "stages_per_step": stages / args.steps,
-                "mh_sweeps_per_step": sweeps / args.steps, "evals_per_step": evals / args.steps,
+                "mh_sweeps_per_step": sweeps / args.steps, "likelihood_sweeps_timed": sweeps + args.steps,
+                "evals_per_step": evals / args.steps,
                 "evals_note": "value counts likelihood evaluations integrated over every observation (first sweep + "
                               "in-box MH proposals); proposals whose rejection was proven before the last observation "
                               "(exact early rejection) are NOT counted and are reported in decisions_per_step; the "

@@ -34,6 +34,8 @@
 extern "C" {
 #endif
 
+#define SMCB_ABI_VERSION 200 /* returned by smcb_version(); the ctypes layer refuses a library that differs */
+
 #define SMCB_OK 0
 #define SMCB_ERR_INVALID (-1)     /* bad argument                               */
 #define SMCB_ERR_CUDA (-2)        /* a CUDA runtime call failed                 */
@@ -109,7 +111,8 @@ int smcb_loglik_bounded(smcb_handle* h, int model, const double* theta_dev, int6
  * are all free refills at once. */
 #define SMCB_PARAM_MM_PATIENCE 3
 /* SMCB_PARAM_PROFILE: non-zero = record CUDA events on the launching stream around the bulk and the tail
- * kernel of every MM_PROGRESS sweep (at most 512 sweeps between two reads); see smcb_profile_read. */
+ * kernel of every MM_PROGRESS sweep (any number of sweeps between two reads: the event list grows on demand);
+ * switching it on starts a new record; see smcb_profile_read. */
 #define SMCB_PARAM_PROFILE 4
 /* SMCB_PARAM_MM_CHUNK: particles per work-queue item of the bulk kernel (default 32). */
 #define SMCB_PARAM_MM_CHUNK 5

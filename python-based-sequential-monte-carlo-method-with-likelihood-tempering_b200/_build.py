@@ -19,6 +19,13 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def header_version():
+    """SMCB_ABI_VERSION of include/smcb200.h (what smcb_version() of a matching library returns)."""
+    import re
+    with open(os.path.join(HERE, "..", "include", "smcb200.h")) as f:
+        return int(re.search(r"#define\s+SMCB_ABI_VERSION\s+(\d+)", f.read()).group(1))
+
+
 def _stale():
     if not os.path.exists(LIB):
         return True

@@ -75,8 +75,15 @@ def load(build_if_missing=True):
     if _LIB is not None:
         return _LIB
     path = _build.LIB
-    if build_if_missing and (not os.path.exists(path) or os.environ.get("SMCB_REBUILD") == "1"):
-        _build.build()
+    if build_if_missing:
+        # no-op when the library is newer than every source and the header; a stale library behind an edited
+        # header would corrupt memory through ctypes instead of raising.  Where there is no nvcc (a box that
+        # received the built library) an existing library is used as it is.
+        try:
+            _build.build(force=os.environ.get("SMCB_REBUILD") == "1")
+        except RuntimeError:
+            if not os.path.exists(path):
+                raise
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing and could not be built; the CUDA library is required "
                            "(there is no CPU fallback)")
@@ -85,6 +92,9 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)          # AttributeError if the .so does not export it
         fn.argtypes = args
         fn.restype = _RESTYPE.get(name, c_int)
+    if lib.smcb_version() != _build.header_version():
+        raise RuntimeError(f"{path} is version {lib.smcb_version()}, include/smcb200.h declares "
+                           f"{_build.header_version()}: rebuild with `python -m smcb200._build --force`")
     _LIB = lib
     return lib
 

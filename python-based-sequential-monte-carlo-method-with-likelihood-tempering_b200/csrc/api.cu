@@ -112,10 +112,8 @@ extern "C" int smcb_destroy(smcb_handle* h) {
     dev_free(&h->fused_plist); dev_free(&h->fused_owner);
     if (h->fused_ctl) cudaFree(h->fused_ctl);
     dev_free(&h->dae_dts);
-    if (h->prof_ev) {
-        for (int i = 0; i < SMCB_PROF_RING * 4; ++i) cudaEventDestroy(h->prof_ev[i]);
-        delete[] h->prof_ev;
-    }
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    h->prof_ev.clear();
     dev_free(&h->floor_cnt); dev_free(&h->resid_q); dev_free(&h->resid_f); dev_free(&h->tile_tot);
     dev_free(&h->tile_tot2); dev_free(&h->mark); dev_free(&h->seq_carry);
     dev_free(&h->mmp.t); dev_free(&h->mmp.P); dev_free(&h->mmp.S0);
@@ -144,7 +142,15 @@ extern "C" int smcb_reserve(smcb_handle* h, int64_t n_max, int d_max) {
     int rc;
     if ((rc = dev_alloc(h, &h->ssr, (size_t)rows * n_max))) return rc;
     h->ssr_rows = rows;
-    h->partial_len = (int64_t)h->sm_count * 8 * 80 + 8192;
+    {   // worst case over the reductions that use it: [blocks][columns] partials followed by one row of results
+        //   smcb_centered_moments, d > 6: 2*sm_count blocks x d(d+1)/2 pairs (528 at d = 32)
+        //   smcb_temper_sums: 8*sm_count blocks x 2*SMCB_MAX_CAND sums;  smcb_colsum: 4*sm_count blocks x d
+        const int64_t npair_max = (int64_t)SMCB_MAX_DIM * (SMCB_MAX_DIM + 1) / 2;
+        int64_t need = ((int64_t)h->sm_count * 2 + 1) * npair_max;
+        const int64_t t = ((int64_t)h->sm_count * 8 + 1) * 2 * SMCB_MAX_CAND;
+        if (t > need) need = t;
+        h->partial_len = need + 8192;
+    }
     if ((rc = dev_alloc(h, &h->partial, (size_t)h->partial_len))) return rc;
     if ((rc = dev_alloc(h, &h->floor_cnt, (size_t)n_max))) return rc;
     if ((rc = dev_alloc(h, &h->resid_q, (size_t)n_max))) return rc;
@@ -259,13 +265,14 @@ extern "C" int smcb_set_param(smcb_handle* h, int key, double value) {
             h->mm_tail_warps = (int)value;
             return SMCB_OK;
         case SMCB_PARAM_PROFILE:
-            if (value != 0 && h->prof_ev == nullptr) {
-                CUDA_TRY(h, cudaSetDevice(h->device));
-                h->prof_ev = new cudaEvent_t[SMCB_PROF_RING * 4];
-                for (int i = 0; i < SMCB_PROF_RING * 4; ++i) CUDA_TRY(h, cudaEventCreate(&h->prof_ev[i]));
+            // switching the recording on starts a new measurement; switching it off keeps what was recorded
+            // until smcb_profile_read
+            if (value != 0) {
+                h->prof_sweeps = 0;
+                h->prof_acc[0] = h->prof_acc[1] = 0.0;
+                h->prof_acc_sweeps = 0;
             }
             h->prof_on = value != 0;
-            h->prof_sweeps = 0;
             return SMCB_OK;
         case SMCB_PARAM_MM_PATIENCE:
             REQUIRE(h, value >= 0 && value <= 1e6, SMCB_ERR_INVALID, "MM_PATIENCE must be in [0, 1e6]");
@@ -292,18 +299,54 @@ extern "C" int smcb_loglik_stats(smcb_handle* h, int64_t* out_host) {
 extern "C" int smcb_profile_read(smcb_handle* h, double* out_host) {
     REQUIRE(h, h && out_host, SMCB_ERR_INVALID, "null pointer");
     out_host[0] = out_host[1] = out_host[2] = 0.0;
-    if (h->prof_ev == nullptr) return SMCB_OK;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    CUDA_TRY(h, cudaDeviceSynchronize());
+    int rc = prof_drain(h);
+    if (rc) return rc;
+    out_host[0] = h->prof_acc[0];
+    out_host[1] = h->prof_acc[1];
+    out_host[2] = (double)h->prof_acc_sweeps;
+    h->prof_acc[0] = h->prof_acc[1] = 0.0;
+    h->prof_acc_sweeps = 0;
+    return SMCB_OK;
+}
+
+// Every recorded sweep is read exactly once: the times of the sweeps in the event list are added to the
+// accumulators and the list starts over (its events are kept and reused).
+int prof_drain(smcb_handle* h) {
+    if (h->prof_sweeps == 0) return SMCB_OK;
+    const size_t last = (size_t)(h->prof_sweeps - 1) * 4 + 3;
+    REQUIRE(h, last < h->prof_ev.size(), SMCB_ERR_STATE, "profiling event list shorter than the recorded sweeps");
+    CUDA_TRY(h, cudaEventSynchronize(h->prof_ev[last]));
     for (int k = 0; k < h->prof_sweeps; ++k) {
         float a = 0.f, b = 0.f;
-        CUDA_TRY(h, cudaEventElapsedTime(&a, h->prof_ev[k * 4 + 0], h->prof_ev[k * 4 + 1]));
-        CUDA_TRY(h, cudaEventElapsedTime(&b, h->prof_ev[k * 4 + 2], h->prof_ev[k * 4 + 3]));
-        out_host[0] += a;
-        out_host[1] += b;
+        CUDA_TRY(h, cudaEventElapsedTime(&a, h->prof_ev[(size_t)k * 4 + 0], h->prof_ev[(size_t)k * 4 + 1]));
+        CUDA_TRY(h, cudaEventElapsedTime(&b, h->prof_ev[(size_t)k * 4 + 2], h->prof_ev[(size_t)k * 4 + 3]));
+        h->prof_acc[0] += a;
+        h->prof_acc[1] += b;
     }
-    out_host[2] = h->prof_sweeps;
+    h->prof_acc_sweeps += h->prof_sweeps;
     h->prof_sweeps = 0;
+    return SMCB_OK;
+}
+
+// Called at the start of a profiled sweep: the list grows SMCB_PROF_RING sweeps at a time (no synchronisation);
+// once it holds SMCB_PROF_CAP sweeps it is drained, which costs one host sync every SMCB_PROF_CAP sweeps.
+int prof_begin_sweep(smcb_handle* h) {
+    if (!h->prof_on) return SMCB_OK;
+    if (h->prof_sweeps >= SMCB_PROF_CAP) {
+        int rc = prof_drain(h);
+        if (rc) return rc;
+    }
+    const size_t need = (size_t)(h->prof_sweeps + 1) * 4;
+    if (h->prof_ev.size() < need) {
+        const size_t grown = h->prof_ev.size() + (size_t)SMCB_PROF_RING * 4;
+        h->prof_ev.reserve(grown);
+        while (h->prof_ev.size() < grown) {
+            cudaEvent_t e;
+            CUDA_TRY(h, cudaEventCreate(&e));
+            h->prof_ev.push_back(e);
+        }
+    }
     return SMCB_OK;
 }
 

@@ -5,12 +5,14 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <vector>
 
 #include "../../include/smcb200.h"
 
-#define SMCB_VERSION 101
+#define SMCB_VERSION SMCB_ABI_VERSION
 #define SMCB_N_STATS 24
-#define SMCB_PROF_RING 512
+#define SMCB_PROF_RING 512      // sweeps per growth step of the profiling event list
+#define SMCB_PROF_CAP 16384     // sweeps after which the list is drained into the accumulators (one host sync)
 #define FULL_MASK 0xffffffffu
 
 struct MmProgressData {
@@ -60,12 +62,14 @@ struct smcb_handle {
     double* fused_plist = nullptr;   // smcb_mh_fused: surviving proposals of a sweep [d][n_max]
     unsigned* fused_owner = nullptr; // ... their particles
     void* fused_ctl = nullptr;       // ... per-sweep counts of surviving proposals
-    int64_t fused_cap = 0;
+    int64_t fused_cap = 0;           // ... particle count (n_max) the two lists were allocated for
     double* dae_dts = nullptr;       // transient reactor model: time steps of the fixed grid
     int dae_n_dt = 0;
     bool prof_on = false;            // per-kernel CUDA-event timing of the MM_PROGRESS sweeps
-    int prof_sweeps = 0;
-    cudaEvent_t* prof_ev = nullptr;  // [SMCB_PROF_RING*4]
+    int prof_sweeps = 0;             // sweeps whose events sit in prof_ev (not yet folded into prof_acc)
+    std::vector<cudaEvent_t> prof_ev;    // 4 events per sweep (bulk start/end, tail start/end); grows on demand
+    double prof_acc[2] = {0.0, 0.0}; // bulk / tail milliseconds of the sweeps already drained
+    long long prof_acc_sweeps = 0;
     int mm_budget = 256;             // attempted steps after which the bulk kernel defers a solve
     int mm_tail_warps = 32;          // one-warp blocks per SM of the tail kernel
     int mm_chunk = 32;               // particles per queue item of the bulk kernel
@@ -150,6 +154,10 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* smem) {
     }
     __syncthreads();
 }
+
+// SMCB_PARAM_PROFILE bookkeeping (api.cu): make room for one more sweep's events / fold recorded sweeps into prof_acc
+int prof_begin_sweep(smcb_handle* h);
+int prof_drain(smcb_handle* h);
 
 // kernels implemented across translation units
 int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, int64_t n,

@@ -333,7 +333,9 @@ extern "C" int smcb_mh_fused(smcb_handle* h, int model, double* theta_dev, int64
     REQUIRE(h, h->ssr != nullptr && n <= h->n_max && D.n_cond <= h->ssr_rows, SMCB_ERR_STATE,
             "smcb_reserve too small for this sweep");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    if (h->fused_cap < n * d) {   // grow-only list of surviving proposals [d][n], their owners, the control block
+    // grow-only list of surviving proposals [d][n] and their owners [n], both sized for the handle's current n_max
+    // (fused_cap = the n_max they were allocated for: smcb_reserve may have grown n_max since)
+    if (h->fused_plist == nullptr || h->fused_cap < h->n_max) {
         if (h->fused_plist) cudaFree(h->fused_plist);
         if (h->fused_owner) cudaFree(h->fused_owner);
         h->fused_plist = nullptr;
@@ -341,7 +343,7 @@ extern "C" int smcb_mh_fused(smcb_handle* h, int model, double* theta_dev, int64
         h->fused_cap = 0;
         CUDA_TRY(h, cudaMalloc((void**)&h->fused_plist, sizeof(double) * h->n_max * SMCB_MAX_DIM));
         CUDA_TRY(h, cudaMalloc((void**)&h->fused_owner, sizeof(unsigned) * h->n_max));
-        h->fused_cap = h->n_max * SMCB_MAX_DIM;
+        h->fused_cap = h->n_max;
     }
     if (!h->fused_ctl) {
         CUDA_TRY(h, cudaMalloc((void**)&h->fused_ctl, sizeof(unsigned) * FUSED_MAX_SWEEPS));

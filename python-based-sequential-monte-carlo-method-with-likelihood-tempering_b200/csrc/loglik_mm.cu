@@ -709,8 +709,8 @@ mm_rate_kernel_f32(const double* __restrict__ theta, int64_t ld, int64_t n,
 // Optional per-kernel timing (SMCB_PARAM_PROFILE): CUDA events on the launching stream around the bulk and the
 // tail kernel of every sweep, read back by smcb_profile_read.
 static inline void prof_mark(smcb_handle* h, int which, cudaStream_t st) {
-    if (!h->prof_on || h->prof_sweeps >= SMCB_PROF_RING) return;
-    cudaEventRecord(h->prof_ev[h->prof_sweeps * 4 + which], st);
+    if (!h->prof_on) return;
+    cudaEventRecord(h->prof_ev[(size_t)h->prof_sweeps * 4 + which], st);   // room made by prof_begin_sweep
 }
 
 // sweep-local counters, the solve queue and the deferred-particle list head
@@ -752,6 +752,10 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
         int a = 0;
         CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, mm_bulk_kernel, BULK_BLOCK, smem));
         h->mm_bulk_blocks_per_sm = a > 0 ? a : 1;
+    }
+    {
+        const int rc = prof_begin_sweep(h);
+        if (rc) return rc;
     }
     unsigned* queue = h->mm_ctl;   // [0] solve queue head, [1] deferred solves, [2] deferred particles, [3] particles to evaluate
     unsigned* hist = h->mm_hist;   // [NBIN] histogram, then [NBIN] scatter cursors

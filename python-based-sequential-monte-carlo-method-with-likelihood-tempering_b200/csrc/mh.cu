@@ -326,6 +326,7 @@ extern "C" int smcb_colsum(smcb_handle* h, const double* theta_dev, int64_t ld, 
     REQUIRE(h, h->partial != nullptr, SMCB_ERR_STATE, "smcb_reserve has not been called");
     cudaStream_t st = as_stream(stream);
     const int nb = moments_grid(h, n);
+    REQUIRE(h, (int64_t)nb * d <= h->partial_len, SMCB_ERR_STATE, "reduction scratch too small");
     colsum_partial_kernel<<<dim3(nb, d), MB, 0, st>>>(theta_dev, ld, n, h->partial);
     LAUNCH_CHECK(h);
     return final_colsum(h, h->partial, nb, d, out_dev, st);
@@ -349,6 +350,7 @@ extern "C" int smcb_centered_moments(smcb_handle* h, const double* theta_dev, in
         default: {
             const int64_t tiles = (n + GEN_TILE - 1) / GEN_TILE;
             nb = (int)((tiles < (int64_t)h->sm_count * 2) ? tiles : (int64_t)h->sm_count * 2);
+            REQUIRE(h, ((int64_t)nb + 1) * npair <= h->partial_len, SMCB_ERR_STATE, "reduction scratch too small");
             moments_general_kernel<<<nb, GEN_THREADS, 0, st>>>(theta_dev, ld, n, d, mean_dev, h->partial);
         }
     }

@@ -78,7 +78,9 @@ class TorchComm:
                                     group=self.group)
 
     def broadcast(self, t, src):
-        self.dist.broadcast(t, src=src, group=self.group)
+        """src is a rank within this communicator's group (torch.distributed wants the global rank)."""
+        g_src = src if self.group is None else self.dist.get_global_rank(self.group, src)
+        self.dist.broadcast(t, src=g_src, group=self.group)
         return t
 
     def barrier(self):
@@ -142,7 +144,7 @@ def sharded_resample(ops, comm, N, n_local, D1, u0, scan_mode, sendbuf, recvbuf,
             if r == rank:
                 carry, tot = ops.counts_sequential(carry)
                 carry_t.copy_(torch.from_numpy(np.asarray(carry, dtype=np.float64)))
-            comm.broadcast(carry_t, src=r)
+            comm.broadcast(carry_t, src=r)          # r is a rank of the communicator's group
             carry = carry_t.cpu().numpy().copy()
         allt = comm.all_gather_i64(tot).cpu().numpy()   # [W, 2] = (floor sum, crossings)
         O, M, pre = [], [], 0
@@ -749,7 +751,8 @@ class Engine:
             gamma_old, logZ, first_step = float(resume["gamma"]), float(resume["log_evidence"]), int(resume["step"]) + 1
             n_eval, n_cut, n_sweeps_total = int(resume["n_eval"]), int(resume["n_eval_cut"]), int(resume["n_sweeps"])
             stages = list(resume["stages"])
-        reached = False
+        reached = resume is not None and gamma_old >= 1.0      # checkpoint taken after the last stage: nothing to do
+        first_step = cfg.itr_max if reached else first_step
         for step in range(first_step, cfg.itr_max):
             if max_stages is not None and step - first_step >= max_stages:
                 break
@@ -782,6 +785,10 @@ class Engine:
                     moved, stage_evals, stage_cut = int(c[1]), int(c[2]), int(c[3])
                     if cfg.early_exit and moved > r_th * N:
                         break
+                    # the reference's step-size rule (Micmem_SMC_main.py:247-248), applied once per fused batch:
+                    # with fused_sweeps = 1 this is the reference's per-sweep rule exactly
+                    if moved < cfg.r_threshold_min * N:
+                        ratio = ratio * 0.5
                     if done < n_mh:
                         F, _ = self.proposal_factor()
             else:

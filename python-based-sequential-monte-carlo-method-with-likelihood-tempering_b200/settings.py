@@ -60,4 +60,16 @@ class Settings:
             raise ValueError("temper_rule must be 'backoff' or 'bisect'")
         if self.scan_mode not in ("fixed", "sequential"):
             raise ValueError("scan_mode must be 'fixed' or 'sequential'")
+        if self.gm_reduction_itr < 1:
+            raise ValueError("gm_reduction_itr must be at least 1 (the back-off loop tests at least one increment)")
+        if not (0.0 < self.gm_reduction_rate < 1.0):
+            raise ValueError("gm_reduction_rate must lie in (0, 1)")
+        if self.itr_max < 2:
+            raise ValueError("itr_max must be at least 2 (stages are numbered 1 .. itr_max-1)")
+        if not (0.0 < self.ess_limit < 1.0):
+            raise ValueError("ess_limit must lie in (0, 1)")
+        if not (0.0 < self.d_gamma_max):
+            raise ValueError("d_gamma_max must be positive")
+        if self.fused_sweeps < 0 or self.mhstep_num < 0 or self.ad_mhstep_num < 0:
+            raise ValueError("sweep counts must not be negative")
         return self
