@@ -325,6 +325,21 @@ def mm_progress_flops(stats_delta, n_particle_evals, n_ex, n_t):
     return 84.0 * (acc + rej) + 34.0 * acc + 18.0 * n_particle_evals * n_ex * n_t + 30.0 * n_particle_evals * n_ex
 
 
+def kinetic_flops_per_eval(n_cond, n_steps, M):
+    """Algorithmic FP64 flop of one plug-flow reactor likelihood (DESIGN.md K1'), reference formulation, every
+    add / multiply / divide / sqrt / exp counted as ONE flop: a right-hand side costs 55 + 31*M (state 20, rate law
+    9 + 31 per Langmuir-Hinshelwood channel incl. its 4 Arrhenius factors, density 18, balances 8), a classical RK4
+    step 4 right-hand sides + 34, a condition n_steps steps + 75 (outlet flows, residuals)."""
+    return float(n_cond) * (n_steps * (4.0 * (55 + 31 * M) + 34.0) + 75.0)
+
+
+DAE_FLOPS_PER_MARCH = 35 * (51 * 21 * 150 + 51 * 3500 + 4 * (51 * 150 + 51 * 200))
+"""Nominal FP64 flop of one transient-reactor march (DESIGN.md K1''): 35 grid steps, each one finite-difference
+Jacobian (51 nodes x 21 perturbed node residuals x ~150 flop), one block-tridiagonal factorisation (51 x ~3500) and
+~4 modified-Newton iterations (residual 51 x 150 + substitution 51 x 200).  Retries and the early steady-state
+exit are not counted: this is a nominal figure, labelled so in the line."""
+
+
 def gather_microbench(pkg, eng, torch, flush):
     """HBM leg: resample-gather of the full particle state with the ancestors of a real stage,
     inputs flushed from L2.  Algorithmic bytes per particle: 4 (ancestor) + 2*(d+1)*8."""
@@ -381,7 +396,7 @@ def main():
         os.dup2(2, 1)
         try:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            comm = pkg.TorchComm()
+            comm = pkg.NcclComm.from_torch_distributed()     # NCCL inside libsmcb200.so; torch only carries the id
             dist.barrier()
             torch.cuda.synchronize()
         finally:
@@ -532,6 +547,25 @@ def main():
                         peak_source="FP32 FFMA micro-benchmark run in this process (smcb_measure_fma_peak)",
                         fma_pipe_lane_slot_frac=5.5 * terms / (ms_lik * 1e-3) / lane_peak,
                         terms_per_s=terms / (ms_lik * 1e-3))
+        roofline["frac"] = roofline["achieved"] / roofline["peak"]
+    if args.workload in ("kinetic", "kinetic32", "kinetic_dae"):
+        evals_step = float(evals) / args.steps / world            # completed evaluations of one step on this rank
+        ms_step = ms_lik / args.steps                             # likelihood launch groups of the one profiled step
+        if args.workload == "kinetic_dae":
+            fl = DAE_FLOPS_PER_MARCH * lik.cond.shape[0]
+            roofline.update(kernel="dae_march_kernel (one block per (particle, condition))", bound="latency",
+                            flop_model="NOMINAL 35 steps x (FD Jacobian + block-tridiagonal factorisation + 4 Newton "
+                                       "iterations) per march (bench.py DAE_FLOPS_PER_MARCH); the kernel is bound by the "
+                                       "serial chain over the 51 nodes and its barriers, not by arithmetic")
+        else:
+            M = lik.n_pairs // 4
+            fl = kinetic_flops_per_eval(lik.cond.shape[0], lik.n_steps, M)
+            roofline.update(kernel=f"kinetic_ssr_kernel<M={M}> (one thread per (particle, condition), RK4 x {lik.n_steps})",
+                            flop_model=f"{fl:.0f} flop per likelihood = n_cond x (n_steps x (4 x (55 + 31 M) + 34) + 75), "
+                                       "every add/mul/div/sqrt/exp counted once (the kernel spends 4 / 7 / 10 FP64 "
+                                       "operations on a division / root / exponential)")
+        roofline.update(achieved=fl * evals_step / (ms_step * 1e-3) / 1e12, flops_per_eval=fl,
+                        evals_per_step_this_rank=evals_step)
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
     g_ms, g_bytes = gather_microbench(pkg, eng, torch, flush)
     roofline_hbm = {"bound": "hbm", "kernel": "gather_kernel (resampling gather of particle state)",

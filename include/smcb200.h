@@ -41,6 +41,8 @@ extern "C" {
 #define SMCB_ERR_CUDA (-2)        /* a CUDA runtime call failed                 */
 #define SMCB_ERR_STATE (-3)       /* call order (e.g. data not set, no reserve) */
 #define SMCB_ERR_UNSUPPORTED (-4) /* size / option outside what is compiled in  */
+#define SMCB_ERR_COMM (-5)        /* an NCCL call failed                        */
+#define SMCB_ERR_USER (-6)        /* the user-supplied likelihood reported an error */
 
 /* likelihood models */
 #define SMCB_MODEL_MM_PROGRESS 1 /* EX/lik:35-77: six progress curves, scipy-RK45 twin */
@@ -48,6 +50,8 @@ extern "C" {
 #define SMCB_MODEL_KINETIC_RK 3  /* methanation-style plug-flow reactor, fixed-step RK4 */
 #define SMCB_MODEL_KINETIC_DAE 4 /* ME/lik:69-277: the reference's transient 357-unknown reactor DAE, implicit Euler to
                                     75 s (data as for KINETIC_RK with the reference's 8 kinetic parameters; n_steps unused) */
+#define SMCB_MODEL_USER 5        /* EX/lik:79-92, ME/fun:70-92: the reference's plug-in is a user-written sim_particle;
+                                    here a user callback that enqueues its own kernels (smcb_set_user_likelihood) */
 
 /* resampling prefix-sum arithmetic */
 #define SMCB_SCAN_SEQUENTIAL 0 /* the reference's sequentially rounded FP64 sum (EX/main:165-174), bit-exact */
@@ -57,6 +61,15 @@ extern "C" {
 #define SMCB_MAX_CAND 16       /* max tempering candidates per pass           */
 
 typedef struct smcb_handle smcb_handle;
+
+/* A user-supplied likelihood (SMCB_MODEL_USER).  The reference's whole plug-in surface is a user-written
+ * `sim_particle(particle) -> llk` (EX/lik:79-92, ME/fun:70-92); its counterpart here is a host function that
+ * ENQUEUES the user's own kernels on `stream` (it must not synchronise): for i < n with active_dev == NULL or
+ * active_dev[i] != 0 it writes lk_dev[i] = log-likelihood of (theta_dev[0*ld+i], ..., theta_dev[(d-1)*ld+i]); other
+ * entries of lk_dev are left untouched.  Returns 0, or non-zero to make the calling smcb_* entry fail with
+ * SMCB_ERR_USER.  `smcb_user.cuh` (next to this header) has the few lines a user kernel needs. */
+typedef int (*smcb_user_loglik_fn)(void* user_data, const double* theta_dev, int64_t ld, int64_t n, int d,
+                                   const uint8_t* active_dev, double* lk_dev, void* stream);
 
 /* ---- lifetime ------------------------------------------------------------------------- */
 int smcb_version(void);
@@ -101,6 +114,8 @@ int smcb_loglik(smcb_handle* h, int model, const double* theta_dev, int64_t ld, 
  * uses it; the other models ignore lkmin_dev. */
 int smcb_loglik_bounded(smcb_handle* h, int model, const double* theta_dev, int64_t ld, int64_t n, int d,
                         const uint8_t* active_dev, const double* lkmin_dev, double* lk_dev, void* stream);
+/* Registers the callback smcb_loglik(..., SMCB_MODEL_USER, ...) dispatches to (NULL removes it). */
+int smcb_set_user_likelihood(smcb_handle* h, smcb_user_loglik_fn fn, void* user_data);
 /* Tunables.  SMCB_PARAM_MM_BUDGET: attempted RK steps after which the bulk MM_PROGRESS kernel hands a
  * solve to the tail kernel (default 256; results do not depend on it). */
 #define SMCB_PARAM_MM_BUDGET 1
@@ -143,6 +158,16 @@ int smcb_lk_max(smcb_handle* h, const double* lk_dev, int64_t n, double* out_dev
  * max_dev points to the (already all-reduced) maximum on the device. */
 int smcb_temper_sums(smcb_handle* h, const double* lk_dev, int64_t n, const double* max_dev,
                      const double* gm_host, int n_cand, double* out_dev, void* stream);
+
+/* Max and sums of one tempering round over ALL shards with a single exchange (north_star: "online logsumexp"):
+ * every rank reduces its shard to (max_r, S1_r[k], S2_r[k]) relative to its OWN maximum, one all-gather moves the
+ * rows, and every rank merges them in rank order with the logsumexp rescale
+ *     max = max_r max_r,   S1[k] = sum_r S1_r[k]*exp((max_r-max)*gm_k),   S2[k] = sum_r S2_r[k]*exp(2(max_r-max)*gm_k).
+ * n_cand <= 3*SMCB_MAX_CAND candidates (gm_host).  out_dev[0] = max, out_dev[1] is left alone (the engine keeps the
+ * accepted sum there), out_dev[2+2k], out_dev[3+2k] = S1[k], S2[k].  Without a communicator (or world == 1) the
+ * result is bit-identical to smcb_lk_max followed by smcb_temper_sums. */
+int smcb_temper_eval(smcb_handle* h, const double* lk_dev, int64_t n, const double* gm_host, int n_cand,
+                     double* out_dev, void* stream);
 
 /* ---- K3: residual-systematic resampling (replaces EX/main:147-184) ----------------------- */
 /* Normalised weights p_weight_i = exp((lk_i-max)*gm)/sum_w  (EX/main:124-130). */
@@ -194,6 +219,28 @@ int smcb_mh_propose(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t
                     const double* F_host, double ratio, const double* low_host, const double* high_host,
                     const double* z_dev, uint64_t seed, uint64_t id_offset, uint32_t stage, uint32_t sweep,
                     double* prop_dev, int64_t ld_prop, uint8_t* inbox_dev, void* stream);
+/* The same proposal with the factor read from device memory (F_dev[d*d] row-major, e.g. the one smcb_moments_merged
+ * left there), so that no host round trip sits between the moment reduction and the proposal. */
+int smcb_mh_propose_dev(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n, int d,
+                        const double* F_dev, double ratio, const double* low_host, const double* high_host,
+                        const double* z_dev, uint64_t seed, uint64_t id_offset, uint32_t stage, uint32_t sweep,
+                        double* prop_dev, int64_t ld_prop, uint8_t* inbox_dev, void* stream);
+/* Moments of ALL shards with a single exchange, plus the proposal factor, on the device (EX/main:212-215 and the
+ * factor inside np.random.multivariate_normal at :220).  Every rank reduces its shard to (n_r, mean_r, M2_r) with
+ * the two-pass arithmetic of np.cov (M2_r centred on the shard's own mean), appends the four MH counters of
+ * smcb_mh_accept (counts_dev, may be NULL), one all-gather moves the rows and every rank merges them in rank order
+ * (Chan et al.): mean = sum n_r mean_r / N,  M2 = sum [M2_r + n_r (mean_r-mean)(mean_r-mean)^T].
+ *   out_dev layout (doubles): [0:4] counters summed over ranks, [4:4+d] mean, [4+d : 4+d+d*d] M2 (the centred
+ *   second-moment SUM; cov = M2/n_total), [4+d+d*d : 4+d+2*d*d] factor F with x = z @ F.
+ * The factor is built from cov (*) w_cov (Hadamard product, EX/main:215; w_cov_host[d*d], NULL = all ones) by a cyclic
+ * Jacobi eigen-decomposition on the device, cov (*) w_cov = V diag(lambda) V^T:  F[j][:] = sqrt(|lambda_j|) * v_j with the
+ * eigenvalues in descending order, every eigenvector signed so that its largest component is positive and
+ * |lambda_j| <= 1e-13 max|lambda| treated as 0.  F^T F = |cov (*) w_cov|, which is what NumPy's SVD-based sampler
+ * draws from; NumPy's own factor (LAPACK's sign and ordering choices) is reproduced only by the host path
+ * (smcb_mh_propose with F_host), which the parity mode with external normals uses.
+ * With world == 1 mean and M2 are bit-identical to smcb_colsum / n followed by smcb_centered_moments. */
+int smcb_moments_merged(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n, int d, int64_t n_total,
+                        const int64_t* counts_dev, const double* w_cov_host, double* out_dev, void* stream);
 /* Accept step (EX/main:231-241): r = exp((lk2-lk1)*gamma)*inbox [* exp(dlp)] >= u; theta/lk updated in place;
  * moved_dev[i] |= r; counts_dev int64[4] += {accepted this sweep, newly moved, in-box proposals
  * (= likelihood evaluations this sweep requested), in-box proposals whose lk2 is -inf (= rejected early
@@ -228,6 +275,32 @@ int smcb_mh_fused(smcb_handle* h, int model, double* theta_dev, int64_t ld, doub
                   double gamma, int n_sweeps, uint64_t seed, uint64_t id_offset, uint32_t stage,
                   uint32_t sweep0, uint8_t* moved_dev, int64_t* counts_dev, void* stream);
 
+/* ---- communicator (SURVEY.md 8(b) smcb_comm_init, 8(e)): NCCL, one process per GPU ----------------------------
+ * The reference has no exchange step (its only parallelism is the local ray fan-out, EX/lik:83-87).  Rank 0 makes
+ * a unique id (smcb_comm_unique_id, 128 bytes), the host program hands it to every rank by any means it likes and
+ * every rank calls smcb_comm_init on its handle.  All collectives below are enqueued on `stream` (no host
+ * synchronisation); with world == 1 they degenerate to device copies or no-ops.  libnccl.so.2 is opened with
+ * dlopen on first use (environment variable SMCB_NCCL_LIB overrides the name). */
+#define SMCB_COMM_ID_BYTES 128
+#define SMCB_OP_SUM 0
+#define SMCB_OP_MAX 1
+int smcb_comm_unique_id(void* out_host, int nbytes);
+int smcb_comm_init(smcb_handle* h, const void* id_host, int nbytes, int rank, int world);
+int smcb_comm_destroy(smcb_handle* h);
+int smcb_comm_rank(const smcb_handle* h);
+int smcb_comm_world(const smcb_handle* h);
+/* recv_dev[r*bytes_per_rank ...] = send_dev[...] of rank r. */
+int smcb_comm_all_gather(smcb_handle* h, const void* send_dev, void* recv_dev, int64_t bytes_per_rank, void* stream);
+/* In-place all-reduce of count doubles, op = SMCB_OP_SUM | SMCB_OP_MAX. */
+int smcb_comm_all_reduce_f64(smcb_handle* h, double* buf_dev, int64_t count, int op, void* stream);
+int smcb_comm_broadcast(smcb_handle* h, void* buf_dev, int64_t bytes, int root, void* stream);
+/* Particle migration of the sharded resampling: send_counts_host[q] doubles go to rank q from consecutive ranges
+ * of send_dev (rank order), recv_counts_host[q] doubles arrive from rank q into consecutive ranges of recv_dev. */
+int smcb_comm_all_to_all_v(smcb_handle* h, const double* send_dev, const int64_t* send_counts_host,
+                           double* recv_dev, const int64_t* recv_counts_host, void* stream);
+/* Number of NCCL operations this handle has enqueued so far. */
+int64_t smcb_collective_count(const smcb_handle* h);
+
 /* ---- utilities ---------------------------------------------------------------------------- */
 /* Philox draws exactly as the kernels make them, for tests: z_dev [n][d], u_dev [n] (either NULL). */
 int smcb_philox_draws(smcb_handle* h, int64_t n, int d, uint64_t seed, uint64_t id_offset, uint32_t stage,
@@ -236,6 +309,12 @@ int smcb_philox_draws(smcb_handle* h, int64_t n, int d, uint64_t seed, uint64_t 
 int smcb_sample_uniform_box(smcb_handle* h, double* theta_dev, int64_t ld, int64_t n, int d,
                             const double* low_host, const double* high_host, uint64_t seed,
                             uint64_t id_offset, void* stream);
+/* Stream-ordered memset to zero (the per-stage reset of the moved mask and the MH counters, EX/main:187-190). */
+int smcb_zero(smcb_handle* h, void* ptr_dev, int64_t bytes, void* stream);
+/* Stream-ordered 2-D device copy, dst[k*ld_dst + i] = src[k*ld_src + i] for k < rows, i < width (unpacks a received
+ * [rows][width] particle chunk into the SoA state). */
+int smcb_copy_rows(smcb_handle* h, const double* src_dev, int64_t ld_src, double* dst_dev, int64_t ld_dst,
+                   int64_t width, int rows, void* stream);
 /* Sustained FP64 FMA and FP32 FMA rates of this device (micro-benchmark, used as the roofline
  * denominator for the compute-bound likelihood kernels): out_host[0]=FP64 FLOP/s, [1]=FP32 FLOP/s.
  * Synchronous. */

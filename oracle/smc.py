@@ -168,6 +168,36 @@ def proposal_factor(cov):
     return np.sqrt(s)[:, None] * v
 
 
+def proposal_factor_eig(cov):
+    """The engine's device-side factor, restated (csrc/mh.cu `moments_merge_factor_kernel`): scale to unit diagonal,
+    cov = D^1/2 R D^1/2; symmetric eigen-decomposition R = V diag(lam) V^T, eigenvalues in descending order, every
+    eigenvector signed so that its largest component is positive, |lam_j| <= 1e-13 max|lam| treated as 0;
+    F[j] = sqrt(|lam_j|) v_j D^1/2, so F^T F = cov: the covariance NumPy's SVD-based sampler draws from.  For given
+    normals the proposals differ from `proposal_factor`'s (LAPACK's ordering and signs, no scaling); in distribution
+    they are the same."""
+    cov = np.atleast_2d(np.asarray(cov, dtype=np.float64))
+    cov = 0.5 * (cov + cov.T)
+    dg = np.diag(cov)
+    sdev = np.where(dg > 0, np.sqrt(np.where(dg > 0, dg, 1.0)), 0.0)
+    pos = sdev > 0
+    R = np.zeros_like(cov)
+    R[np.ix_(pos, pos)] = cov[np.ix_(pos, pos)] / (sdev[pos][:, None] * sdev[pos][None, :])
+    R[np.diag_indices_from(R)] = pos.astype(np.float64)
+    lam, V = np.linalg.eigh(R)
+    order = np.argsort(-lam, kind="stable")
+    lam, V = lam[order], V[:, order]
+    lmax = np.max(np.abs(lam)) if lam.size else 0.0
+    F = np.zeros_like(cov)
+    for j in range(lam.size):
+        v = V[:, j]
+        k = int(np.argmax(np.abs(v)))
+        sgn = -1.0 if v[k] < 0 else 1.0
+        al = abs(lam[j])
+        sc = 0.0 if al <= 1e-13 * lmax else sgn * math.sqrt(al)
+        F[j] = (sc * v) * sdev
+    return F
+
+
 def particle_cov(p_filt):
     """Population covariance, `np.cov(p_filt.T, bias=True)` (`Micmem_SMC_main.py:212`)."""
     return np.atleast_2d(np.cov(np.asarray(p_filt).T, bias=True))
@@ -279,12 +309,13 @@ class Trace:
 
 
 def run(loglik, p_pred, low, high, cfg: Settings, stream, lk0=None, hook=None, resampler=None, early_exit=True,
-        log_prior_ratio=None):
+        log_prior_ratio=None, factor=None):
     """Whole tempered-SMC run.  Returns (particles, lk, Trace).
 
     resampler: `resample_sequential` (the reference, default) or `resample_fixed` (the engine's
     shard-invariant arithmetic); early_exit=False runs all nMH sweeps (BASELINE config 5)."""
     resampler = resampler or resample_sequential
+    factor = factor or proposal_factor     # NumPy's SVD factor (the reference); proposal_factor_eig = the device's
     p_pred = np.array(p_pred, dtype=np.float64)
     N, d = p_pred.shape
     tr = Trace()
@@ -311,7 +342,7 @@ def run(loglik, p_pred, low, high, cfg: Settings, stream, lk0=None, hook=None, r
         n_run = 0
         for j in range(nMH):
             cov_m = particle_cov(p_filt) * w_cov
-            F = proposal_factor(cov_m)
+            F = factor(cov_m)
             Z = stream.normals(N, d)
             U = stream.uniforms(N)
             if hook is not None:

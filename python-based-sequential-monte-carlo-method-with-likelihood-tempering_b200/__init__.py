@@ -13,11 +13,12 @@ or through the `smcb200` alias module at the repository root.
 from . import _lib
 from .settings import Settings
 from .prior import UniformBox, IndependentPrior
-from .likelihood import MMProgress, MMRate, KineticRK, KineticDAE
+from .likelihood import MMProgress, MMRate, KineticRK, KineticDAE, UserKernelLikelihood, CallableLikelihood
 from .artefacts import RunWriter
 
-__all__ = ["Settings", "UniformBox", "IndependentPrior", "MMProgress", "MMRate", "KineticRK", "KineticDAE", "RunWriter", "Engine", "run", "build",
-           "LocalComm", "TorchComm", "migration_plan"]
+__all__ = ["Settings", "UniformBox", "IndependentPrior", "MMProgress", "MMRate", "KineticRK", "KineticDAE", "UserKernelLikelihood", "CallableLikelihood",
+           "RunWriter", "Engine", "run", "build",
+           "LocalComm", "TorchComm", "NcclComm", "migration_plan"]
 
 
 def build(force=False):
@@ -26,9 +27,15 @@ def build(force=False):
     return _build.build(force=force)
 
 
+def build_user_library(src, out=None, force=False):
+    """nvcc -> shared library for a user-written likelihood kernel (see include/smcb_user.cuh)."""
+    from . import _build
+    return _build.build_user_library(src, out, force)
+
+
 def __getattr__(name):
     # engine imports torch; keep `import package` light for build-only use
-    if name in ("Engine", "LocalComm", "TorchComm", "migration_plan", "Result", "StageRecord"):
+    if name in ("Engine", "LocalComm", "TorchComm", "NcclComm", "migration_plan", "Result", "StageRecord"):
         from . import engine
         return getattr(engine, name)
     if name == "run":

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsmcb200.so")
-SOURCES = ["api.cu", "loglik_mm.cu", "temper.cu", "resample.cu", "mh.cu", "kinetic.cu", "dae.cu"]
+SOURCES = ["api.cu", "loglik_mm.cu", "temper.cu", "resample.cu", "mh.cu", "kinetic.cu", "dae.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
@@ -55,11 +55,27 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
+
+
+def build_user_library(src, out=None, force=False):
+    """Compile a user-written likelihood (one .cu including include/smcb_user.cuh) into a shared library for sm_100a.
+    Returns the path of the library."""
+    src = os.path.abspath(src)
+    out = out or os.path.join(os.path.dirname(src), "lib" + os.path.splitext(os.path.basename(src))[0] + ".so")
+    inc = os.path.abspath(os.path.join(HERE, "..", "include"))
+    deps = [src, os.path.join(inc, "smcb_user.cuh"), os.path.join(inc, "smcb200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-I", inc, src, "-o", out, "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    return out
 
 
 if __name__ == "__main__":

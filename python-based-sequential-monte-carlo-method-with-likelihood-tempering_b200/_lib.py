@@ -52,12 +52,32 @@ _SIGNATURES = {
     "smcb_philox_draws": [p_void, c_i64, c_int, c_u64, c_u64, c_u32, c_u32, p_void, p_void, p_void],
     "smcb_sample_uniform_box": [p_void, p_void, c_i64, c_i64, c_int, p_void, p_void, c_u64, c_u64, p_void],
     "smcb_measure_fma_peak": [p_void, p_void],
+    "smcb_set_user_likelihood": [p_void, p_void, p_void],
+    "smcb_zero": [p_void, p_void, c_i64, p_void],
+    "smcb_copy_rows": [p_void, p_void, c_i64, p_void, c_i64, c_i64, c_int, p_void],
+    "smcb_temper_eval": [p_void, p_void, c_i64, p_void, c_int, p_void, p_void],
+    "smcb_mh_propose_dev": [p_void, p_void, c_i64, c_i64, c_int, p_void, c_dbl, p_void, p_void, p_void, c_u64, c_u64,
+                            c_u32, c_u32, p_void, c_i64, p_void, p_void],
+    "smcb_moments_merged": [p_void, p_void, c_i64, c_i64, c_int, c_i64, p_void, p_void, p_void, p_void],
+    "smcb_comm_unique_id": [p_void, c_int],
+    "smcb_comm_init": [p_void, p_void, c_int, c_int, c_int],
+    "smcb_comm_destroy": [p_void],
+    "smcb_comm_rank": [p_void],
+    "smcb_comm_world": [p_void],
+    "smcb_comm_all_gather": [p_void, p_void, p_void, c_i64, p_void],
+    "smcb_comm_all_reduce_f64": [p_void, p_void, c_i64, c_int, p_void],
+    "smcb_comm_broadcast": [p_void, p_void, c_i64, c_int, p_void],
+    "smcb_comm_all_to_all_v": [p_void, p_void, p_void, p_void, p_void, p_void],
+    "smcb_collective_count": [p_void],
 }
-_RESTYPE = {"smcb_last_error": C.c_char_p, "smcb_launch_count": c_i64}
+# host callback of a user-supplied likelihood (smcb_user_loglik_fn)
+USER_LOGLIK_FN = C.CFUNCTYPE(c_int, p_void, p_void, c_i64, c_i64, c_int, p_void, p_void, p_void)
+_RESTYPE = {"smcb_last_error": C.c_char_p, "smcb_launch_count": c_i64, "smcb_collective_count": c_i64}
 
 EXPORTS = tuple(_SIGNATURES)
 
-MODEL_MM_PROGRESS, MODEL_MM_RATE, MODEL_KINETIC_RK, MODEL_KINETIC_DAE = 1, 2, 3, 4
+MODEL_MM_PROGRESS, MODEL_MM_RATE, MODEL_KINETIC_RK, MODEL_KINETIC_DAE, MODEL_USER = 1, 2, 3, 4, 5
+OP_SUM, OP_MAX, COMM_ID_BYTES = 0, 1, 128
 SCAN_SEQUENTIAL, SCAN_FIXED = 0, 1
 MAX_DIM, MAX_CAND = 32, 16
 KIN_NCOND_FIELDS = 10

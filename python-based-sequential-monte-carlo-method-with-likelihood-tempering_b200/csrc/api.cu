@@ -119,6 +119,8 @@ extern "C" int smcb_destroy(smcb_handle* h) {
     dev_free(&h->mmp.t); dev_free(&h->mmp.P); dev_free(&h->mmp.S0);
     dev_free(&h->mmr.S); dev_free(&h->mmr.v); dev_free(&h->mmr.Sv32);
     dev_free(&h->kin.cond); dev_free(&h->kin.obs); dev_free(&h->kin.base); dev_free(&h->kin.est_pos);
+    smcb_comm_destroy(h);
+    dev_free(&h->comm_send); dev_free(&h->comm_recv);
     delete h;
     return SMCB_OK;
 }
@@ -240,9 +242,46 @@ extern "C" int smcb_loglik_bounded(smcb_handle* h, int model, const double* thet
             return launch_loglik_kinetic(h, theta_dev, ld, n, d, active_dev, lk_dev, st);
         case SMCB_MODEL_KINETIC_DAE:
             return launch_loglik_dae(h, theta_dev, ld, n, d, active_dev, lk_dev, st);
+        case SMCB_MODEL_USER: {
+            REQUIRE(h, h->user_fn != nullptr, SMCB_ERR_STATE, "smcb_set_user_likelihood has not been called");
+            REQUIRE(h, d >= 1 && d <= SMCB_MAX_DIM, SMCB_ERR_INVALID, "bad d");
+            if (n == 0) return SMCB_OK;
+            // the callback enqueues the user's kernels on `stream`; lkmin is advisory and not passed on
+            const int urc = h->user_fn(h->user_data, theta_dev, ld, n, d, active_dev, lk_dev, stream);
+            if (urc != 0) return smcb_fail(h, SMCB_ERR_USER, "user likelihood returned %d", urc);
+            h->launches++;
+            const cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess)
+                return smcb_fail(h, SMCB_ERR_CUDA, "user likelihood left a CUDA error: %s", cudaGetErrorString(e));
+            return SMCB_OK;
+        }
         default:
             return smcb_fail(h, SMCB_ERR_INVALID, "smcb_loglik: unknown model %d", model);
     }
+}
+
+extern "C" int smcb_zero(smcb_handle* h, void* ptr_dev, int64_t bytes, void* stream) {
+    REQUIRE(h, h && ptr_dev && bytes >= 0, SMCB_ERR_INVALID, "bad argument");
+    if (bytes > 0) CUDA_TRY(h, cudaMemsetAsync(ptr_dev, 0, (size_t)bytes, as_stream(stream)));
+    return SMCB_OK;
+}
+
+extern "C" int smcb_copy_rows(smcb_handle* h, const double* src_dev, int64_t ld_src, double* dst_dev, int64_t ld_dst,
+                              int64_t width, int rows, void* stream) {
+    REQUIRE(h, h && src_dev && dst_dev && width >= 0 && rows >= 0 && ld_src >= width && ld_dst >= width,
+            SMCB_ERR_INVALID, "bad argument");
+    if (width > 0 && rows > 0)
+        CUDA_TRY(h, cudaMemcpy2DAsync(dst_dev, sizeof(double) * (size_t)ld_dst, src_dev, sizeof(double) * (size_t)ld_src,
+                                      sizeof(double) * (size_t)width, (size_t)rows, cudaMemcpyDeviceToDevice,
+                                      as_stream(stream)));
+    return SMCB_OK;
+}
+
+extern "C" int smcb_set_user_likelihood(smcb_handle* h, smcb_user_loglik_fn fn, void* user_data) {
+    REQUIRE(h, h != nullptr, SMCB_ERR_INVALID, "null handle");
+    h->user_fn = fn;
+    h->user_data = user_data;
+    return SMCB_OK;
 }
 
 extern "C" int smcb_set_param(smcb_handle* h, int key, double value) {

@@ -78,6 +78,19 @@ int load_nccl(smcb_handle* h) {
                              __FILE__, __LINE__);                                                           \
     } while (0)
 
+int comm_staging(smcb_handle* h) {
+    const int rows = h->world > 1 ? h->world : 1;
+    if (h->comm_send == nullptr)
+        CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&h->comm_send), sizeof(double) * SMCB_COMM_ROW));
+    if (h->comm_recv == nullptr || h->comm_recv_rows < rows) {
+        if (h->comm_recv) cudaFree(h->comm_recv);
+        h->comm_recv = nullptr;
+        CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&h->comm_recv), sizeof(double) * SMCB_COMM_ROW * (size_t)rows));
+        h->comm_recv_rows = rows;
+    }
+    return SMCB_OK;
+}
+
 extern "C" int smcb_comm_unique_id(void* out_host, int nbytes) {
     if (out_host == nullptr || nbytes < (int)sizeof(ncclUniqueId))
         return smcb_fail(nullptr, SMCB_ERR_INVALID, "smcb_comm_unique_id: need a buffer of >= %d bytes",
@@ -106,18 +119,8 @@ extern "C" int smcb_comm_init(smcb_handle* h, const void* id_host, int nbytes, i
     h->comm = c;
     h->rank = rank;
     h->world = world;
-    // staging for the small all-gathers of the stage loop: one row per rank, rows of at most COMM_ROW doubles
-    if (h->comm_send == nullptr) {
-        CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&h->comm_send), sizeof(double) * SMCB_COMM_ROW));
-        CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&h->comm_recv), sizeof(double) * SMCB_COMM_ROW * (size_t)world));
-        h->comm_recv_rows = world;
-    } else if (h->comm_recv_rows < world) {
-        cudaFree(h->comm_recv);
-        h->comm_recv = nullptr;
-        CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&h->comm_recv), sizeof(double) * SMCB_COMM_ROW * (size_t)world));
-        h->comm_recv_rows = world;
-    }
-    return SMCB_OK;
+    // staging for the small all-gathers of the stage loop: one row per rank, rows of at most SMCB_COMM_ROW doubles
+    return comm_staging(h);
 }
 
 extern "C" int smcb_comm_destroy(smcb_handle* h) {

@@ -13,6 +13,7 @@
 #define SMCB_N_STATS 24
 #define SMCB_PROF_RING 512      // sweeps per growth step of the profiling event list
 #define SMCB_PROF_CAP 16384     // sweeps after which the list is drained into the accumulators (one host sync)
+#define SMCB_COMM_ROW 1280      // doubles per rank in the small all-gathers of the stage loop (d = 32 moments: 1093)
 #define FULL_MASK 0xffffffffu
 
 struct MmProgressData {
@@ -87,6 +88,16 @@ struct smcb_handle {
     MmProgressData mmp;
     MmRateData mmr;
     KineticData kin;
+    // communicator (comm.cu): NCCL, one process per GPU; world == 1 without smcb_comm_init
+    void* comm = nullptr;            // ncclComm_t
+    int rank = 0, world = 1;
+    int64_t collectives = 0;         // NCCL operations enqueued so far
+    double* comm_send = nullptr;     // [SMCB_COMM_ROW] this rank's row of a small all-gather
+    double* comm_recv = nullptr;     // [world][SMCB_COMM_ROW]
+    int comm_recv_rows = 0;
+    // user-supplied likelihood (SMCB_MODEL_USER): host callback that enqueues the user's kernels
+    smcb_user_loglik_fn user_fn = nullptr;
+    void* user_data = nullptr;
 };
 
 extern char g_create_err[512];
@@ -158,6 +169,11 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double* smem) {
 // SMCB_PARAM_PROFILE bookkeeping (api.cu): make room for one more sweep's events / fold recorded sweeps into prof_acc
 int prof_begin_sweep(smcb_handle* h);
 int prof_drain(smcb_handle* h);
+
+// comm.cu: recv_dev[r*count + i] = send_dev[i] of rank r (a device copy when world == 1)
+int comm_all_gather_f64(smcb_handle* h, const double* send_dev, double* recv_dev, int64_t count, cudaStream_t st);
+// small staging row / table for the all-gathers of the stage loop (allocated on first use, also without NCCL)
+int comm_staging(smcb_handle* h);
 
 // kernels implemented across translation units
 int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, int64_t n,

@@ -123,14 +123,23 @@ __global__ void unpack_sym_kernel(const double* __restrict__ packed, int d, doub
 
 // ---- proposal -------------------------------------------------------------------------------------
 // DT>0: compile-time dimension (registers, fully unrolled); DT==0: run-time d<=32 (local array).
+// F_dev != nullptr: the factor is read from device memory (staged in shared memory) instead of the parameter block.
 template <int DT>
 __global__ void __launch_bounds__(MB)
 propose_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, int d_rt, const __grid_constant__ MhParams prm,
-               double ratio, const double* __restrict__ z_ext, uint64_t seed, uint64_t id_offset, uint32_t stage,
-               uint32_t sweep, double* __restrict__ prop, int64_t ld_prop, uint8_t* __restrict__ inbox) {
+               const double* __restrict__ F_dev, double ratio, const double* __restrict__ z_ext, uint64_t seed,
+               uint64_t id_offset, uint32_t stage, uint32_t sweep, double* __restrict__ prop, int64_t ld_prop,
+               uint8_t* __restrict__ inbox) {
+    const int d = DT ? DT : d_rt;
+    __shared__ double sF[(DT ? DT * DT : SMCB_MAX_DIM * SMCB_MAX_DIM)];
+    if (F_dev != nullptr) {
+        for (int k = threadIdx.x; k < d * d; k += MB) sF[k] = F_dev[k];
+    } else {
+        for (int k = threadIdx.x; k < d * d; k += MB) sF[k] = prm.F[k];
+    }
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * MB + threadIdx.x;
     if (i >= n) return;
-    const int d = DT ? DT : d_rt;
     double step[DT ? DT : SMCB_MAX_DIM];
 #pragma unroll
     for (int k = 0; k < (DT ? DT : SMCB_MAX_DIM); ++k) step[k] = 0.0;
@@ -145,10 +154,10 @@ propose_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, int d_rt
             philox_normal2(seed, id_offset + (uint64_t)i, stage, sweep, (uint32_t)(j >> 1), &z0, &z1);
         }
 #pragma unroll
-        for (int k = 0; k < d; ++k) step[k] += z0 * prm.F[j * d + k];
+        for (int k = 0; k < d; ++k) step[k] += z0 * sF[j * d + k];
         if (j + 1 < d) {
 #pragma unroll
-            for (int k = 0; k < d; ++k) step[k] += z1 * prm.F[(j + 1) * d + k];
+            for (int k = 0; k < d; ++k) step[k] += z1 * sF[(j + 1) * d + k];
         }
     }
     bool ok = true;
@@ -309,6 +318,163 @@ __global__ void sample_box_kernel(double* __restrict__ theta, int64_t ld, int64_
     }
 }
 
+// ---- merged moments + proposal factor ---------------------------------------------------------------------------
+// Row of one shard in the all-gather: [0:4] MH counters, [4] n_r, [5:5+d] column sums, [5+d:5+d+d*d] M2_r (second
+// moments centred on the shard's own mean colsum_r/n_r, full symmetric matrix).
+__global__ void moments_row_kernel(const unsigned long long* __restrict__ counts, double n_local, double* __restrict__ row) {
+    const int t = threadIdx.x;
+    if (t < 4) row[t] = counts ? (double)counts[t] : 0.0;
+    if (t == 4) row[4] = n_local;
+}
+// mean_r = colsum_r / n_r, in place after the column sums (what `mean.div_(N)` did on the host side of round 1)
+__global__ void moments_mean_kernel(const double* __restrict__ colsum, double n_local, int d, double* __restrict__ mean) {
+    const int t = threadIdx.x;
+    if (t < d) mean[t] = colsum[t] / n_local;
+}
+
+struct WCov {
+    double w[SMCB_MAX_DIM * SMCB_MAX_DIM];
+    int use;
+};
+
+// One warp.  Merge in rank order (identical bits on every rank), then cyclic Jacobi on cov (*) w_cov.
+__global__ void __launch_bounds__(32)
+moments_merge_factor_kernel(const double* __restrict__ rows, int world, int stride, int d, double n_total,
+                            const __grid_constant__ WCov wc, double* __restrict__ out) {
+    __shared__ double A[SMCB_MAX_DIM][SMCB_MAX_DIM + 1];
+    __shared__ double V[SMCB_MAX_DIM][SMCB_MAX_DIM + 1];
+    __shared__ double mean[SMCB_MAX_DIM], lam[SMCB_MAX_DIM], sdev[SMCB_MAX_DIM];
+    __shared__ int order[SMCB_MAX_DIM];
+    const int lane = threadIdx.x;
+    if (lane < 4) {
+        double c = 0.0;
+        for (int r = 0; r < world; ++r) c += rows[(size_t)r * stride + lane];
+        out[lane] = c;
+    }
+    if (lane < d) {
+        double m;
+        if (world == 1) {
+            m = rows[5 + d + d * d + lane];          // the shard mean the centred pass used (bit-identical to round 1)
+        } else {
+            double sum = 0.0;
+            for (int r = 0; r < world; ++r) sum += rows[(size_t)r * stride + 5 + lane];
+            m = sum / n_total;
+        }
+        mean[lane] = m;
+        out[4 + lane] = m;
+    }
+    __syncwarp();
+    for (int idx = lane; idx < d * d; idx += 32) {
+        int a = idx / d, b = idx - a * d;
+        if (a > b) { const int c = a; a = b; b = c; }          // canonical (a <= b): exactly symmetric output
+        double acc = 0.0;
+        for (int r = 0; r < world; ++r) {
+            const double* row = rows + (size_t)r * stride;
+            double m2 = row[5 + d + a * d + b];
+            if (world > 1) {
+                const double nr = row[4];
+                const double da = row[5 + a] / nr - mean[a], db = row[5 + b] / nr - mean[b];
+                m2 = fma(nr * da, db, m2);                     // Chan et al.: + n_r (mean_r - mean)(mean_r - mean)^T
+            }
+            acc += m2;
+        }
+        out[4 + d + idx] = acc;
+        const int i = idx / d, j = idx - i * d;
+        A[i][j] = (acc / n_total) * (wc.use ? wc.w[idx] : 1.0);   // cov (*) w_cov (Micmem_SMC_main.py:212-215)
+        V[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    // symmetrise against an asymmetric w_cov (the reference's is symmetric)
+    for (int idx = lane; idx < d * d; idx += 32) {
+        const int i = idx / d, j = idx - i * d;
+        if (i < j) {
+            const double v = 0.5 * (A[i][j] + A[j][i]);
+            A[i][j] = v;
+            A[j][i] = v;
+        }
+    }
+    __syncwarp();
+    // Scale to unit diagonal first, C = D^1/2 R D^1/2: parameters of very different magnitude (methanation: 1e8 next to
+    // 1) would otherwise push the small eigenvalues of C below the rounding noise of the large ones.  The factor is
+    // then F = sqrt(|Lambda|) V^T D^1/2 with R = V Lambda V^T, and F^T F = C.
+    if (lane < d) sdev[lane] = (A[lane][lane] > 0.0) ? sqrt(A[lane][lane]) : 0.0;
+    __syncwarp();
+    for (int idx = lane; idx < d * d; idx += 32) {
+        const int i = idx / d, j = idx - i * d;
+        const double si = sdev[i], sj = sdev[j];
+        double v = (si > 0.0 && sj > 0.0) ? A[i][j] / (si * sj) : 0.0;
+        if (i == j) v = (si > 0.0) ? 1.0 : 0.0;
+        A[i][j] = v;
+    }
+    __syncwarp();
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        if (lane < d)
+            for (int a = 0; a < d; ++a) {
+                const double v = A[a][lane];
+                if (a == lane) dg = fma(v, v, dg);
+                else off = fma(v, v, off);
+            }
+        off = warp_sum(off);
+        dg = warp_sum(dg);
+        if (!(off > 1e-40 * dg)) break;                         // off-diagonal below 1e-20 relative (or all zero / NaN)
+        for (int p = 0; p < d - 1; ++p)
+            for (int q = p + 1; q < d; ++q) {
+                const double apq = A[p][q], app = A[p][p], aqq = A[q][q];
+                __syncwarp();
+                if (apq == 0.0) continue;                       // warp-uniform
+                const double tau = (aqq - app) / (2.0 * apq);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
+                const double c = 1.0 / sqrt(fma(t, t, 1.0)), sn = t * c;
+                if (lane < d) {                                  // columns p, q
+                    const double akp = A[lane][p], akq = A[lane][q];
+                    A[lane][p] = c * akp - sn * akq;
+                    A[lane][q] = sn * akp + c * akq;
+                    const double vkp = V[lane][p], vkq = V[lane][q];
+                    V[lane][p] = c * vkp - sn * vkq;
+                    V[lane][q] = sn * vkp + c * vkq;
+                }
+                __syncwarp();
+                if (lane < d) {                                  // rows p, q
+                    const double apk = A[p][lane], aqk = A[q][lane];
+                    A[p][lane] = c * apk - sn * aqk;
+                    A[q][lane] = sn * apk + c * aqk;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    A[p][q] = 0.0;
+                    A[q][p] = 0.0;
+                }
+                __syncwarp();
+            }
+    }
+    if (lane < d) lam[lane] = A[lane][lane];
+    __syncwarp();
+    double lmax = 0.0;
+    for (int k = 0; k < d; ++k) lmax = fmax(lmax, fabs(lam[k]));
+    if (lane < d) {                                              // descending order, index breaks ties
+        int rank = 0;
+        for (int k = 0; k < d; ++k) rank += (lam[k] > lam[lane]) || (lam[k] == lam[lane] && k < lane);
+        order[rank] = lane;
+    }
+    __syncwarp();
+    double* F = out + 4 + d + d * d;
+    if (lane < d) {
+        const int j = order[lane];
+        double big = -1.0, sgn = 1.0;
+        for (int k = 0; k < d; ++k) {
+            const double v = V[k][j];
+            if (fabs(v) > big) {
+                big = fabs(v);
+                sgn = (v < 0.0) ? -1.0 : 1.0;
+            }
+        }
+        const double al = fabs(lam[j]);
+        const double sc = (al <= 1e-13 * lmax) ? 0.0 : sgn * sqrt(al);
+        for (int k = 0; k < d; ++k) F[lane * d + k] = (sc * V[k][j]) * sdev[k];
+    }
+}
+
 inline int moments_grid(const smcb_handle* h, int64_t n) {
     int64_t nb = (n + MB - 1) / MB;
     const int64_t cap = (int64_t)h->sm_count * 4;
@@ -379,8 +545,8 @@ extern "C" int smcb_mh_propose(smcb_handle* h, const double* theta_dev, int64_t 
     const unsigned grid = (unsigned)((n + MB - 1) / MB);
     cudaStream_t st = as_stream(stream);
 #define PROPOSE(DT)                                                                                              \
-    propose_kernel<DT><<<grid, MB, 0, st>>>(theta_dev, ld, n, d, prm, ratio, z_dev, seed, id_offset, stage, sweep, \
-                                            prop_dev, ld_prop, inbox_dev)
+    propose_kernel<DT><<<grid, MB, 0, st>>>(theta_dev, ld, n, d, prm, nullptr, ratio, z_dev, seed, id_offset, stage, \
+                                            sweep, prop_dev, ld_prop, inbox_dev)
     switch (d) {
         case 1: PROPOSE(1); break;
         case 2: PROPOSE(2); break;
@@ -392,6 +558,64 @@ extern "C" int smcb_mh_propose(smcb_handle* h, const double* theta_dev, int64_t 
         default: PROPOSE(0);
     }
 #undef PROPOSE
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+extern "C" int smcb_mh_propose_dev(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n, int d,
+                                   const double* F_dev, double ratio, const double* low_host, const double* high_host,
+                                   const double* z_dev, uint64_t seed, uint64_t id_offset, uint32_t stage,
+                                   uint32_t sweep, double* prop_dev, int64_t ld_prop, uint8_t* inbox_dev, void* stream) {
+    REQUIRE(h, h && theta_dev && F_dev && low_host && high_host && prop_dev && inbox_dev, SMCB_ERR_INVALID,
+            "null pointer");
+    REQUIRE(h, n > 0 && d >= 1 && d <= SMCB_MAX_DIM && ld >= n && ld_prop >= n, SMCB_ERR_INVALID, "bad size");
+    REQUIRE(h, sweep < (1u << 24), SMCB_ERR_INVALID, "sweep index too large");
+    MhParams prm;
+    memset(&prm, 0, sizeof(prm));
+    memcpy(prm.low, low_host, sizeof(double) * d);
+    memcpy(prm.high, high_host, sizeof(double) * d);
+    const unsigned grid = (unsigned)((n + MB - 1) / MB);
+    cudaStream_t st = as_stream(stream);
+#define PROPOSE(DT)                                                                                              \
+    propose_kernel<DT><<<grid, MB, 0, st>>>(theta_dev, ld, n, d, prm, F_dev, ratio, z_dev, seed, id_offset, stage, \
+                                            sweep, prop_dev, ld_prop, inbox_dev)
+    switch (d) {
+        case 1: PROPOSE(1); break;
+        case 2: PROPOSE(2); break;
+        case 3: PROPOSE(3); break;
+        case 4: PROPOSE(4); break;
+        case 5: PROPOSE(5); break;
+        case 6: PROPOSE(6); break;
+        case 8: PROPOSE(8); break;
+        default: PROPOSE(0);
+    }
+#undef PROPOSE
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+extern "C" int smcb_moments_merged(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n, int d, int64_t n_total,
+                                   const int64_t* counts_dev, const double* w_cov_host, double* out_dev, void* stream) {
+    REQUIRE(h, h && theta_dev && out_dev && n > 0 && d >= 1 && d <= SMCB_MAX_DIM && ld >= n && n_total >= n,
+            SMCB_ERR_INVALID, "bad argument");
+    int rc = comm_staging(h);
+    if (rc) return rc;
+    const int stride = 5 + d + d * d + d;           // the shard mean rides along at the end of the row (world == 1 path)
+    REQUIRE(h, stride <= SMCB_COMM_ROW, SMCB_ERR_UNSUPPORTED, "row too long for the staging buffer");
+    cudaStream_t st = as_stream(stream);
+    double* row = h->comm_send;
+    double* mean_r = row + 5 + d + d * d;
+    moments_row_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned long long*>(counts_dev), (double)n, row);
+    LAUNCH_CHECK(h);
+    if ((rc = smcb_colsum(h, theta_dev, ld, n, d, row + 5, stream))) return rc;
+    moments_mean_kernel<<<1, 32, 0, st>>>(row + 5, (double)n, d, mean_r);
+    LAUNCH_CHECK(h);
+    if ((rc = smcb_centered_moments(h, theta_dev, ld, n, d, mean_r, row + 5 + d, stream))) return rc;
+    if ((rc = comm_all_gather_f64(h, row, h->comm_recv, stride, st))) return rc;
+    WCov wc;
+    wc.use = w_cov_host != nullptr;
+    if (wc.use) memcpy(wc.w, w_cov_host, sizeof(double) * d * d);
+    moments_merge_factor_kernel<<<1, 32, 0, st>>>(h->comm_recv, h->world, stride, d, (double)n_total, wc, out_dev);
     LAUNCH_CHECK(h);
     return SMCB_OK;
 }

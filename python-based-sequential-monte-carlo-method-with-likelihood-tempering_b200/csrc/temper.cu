@@ -115,6 +115,31 @@ __global__ void weights_kernel(const double* __restrict__ lk, int64_t n, const d
     w[i] = __ddiv_rn(exp(__dmul_rn(d, gm)), sum_w_dev[0]);
 }
 
+// Merge of the per-shard rows (max_r, S1_r[k], S2_r[k]) of one tempering round, in rank order (every rank computes
+// the same bits): logsumexp rescale to the global maximum.  One block; thread k owns candidate k.
+struct GmWide {
+    double gm[3 * SMCB_MAX_CAND];
+};
+__global__ void temper_merge_kernel(const double* __restrict__ rows, int world, int stride, int n_cand,
+                                    const GmWide g, double* __restrict__ out) {
+    double mx = -INFINITY;
+    for (int r = 0; r < world; ++r) mx = fmax(mx, rows[(size_t)r * stride]);
+    if (threadIdx.x == 0) out[0] = mx;
+    const int k = threadIdx.x;
+    if (k >= n_cand) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = 0; r < world; ++r) {
+        const double* row = rows + (size_t)r * stride;
+        const double mr = row[0];
+        if (world > 1 && mr == -INFINITY) continue;       // a shard without a finite likelihood carries no weight
+        const double f = exp((mr - mx) * g.gm[k]);        // exactly 1 for the shard that holds the maximum
+        s1 += row[1 + 2 * k] * f;
+        s2 += row[2 + 2 * k] * (f * f);
+    }
+    out[2 + 2 * k] = s1;
+    out[3 + 2 * k] = s2;
+}
+
 inline int reduce_grid(const smcb_handle* h, int64_t n) {
     int64_t nb = (n + RB * 2 - 1) / (RB * 2);
     const int64_t cap = (int64_t)h->sm_count * 8;
@@ -186,6 +211,29 @@ extern "C" int smcb_weights(smcb_handle* h, const double* lk_dev, int64_t n, con
     REQUIRE(h, h && lk_dev && max_dev && sum_w_dev && w_dev && n > 0, SMCB_ERR_INVALID, "null pointer or n<=0");
     weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(lk_dev, n, max_dev, gm, sum_w_dev,
                                                                              w_dev);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+
+extern "C" int smcb_temper_eval(smcb_handle* h, const double* lk_dev, int64_t n, const double* gm_host, int n_cand,
+                                double* out_dev, void* stream) {
+    REQUIRE(h, h && lk_dev && gm_host && out_dev && n > 0, SMCB_ERR_INVALID, "null pointer or n<=0");
+    REQUIRE(h, n_cand >= 1 && n_cand <= 3 * SMCB_MAX_CAND, SMCB_ERR_INVALID, "n_cand out of range");
+    int rc = comm_staging(h);
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    double* row = h->comm_send;                      // [0] = shard max, [1+2k], [2+2k] = sums relative to it
+    if ((rc = smcb_lk_max(h, lk_dev, n, row, stream))) return rc;
+    for (int o = 0; o < n_cand; o += SMCB_MAX_CAND) {
+        const int len = (n_cand - o < SMCB_MAX_CAND) ? n_cand - o : SMCB_MAX_CAND;
+        if ((rc = smcb_temper_sums(h, lk_dev, n, row, gm_host + o, len, row + 1 + 2 * o, stream))) return rc;
+    }
+    const int stride = 1 + 2 * n_cand;
+    if ((rc = comm_all_gather_f64(h, row, h->comm_recv, stride, st))) return rc;
+    GmWide g;
+    for (int k = 0; k < 3 * SMCB_MAX_CAND; ++k) g.gm[k] = (k < n_cand) ? gm_host[k] : 0.0;
+    temper_merge_kernel<<<1, 64, 0, st>>>(h->comm_recv, h->world, stride, n_cand, g, out_dev);
     LAUNCH_CHECK(h);
     return SMCB_OK;
 }

@@ -53,7 +53,9 @@ class LocalComm:
 
 
 class TorchComm:
-    """`torch.distributed` (NCCL over NVLink on GPUs; gloo in CPU tests)."""
+    """`torch.distributed` collectives.  NOT the product path: it exists so that the exchange logic of
+    `sharded_resample` can be exercised on the CPU (gloo, tests/test_sharding_gloo.py).  An Engine given a TorchComm
+    builds an `NcclComm` over the same ranks and uses that."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -85,6 +87,94 @@ class TorchComm:
 
     def barrier(self):
         self.dist.barrier(group=self.group)
+
+
+class NcclComm:
+    """The communicator of the product path: NCCL inside libsmcb200.so (`smcb_comm_init`), one process per GPU.
+    Every exchange is enqueued on the engine's CUDA stream by the library itself; torch.distributed is not on the
+    data path (it is used once, optionally, to hand rank 0's NCCL unique id to the other ranks).
+
+    The communicator belongs to a library handle, which this object owns and lends to every Engine constructed with
+    it (creating an NCCL communicator costs far more than a sampler run, so it is made once per process)."""
+
+    def __init__(self, unique_id, rank, world, device=None):
+        self.lib = _lib.load()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device_index = device if isinstance(device, int) else (torch.device(device).index or 0)
+        self.rank, self.world = int(rank), int(world)
+        self.handle = _lib.p_void()
+        rc = self.lib.smcb_create(self.device_index, _lib.C.byref(self.handle))
+        if rc != 0:
+            raise _lib.SmcbError(rc, self.lib.smcb_last_error(None).decode())
+        buf = _lib.C.create_string_buffer(bytes(unique_id), _lib.COMM_ID_BYTES)
+        _lib.check(self.handle, self.lib.smcb_comm_init(self.handle, buf, _lib.COMM_ID_BYTES, self.rank, self.world))
+
+    @staticmethod
+    def unique_id():
+        """128 bytes made by rank 0 and handed to every rank (any transport)."""
+        lib = _lib.load()
+        buf = _lib.C.create_string_buffer(_lib.COMM_ID_BYTES)
+        rc = lib.smcb_comm_unique_id(buf, _lib.COMM_ID_BYTES)
+        if rc != 0:
+            raise _lib.SmcbError(rc, lib.smcb_last_error(None).decode())
+        return buf.raw
+
+    _from_torch = {}
+
+    @classmethod
+    def from_torch_distributed(cls, group=None):
+        """Builds the communicator over the ranks of an initialised torch.distributed group: rank 0's unique id
+        travels through `broadcast_object_list`; nothing else of torch.distributed is used afterwards."""
+        import torch.distributed as dist
+        key = (id(group), torch.cuda.current_device())
+        if key in cls._from_torch:
+            return cls._from_torch[key]
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        src = 0 if group is None else dist.get_global_rank(group, 0)
+        dist.broadcast_object_list(box, src=src, group=group)
+        comm = cls(box[0], rank, world)
+        cls._from_torch[key] = comm
+        return comm
+
+    # exchanges used by sharded_resample (device tensors in, enqueued on the current stream)
+    def _st(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def all_gather_i64(self, t):
+        t = t.contiguous()
+        out = torch.empty((self.world, t.numel()), dtype=t.dtype, device=t.device)
+        _lib.check(self.handle, self.lib.smcb_comm_all_gather(self.handle, t.data_ptr(), out.data_ptr(),
+                                                             t.numel() * t.element_size(), self._st()))
+        return out
+
+    def all_to_all(self, out, inp, out_splits, in_splits):
+        sc = np.ascontiguousarray(in_splits, dtype=np.int64)
+        rc_ = np.ascontiguousarray(out_splits, dtype=np.int64)
+        _lib.check(self.handle, self.lib.smcb_comm_all_to_all_v(self.handle, inp.data_ptr(), sc.ctypes.data,
+                                                               out.data_ptr(), rc_.ctypes.data, self._st()))
+
+    def broadcast(self, t, src):
+        _lib.check(self.handle, self.lib.smcb_comm_broadcast(self.handle, t.data_ptr(), t.numel() * t.element_size(),
+                                                            int(src), self._st()))
+        return t
+
+    def all_reduce_sum(self, t):
+        _lib.check(self.handle, self.lib.smcb_comm_all_reduce_f64(self.handle, t.data_ptr(), t.numel(), _lib.OP_SUM,
+                                                                 self._st()))
+        return t
+
+    def all_reduce_max(self, t):
+        _lib.check(self.handle, self.lib.smcb_comm_all_reduce_f64(self.handle, t.data_ptr(), t.numel(), _lib.OP_MAX,
+                                                                 self._st()))
+        return t
+
+    def barrier(self):
+        torch.cuda.current_stream().synchronize()
+
+    def collective_count(self):
+        return int(self.lib.smcb_collective_count(self.handle))
 
 
 def fixed_crossings(s, N, u0q):
@@ -161,9 +251,13 @@ def sharded_resample(ops, comm, N, n_local, D1, u0, scan_mode, sendbuf, recvbuf,
     comm.all_to_all(recvbuf[: D1 * sum(recv)], sendbuf[: D1 * sum(send)], [D1 * c for c in recv],
                     [D1 * c for c in send])
     off = 0
+    unpack = getattr(ops, "unpack", None)
     for r in range(W):
         if recv[r]:
-            state_out[:, off:off + recv[r]].copy_(recvbuf[D1 * off: D1 * (off + recv[r])].view(D1, recv[r]))
+            if unpack is not None:      # device: a 2-D copy of the library
+                unpack(recvbuf, D1 * off, recv[r], state_out, off)
+            else:
+                state_out[:, off:off + recv[r]].copy_(recvbuf[D1 * off: D1 * (off + recv[r])].view(D1, recv[r]))
             off += recv[r]
     return plan["filled"]
 
@@ -194,6 +288,11 @@ class _DeviceShardOps:
                                          carry.ctypes.data, 0, e.id_offset, e.counts.data_ptr(), tot.data_ptr(),
                                          e._stream))
         return carry, tot
+
+    def unpack(self, recvbuf, src_off, width, state_out, dst_off):
+        e = self.e
+        e._ck(e.lib.smcb_copy_rows(e.h, recvbuf[src_off:].data_ptr(), width, state_out[:, dst_off:].data_ptr(),
+                                   state_out.stride(0), width, e.d + 1, e._stream))
 
     def expand_and_pack(self, m_loc, send, sendbuf):
         e = self.e
@@ -328,12 +427,19 @@ class Engine:
         self.d = prior.d
         if likelihood.d != self.d:
             raise ValueError(f"prior has {self.d} parameters, likelihood expects {likelihood.d}")
-        self.comm = comm or LocalComm()
         if device is None:
             device = torch.cuda.current_device()
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
         torch.cuda.set_device(self.device)
-        self.h = _acquire_handle(self.lib, self.device.index)
+        if isinstance(comm, TorchComm):
+            comm = NcclComm.from_torch_distributed(comm.group) if comm.world > 1 else None
+        self.comm = comm or LocalComm()
+        if isinstance(self.comm, NcclComm):
+            if self.comm.device_index != self.device.index:
+                raise ValueError("the communicator was made on another device")
+            self.h, self._own_handle = self.comm.handle, False      # the communicator lives in this handle
+        else:
+            self.h, self._own_handle = _acquire_handle(self.lib, self.device.index), True
         for key, val in ((_lib.PARAM_MM_BUDGET, self.cfg.mm_budget), (_lib.PARAM_MM_REFILL_MIN, self.cfg.mm_refill_min),
                          (_lib.PARAM_MM_PATIENCE, self.cfg.mm_patience), (_lib.PARAM_MM_CHUNK, self.cfg.mm_chunk),
                          (_lib.PARAM_MM_TAIL_WARPS, self.cfg.mm_tail_warps)):
@@ -361,9 +467,13 @@ class Engine:
         self.anc = torch.zeros(self.cap, dtype=torch.int32, device=dev)
         self.scal = torch.zeros(128, dtype=f64, device=dev)      # [0]=max, [1]=accepted sum_w, [2:]=tempering sums
         self.filled_hist = torch.zeros(max(self.cfg.itr_max, 1) + 1, dtype=torch.int64, device=dev)
-        self._h_mom = torch.zeros(self.d + self.d * self.d, dtype=f64).pin_memory()
-        self._h_cnt = torch.zeros(4, dtype=torch.int64).pin_memory()
-        self.mom = torch.zeros(self.d + self.d * self.d, dtype=f64, device=dev)
+        # sweep block (smcb_moments_merged): [0:4] MH counters over all ranks, [4:4+d] mean, then M2 [d*d], then the
+        # device-side proposal factor F [d*d]; its first part comes back to the host once per sweep
+        dd = self.d * self.d
+        self.blk = torch.zeros(4 + self.d + 2 * dd, dtype=f64, device=dev)
+        self._h_blk = torch.zeros(4 + self.d + dd, dtype=f64).pin_memory()
+        self._h_scal = torch.zeros(128, dtype=f64).pin_memory()
+        self._w_cov_c = np.ascontiguousarray(self.cfg.w_cov(self.d), dtype=np.float64)
         self.icnt = torch.zeros(8, dtype=torch.int64, device=dev)  # [0:4] MH counters, [4:6] totals, [6] filled
         self.sendbuf = None
         self._w_cov = None
@@ -387,7 +497,8 @@ class Engine:
     def close(self):
         """Park the library handle (with its device scratch) for the next Engine on this device."""
         if getattr(self, "h", None):
-            _release_handle(self.device.index, self.h)
+            if self._own_handle:
+                _release_handle(self.device.index, self.h)
             self.h = None
 
     def __del__(self):
@@ -525,23 +636,20 @@ class Engine:
         and leaves max in scal[0], the accepted sum_w in scal[1]."""
         cfg, N = self.cfg, self.N
         st = self._stream
-        with self._timed("temper"):
-            self._ck(self.lib.smcb_lk_max(self.h, self.lk.data_ptr(), self.n, self.scal.data_ptr(), st))
-        self.comm.all_reduce_max(self.scal[0:1])
-        sums = self.scal[2:2 + 2 * _lib.MAX_CAND]
+        sums = self.scal[2:2 + 6 * _lib.MAX_CAND]
 
         def eval_batch(gms):
-            """Sums for up to 3*MAX_CAND increments: launches of <= MAX_CAND candidates back to back, ONE D2H."""
+            """Global max and sums for up to 3*MAX_CAND increments: per-shard reductions, ONE exchange (all-gather of
+            the shard rows, logsumexp merge on the device: smcb_temper_eval), one D2H."""
             g = np.ascontiguousarray(gms, dtype=np.float64)
-            for o in range(0, len(g), _lib.MAX_CAND):
-                part = g[o:o + _lib.MAX_CAND]
-                dst = self.scal[2 + 2 * o: 2 + 2 * (o + len(part))]
-                with self._timed("temper"):
-                    self._ck(self.lib.smcb_temper_sums(self.h, self.lk.data_ptr(), self.n, self.scal.data_ptr(),
-                                                       part.ctypes.data, len(part), dst.data_ptr(), st))
-            self.comm.all_reduce_sum(self.scal[2: 2 + 2 * len(g)])
-            host = self.scal[: 2 + 2 * len(g)].cpu().numpy()   # one D2H: max + sums
-            return float(host[0]), host[2:]
+            with self._timed("temper"):
+                self._ck(self.lib.smcb_temper_eval(self.h, self.lk.data_ptr(), self.n, g.ctypes.data, len(g),
+                                                   self.scal.data_ptr(), st))
+            k = 2 + 2 * len(g)
+            self._h_scal[:k].copy_(self.scal[:k], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            host = self._h_scal[:k].numpy()
+            return float(host[0]), host[2:].copy()
 
         if cfg.temper_rule == "backoff":
             # candidate list of the reference's geometric back-off (Micmem_SMC_main.py:111-141)
@@ -644,39 +752,47 @@ class Engine:
         return filled
 
     # -------------------------------------------------------------------------------- K4
-    def _launch_moments(self):
-        """Enqueue column sums and centred second moments of the current particles (device + collectives only)."""
-        st, d = self._stream, self.d
+    def _launch_moments(self, with_counts=False):
+        """Enqueue the merged moment reduction of the current particles (smcb_moments_merged): shard-local two-pass
+        moments, ONE all-gather that also carries the MH counters of the sweep just finished, merge and device-side
+        proposal factor.  Leaves counters | mean | M2 | F in `self.blk`."""
         with self._timed("moments"):
-            self._ck(self.lib.smcb_colsum(self.h, self.state.data_ptr(), self.n, self.n, d, self.mom.data_ptr(), st))
-        mean = self.mom[:d]
-        self.comm.all_reduce_sum(mean)
-        mean.div_(float(self.N))
-        cov_t = self.mom[d:d + d * d]
-        with self._timed("moments"):
-            self._ck(self.lib.smcb_centered_moments(self.h, self.state.data_ptr(), self.n, self.n, d,
-                                                    mean.data_ptr(), cov_t.data_ptr(), st))
-        self.comm.all_reduce_sum(cov_t)
+            self._ck(self.lib.smcb_moments_merged(self.h, self.state.data_ptr(), self.n, self.n, self.d, self.N,
+                                                  self.icnt.data_ptr() if with_counts else None,
+                                                  self._w_cov_c.ctypes.data, self.blk.data_ptr(), self._stream))
+
+    def _read_block(self, with_moments):
+        """Counters (and, for the host-side factor, mean and M2) of the last merged reduction: one D2H, one sync."""
+        k = 4 + (self.d + self.d * self.d if with_moments else 0)
+        self._h_blk[:k].copy_(self.blk[:k], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._h_blk.numpy()
 
     def _factor_from_moments(self, cov_sum):
         """cov = np.cov(p_filt.T, bias=True) * w_cov, factorised the way NumPy's legacy multivariate_normal
         does (SVD): x = z @ (sqrt(s)[:,None] * Vt)."""
         d = self.d
         cov = np.array(cov_sum, dtype=np.float64).reshape(d, d) / float(self.N)
-        if self._w_cov is None:
-            self._w_cov = self.cfg.w_cov(d)
-        cov = cov * self._w_cov
+        cov = cov * self._w_cov_c
         (u, sv, v) = np.linalg.svd(cov)
         return np.ascontiguousarray(np.sqrt(sv)[:, None] * v), cov
 
     def proposal_factor(self):
-        """Moments of the current particles -> (F, cov) (`Micmem_SMC_main.py:212-215` + the factor of :220)."""
+        """Moments of the current particles -> (F, cov) (`Micmem_SMC_main.py:212-215` + the factor of :220),
+        NumPy's SVD factor computed on the host."""
         self._launch_moments()
         d = self.d
-        return self._factor_from_moments(self.mom[d:d + d * d].cpu().numpy())
+        blk = self._read_block(True)
+        return self._factor_from_moments(blk[4 + d:4 + d + d * d])
+
+    def device_factor(self):
+        """The factor the device built in the last merged reduction (Jacobi eigen-decomposition), as a host array."""
+        d = self.d
+        return self.blk[4 + d + d * d:4 + d + 2 * d * d].cpu().numpy().reshape(d, d)
 
     def mh_sweep(self, gamma, F, ratio, stage, sweep, Z=None, U=None):
-        """One sweep: propose, evaluate in-box proposals, accept.  MH counters accumulate in icnt[0:2]."""
+        """One sweep: propose, evaluate in-box proposals, accept.  MH counters accumulate in icnt[0:4].
+        F: host factor [d, d], or None to use the one the last merged moment reduction left on the device."""
         st, lib, h, d = self._stream, self.lib, self.h, self.d
         seed = self.cfg.seed
         z_ptr = u_ptr = None
@@ -686,11 +802,19 @@ class Engine:
         if U is not None:
             Ut = torch.as_tensor(U, dtype=torch.float64).to(self.device).contiguous()
             u_ptr = Ut.data_ptr()
-        F = np.ascontiguousarray(F, dtype=np.float64)
         with self._timed("propose"):
-            self._ck(lib.smcb_mh_propose(h, self.state.data_ptr(), self.n, self.n, d, F.ctypes.data, ratio,
-                                         self._low.ctypes.data, self._high.ctypes.data, z_ptr, seed, self.id_offset,
-                                         stage, sweep, self.prop.data_ptr(), self.n, self.inbox.data_ptr(), st))
+            if F is None:      # the factor smcb_moments_merged left on the device
+                F_dev = self.blk[4 + d + d * d:]
+                self._ck(lib.smcb_mh_propose_dev(h, self.state.data_ptr(), self.n, self.n, d, F_dev.data_ptr(), ratio,
+                                                 self._low.ctypes.data, self._high.ctypes.data, z_ptr, seed,
+                                                 self.id_offset, stage, sweep, self.prop.data_ptr(), self.n,
+                                                 self.inbox.data_ptr(), st))
+            else:
+                F = np.ascontiguousarray(F, dtype=np.float64)
+                self._ck(lib.smcb_mh_propose(h, self.state.data_ptr(), self.n, self.n, d, F.ctypes.data, ratio,
+                                             self._low.ctypes.data, self._high.ctypes.data, z_ptr, seed,
+                                             self.id_offset, stage, sweep, self.prop.data_ptr(), self.n,
+                                             self.inbox.data_ptr(), st))
         dlp_ptr = None
         if self.dlp is not None:
             # log p(theta') - log p(theta) over the normal components: pp = exp(px*gamma) * p0_2/p0_1 (main:369)
@@ -763,14 +887,17 @@ class Engine:
             filled = self.resample(gm, u0)
             if keep_ancestors and self.comm.world == 1:
                 ancestors.append(self.anc[: self.n].cpu().numpy().astype(np.int64))
-            self.moved.zero_()
-            self.icnt[:4].zero_()
+            self._ck(self.lib.smcb_zero(self.h, self.moved.data_ptr(), self.n, self._stream))
+            self._ck(self.lib.smcb_zero(self.h, self.icnt.data_ptr(), 32, self._stream))
             ratio = 1.0
             if gamma_new >= 1.0:
                 n_mh, r_th = cfg.ad_mhstep_num, cfg.r_threshold_f
             else:
                 n_mh, r_th = cfg.mhstep_num, cfg.r_threshold
             n_run, moved, stage_evals, stage_cut = 0, 0, 0, 0
+            # Host-side factor (NumPy's SVD, reproduces the reference's proposals for given normals) in parity mode
+            # and for the fused kernel, which takes a host factor; the device's own Jacobi factor otherwise.
+            host_factor = cfg.factor == "host" or (cfg.factor == "auto" and (stream is not None or hook is not None))
             if cfg.fused_sweeps > 0:
                 F, _ = self.proposal_factor()
                 done = 0
@@ -779,10 +906,10 @@ class Engine:
                     self.mh_fused(gamma_new, F, ratio, step, done, k)
                     done += k
                     n_run += k
-                    cnt = self.icnt[:4].clone()
-                    self.comm.all_reduce_sum(cnt)
-                    c = cnt.cpu().numpy()
-                    moved, stage_evals, stage_cut = int(c[1]), int(c[2]), int(c[3])
+                    # counters of the batch and the moments the next batch needs: one exchange, one rendezvous
+                    self._launch_moments(with_counts=True)
+                    blk = self._read_block(True)
+                    moved, stage_evals, stage_cut = int(blk[1]), int(blk[2]), int(blk[3])
                     if cfg.early_exit and moved > r_th * N:
                         break
                     # the reference's step-size rule (Micmem_SMC_main.py:247-248), applied once per fused batch:
@@ -790,17 +917,19 @@ class Engine:
                     if moved < cfg.r_threshold_min * N:
                         ratio = ratio * 0.5
                     if done < n_mh:
-                        F, _ = self.proposal_factor()
+                        F, _ = self._factor_from_moments(blk[4 + d:4 + d + d * d])
             else:
-                # One host<->device rendezvous per sweep: after a sweep has been enqueued, the moments the NEXT
-                # sweep would need are enqueued speculatively, and the sweep's counters come back together with
-                # them (if the early-exit rule then stops the stage the moment kernels were wasted: ~20 us).
+                # One exchange and one host<->device rendezvous per sweep: after a sweep's accept kernel the merged
+                # reduction gathers its counters TOGETHER with the moments the next sweep needs (if the early-exit
+                # rule then stops the stage those moments were wasted: ~20 us).
                 dd = d + d * d
                 self._launch_moments()
-                self._h_mom.copy_(self.mom, non_blocking=True)
-                torch.cuda.current_stream(self.device).synchronize()
+                if host_factor:
+                    blk = self._read_block(True)
                 for j in range(n_mh):
-                    F, cov = self._factor_from_moments(self._h_mom[d:dd].numpy())
+                    F = cov = None
+                    if host_factor:
+                        F, cov = self._factor_from_moments(blk[4 + d:4 + dd])
                     Z = stream.normals(N, d) if stream is not None else None
                     U = stream.uniforms(N) if stream is not None else None
                     if Z is not None and self.comm.world > 1:
@@ -810,17 +939,9 @@ class Engine:
                         hook("sweep", step=step, j=j, engine=self, F=F, cov=cov, gamma=gamma_new, ratio=ratio)
                     self.mh_sweep(gamma_new, F, ratio, step, j, Z, U)
                     n_run += 1
-                    cnt = self.icnt[:4]
-                    if self.comm.world > 1:
-                        cnt = cnt.clone()
-                        self.comm.all_reduce_sum(cnt)
-                    self._h_cnt.copy_(cnt, non_blocking=True)
-                    if j + 1 < n_mh:
-                        self._launch_moments()
-                        self._h_mom.copy_(self.mom, non_blocking=True)
-                    torch.cuda.current_stream(self.device).synchronize()
-                    c = self._h_cnt.numpy()
-                    moved, stage_evals, stage_cut = int(c[1]), int(c[2]), int(c[3])
+                    self._launch_moments(with_counts=True)
+                    blk = self._read_block(host_factor)
+                    moved, stage_evals, stage_cut = int(blk[1]), int(blk[2]), int(blk[3])
                     if cfg.early_exit and moved > r_th * N:
                         break
                     if moved < cfg.r_threshold_min * N:

@@ -118,3 +118,77 @@ class KineticDAE(KineticRK):
         super().__init__(cond, obs, base, est_pos, n_steps=1, names=names)
         if self.n_pairs != 4:
             raise ValueError("the transient reactor model takes the reference's 8 kinetic parameters + sigma")
+
+
+class UserKernelLikelihood:
+    """A likelihood compiled by the user (SMCB_MODEL_USER): a shared library exporting a host function of type
+    `smcb_user_loglik_fn` (include/smcb200.h) that enqueues the user's own kernels; `include/smcb_user.cuh` holds the
+    few lines such a kernel needs and `examples/user_gauss.cu` is a complete one.  Counterpart of writing a new
+    `sim_particle` for the reference (`SMC_example/Micmem_likelihood.py:79-92`,
+    `SMC_methanation/methanation_functions.py:70-92`)."""
+    model_id = _lib.MODEL_USER
+
+    def __init__(self, library, symbol, d, n_obs=0, user_data=None, names=None):
+        import ctypes as C
+        self.dll = C.CDLL(library) if isinstance(library, (str, bytes, os.PathLike)) else library
+        self._fn = C.cast(getattr(self.dll, symbol), C.c_void_p)
+        self._user_data = user_data
+        self.d, self.n_obs = int(d), int(n_obs)
+        self.names = tuple(names) if names is not None else tuple(f"p{i}" for i in range(self.d))
+
+    def upload(self, lib, handle):
+        _lib.check(handle, lib.smcb_set_user_likelihood(handle, self._fn, self._user_data))
+
+
+class _DevView:
+    """Zero-copy torch view of device memory the library owns (through __cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape, typestr, strides=None):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": strides}
+
+
+class CallableLikelihood:
+    """Any Python callable on device tensors as the likelihood (SMCB_MODEL_USER through a ctypes trampoline):
+
+        fn(theta, active, lk_out)      theta  [d, n] float64 CUDA tensor (SoA view, row stride >= n)
+                                       active [n] uint8 CUDA tensor or None: particles to evaluate
+                                       lk_out [n] float64 CUDA tensor
+
+    `fn` either writes lk_out in place (entries of inactive particles are ignored and restored) or returns a [n]
+    tensor.  It runs on the sampler's CUDA stream (torch's current stream inside the call) and must not synchronise.
+    The counterpart of handing the reference a new `sim_particle` (`SMC_example/Micmem_likelihood.py:79-92`)."""
+    model_id = _lib.MODEL_USER
+
+    def __init__(self, fn, d, n_obs=0, names=None):
+        self.fn, self.d, self.n_obs = fn, int(d), int(n_obs)
+        self.names = tuple(names) if names is not None else tuple(f"p{i}" for i in range(self.d))
+        self.error = None
+        self._cb = _lib.USER_LOGLIK_FN(self._trampoline)     # keeps the C thunk alive as long as this object
+
+    def _trampoline(self, user, theta_p, ld, n, d, active_p, lk_p, stream):
+        import contextlib
+        import torch
+        try:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            theta = torch.as_tensor(_DevView(theta_p, (d, n), "<f8", (ld * 8, 8)), device=dev)
+            lk = torch.as_tensor(_DevView(lk_p, (n,), "<f8"), device=dev)
+            active = torch.as_tensor(_DevView(active_p, (n,), "|u1"), device=dev) if active_p else None
+            cur = torch.cuda.current_stream(dev)
+            ctx = contextlib.nullcontext() if (stream or 0) == cur.cuda_stream else \
+                torch.cuda.stream(torch.cuda.ExternalStream(stream or 0, device=dev))
+            with ctx:
+                keep = lk.clone() if active is not None else None
+                out = self.fn(theta, active, lk)
+                if out is not None and out.data_ptr() != lk.data_ptr():
+                    lk.copy_(out)
+                if active is not None:                     # masked particles keep their old value
+                    torch.where(active.bool(), lk, keep, out=lk)
+            return 0
+        except Exception as e:                             # an exception must not unwind through the C frames
+            self.error = e
+            return 1
+
+    def upload(self, lib, handle):
+        import ctypes as C
+        _lib.check(handle, lib.smcb_set_user_likelihood(handle, C.cast(self._cb, C.c_void_p), None))

@@ -40,6 +40,10 @@ class Settings:
     mm_patience: int = 3                # ... and for how many steps (results do not depend on these three)
     fused_sweeps: int = 0               # >0: run this many sweeps per launch with a frozen proposal factor
     bisect_iters: int = 60
+    factor: str = "auto"                # proposal factor: "host" = NumPy's SVD factor on the host (reproduces the reference's
+                                        # proposals for given normals), "device" = Jacobi eigen-factor on the device (same
+                                        # proposal distribution, no host round trip), "auto" = host when the random inputs
+                                        # are supplied (parity mode), device otherwise
 
     @property
     def inv_Np(self):
@@ -60,6 +64,8 @@ class Settings:
             raise ValueError("temper_rule must be 'backoff' or 'bisect'")
         if self.scan_mode not in ("fixed", "sequential"):
             raise ValueError("scan_mode must be 'fixed' or 'sequential'")
+        if self.factor not in ("auto", "host", "device"):
+            raise ValueError("factor must be 'auto', 'host' or 'device'")
         if self.gm_reduction_itr < 1:
             raise ValueError("gm_reduction_itr must be at least 1 (the back-off loop tests at least one increment)")
         if not (0.0 < self.gm_reduction_rate < 1.0):

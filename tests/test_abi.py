@@ -58,7 +58,8 @@ def test_model_ids_and_likelihood_specs_match_the_header(pkg):
     import numpy as np
     text = open(os.path.join(ROOT, "include", "smcb200.h")).read()
     ids = {k: int(v) for k, v in re.findall(r"#define\s+SMCB_MODEL_([A-Z_]+)\s+(\d+)", text)}
-    assert ids == {"MM_PROGRESS": 1, "MM_RATE": 2, "KINETIC_RK": 3, "KINETIC_DAE": 4}
+    assert ids == {"MM_PROGRESS": 1, "MM_RATE": 2, "KINETIC_RK": 3, "KINETIC_DAE": 4, "USER": 5}
+    assert pkg.UserKernelLikelihood.model_id == pkg.CallableLikelihood.model_id == 5
     assert (pkg.MMProgress.model_id, pkg.MMRate.model_id, pkg.KineticRK.model_id, pkg.KineticDAE.model_id) == (1, 2, 3, 4)
     cond = np.ones((3, pkg._lib.KIN_NCOND_FIELDS))
     obs = np.zeros((5, 3))

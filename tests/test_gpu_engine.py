@@ -98,7 +98,7 @@ def test_philox_run_matches_oracle_loop_mm_rate(pkg, scan_mode):
     res = eng.run(keep_ancestors=True)
     rs = smc.resample_fixed if scan_mode == "fixed" else smc.resample_sequential
     p, lk, tr = smc.run(lambda th: mm.loglik_rate(th, lik.S, lik.v), p0, prior.low, prior.high,
-                        smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=rs)
+                        smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=rs, factor=smc.proposal_factor_eig)
     assert np.array_equal(np.array(res.betas), np.array(tr.gamma))
     assert res.n_mh == tr.n_mh and res.n_moved == tr.moved
     for a, b in zip(res.ancestors, tr.ancestors):
@@ -121,7 +121,8 @@ def test_odd_and_tiny_particle_counts(pkg, N):
     p0 = eng.particles().cpu().numpy()
     res = eng.run(keep_ancestors=True)
     p, lk, tr = smc.run(lambda th: mm.loglik_rate(th, lik.S, lik.v), p0, prior.low, prior.high,
-                        smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed)
+                        smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed,
+                        factor=smc.proposal_factor_eig)
     assert np.array_equal(np.array(res.betas), np.array(tr.gamma))
     assert res.n_mh == tr.n_mh and res.n_moved == tr.moved
     for a, b in zip(res.ancestors, tr.ancestors):
@@ -144,7 +145,8 @@ def test_mm_progress_small_odd_run(pkg, golden):
         p0 = eng.particles().cpu().numpy()
         res = eng.run(keep_ancestors=True)
         p, lk, tr = smc.run(lambda th: cmm.loglik_progress(th, *d)[0], p0, prior.low, prior.high,
-                            smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed)
+                            smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed,
+                        factor=smc.proposal_factor_eig)
         assert np.array_equal(np.array(res.betas), np.array(tr.gamma))
         assert res.n_mh == tr.n_mh and res.n_moved == tr.moved
         for a, b in zip(res.ancestors, tr.ancestors):
@@ -172,7 +174,7 @@ def test_mixed_normal_uniform_prior_matches_oracle_loop(pkg):
     res = eng.run(keep_ancestors=True)
     p, lk, tr = smc.run(lambda th: mm.loglik_rate(th, lik.S, lik.v), p0, prior.low, prior.high,
                         smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed,
-                        log_prior_ratio=prior.log_ratio)
+                        log_prior_ratio=prior.log_ratio, factor=smc.proposal_factor_eig)
     assert np.array_equal(np.array(res.betas), np.array(tr.gamma))
     assert res.n_mh == tr.n_mh and res.n_moved == tr.moved
     for a, b in zip(res.ancestors, tr.ancestors):
@@ -180,7 +182,8 @@ def test_mixed_normal_uniform_prior_matches_oracle_loop(pkg):
     assert np.abs(res.particles - p).max() < 1e-9 and np.abs(res.lk / lk - 1).max() < 1e-9
     # the ratio does matter here: the same run with the uniform box alone ends elsewhere
     p_u, _, tr_u = smc.run(lambda th: mm.loglik_rate(th, lik.S, lik.v), p0, prior.low, prior.high,
-                           smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed)
+                           smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed,
+                        factor=smc.proposal_factor_eig)
     assert tr_u.moved != tr.moved
     # log-ratio form == the reference's pdf-ratio form where the pdfs are representable
     th_a, th_b = p[:100], p0[:100]
@@ -238,7 +241,8 @@ def test_kinetic_run_matches_oracle_loop(pkg):
     p0 = eng.particles().cpu().numpy()
     res = eng.run(keep_ancestors=True)
     p, lk, tr = smc.run(lambda th: kinetic.loglik(th, cond, obs, base, kinetic.EST_POSITION, 20), p0, low, high,
-                        smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed)
+                        smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed,
+                        factor=smc.proposal_factor_eig)
     assert res.reached_one
     assert np.array_equal(np.array(res.betas), np.array(tr.gamma))
     for a, b in zip(res.ancestors, tr.ancestors):

@@ -445,7 +445,8 @@ def test_resample_full_size_properties(abi):
 
 
 # ------------------------------------------------------------------------------------ K4 MH
-@pytest.mark.parametrize("d,n", [(1, 100), (3, 1000), (5, 4097), (8, 3000), (32, 2500)])
+@pytest.mark.parametrize("d,n", [(1, 100), (3, 1000), (5, 4097), (8, 3000), (32, 2500), (32, (1 << 16) + 5),
+                                 (26, 1 << 15)])
 def test_moments_match_numpy_cov(abi, d, n):
     rs = np.random.RandomState(d)
     X = rs.normal(0, 1, (n, d)) @ rs.normal(0, 1, (d, d)) + rs.uniform(1e3, 1e6, d)   # large offsets (H4)
@@ -460,6 +461,86 @@ def test_moments_match_numpy_cov(abi, d, n):
     want = np.atleast_2d(np.cov(X.T, bias=True))
     assert np.abs(cov - want).max() <= 1e-10 * np.abs(want).max()
     assert np.array_equal(cov, cov.T)
+
+
+@pytest.mark.parametrize("d,n", [(1, 100), (3, 1000), (3, (1 << 18) + 1), (5, 4097), (32, 70000)])
+def test_merged_moments_and_device_factor(abi, d, n):
+    """smcb_moments_merged on one shard: counters pass through, mean and M2 are bit-identical to smcb_colsum / n and
+    smcb_centered_moments, the device's Jacobi factor satisfies F^T F = cov (*) w_cov and equals the oracle's twin."""
+    rs = np.random.RandomState(100 + d)
+    scale = 10.0 ** rs.uniform(-2, 6, d)                      # parameters of very different magnitude (methanation)
+    X = (rs.normal(0, 1, (n, d)) @ rs.normal(0, 1, (d, d))) * scale + rs.uniform(1e3, 1e6, d)
+    th = abi.t(X.T)
+    mom = abi.zeros(d + d * d)
+    abi.ck(abi.lib.smcb_colsum(abi.h, th.data_ptr(), n, n, d, mom.data_ptr(), None))
+    mean = abi.t(mom[:d].cpu().numpy() / n)                  # IEEE division, as np.cov's X.mean() (torch's tensor / scalar
+    mom[:d] = mean                                           # on the GPU multiplies by the reciprocal: 1 ulp off)
+    abi.ck(abi.lib.smcb_centered_moments(abi.h, th.data_ptr(), n, n, d, mom.data_ptr(), mom[d:].data_ptr(), None))
+    cnt = abi.t(np.array([5, 7, 11, 13, 0, 0, 0, 0]), torch.int64)
+    w = np.full((d, d), 0.5)
+    blk = abi.zeros(4 + d + 2 * d * d)
+    abi.ck(abi.lib.smcb_moments_merged(abi.h, th.data_ptr(), n, n, d, n, cnt.data_ptr(), w.ctypes.data, blk.data_ptr(), None))
+    b = blk.cpu().numpy()
+    assert np.array_equal(b[:4], [5, 7, 11, 13])
+    assert np.array_equal(b[4:4 + d], mean.cpu().numpy())
+    assert np.array_equal(b[4 + d:4 + d + d * d], mom[d:].cpu().numpy())
+    cov = b[4 + d:4 + d + d * d].reshape(d, d) / n * w
+    F = b[4 + d + d * d:].reshape(d, d)
+    sd = np.sqrt(np.diag(cov))
+    assert np.abs((F.T @ F - cov) / np.outer(sd, sd)).max() < 1e-12
+    Fo = smc.proposal_factor_eig(cov)
+    assert np.abs((F - Fo) / sd[None, :]).max() < 1e-9
+
+
+def test_merged_moments_degenerate_clouds(abi):
+    """One particle, two particles, a constant column: zero or rank-deficient covariance gives zero factor rows, not NaN."""
+    for X in (np.array([[1.0, 2.0, 3.0]]), np.array([[1.0, 2.0, 3.0], [2.0, 2.5, 3.0]]),
+              np.c_[np.arange(50.0), np.full(50, 7.0), np.arange(50.0) ** 2]):
+        n, d = X.shape
+        th = abi.t(X.T)
+        blk = abi.zeros(4 + d + 2 * d * d)
+        abi.ck(abi.lib.smcb_moments_merged(abi.h, th.data_ptr(), n, n, d, n, None, None, blk.data_ptr(), None))
+        b = blk.cpu().numpy()
+        F = b[4 + d + d * d:].reshape(d, d)
+        cov = np.atleast_2d(np.cov(X.T, bias=True))
+        assert np.all(np.isfinite(F)) and np.abs(F.T @ F - cov).max() <= 1e-12 * max(np.abs(cov).max(), 1.0)
+        assert np.abs(F - smc.proposal_factor_eig(cov)).max() < 1e-9
+
+
+def test_temper_eval_equals_max_then_sums(abi):
+    """smcb_temper_eval without a communicator: bit-identical to smcb_lk_max + smcb_temper_sums, for up to 48 candidates."""
+    n = 100003
+    lk = np.random.RandomState(9).normal(300, 80, n)
+    lk[5] = -np.inf
+    t = abi.t(lk)
+    gms = np.ascontiguousarray([0.7 ** k for k in range(40)])
+    a, b = abi.zeros(2 + 96), abi.zeros(2 + 96)
+    abi.ck(abi.lib.smcb_temper_eval(abi.h, t.data_ptr(), n, gms.ctypes.data, 40, a.data_ptr(), None))
+    abi.ck(abi.lib.smcb_lk_max(abi.h, t.data_ptr(), n, b.data_ptr(), None))
+    for o in range(0, 40, 16):
+        g = np.ascontiguousarray(gms[o:o + 16])
+        abi.ck(abi.lib.smcb_temper_sums(abi.h, t.data_ptr(), n, b.data_ptr(), g.ctypes.data, len(g),
+                                        b[2 + 2 * o:].data_ptr(), None))
+    assert a[0].item() == lk.max()
+    assert torch.equal(a[2:82], b[2:82])
+
+
+def test_proposal_with_device_factor_equals_host_factor(abi):
+    n, d, seed = 3001, 5, 3
+    rs = np.random.RandomState(2)
+    X = rs.normal(0, 1, (n, d))
+    F = np.ascontiguousarray(rs.normal(0, 0.3, (d, d)))
+    low, high = np.full(d, -1.5), np.full(d, 1.5)
+    th, Fd = abi.t(X.T), abi.t(F)
+    outs = []
+    for dev in (False, True):
+        prop, inbox = abi.zeros(d, n), abi.zeros(n, dtype=torch.uint8)
+        fn = abi.lib.smcb_mh_propose_dev if dev else abi.lib.smcb_mh_propose
+        abi.ck(fn(abi.h, th.data_ptr(), n, n, d, Fd.data_ptr() if dev else F.ctypes.data, 0.5, low.ctypes.data,
+                  high.ctypes.data, None, seed, 0, 2, 1, prop.data_ptr(), n, inbox.data_ptr(), None))
+        outs.append((prop.cpu().numpy(), inbox.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert 0 < outs[0][1].sum() < n
 
 
 def test_philox_draws_match_numpy_twin(abi):

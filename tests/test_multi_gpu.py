@@ -26,44 +26,69 @@ def _worker(rank, world, port, n, model, out):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    lik, prior = _problem(pkg, model)
-    eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=n), comm=pkg.TorchComm())
+    lik, prior, cfg_kw = _problem(pkg, model)
+    comm = pkg.NcclComm.from_torch_distributed()          # the library's own NCCL communicator (smcb_comm_init)
+    eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=n, **cfg_kw), comm=comm)
     eng.sample_prior()
     res = eng.run()
     np.savez(os.path.join(out, f"rank{rank}.npz"), particles=res.particles, lk=res.lk, betas=np.array(res.betas),
              n_mh=np.array(res.n_mh), moved=np.array(res.n_moved), logz=res.log_evidence, ess=np.array(res.ess),
-             filled=np.array([s.filled for s in res.stages]))
+             filled=np.array([s.filled for s in res.stages]), collectives=comm.collective_count(),
+             sweeps=int(sum(res.n_mh)))
     eng.close()
     dist.destroy_process_group()
 
 
 def _problem(pkg, model):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    box3 = pkg.UniformBox([0, 0, 0], [10, 10, 10])
     if model == "mm_progress":
         g = np.load(os.path.join(root, "tests", "golden", "mm_reference_run.npz"))
-        return pkg.MMProgress(g["data_t"], g["data_P"], g["data_S0"]), pkg.UniformBox([0, 0, 0], [10, 10, 10])
-    return pkg.MMRate.synthetic(500), pkg.UniformBox([0, 0, 0], [10, 10, 10])
+        return pkg.MMProgress(g["data_t"], g["data_P"], g["data_S0"]), box3, {}
+    if model == "kinetic32":
+        # BASELINE config 5 shape: 32-parameter family, fused sweeps with the early exit disabled
+        kf = np.load(os.path.join(root, "tests", "golden", "kinetic_synth.npz"))
+        base = kf["base16"]
+        lo, hi = base[:32] * 0.8, base[:32] * 1.2
+        lik = pkg.KineticRK(kf["cond"][:6], kf["obs16"][:, :6], base, np.arange(32, dtype=np.int32), n_steps=10)
+        return lik, pkg.UniformBox(np.minimum(lo, hi), np.maximum(lo, hi)), dict(
+            fused_sweeps=4, mhstep_num=4, ad_mhstep_num=4, early_exit=False)
+    return pkg.MMRate.synthetic(500), box3, {}
 
 
-@pytest.mark.parametrize("model,n", [("mm_rate", 1 << 14), ("mm_progress", 1 << 14)])
+@pytest.mark.parametrize("model,n", [("mm_rate", 1 << 14), ("mm_progress", 1 << 14), ("kinetic32", 1 << 12)])
 def test_sharded_run_reproduces_single_gpu_run(pkg, tmp_path, model, n):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(world, _free_port(), n, model, str(tmp_path)), nprocs=world, join=True)
-    lik, prior = _problem(pkg, model)
-    eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=n))
+    lik, prior, cfg_kw = _problem(pkg, model)
+    eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=n, **cfg_kw))
     eng.sample_prior()
     ref = eng.run()
     eng.close()
     parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
     P = np.concatenate([p["particles"] for p in parts])
     L = np.concatenate([p["lk"] for p in parts])
+    loose = model == "kinetic32"
     for p in parts:                                        # every rank holds the same scalars
         assert np.array_equal(p["betas"], np.array(ref.betas))
-        assert np.array_equal(p["n_mh"], np.array(ref.n_mh)) and np.array_equal(p["moved"], np.array(ref.n_moved))
-        assert abs(float(p["logz"]) / ref.log_evidence - 1) < 1e-10
-        assert np.abs(p["ess"] / np.array(ref.ess) - 1).max() < 1e-10
+        assert np.array_equal(p["n_mh"], np.array(ref.n_mh))
+        assert np.array_equal(p["betas"], parts[0]["betas"]) and np.array_equal(p["moved"], parts[0]["moved"])
+        if loose:
+            assert np.abs(p["moved"] - np.array(ref.n_moved)).max() <= max(2, 0.005 * n)
+        else:
+            assert np.array_equal(p["moved"], np.array(ref.n_moved))
+        assert abs(float(p["logz"]) / ref.log_evidence - 1) < (1e-6 if loose else 1e-10)
+        assert np.abs(p["ess"] / np.array(ref.ess) - 1).max() < (1e-6 if loose else 1e-10)
     assert P.shape == ref.particles.shape
-    assert np.abs(P - ref.particles).max() < 1e-8 and np.abs(L / ref.lk - 1).max() < 1e-8
+    if model == "kinetic32":
+        # the ill-conditioned particles of this family amplify the last-bit differences of the merged moments
+        # (DESIGN.md K1'): same schedule and counts above, particles to 1e-5 relative
+        assert np.abs(P / ref.particles - 1).max() < 1e-5
+    else:
+        assert np.abs(P - ref.particles).max() < 1e-8 and np.abs(L / ref.lk - 1).max() < 1e-8
+    # one exchange per tempering round and per sweep (+ the stage's first moments), two per resampling
+    stages, sweeps = len(ref.betas), int(parts[0]["sweeps"])
+    assert int(parts[0]["collectives"]) <= 4 * stages + sweeps + 8 * stages, parts[0]["collectives"]
