@@ -14,7 +14,8 @@ construction, H2D of the particles from pinned host memory, the run, D2H of post
 Workloads (BASELINE.json configs):
   mm_progress   config 2: Michaelis-Menten progress curves (the reference's six CSVs, 240
                 observations), 2^20 particles per GPU, FP64, scipy-RK45-twin arithmetic.  DEFAULT.
-  mm_rate       config 4 shape: 10 000 rate-law observations, 2^22 particles per GPU (--particles)
+  mm_rate       config 4 shape: 10 000 rate-law observations, 2^22 particles per GPU (--particles), direct FP32 sum
+  mm_rate_suff  config 4, sufficient-statistic form (A(Km), B(Km) tabulated once): 2^23 particles per GPU = 2^26 on 8
   kinetic       config 3: methanation-style reactor, d=5, 30 conditions, RK4 x 50, 2^18 particles
   kinetic_dae   SURVEY 8(f) N3: the reference's transient reactor DAE, 30 conditions, the reference's N = 1000
   kinetic32     config 5: 32-parameter kinetic family, 10 fused MH sweeps per stage, 2^21 particles per GPU
@@ -51,7 +52,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="mm_progress", choices=["mm_progress", "mm_rate", "kinetic", "kinetic32", "kinetic_dae"])
+    ap.add_argument("--workload", default="mm_progress", choices=["mm_progress", "mm_rate", "mm_rate_suff", "kinetic", "kinetic32", "kinetic_dae"])
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (0 = workload default)")
     ap.add_argument("--total-particles", type=int, default=0,
                     help="strong scaling: this many particles in total, split evenly over the GPUs")
@@ -79,6 +80,13 @@ def make_workload(pkg, name, n_per_gpu):
         n = n_per_gpu or (1 << 22)
         cfg = dict()
         desc = "synthetic Michaelis-Menten rate law, 10k observations, FP32 terms / FP64 accumulation"
+    elif name == "mm_rate_suff":
+        lik = pkg.MMRate.synthetic(10000, form="sufficient", km_range=(0.0, 10.0))
+        prior = pkg.UniformBox([0, 0, 0], [10, 10, 10], names=["Vmax", "Km", "sigma"])
+        n = n_per_gpu or (1 << 23)
+        cfg = dict()
+        desc = ("synthetic Michaelis-Menten rate law, 10k observations, sufficient-statistic form (sum v^2, A(Km), B(Km) "
+                "tabulated once; FP64), BASELINE config 4: 2^26 particles over 8 GPUs = 2^23 per GPU")
     elif name == "kinetic":
         cond, base, obs, low, high = kf["cond"], kf["base4"], kf["obs4"], kf["low4"], kf["high4"]
         lik = pkg.KineticRK(cond, obs, base, kf["est4"], n_steps=50)
@@ -261,7 +269,7 @@ def cpu_baseline_dae(per_core=2):
 REF_PARTICLES = 128      # particles of one reference-arm step (fixed: the same sample on every box)
 DATA_LABEL = {"mm_progress": "observations: the reference's own six CSVs (SMC_example/data/mm_pseudo_data_0..5.csv, 6x40 "
                              "points, carried in tests/golden/mm_reference_run.npz); prior particles: synthetic, U[0,10]^3",
-              "mm_rate": "synthetic", "kinetic": "synthetic", "kinetic32": "synthetic", "kinetic_dae": "synthetic"}
+              "mm_rate": "synthetic", "mm_rate_suff": "synthetic", "kinetic": "synthetic", "kinetic32": "synthetic", "kinetic_dae": "synthetic"}
 
 
 def run_reference_arm(args):
@@ -340,22 +348,29 @@ Jacobian (51 nodes x 21 perturbed node residuals x ~150 flop), one block-tridiag
 exit are not counted: this is a nominal figure, labelled so in the line."""
 
 
-def gather_microbench(pkg, eng, torch, flush):
-    """HBM leg: resample-gather of the full particle state with the ancestors of a real stage,
-    inputs flushed from L2.  Algorithmic bytes per particle: 4 (ancestor) + 2*(d+1)*8."""
+def resample_microbench(pkg, eng, torch, flush):
+    """HBM leg: the whole of K3 (weights -> counts -> offsets -> ancestors -> gather) as the single kernel the
+    single-GPU engine runs, on the weights of a real first stage (prior cloud, the tempering step's own max / gm /
+    sum_w), inputs flushed from L2.  Algorithmic bytes per particle: 8 (weight) + 4 + 4 (ancestor
+    write / read) + 2*(d+1)*8 (state read + write)."""
     n, D1 = eng.n, eng.d + 1
+    eng.sample_prior()
+    eng.sim_particle()
+    t = eng.temper(0.0)
     ms = []
     for _ in range(5):
         flush()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng._ck(eng.lib.smcb_gather(eng.h, eng.state.data_ptr(), n, eng.anc.data_ptr(), n, D1, eng.state2.data_ptr(), n,
-                                    eng._stream))
+        eng._ck(eng.lib.smcb_resample_fused(eng.h, eng.lk.data_ptr(), None, n, eng.scal.data_ptr(), t["gm"],
+                                            eng.scal[1:].data_ptr(), 0.375, eng.state.data_ptr(), n, D1,
+                                            eng.state2.data_ptr(), n, eng.anc.data_ptr(), None,
+                                            eng.icnt[6:7].data_ptr(), eng._stream))
         e1.record()
         e1.synchronize()
         ms.append(e0.elapsed_time(e1))
     best = float(np.median(ms))
-    nbytes = n * (4 + 2 * D1 * 8)
+    nbytes = n * (8 + 4 + 4 + 2 * D1 * 8)
     return best, nbytes
 
 
@@ -548,6 +563,13 @@ def main():
                         fma_pipe_lane_slot_frac=5.5 * terms / (ms_lik * 1e-3) / lane_peak,
                         terms_per_s=terms / (ms_lik * 1e-3))
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
+    if args.workload == "mm_rate_suff":
+        # HBM-bound: 24 B of parameters + 1 B of mask in, 8 B out per evaluated particle
+        nbytes = 33.0 * float(evals // world)
+        roofline.update(bound="hbm", kernel="mm_rate_kernel_suff (two 14-term Clenshaw sums per particle)",
+                        achieved=nbytes / (ms_lik * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s", peak_source=hbm_src,
+                        bytes_model="33 B per evaluated particle (3 parameters + mask in, log-likelihood out)")
+        roofline["frac"] = roofline["achieved"] / roofline["peak"]
     if args.workload in ("kinetic", "kinetic32", "kinetic_dae"):
         evals_step = float(evals) / args.steps / world            # completed evaluations of one step on this rank
         ms_step = ms_lik / args.steps                             # likelihood launch groups of the one profiled step
@@ -567,16 +589,15 @@ def main():
         roofline.update(achieved=fl * evals_step / (ms_step * 1e-3) / 1e12, flops_per_eval=fl,
                         evals_per_step_this_rank=evals_step)
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
-    g_ms, g_bytes = gather_microbench(pkg, eng, torch, flush)
-    roofline_hbm = {"bound": "hbm", "kernel": "gather_kernel (resampling gather of particle state)",
-                    "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak,
-                    # DRAM bytes of one launch from the ncu --set full capture (profiles/ncu_stage_kernels_r01.md: 151.0 MB
-                    # read + 91.1 MB written for 2^22 particles, d = 3; the writes lag the kernel in the 126 MB L2),
-                    # scaled to this launch's particle count - not re-measured here
-                    "traffic": (242.1e6 / (1 << 22)) * eng.n if eng.d == 3 else None,
-                    "traffic_source": "ncu capture profiles/ncu_stage_kernels_r01.md, per particle x particles of this launch",
-                    "peak_source": hbm_src, "launch_ms": g_ms, "bytes": g_bytes}
+    roofline_hbm = None
+    if world == 1:
+        g_ms, g_bytes = resample_microbench(pkg, eng, torch, flush)
+        roofline_hbm = {"bound": "hbm", "kernel": "resample_fused_kernel (all of K3 in one launch: weights, counts, look-back "
+                                                  "scan, ancestors, gather of the particle state)",
+                        "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                        "bytes_model": "8 (weight) + 4 + 4 (ancestor) + 2 (d+1) 8 (state) per particle, SURVEY.md 8(d)",
+                        "peak_source": hbm_src, "launch_ms": g_ms, "bytes": g_bytes}
 
     # ---- BASELINE config 1: the reference's own problem size (N = 1000, its seed and random stream) -----------
     config1 = None

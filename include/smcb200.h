@@ -90,6 +90,14 @@ int smcb_set_data_mm_progress(smcb_handle* h, const double* t_host, const double
  * in 64-observation tiles and FP64 across tiles. */
 int smcb_set_data_mm_rate(smcb_handle* h, const double* S_host, const double* v_host,
                           int64_t n_obs, int precision);
+/* The same likelihood in its sufficient-statistic form: the residual sum of squares is
+ * sum v^2 - 2 Vmax A(Km) + Vmax^2 B(Km) with A = sum v_i S_i/(Km+S_i), B = sum S_i^2/(Km+S_i)^2; A and B are tabulated
+ * once (piecewise Chebyshev in Km over [km_lo, km_hi], summed in long double on the host, accurate to the last bits
+ * of FP64) and a likelihood then costs ~60 flop whatever n_obs is.  Agreement with the direct FP64 sum: better than
+ * 1e-9 relative on the log-likelihood (tests/test_gpu_kernels.py; the cancellation in the three-term form is what
+ * limits it, not the tables).  Particles with Km outside [km_lo, km_hi] take the direct FP64 sum.  Synchronous. */
+int smcb_set_data_mm_rate_sufficient(smcb_handle* h, const double* S_host, const double* v_host, int64_t n_obs,
+                                     double km_lo, double km_hi);
 /* Methanation-style reactor (ME/lik:44-66,204-208,289-298; reactor definition in DESIGN.md).
  * cond: [n_cond][SMCB_KIN_NCOND_FIELDS] row-major operating conditions
  *       (Ca,Cb,Cc,Cd,Ce inlet [mol/m3], T_in [K], T_jacket [K], u_in [m/s], void, length [m]);
@@ -200,6 +208,17 @@ int smcb_ancestors(smcb_handle* h, const int32_t* counts_dev, int64_t n, int64_t
 /* Vectorised gather of particle state: dst[k*ld_dst+s] = src[k*ld_src+anc[s]] for k<rows, s<m. */
 int smcb_gather(smcb_handle* h, const double* src_dev, int64_t ld_src, const int32_t* ancestors_dev,
                 int64_t m, int rows, double* dst_dev, int64_t ld_dst, void* stream);
+
+/* The whole of K3 for one shard in ONE kernel (FIXED arithmetic): weights (from lk_dev, max_dev, gm, sum_w_dev exactly as
+ * smcb_weights computes them, or explicit normalised weights w_dev with lk_dev = NULL), floor counts and fixed-point
+ * residuals, copy counts, output offsets (decoupled look-back over 2048-particle tiles), ancestors and the gather
+ * dst[k*ld_dst+s] = src[k*ld_src+anc[s]] of `rows` rows.  Same counts, ancestors and clamp / pad rule as
+ * smcb_resample_counts(SMCB_SCAN_FIXED) + smcb_ancestors + smcb_gather, bit for bit.  ancestors_dev / counts_dev may be
+ * NULL; filled_dev int64[1] = sum of the counts. */
+int smcb_resample_fused(smcb_handle* h, const double* lk_dev, const double* w_dev, int64_t n, const double* max_dev,
+                        double gm, const double* sum_w_dev, double u0, const double* src_dev, int64_t ld_src, int rows,
+                        double* dst_dev, int64_t ld_dst, int32_t* ancestors_dev, int32_t* counts_dev,
+                        int64_t* filled_dev, void* stream);
 
 /* ---- K4: Metropolis-Hastings mutation (replaces EX/main:209-249) ------------------------- */
 /* Column sums: out_dev[k] = sum_i theta[k][i]. */

@@ -23,6 +23,7 @@ _SIGNATURES = {
     "smcb_launch_count": [p_void],
     "smcb_set_data_mm_progress": [p_void, p_void, p_void, p_void, c_int, c_int],
     "smcb_set_data_mm_rate": [p_void, p_void, p_void, c_i64, c_int],
+    "smcb_set_data_mm_rate_sufficient": [p_void, p_void, p_void, c_i64, c_dbl, c_dbl],
     "smcb_set_data_kinetic": [p_void, p_void, p_void, c_int, p_void, c_int, p_void, c_int, c_int],
     "smcb_loglik": [p_void, c_int, p_void, c_i64, c_i64, c_int, p_void, p_void, p_void],
     "smcb_loglik_bounded": [p_void, c_int, p_void, c_i64, c_i64, c_int, p_void, p_void, p_void, p_void],
@@ -37,6 +38,8 @@ _SIGNATURES = {
                              p_void],
     "smcb_resample_totals": [p_void, p_void, c_i64, c_i64, p_void, p_void],
     "smcb_ancestors": [p_void, p_void, c_i64, c_i64, p_void, p_void, p_void],
+    "smcb_resample_fused": [p_void, p_void, p_void, c_i64, p_void, c_dbl, p_void, c_dbl, p_void, c_i64, c_int, p_void,
+                            c_i64, p_void, p_void, p_void, p_void],
     "smcb_gather": [p_void, p_void, c_i64, p_void, c_i64, c_int, p_void, c_i64, p_void],
     "smcb_colsum": [p_void, p_void, c_i64, c_i64, c_int, p_void, p_void],
     "smcb_centered_moments": [p_void, p_void, c_i64, c_i64, c_int, p_void, p_void, p_void],

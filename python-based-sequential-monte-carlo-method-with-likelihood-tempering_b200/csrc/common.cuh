@@ -28,9 +28,14 @@ struct MmRateData {
     double* v = nullptr;
     float2* Sv32 = nullptr;  // [n_obs] packed (S, v) FP32
     int64_t n_obs = 0;
-    int precision = 64;
+    int precision = 64;    // 64 / 32: arithmetic of the direct sum; 0: sufficient-statistic form (tables below)
     double sum_v2 = 0.0;   // sum v^2 (host, FP64)
+    // sufficient-statistic form (smcb_set_data_mm_rate_sufficient): Chebyshev tables of A(Km), B(Km)
+    double* suff = nullptr;      // [SUFF_INT][2][SUFF_M] coefficients, then [SUFF_INT] centres, [SUFF_INT] 1/half-widths
+    double suff_s0 = 0.0, suff_ulo = 0.0, suff_uhi = 0.0, suff_inv_log2rho = 0.0;
 };
+constexpr int SMCB_SUFF_INT = 64;   // geometric intervals in u = Km + min(S)
+constexpr int SMCB_SUFF_M = 14;     // Chebyshev coefficients per interval (degree 13)
 
 struct KineticData {
     double* cond = nullptr;   // [n_cond][SMCB_KIN_NCOND_FIELDS]
@@ -85,6 +90,7 @@ struct smcb_handle {
     int64_t* tile_tot2 = nullptr;    // second tile array (ancestor expansion)
     int32_t* mark = nullptr;         // [n_max] head marks for the ancestor fill
     double* seq_carry = nullptr;     // [4] sequential-scan carry (device)
+    unsigned* rs_ctl = nullptr;      // [4] tile counter of the single-pass resampling kernel
     MmProgressData mmp;
     MmRateData mmr;
     KineticData kin;

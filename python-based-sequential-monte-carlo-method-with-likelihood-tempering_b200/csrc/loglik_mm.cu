@@ -704,6 +704,54 @@ mm_rate_kernel_f32(const double* __restrict__ theta, int64_t ld, int64_t n,
             }
 }
 
+// Sufficient-statistic form (tables built by smcb_set_data_mm_rate_sufficient): per particle two Clenshaw sums of 14 terms.
+// HBM-bound: 24 B of parameters in, 8 B out.  A Km outside the tabulated range takes the direct FP64 sum.
+constexpr int SUFF_BLOCK = 256;
+__global__ void __launch_bounds__(SUFF_BLOCK)
+mm_rate_kernel_suff(const double* __restrict__ theta, int64_t ld, int64_t n, const uint8_t* __restrict__ active,
+                    const double* __restrict__ tab, double s0, double u_lo, double u_hi, double inv_log2rho,
+                    double sum_v2, const double* __restrict__ gS, const double* __restrict__ gv, int64_t n_obs,
+                    double* __restrict__ lk) {
+    constexpr int NI = SMCB_SUFF_INT, M = SMCB_SUFF_M;
+    __shared__ double sT[NI * 2 * M + 2 * NI];
+    for (int k = threadIdx.x; k < NI * 2 * M + 2 * NI; k += SUFF_BLOCK) sT[k] = tab[k];
+    __syncthreads();
+    const int64_t p = (int64_t)blockIdx.x * SUFF_BLOCK + threadIdx.x;
+    if (p >= n || (active != nullptr && !active[p])) return;
+    const double Vmax = theta[p], Km = theta[ld + p], sigma = theta[2 * ld + p];
+    if (!(sigma > 0)) {
+        lk[p] = -INFINITY;
+        return;
+    }
+    const double u = Km + s0;
+    double ssr;
+    if (u >= u_lo && u <= u_hi) {
+        int j = (int)(log2(u / u_lo) * inv_log2rho);
+        j = j < 0 ? 0 : (j > NI - 1 ? NI - 1 : j);
+        const double t = (u - sT[NI * 2 * M + j]) * sT[NI * 2 * M + NI + j], t2 = 2.0 * t;
+        const double* ca = sT + (size_t)(j * 2) * M;
+        const double* cb = ca + M;
+        double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;   // Clenshaw
+#pragma unroll
+        for (int k = M - 1; k >= 1; --k) {
+            const double na = fma(t2, a1, ca[k] - a2), nb = fma(t2, b1, cb[k] - b2);
+            a2 = a1; a1 = na;
+            b2 = b1; b1 = nb;
+        }
+        const double A = fma(t, a1, ca[0] - a2), B = fma(t, b1, cb[0] - b2);
+        ssr = fma(Vmax, fma(Vmax, B, -2.0 * A), sum_v2);   // sum v^2 - 2 Vmax A + Vmax^2 B
+    } else {
+        double acc = 0.0;
+        for (int64_t i = 0; i < n_obs; ++i) {
+            const double r = gv[i] + mmsolve::mm_rate(-Vmax, Km, gS[i]);
+            acc = fma(r, r, acc);
+        }
+        ssr = acc;
+    }
+    const double s2 = sigma * sigma;
+    lk[p] = -0.5 * (double)n_obs * log(2 * M_PI * s2) - ssr / (2 * s2);
+}
+
 }  // namespace
 
 // Optional per-kernel timing (SMCB_PARAM_PROFILE): CUDA events on the launching stream around the bulk and the
@@ -830,7 +878,11 @@ int launch_loglik_mm_rate(smcb_handle* h, const double* theta, int64_t ld, int64
     if (n == 0) return SMCB_OK;
     const int64_t grid = (n + RATE_BLOCK - 1) / RATE_BLOCK;
     const int64_t per_block = (int64_t)RATE_BLOCK * 2 * RATE_PAIRS;
-    if (D.precision == 32)   // four particles per thread
+    if (D.precision == 0)
+        mm_rate_kernel_suff<<<(unsigned)((n + SUFF_BLOCK - 1) / SUFF_BLOCK), SUFF_BLOCK, 0, st>>>(
+            theta, ld, n, active, D.suff, D.suff_s0, D.suff_ulo, D.suff_uhi, D.suff_inv_log2rho, D.sum_v2, D.S, D.v,
+            D.n_obs, lk);
+    else if (D.precision == 32)   // four particles per thread
         mm_rate_kernel_f32<<<(unsigned)((n + per_block - 1) / per_block), RATE_BLOCK, 0, st>>>(
             theta, ld, n, active, D.Sv32, D.n_obs, lk);
     else

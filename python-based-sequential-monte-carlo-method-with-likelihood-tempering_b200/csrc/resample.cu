@@ -381,6 +381,191 @@ gather_kernel(const double* __restrict__ src, int64_t ld_src, const int32_t* __r
     for (; k < rows; ++k) dst[(int64_t)k * ld_dst + s] = src[(int64_t)k * ld_src + a];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Single-pass resampling (one shard, FIXED arithmetic): weights -> floor counts / fixed-point residuals -> copy
+// counts -> output offsets -> ancestors -> gather of the particle state, in ONE kernel.
+//
+// The copies placed before particle j number  sum_{i<j} floor_i + cross(s_{j-1})  (the crossing counts telescope),
+// so two global prefixes suffice: the floor counts and the exact fixed-point residual sums.  Tiles of 2048 particles
+// take their prefixes from a decoupled look-back chain (tile ids handed out by an atomic counter, so a tile only
+// ever waits for tiles that are already running); both prefixes fit one 64-bit word each with a 2-bit status on top
+// (residual prefix < 2^62 because the residuals of a normalised weight vector sum to < 1; floor prefix < 2^31).
+// A tile then expands its own slice of the output cooperatively: output slot s finds its particle by a binary search
+// over the tile's 2048 inclusive end offsets in shared memory, which costs the same for one particle with 10^5
+// copies as for 10^5 particles with one, and moves the particle's rows at once.  HBM traffic per particle:
+// 8 B (log-likelihood) + 4 B (ancestor) + 2 (d+1) 8 B (state), against 8 + 4 + 4 + 2 (d+1) 8 algorithmic
+//  and ~150 B for the chain of kernels this replaces on a single GPU.
+constexpr unsigned long long LB_VAL = (1ULL << 62) - 1;
+constexpr unsigned long long LB_READY = 1ULL << 62;
+
+__device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
+__global__ void __launch_bounds__(SB)
+resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ w_in, int64_t n,
+                      const double* __restrict__ max_dev, double gm, const double* __restrict__ sum_w_dev, double Nd,
+                      double inv_Np, uint64_t u0q, unsigned long long* agg /*[2*tiles]: q, floor|ready*/,
+                      unsigned long long* inc /*[2*tiles]*/, unsigned* __restrict__ tile_counter, const double* __restrict__ src, int64_t ld_src, int rows,
+                      double* __restrict__ dst, int64_t ld_dst, int32_t* __restrict__ anc_out,
+                      int32_t* __restrict__ counts_out, int64_t* __restrict__ filled_out) {
+    __shared__ unsigned long long sm_q[32];
+    __shared__ long long sm_f[32];
+    __shared__ unsigned s_end[TILE];          // inclusive end offset of every particle of the tile, relative to the tile's first slot
+    __shared__ unsigned long long s_base[2];
+    __shared__ unsigned s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    const int64_t base = (int64_t)tile * TILE + (int64_t)threadIdx.x * IPT;   // blocked layout
+    const uint64_t N = (uint64_t)n;
+
+    // ---- 1. weights, floor counts, fixed-point residuals (the arithmetic of weights_kernel + prepare_kernel) ----
+    unsigned long long q[IPT];
+    int32_t fl[IPT];
+    unsigned long long tq = 0;
+    long long tf = 0;
+    const double mx = w_in ? 0.0 : max_dev[0], sw = w_in ? 1.0 : sum_w_dev[0];
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        q[k] = 0;
+        fl[k] = 0;
+        if (base + k < n) {
+            double wj;
+            if (w_in != nullptr) {
+                wj = w_in[base + k];
+            } else {
+                const double d = __dsub_rn(lk[base + k], mx);
+                wj = __ddiv_rn(exp(__dmul_rn(d, gm)), sw);              // Micmem_SMC_main.py:124-130
+            }
+            const double f = trunc(__dmul_rn(wj, Nd));                  // np.trunc(p_weight*n_particle)
+            const double r = __dsub_rn(wj, __dmul_rn(f, inv_Np));       // p_weight - p_is*inv_Np
+            double rq = r * TWO62;
+            rq = (rq > 0.0) ? rq : 0.0;
+            q[k] = (unsigned long long)__double2ull_rn(rq);
+            fl[k] = (int32_t)f;
+            tq += q[k];
+            tf += fl[k];
+        }
+    }
+    unsigned long long bq;
+    long long bf;
+    const unsigned long long ex_q = block_exclusive_scan<unsigned long long>(tq, 0ULL, OpAdd(), sm_q, &bq);
+    const long long ex_f = block_exclusive_scan<long long>(tf, 0LL, OpAdd(), sm_f, &bf);
+
+    // ---- 2. decoupled look-back: exclusive prefixes of this tile ----
+    // Every tile publishes (q, floor) twice, each into write-once words: its own aggregate, later its inclusive
+    // prefix.  The floor word carries the 2-bit "ready" mark and is stored after the q word (fence in between), so a
+    // reader that has seen the mark reads a q of the same publication.
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned long long pre_q = 0, pre_f = 0;
+        if (tile > 0) {
+            if (lane == 0) {
+                agg[2 * (size_t)tile] = bq;
+                __threadfence();
+                atomicExch(&agg[2 * (size_t)tile + 1], LB_READY | (unsigned long long)bf);
+            }
+            long long look = (long long)tile - 1;
+            for (;;) {
+                const long long i = look - lane;
+                bool is_inc = true;                      // tiles before tile 0: inclusive prefix 0
+                unsigned long long vq = 0, vf = 0;
+                if (i >= 0) {
+                    for (;;) {
+                        vf = ld_volatile(&inc[2 * (size_t)i + 1]);
+                        if (vf >> 62) break;
+                        vf = ld_volatile(&agg[2 * (size_t)i + 1]);
+                        if (vf >> 62) {
+                            is_inc = false;
+                            break;
+                        }
+                    }
+                    __threadfence();
+                    vq = ld_volatile(is_inc ? &inc[2 * (size_t)i] : &agg[2 * (size_t)i]);
+                    vf &= LB_VAL;
+                }
+                // aggregates of the nearer tiles up to, and including, the nearest inclusive prefix
+                const unsigned inc_mask = __ballot_sync(FULL_MASK, is_inc);
+                const int stop = inc_mask ? (__ffs(inc_mask) - 1) : 32;
+                unsigned long long cq = (lane <= stop) ? vq : 0, cf = (lane <= stop) ? vf : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    cq += __shfl_xor_sync(FULL_MASK, cq, o);
+                    cf += __shfl_xor_sync(FULL_MASK, cf, o);
+                }
+                pre_q += cq;
+                pre_f += cf;
+                if (stop < 32) break;
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            inc[2 * (size_t)tile] = pre_q + bq;
+            __threadfence();
+            atomicExch(&inc[2 * (size_t)tile + 1], LB_READY | (pre_f + (unsigned long long)bf));
+            s_base[0] = pre_q;
+            s_base[1] = pre_f;
+        }
+    }
+    __syncthreads();
+    const unsigned long long base_q = s_base[0];
+    const long long base_f = (long long)s_base[1];
+
+    // ---- 3. copy counts and output offsets ----
+    // first output slot of the tile: floor prefix + thresholds crossed before its first particle
+    const long long tile_c0 = (tile == 0) ? 0 : crossings(base_q, N, u0q);
+    const long long tile_off = base_f + tile_c0;
+    unsigned long long sq = base_q + ex_q;
+    long long c_prev = crossings(sq, N, u0q);
+    if (base == 0) c_prev = 0;                 // nothing is crossed before the first particle of the run
+    long long off = base_f + ex_f + c_prev;    // copies placed before this thread's first particle
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+        sq += q[k];
+        const long long c = crossings(sq, N, u0q);
+        const int32_t cnt = fl[k] + (int32_t)(c - c_prev);
+        c_prev = c;
+        off += cnt;
+        s_end[threadIdx.x * IPT + k] = (unsigned)(off - tile_off);
+        if (counts_out != nullptr && base + k < n) counts_out[base + k] = cnt;
+    }
+    __syncthreads();
+    const long long tile_total = (long long)s_end[TILE - 1];
+    if (tile == (unsigned)(n_tiles - 1) && threadIdx.x == 0) filled_out[0] = tile_off + tile_total;
+
+    // ---- 4. cooperative expansion + gather of this tile's output slots ----
+    const int64_t tile_first = (int64_t)tile * TILE;
+    for (long long sl = threadIdx.x; sl < tile_total; sl += SB) {
+        const long long slot = tile_off + sl;
+        if (slot >= n) break;                  // copies beyond N are dropped (monotone in sl)
+        int lo = 0, hi = TILE - 1;             // smallest i with s_end[i] > sl
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_end[mid] > (unsigned)sl) hi = mid;
+            else lo = mid + 1;
+        }
+        const int64_t a = tile_first + lo;
+        anc_out[slot] = (int32_t)a;
+        for (int k = 0; k < rows; ++k) dst[(int64_t)k * ld_dst + slot] = src[(int64_t)k * ld_src + a];
+    }
+}
+
+// slots [filled, n) of a mis-filled resampling (the reference does not guard the rounding of its running sum,
+// SURVEY.md H2) repeat the last ancestor
+__global__ void resample_pad_kernel(const int64_t* __restrict__ filled, int64_t n, const double* __restrict__ src,
+                                    int64_t ld_src, int rows, double* __restrict__ dst, int64_t ld_dst,
+                                    int32_t* __restrict__ anc) {
+    const int64_t f = filled[0];
+    if (f >= n) return;
+    const int32_t a = (f > 0) ? anc[f - 1] : 0;
+    for (int64_t s = f + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+        anc[s] = a;
+        for (int k = 0; k < rows; ++k) dst[(int64_t)k * ld_dst + s] = src[(int64_t)k * ld_src + a];
+    }
+}
+
 inline int64_t tiles_of(int64_t n) { return (n + TILE - 1) / TILE; }
 
 }  // namespace
@@ -473,6 +658,39 @@ extern "C" int smcb_gather(smcb_handle* h, const double* src_dev, int64_t ld_src
     REQUIRE(h, h && src_dev && ancestors_dev && dst_dev && m > 0 && rows > 0, SMCB_ERR_INVALID, "bad argument");
     gather_kernel<<<(unsigned)((m + 255) / 256), 256, 0, as_stream(stream)>>>(src_dev, ld_src, ancestors_dev, m, rows,
                                                                             dst_dev, ld_dst);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
+}
+
+
+extern "C" int smcb_resample_fused(smcb_handle* h, const double* lk_dev, const double* w_dev, int64_t n,
+                                   const double* max_dev, double gm, const double* sum_w_dev, double u0,
+                                   const double* src_dev, int64_t ld_src, int rows, double* dst_dev, int64_t ld_dst,
+                                   int32_t* ancestors_dev, int32_t* counts_dev, int64_t* filled_dev, void* stream) {
+    REQUIRE(h, h && src_dev && dst_dev && filled_dev && n > 0 && rows > 0 && ld_src >= n && ld_dst >= n,
+            SMCB_ERR_INVALID, "bad argument");
+    REQUIRE(h, w_dev != nullptr || (lk_dev && max_dev && sum_w_dev), SMCB_ERR_INVALID,
+            "give either normalised weights or (lk, max, sum_w)");
+    REQUIRE(h, h->mark != nullptr && n <= h->n_max, SMCB_ERR_STATE, "smcb_reserve too small");
+    REQUIRE(h, n < (1LL << 31), SMCB_ERR_UNSUPPORTED, "n must be below 2^31");
+    REQUIRE(h, u0 >= 0.0 && u0 < 1.0, SMCB_ERR_INVALID, "u0 must lie in [0,1)");
+    cudaStream_t st = as_stream(stream);
+    const int64_t nt = tiles_of(n);
+    // look-back words live in the two tile arrays of the chain this kernel replaces
+    unsigned long long* agg = reinterpret_cast<unsigned long long*>(h->tile_tot);
+    unsigned long long* inc = reinterpret_cast<unsigned long long*>(h->tile_tot2);
+    unsigned* counter = h->rs_ctl;
+    CUDA_TRY(h, cudaMemsetAsync(agg, 0, sizeof(unsigned long long) * 2 * (size_t)nt, st));
+    CUDA_TRY(h, cudaMemsetAsync(inc, 0, sizeof(unsigned long long) * 2 * (size_t)nt, st));
+    CUDA_TRY(h, cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+    int32_t* anc = ancestors_dev ? ancestors_dev : h->mark;
+    const double Nd = (double)n;
+    const uint64_t u0q = (uint64_t)llrint(u0 * TWO62);
+    resample_fused_kernel<<<(unsigned)nt, SB, 0, st>>>(lk_dev, w_dev, n, max_dev, gm, sum_w_dev, Nd, 1.0 / Nd, u0q, agg, inc,
+                                                      counter, src_dev, ld_src, rows, dst_dev, ld_dst, anc, counts_dev,
+                                                      filled_dev);
+    LAUNCH_CHECK(h);
+    resample_pad_kernel<<<8, 256, 0, st>>>(filled_dev, n, src_dev, ld_src, rows, dst_dev, ld_dst, anc);
     LAUNCH_CHECK(h);
     return SMCB_OK;
 }

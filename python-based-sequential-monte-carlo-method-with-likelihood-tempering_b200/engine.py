@@ -721,15 +721,28 @@ class Engine:
         st, lib, h = self._stream, self.lib, self.h
         mode = _SCAN[self.cfg.scan_mode]
         self._u0 = float(u0)
+        tot = self.icnt[4:6]
+        filled_t = self.icnt[6:7]
+        D1, W = self.d + 1, self.comm.world
+        if W == 1 and mode == _lib.SCAN_FIXED:
+            # the whole of K3 in one kernel: weights, counts, offsets, ancestors and the gather of the state
+            w_ptr = None
+            if weights is not None:
+                self.w.copy_(torch.as_tensor(weights, dtype=torch.float64))
+                w_ptr = self.w.data_ptr()
+            with self._timed("resample_fused"):
+                self._ck(lib.smcb_resample_fused(h, self.lk.data_ptr(), w_ptr, self.n, self.scal.data_ptr(), gm,
+                                                 self.scal[1:].data_ptr(), u0, self.state.data_ptr(), self.n, D1,
+                                                 self.state2.data_ptr(), self.n, self.anc.data_ptr(), None,
+                                                 filled_t.data_ptr(), st))
+            self.state, self.state2 = self.state2, self.state
+            return None   # filled count stays on the device (icnt[6]); read lazily
         if weights is not None:
             self.w.copy_(torch.as_tensor(weights, dtype=torch.float64))
         else:
             with self._timed("weights"):
                 self._ck(lib.smcb_weights(h, self.lk.data_ptr(), self.n, self.scal.data_ptr(), gm,
                                           self.scal[1:].data_ptr(), self.w.data_ptr(), st))
-        tot = self.icnt[4:6]
-        filled_t = self.icnt[6:7]
-        D1, W = self.d + 1, self.comm.world
         if W == 1:
             with self._timed("resample_scan"):
                 self._ck(lib.smcb_resample_counts(h, self.w.data_ptr(), self.n, self.N, u0, mode, None, 0, 0,

@@ -56,25 +56,36 @@ class MMRate:
     d = 3
     names = ("Vmax", "Km", "sigma")
 
-    def __init__(self, S, v, precision=64):
+    def __init__(self, S, v, precision=64, form="direct", km_range=(0.0, 10.0)):
+        """form = "direct": every likelihood sums over the observations (FP64 or FP32 terms, `precision`);
+        form = "sufficient": sum v^2, A(Km) = sum v S/(Km+S) and B(Km) = sum S^2/(Km+S)^2 are tabulated once over
+        km_range (the prior's Km interval) and a likelihood costs O(1) (smcb_set_data_mm_rate_sufficient)."""
         self.S, self.v, self.precision = _f64(S), _f64(v), int(precision)
         if self.S.ndim != 1 or self.S.shape != self.v.shape:
             raise ValueError("S and v must be 1-D arrays of equal length")
+        if form not in ("direct", "sufficient"):
+            raise ValueError("form must be 'direct' or 'sufficient'")
+        self.form, self.km_range = form, (float(km_range[0]), float(km_range[1]))
 
     @classmethod
-    def synthetic(cls, n_obs=10000, Vmax=1.2, Km=0.5, sigma=0.02, seed=20250205, precision=64):
+    def synthetic(cls, n_obs=10000, Vmax=1.2, Km=0.5, sigma=0.02, seed=20250205, precision=64, form="direct",
+                  km_range=(0.0, 10.0)):
         rs = np.random.RandomState(seed)
         S = np.exp(rs.uniform(np.log(0.05), np.log(20.0), n_obs))
         v = Vmax * S / (Km + S) + sigma * rs.standard_normal(n_obs)
-        return cls(S, v, precision)
+        return cls(S, v, precision, form, km_range)
 
     @property
     def n_obs(self):
         return self.S.size
 
     def upload(self, lib, handle):
-        _lib.check(handle, lib.smcb_set_data_mm_rate(handle, self.S.ctypes.data, self.v.ctypes.data,
-                                                     self.S.size, self.precision))
+        if self.form == "sufficient":
+            _lib.check(handle, lib.smcb_set_data_mm_rate_sufficient(handle, self.S.ctypes.data, self.v.ctypes.data,
+                                                                    self.S.size, self.km_range[0], self.km_range[1]))
+        else:
+            _lib.check(handle, lib.smcb_set_data_mm_rate(handle, self.S.ctypes.data, self.v.ctypes.data,
+                                                         self.S.size, self.precision))
 
 
 class KineticRK:

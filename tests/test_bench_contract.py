@@ -51,7 +51,8 @@ def _check_main_line(out, n_gpus, steps, warmup):
     assert r["frac"] is not None and 0 < r["frac"] < 1 and r["achieved"] > 0 and r["peak"] > 0
     # the kernel time and the flop count behind `achieved` cover the same sweeps: every profiled sweep was read
     assert r["launches"] == j["likelihood_sweeps_timed"], (r["launches"], j["likelihood_sweeps_timed"])
-    assert j["roofline_hbm"]["frac"] > 0
+    if n_gpus == 1:
+        assert j["roofline_hbm"]["frac"] > 0
     e = j["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     c = j["clocks"]

@@ -110,6 +110,25 @@ def test_philox_run_matches_oracle_loop_mm_rate(pkg, scan_mode):
     eng.close()
 
 
+def test_sufficient_statistic_run_equals_direct_run(pkg):
+    """The whole sampler on the rate-law likelihood in its sufficient-statistic form ends where the direct FP64 sum
+    does: same schedule, same sweep and moved counts, same ancestors, particles to 1e-8."""
+    N, seed = 8192, 5
+    out = []
+    for form in ("direct", "sufficient"):
+        lik = pkg.MMRate.synthetic(2000, form=form)
+        eng = pkg.Engine(lik, pkg.UniformBox([0, 0, 0], [10, 10, 10]), pkg.Settings(n_particle=N, seed=seed))
+        eng.sample_prior()
+        out.append(eng.run(keep_ancestors=True))
+        eng.close()
+    a, b = out
+    assert a.reached_one and b.reached_one and a.betas == b.betas and a.n_mh == b.n_mh and a.n_moved == b.n_moved
+    for x, y in zip(a.ancestors, b.ancestors):
+        assert np.array_equal(x, y)
+    assert abs(a.log_evidence / b.log_evidence - 1) < 1e-9
+    assert np.abs(a.particles - b.particles).max() < 1e-8 and np.abs(a.lk / b.lk - 1).max() < 1e-8
+
+
 @pytest.mark.parametrize("N", [1, 2, 37, 999, 4099])
 def test_odd_and_tiny_particle_counts(pkg, N):
     """Ragged sizes through the whole loop (odd leading dimensions: rows of the state are then only 8-byte
@@ -146,7 +165,7 @@ def test_mm_progress_small_odd_run(pkg, golden):
         res = eng.run(keep_ancestors=True)
         p, lk, tr = smc.run(lambda th: cmm.loglik_progress(th, *d)[0], p0, prior.low, prior.high,
                             smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed,
-                        factor=smc.proposal_factor_eig)
+                            factor=smc.proposal_factor_eig)
         assert np.array_equal(np.array(res.betas), np.array(tr.gamma))
         assert res.n_mh == tr.n_mh and res.n_moved == tr.moved
         for a, b in zip(res.ancestors, tr.ancestors):
@@ -183,7 +202,7 @@ def test_mixed_normal_uniform_prior_matches_oracle_loop(pkg):
     # the ratio does matter here: the same run with the uniform box alone ends elsewhere
     p_u, _, tr_u = smc.run(lambda th: mm.loglik_rate(th, lik.S, lik.v), p0, prior.low, prior.high,
                            smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed,
-                        factor=smc.proposal_factor_eig)
+                           factor=smc.proposal_factor_eig)
     assert tr_u.moved != tr.moved
     # log-ratio form == the reference's pdf-ratio form where the pdfs are representable
     th_a, th_b = p[:100], p0[:100]

@@ -181,6 +181,33 @@ def test_mm_rate_fp64_and_fp32(abi, n_obs):
         assert _rel(got, want).max() < tol, (prec, _rel(got, want).max())
 
 
+@pytest.mark.parametrize("n_obs", [1, 63, 10000])
+def test_mm_rate_sufficient_statistic_form_matches_direct_sum(abi, n_obs):
+    """sum v^2 - 2 Vmax A(Km) + Vmax^2 B(Km) with tabulated A, B against the direct sum of the
+    oracle, over the prior box, around the data-generating point (where the three terms cancel to 6e-4 of their
+    size) and outside the tabulated Km range (direct-sum branch).  Stated bound: 1e-9 relative on the log-likelihood."""
+    rs = np.random.RandomState(3)
+    S = np.exp(rs.uniform(np.log(0.05), np.log(20.0), n_obs))
+    v = 1.2 * S / (0.5 + S) + 0.02 * rs.standard_normal(n_obs)
+    abi.ck(abi.lib.smcb_set_data_mm_rate_sufficient(abi.h, S.ctypes.data, v.ctypes.data, n_obs, 0.0, 10.0))
+    prior = rs.uniform(0, 10, (5000, 3))
+    prior[5, 2] = 0.0                                  # sigma = 0
+    prior[6, 1] = 0.0                                  # Km at the lower edge of the table
+    prior[7, 1] = 10.0                                 # ... and at the upper edge
+    post = np.c_[1.2 + 1e-3 * rs.standard_normal(3000), 0.5 + 2e-3 * rs.standard_normal(3000),
+                 0.02 + 2e-4 * rs.standard_normal(3000)]
+    outside = np.c_[rs.uniform(0, 10, 200), rs.uniform(10.0001, 50, 200), rs.uniform(0.01, 10, 200)]
+    for th, tol in ((prior, 1e-11), (post, 1e-9), (outside, 1e-12)):
+        want = mm.loglik_rate(th, S, v)
+        got = abi.loglik(2, th)
+        assert _rel(got, want).max() < tol, _rel(got, want).max()
+    assert abi.loglik(2, prior)[5] == -np.inf
+    # masked particles keep their old value
+    act = (np.arange(len(post)) % 3 == 0).astype(np.uint8)
+    got = abi.loglik(2, post, active=act)
+    assert np.all(got[act == 0] == 0.0) and _rel(got[act == 1], mm.loglik_rate(post, S, v)[act == 1]).max() < 1e-9
+
+
 # ------------------------------------------------------------------------------------ K1' kinetic
 @pytest.mark.parametrize("n_pairs,d", [(4, 5), (16, 32)])
 def test_kinetic_matches_oracle(abi, n_pairs, d):
@@ -369,6 +396,63 @@ def test_resample_fixed_matches_integer_twin(abi, n, seed, u0):
     assert np.array_equal(c, c_ref)
     assert tot[0] == info["n_floor"] and tot[1] == info["q_total"]
     assert np.array_equal(a, smc.fit_ancestors(a_ref, n))
+
+
+def _resample_fused(abi, w, u0, D1=4, lk=None, mx=0.0, gm=0.0, sum_w=1.0):
+    """smcb_resample_fused on explicit weights (or on lk / max / gm / sum_w); returns counts, ancestors, filled, dst."""
+    n = (w if w is not None else lk).shape[0]
+    src = torch.arange(D1 * n, dtype=torch.float64, device=abi.dev).reshape(D1, n) * 0.5 + 1.0
+    dst = torch.full_like(src, -1.0)
+    counts, anc = abi.zeros(n, dtype=torch.int32), abi.zeros(n, dtype=torch.int32)
+    filled = abi.zeros(1, dtype=torch.int64)
+    wt = abi.t(w) if w is not None else None
+    lkt = abi.t(lk) if lk is not None else None
+    sc = abi.t(np.array([mx, sum_w]))
+    abi.ck(abi.lib.smcb_resample_fused(abi.h, lkt.data_ptr() if lkt is not None else None,
+                                       wt.data_ptr() if wt is not None else None, n, sc.data_ptr(), gm,
+                                       sc[1:].data_ptr(), u0, src.data_ptr(), n, D1, dst.data_ptr(), n, anc.data_ptr(),
+                                       counts.data_ptr(), filled.data_ptr(), None))
+    torch.cuda.synchronize()
+    return (counts.cpu().numpy().astype(np.int64), anc.cpu().numpy().astype(np.int64), int(filled.item()),
+            src.cpu().numpy(), dst.cpu().numpy())
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (7, 2), (1000, 3), (2048, 4), (2049, 5), (5000, 6), (65536, 7),
+                                    ((1 << 20) + 77, 8)])
+@pytest.mark.parametrize("u0", [0.0, 0.37, 0.999999])
+def test_fused_resampling_equals_the_kernel_chain(abi, n, seed, u0):
+    """One kernel (look-back scan + cooperative expansion + gather) against counts -> ancestors -> gather and the
+    exact-integer twin of the oracle: counts, ancestors, filled count and the moved rows, bit for bit."""
+    w = _weights(n, seed)
+    c_ref, a_ref, _, f_ref = _resample(abi, w, u0, 1)
+    c, a, filled, src, dst = _resample_fused(abi, w, u0)
+    assert filled == f_ref and np.array_equal(c, c_ref) and np.array_equal(a, a_ref)
+    assert np.array_equal(dst, src[:, a])
+    if n <= 65536:
+        a_o, c_o, info = smc.resample_fixed(w, u0)
+        assert np.array_equal(c, c_o) and np.array_equal(a, smc.fit_ancestors(a_o, n)) and filled == info["n_filled"]
+
+
+def test_fused_resampling_skewed_weights_and_weights_on_the_fly(abi):
+    # one particle takes (almost) everything: a single tile expands the whole output
+    n = 300001
+    w = np.full(n, 1e-9 / n)
+    w[123457] = 1.0 - w.sum() + w[123457]
+    c_ref, a_ref, _, f_ref = _resample(abi, w, 0.25, 1)
+    c, a, filled, src, dst = _resample_fused(abi, w, 0.25)
+    assert filled == f_ref and np.array_equal(c, c_ref) and np.array_equal(a, a_ref) and np.array_equal(dst, src[:, a])
+    assert c[123457] >= n - 1
+    # weights computed inside the kernel = smcb_weights followed by the chain
+    rs = np.random.RandomState(1)
+    lk = rs.normal(-500, 40, 70001)
+    gm = 0.013
+    mx = lk.max()
+    sum_w = float(np.exp((lk - mx) * gm).sum())
+    lkt, sc, wd = abi.t(lk), abi.t(np.array([mx, sum_w])), abi.zeros(len(lk))
+    abi.ck(abi.lib.smcb_weights(abi.h, lkt.data_ptr(), len(lk), sc.data_ptr(), gm, sc[1:].data_ptr(), wd.data_ptr(), None))
+    c_ref, a_ref, _, f_ref = _resample(abi, wd.cpu().numpy(), 0.7, 1)
+    c, a, filled, src, dst = _resample_fused(abi, None, 0.7, lk=lk, mx=mx, gm=gm, sum_w=sum_w)
+    assert filled == f_ref and np.array_equal(c, c_ref) and np.array_equal(a, a_ref) and np.array_equal(dst, src[:, a])
 
 
 def test_resample_golden_stage_weights(abi, golden):
