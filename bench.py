@@ -14,6 +14,7 @@ construction, H2D of the particles from pinned host memory, the run, D2H of post
 Workloads (BASELINE.json configs):
   mm_progress   config 2: Michaelis-Menten progress curves (the reference's six CSVs, 240
                 observations), 2^20 particles per GPU, FP64, scipy-RK45-twin arithmetic.  DEFAULT.
+  mm_progress_exact  the same problem with the closed-form (Wright omega) progress curves: throughput mode, labelled
   mm_rate       config 4 shape: 10 000 rate-law observations, 2^22 particles per GPU (--particles), direct FP32 sum
   mm_rate_suff  config 4, sufficient-statistic form (A(Km), B(Km) tabulated once): 2^23 particles per GPU = 2^26 on 8
   kinetic       config 3: methanation-style reactor, d=5, 30 conditions, RK4 x 50, 2^18 particles
@@ -52,7 +53,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="mm_progress", choices=["mm_progress", "mm_rate", "mm_rate_suff", "kinetic", "kinetic32", "kinetic_dae"])
+    ap.add_argument("--workload", default="mm_progress", choices=["mm_progress", "mm_progress_exact", "mm_rate", "mm_rate_suff", "kinetic", "kinetic32", "kinetic_dae"])
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (0 = workload default)")
     ap.add_argument("--total-particles", type=int, default=0,
                     help="strong scaling: this many particles in total, split evenly over the GPUs")
@@ -74,6 +75,14 @@ def make_workload(pkg, name, n_per_gpu):
         n = n_per_gpu or (1 << 20)
         cfg = dict()
         desc = "Michaelis-Menten tempered SMC, 6x40 progress-curve observations (reference CSVs), FP64 scipy-RK45 twin"
+    elif name == "mm_progress_exact":
+        g = np.load(GOLDEN)
+        lik = pkg.MMProgress(g["data_t"], g["data_P"], g["data_S0"], integrator="exact")
+        prior = pkg.UniformBox([0, 0, 0], [10, 10, 10], names=["Vmax", "Km", "sigma"])
+        n = n_per_gpu or (1 << 20)
+        cfg = dict()
+        desc = ("THROUGHPUT MODE, not the reference's likelihood: Michaelis-Menten progress curves in closed form (Wright "
+                "omega; the converged solution of the reference's ODE, up to 3e-3 relative from its rtol-1e-3 numbers), FP64")
     elif name == "mm_rate":
         lik = pkg.MMRate.synthetic(10000, precision=32)
         prior = pkg.UniformBox([0, 0, 0], [10, 10, 10], names=["Vmax", "Km", "sigma"])
@@ -267,7 +276,8 @@ def cpu_baseline_dae(per_core=2):
 
 
 REF_PARTICLES = 128      # particles of one reference-arm step (fixed: the same sample on every box)
-DATA_LABEL = {"mm_progress": "observations: the reference's own six CSVs (SMC_example/data/mm_pseudo_data_0..5.csv, 6x40 "
+DATA_LABEL = {"mm_progress_exact": "observations: the reference's own six CSVs; prior particles: synthetic, U[0,10]^3",
+              "mm_progress": "observations: the reference's own six CSVs (SMC_example/data/mm_pseudo_data_0..5.csv, 6x40 "
                              "points, carried in tests/golden/mm_reference_run.npz); prior particles: synthetic, U[0,10]^3",
               "mm_rate": "synthetic", "mm_rate_suff": "synthetic", "kinetic": "synthetic", "kinetic32": "synthetic", "kinetic_dae": "synthetic"}
 
@@ -562,6 +572,15 @@ def main():
                         peak_source="FP32 FFMA micro-benchmark run in this process (smcb_measure_fma_peak)",
                         fma_pipe_lane_slot_frac=5.5 * terms / (ms_lik * 1e-3) / lane_peak,
                         terms_per_s=terms / (ms_lik * 1e-3))
+        roofline["frac"] = roofline["achieved"] / roofline["peak"]
+    if args.workload == "mm_progress_exact":
+        # per observation: Taylor predictor 14 + one order-4 correction (1 log, 2 divisions, 12 others) + residual 3
+        fl = 32.0 * lik.n_obs
+        ev = float(evals // world)
+        roofline.update(kernel="mm_exact_kernel (one thread per particle, Wright omega by continuation in time)",
+                        achieved=fl * ev / (ms_lik * 1e-3) / 1e12, flops_per_eval=fl,
+                        flop_model="32 flop per observation (predictor 14, one Fritsch-Shafer-Crowley correction 15 with "
+                                   "log and divisions counted once, residual 3)")
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
     if args.workload == "mm_rate_suff":
         # HBM-bound: 24 B of parameters + 1 B of mask in, 8 B out per evaluated particle

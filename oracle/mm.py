@@ -118,3 +118,23 @@ def loglik_rate(theta, S, v, dtype=np.float64):
         out[a:b] = -0.5 * n * np.log(2 * np.pi * sg ** 2) - ssr / (2 * sg ** 2)
     out[theta[:, 2] <= 0] = -np.inf
     return out
+
+
+def loglik_progress_exact(theta, data_t, data_P, data_S0):
+    """The same likelihood with the CONVERGED solution of `mm_ode` (`Micmem_likelihood.py:14-15`) in closed form,
+    S(t) = Km * wrightomega(ln(S0/Km) + (S0 - Vmax t)/Km)   - the oracle of the engine's throughput
+    integrator SMCB_MM_EXACT.  It is NOT the reference's number: that is defined by scipy's RK45 at rtol 1e-3 and
+    differs from this by up to ~3e-3 relative.  theta: [n, 3] -> lk[n]."""
+    from scipy.special import wrightomega
+    theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+    Vmax, Km, sigma = theta[:, 0:1], theta[:, 1:2], theta[:, 2]
+    n_t = data_t.shape[1]
+    total = np.zeros(theta.shape[0])
+    with np.errstate(all="ignore"):
+        for e in range(data_t.shape[0]):
+            S0 = float(data_S0[e])
+            z = np.log(S0 / Km) + (S0 - Vmax * data_t[e][None, :]) / Km
+            S = np.where(Km > 0, Km * wrightomega(z).real, np.maximum(S0 - Vmax * data_t[e][None, :], 0.0))
+            r = data_P[e][None, :] - (S0 - S)
+            total += -0.5 * n_t * np.log(2 * np.pi * sigma ** 2) - np.sum(r * r, axis=1) / (2 * sigma ** 2)
+    return np.where(sigma > 0, total, -np.inf)

@@ -85,6 +85,7 @@ SCAN_SEQUENTIAL, SCAN_FIXED = 0, 1
 MAX_DIM, MAX_CAND = 32, 16
 KIN_NCOND_FIELDS = 10
 PARAM_MM_BUDGET, PARAM_MM_REFILL_MIN, PARAM_MM_PATIENCE, PARAM_PROFILE, PARAM_MM_CHUNK, PARAM_MM_TAIL_WARPS = 1, 2, 3, 4, 5, 6
+PARAM_MM_INTEGRATOR, MM_RK45_SCIPY, MM_EXACT = 7, 0, 1
 N_STATS = 24
 
 

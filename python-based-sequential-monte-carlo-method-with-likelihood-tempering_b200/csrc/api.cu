@@ -379,6 +379,11 @@ extern "C" int smcb_set_param(smcb_handle* h, int key, double value) {
             }
             h->prof_on = value != 0;
             return SMCB_OK;
+        case SMCB_PARAM_MM_INTEGRATOR:
+            REQUIRE(h, value == SMCB_MM_RK45_SCIPY || value == SMCB_MM_EXACT, SMCB_ERR_INVALID,
+                    "MM_INTEGRATOR must be SMCB_MM_RK45_SCIPY or SMCB_MM_EXACT");
+            h->mm_integrator = (int)value;
+            return SMCB_OK;
         case SMCB_PARAM_MM_PATIENCE:
             REQUIRE(h, value >= 0 && value <= 1e6, SMCB_ERR_INVALID, "MM_PATIENCE must be in [0, 1e6]");
             h->mm_patience = (int)value;

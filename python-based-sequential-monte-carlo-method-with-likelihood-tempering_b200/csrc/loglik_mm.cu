@@ -35,6 +35,8 @@
 // particle whose bound falls below it reports -inf: the accept/reject decision, hence the whole run, is
 // exactly what it would have been.  Stiff proposals are almost always hopeless ones, so this removes most of
 // the serial tail from MH sweeps; the first sweep has no threshold and keeps it.
+#include <algorithm>
+
 #include "common.cuh"
 #include "mm_solver.cuh"
 
@@ -540,6 +542,103 @@ mm_predict_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, cons
         for (int i = s.i_eval; i < n_t; ++i) out[i] = NAN;
 }
 
+// ------------------------------------------------------------------------------ exact integrator (throughput mode)
+// the progress curve has the closed form  S(t) = Km * omega(z),
+//     z(t) = ln(S0/Km) + (S0 - Vmax t)/Km,      omega + ln(omega) = z   (Wright omega = Lambert W of e^z),
+// which needs no step-size control, has no stiff tail and is the CONVERGED solution of the reference's ODE
+// (Micmem_likelihood.py:14-15) - not the reference's likelihood, which is defined by scipy's RK45 at rtol 1e-3 and
+// differs from the converged one by up to 2.9e-3 relative.  It is therefore a separate, labelled
+// integrator (SMCB_MM_EXACT) with its own oracle twin (oracle/mm.py: loglik_progress_exact) and is never used for the
+// parity line.
+//
+// omega is evaluated in log space (S0/Km reaches 1e5 and more: e^z overflows) by the Fritsch-Shafer-Crowley
+// iteration (order 4), started along an experiment from the previous observation time through d omega/dz =
+// omega/(1+omega) (third-order Taylor step; one iteration then suffices while |dz| <= 1/2), otherwise from the
+// asymptotic forms e^z/(1+e^z) (z < 1) and z - ln z + ln z / z (z >= 1) with three iterations.
+__device__ __forceinline__ double fsc_step(double w, double z) {
+    const double r = z - w - log(w);
+    const double w1 = 1.0 + w;
+    const double q = w1 * (w1 + (2.0 / 3.0) * r);
+    return w * (1.0 + (r / w1) * ((q - 0.5 * r) / (q - r)));
+}
+__device__ __forceinline__ double wright_omega(double z) {
+    if (z < -700.0) return 0.0;                      // omega < 1e-304
+    double w;
+    if (z < 1.0) {
+        const double e = exp(z);
+        w = e / (1.0 + e);
+    } else {
+        const double l = log(z);
+        w = z - l + l / z;
+    }
+    w = fsc_step(w, z);
+    w = fsc_step(w, z);
+    return fsc_step(w, z);
+}
+
+__global__ void __launch_bounds__(128)
+mm_exact_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const uint8_t* __restrict__ active,
+                const double* __restrict__ g_t, const double* __restrict__ g_P, const double* __restrict__ g_S0,
+                int n_ex, int n_t, double* __restrict__ lk, double* __restrict__ pred) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SharedData D = stage_data(smem, g_t, g_P, g_S0, n_ex, n_t);
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n || (active != nullptr && !active[p])) return;
+    const double Vmax = theta[p], Km = theta[ld + p], sigma = theta[2 * ld + p];
+    if (pred == nullptr && !(sigma > 0)) {
+        lk[p] = -INFINITY;                            // Micmem_likelihood.py:53-54
+        return;
+    }
+    const double iKm = 1.0 / Km, k = Vmax * iKm;
+    double total = 0.0;
+    const double s2 = sigma * sigma;
+    const double c0 = -0.5 * n_t * log(2 * M_PI * s2), inv_den = 1.0 / (2 * s2);
+    for (int e = 0; e < n_ex; ++e) {
+        const mmsolve::ObsPair* obs = D.obs + (size_t)e * n_t;
+        const double S0 = D.S0[e];
+        const double y0 = S0 * iKm;
+        const double z0 = log(y0) + y0;               // z at t = 0: omega(z0) = y0 exactly
+        double t = D.t0[e];
+        double z_prev = z0 - k * t;
+        double w = (t == 0.0) ? y0 : wright_omega(z_prev);
+        double ssr = 0.0;
+        for (int i = 0; i < n_t; ++i) {
+            double S;
+            if (!(Km > 0.0)) {
+                S = fmax(S0 - Vmax * t, 0.0);         // Km -> 0: zero-order kinetics until the substrate is gone
+            } else {
+                const double z = z0 - k * t;
+                const double dz = z - z_prev;
+                if (i > 0) {
+                    if (fabs(dz) <= 0.5 && w > 0.0) {
+                        // Taylor step along d omega/dz = omega/(1+omega): first derivative d1 = w/(1+w), second
+                        // d2 = d1/(1+w)^2, third d3 = d2 (1-2w)/(1+w)^2; then one order-4 correction
+                        const double a = 1.0 / (1.0 + w), d1 = w * a, a2 = a * a, d2 = d1 * a2;
+                        const double d3 = d2 * (1.0 - 2.0 * w) * a2;
+                        const double wp = w + dz * (d1 + dz * (0.5 * d2 + dz * (1.0 / 6.0) * d3));
+                        w = (wp > 0.0) ? fsc_step(wp, z) : wright_omega(z);
+                    } else {
+                        w = wright_omega(z);
+                    }
+                }
+                z_prev = z;
+                S = Km * w;
+            }
+            const mmsolve::ObsPair o = obs[i];
+            const double Pm = S0 - S;                 // Micmem_likelihood.py:32
+            if (pred != nullptr) {
+                pred[((size_t)p * n_ex + e) * n_t + i] = Pm;
+            } else {
+                const double r = o.P - Pm;
+                ssr = fma(r, r, ssr);
+            }
+            t = o.t_next;
+        }
+        total += c0 - ssr * inv_den;                  // summed in experiment order (:70-73)
+    }
+    if (pred == nullptr) lk[p] = total;
+}
+
 // ------------------------------------------------------------------------------ MM_RATE
 // ll = -0.5*n*log(2 pi sigma^2) - sum_i (v_i - Vmax*S_i/(Km+S_i))^2 / (2 sigma^2)
 // Compute-bound: 10^4 observations per particle against 32 B of particle data.  Observations are streamed
@@ -716,40 +815,42 @@ mm_rate_kernel_suff(const double* __restrict__ theta, int64_t ld, int64_t n, con
     __shared__ double sT[NI * 2 * M + 2 * NI];
     for (int k = threadIdx.x; k < NI * 2 * M + 2 * NI; k += SUFF_BLOCK) sT[k] = tab[k];
     __syncthreads();
-    const int64_t p = (int64_t)blockIdx.x * SUFF_BLOCK + threadIdx.x;
-    if (p >= n || (active != nullptr && !active[p])) return;
-    const double Vmax = theta[p], Km = theta[ld + p], sigma = theta[2 * ld + p];
-    if (!(sigma > 0)) {
-        lk[p] = -INFINITY;
-        return;
-    }
-    const double u = Km + s0;
-    double ssr;
-    if (u >= u_lo && u <= u_hi) {
-        int j = (int)(log2(u / u_lo) * inv_log2rho);
-        j = j < 0 ? 0 : (j > NI - 1 ? NI - 1 : j);
-        const double t = (u - sT[NI * 2 * M + j]) * sT[NI * 2 * M + NI + j], t2 = 2.0 * t;
-        const double* ca = sT + (size_t)(j * 2) * M;
-        const double* cb = ca + M;
-        double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;   // Clenshaw
+    // grid-stride: the 14.7 KB table is staged once per block, not once per 256 particles
+    for (int64_t p = (int64_t)blockIdx.x * SUFF_BLOCK + threadIdx.x; p < n; p += (int64_t)gridDim.x * SUFF_BLOCK) {
+        if (active != nullptr && !active[p]) continue;
+        const double Vmax = theta[p], Km = theta[ld + p], sigma = theta[2 * ld + p];
+        if (!(sigma > 0)) {
+            lk[p] = -INFINITY;
+            continue;
+        }
+        const double u = Km + s0;
+        double ssr;
+        if (u >= u_lo && u <= u_hi) {
+            int j = (int)(log2(u / u_lo) * inv_log2rho);
+            j = j < 0 ? 0 : (j > NI - 1 ? NI - 1 : j);
+            const double t = (u - sT[NI * 2 * M + j]) * sT[NI * 2 * M + NI + j], t2 = 2.0 * t;
+            const double* ca = sT + (size_t)(j * 2) * M;
+            const double* cb = ca + M;
+            double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;   // Clenshaw
 #pragma unroll
-        for (int k = M - 1; k >= 1; --k) {
-            const double na = fma(t2, a1, ca[k] - a2), nb = fma(t2, b1, cb[k] - b2);
-            a2 = a1; a1 = na;
-            b2 = b1; b1 = nb;
+            for (int k = M - 1; k >= 1; --k) {
+                const double na = fma(t2, a1, ca[k] - a2), nb = fma(t2, b1, cb[k] - b2);
+                a2 = a1; a1 = na;
+                b2 = b1; b1 = nb;
+            }
+            const double A = fma(t, a1, ca[0] - a2), B = fma(t, b1, cb[0] - b2);
+            ssr = fma(Vmax, fma(Vmax, B, -2.0 * A), sum_v2);   // sum v^2 - 2 Vmax A + Vmax^2 B
+        } else {
+            double acc = 0.0;
+            for (int64_t i = 0; i < n_obs; ++i) {
+                const double r = gv[i] + mmsolve::mm_rate(-Vmax, Km, gS[i]);
+                acc = fma(r, r, acc);
+            }
+            ssr = acc;
         }
-        const double A = fma(t, a1, ca[0] - a2), B = fma(t, b1, cb[0] - b2);
-        ssr = fma(Vmax, fma(Vmax, B, -2.0 * A), sum_v2);   // sum v^2 - 2 Vmax A + Vmax^2 B
-    } else {
-        double acc = 0.0;
-        for (int64_t i = 0; i < n_obs; ++i) {
-            const double r = gv[i] + mmsolve::mm_rate(-Vmax, Km, gS[i]);
-            acc = fma(r, r, acc);
-        }
-        ssr = acc;
+        const double s2 = sigma * sigma;
+        lk[p] = -0.5 * (double)n_obs * log(2 * M_PI * s2) - ssr / (2 * s2);
     }
-    const double s2 = sigma * sigma;
-    lk[p] = -0.5 * (double)n_obs * log(2 * M_PI * s2) - ssr / (2 * s2);
 }
 
 }  // namespace
@@ -779,6 +880,13 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     REQUIRE(h, smem <= 200 * 1024, SMCB_ERR_UNSUPPORTED, "data set too large for shared-memory staging");
     REQUIRE(h, n * (int64_t)D.n_ex < (1LL << 31), SMCB_ERR_UNSUPPORTED, "too many solves for one launch");
     const unsigned un = (unsigned)n;
+    if (h->mm_integrator == SMCB_MM_EXACT) {          // closed-form progress curves: no ordering, no tail, no bound
+        if (smem > 48 * 1024)
+            CUDA_TRY(h, cudaFuncSetAttribute(mm_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mm_exact_kernel<<<(un + 127) / 128, 128, smem, st>>>(theta, ld, n, active, D.t, D.P, D.S0, D.n_ex, D.n_t, lk, pred);
+        LAUNCH_CHECK(h);
+        return SMCB_OK;
+    }
     if (pred != nullptr) {
         const unsigned tasks = un * (unsigned)D.n_ex;
         if (smem > 48 * 1024)
@@ -879,7 +987,8 @@ int launch_loglik_mm_rate(smcb_handle* h, const double* theta, int64_t ld, int64
     const int64_t grid = (n + RATE_BLOCK - 1) / RATE_BLOCK;
     const int64_t per_block = (int64_t)RATE_BLOCK * 2 * RATE_PAIRS;
     if (D.precision == 0)
-        mm_rate_kernel_suff<<<(unsigned)((n + SUFF_BLOCK - 1) / SUFF_BLOCK), SUFF_BLOCK, 0, st>>>(
+        mm_rate_kernel_suff<<<(unsigned)std::min<int64_t>((n + SUFF_BLOCK - 1) / SUFF_BLOCK, (int64_t)h->sm_count * 8),
+                              SUFF_BLOCK, 0, st>>>(
             theta, ld, n, active, D.suff, D.suff_s0, D.suff_ulo, D.suff_uhi, D.suff_inv_log2rho, D.sum_v2, D.S, D.v,
             D.n_obs, lk);
     else if (D.precision == 32)   // four particles per thread

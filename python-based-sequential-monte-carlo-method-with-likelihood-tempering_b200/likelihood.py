@@ -22,10 +22,17 @@ class MMProgress:
     d = 3
     names = ("Vmax", "Km", "sigma")
 
-    def __init__(self, t, P_obs, S0):
+    def __init__(self, t, P_obs, S0, integrator="rk45_scipy"):
+        """integrator = "rk45_scipy": scipy's adaptive RK45 step for step (the reference's likelihood; parity mode).
+        integrator = "exact": the closed form S(t) = Km * wrightomega(ln(S0/Km) + (S0 - Vmax t)/Km), the converged
+        solution of the same ODE (throughput mode: cost independent of stiffness; NOT the reference's rtol-1e-3
+        numbers)."""
         self.t, self.P_obs, self.S0 = _f64(t), _f64(P_obs), _f64(S0)
         if self.t.ndim != 2 or self.t.shape != self.P_obs.shape or self.S0.shape != (self.t.shape[0],):
             raise ValueError("t, P_obs must be [n_ex, n_t] and S0 [n_ex]")
+        if integrator not in ("rk45_scipy", "exact"):
+            raise ValueError("integrator must be 'rk45_scipy' or 'exact'")
+        self.integrator = integrator
 
     @classmethod
     def from_csv(cls, base_path="data/mm_pseudo_data", n_ex=6):
@@ -48,6 +55,8 @@ class MMProgress:
         _lib.check(handle, lib.smcb_set_data_mm_progress(
             handle, self.t.ctypes.data, self.P_obs.ctypes.data, self.S0.ctypes.data,
             self.t.shape[0], self.t.shape[1]))
+        _lib.check(handle, lib.smcb_set_param(handle, _lib.PARAM_MM_INTEGRATOR,
+                                              float(_lib.MM_EXACT if self.integrator == "exact" else _lib.MM_RK45_SCIPY)))
 
 
 class MMRate:

@@ -110,6 +110,34 @@ def test_philox_run_matches_oracle_loop_mm_rate(pkg, scan_mode):
     eng.close()
 
 
+def test_exact_integrator_run_matches_oracle_loop(pkg, golden):
+    """MMProgress(integrator="exact") through the whole sampler against the oracle loop on the closed-form likelihood."""
+    N, seed = 2048, 9
+    d = (golden["data_t"], golden["data_P"], golden["data_S0"])
+    lik = pkg.MMProgress(*d, integrator="exact")
+    prior = pkg.UniformBox([0, 0, 0], [10, 10, 10])
+    eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N, seed=seed))
+    eng.sample_prior()
+    p0 = eng.particles().cpu().numpy()
+    res = eng.run(keep_ancestors=True)
+    p, lk, tr = smc.run(lambda th: mm.loglik_progress_exact(th, *d), p0, prior.low, prior.high,
+                        smc.Settings(n_particle=N), smc.PhiloxStream(seed), resampler=smc.resample_fixed,
+                        factor=smc.proposal_factor_eig)
+    assert res.reached_one and np.array_equal(np.array(res.betas), np.array(tr.gamma))
+    assert res.n_mh == tr.n_mh and res.n_moved == tr.moved
+    for a, b in zip(res.ancestors, tr.ancestors):
+        assert np.array_equal(a, b)
+    assert np.abs(res.particles - p).max() < 1e-8 and np.abs(res.lk / lk - 1).max() < 1e-8
+    m = res.particles.mean(0)
+    assert abs(m[0] - 1.2) < 0.15 and abs(m[1] - 0.5) < 0.15 and abs(m[2] - 0.02) < 0.005
+    eng.close()
+    # the next engine on this (pooled) handle is back on the reference's integrator
+    eng2 = pkg.Engine(pkg.MMProgress(*d), prior, pkg.Settings(n_particle=8))
+    lk_ref = eng2.sim_particle(np.tile([[1.2, 0.5, 0.02]], (8, 1))).cpu().numpy()
+    assert abs(lk_ref[0] - 593.96356847) < 1e-6
+    eng2.close()
+
+
 def test_sufficient_statistic_run_equals_direct_run(pkg):
     """The whole sampler on the rate-law likelihood in its sufficient-statistic form ends where the direct FP64 sum
     does: same schedule, same sweep and moved counts, same ancestors, particles to 1e-8."""

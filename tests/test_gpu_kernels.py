@@ -65,6 +65,22 @@ def test_mm_progress_step_counts_match_c_oracle(mm_abi, golden):
     assert _rel(got, want).max() < 1e-9
 
 
+def test_mm_progress_prior_cloud_of_65536_particles_matches_c_oracle(mm_abi, golden):
+    """SURVEY.md 8(d) C2 subset: a 2^16-particle prior cloud (the first 65536 particles of the bench's Philox prior
+    sample, 393 216 solves, stiff ones included) against the C twin of scipy's RK45: every log-likelihood to 1e-9
+    relative (bar 1e-5) and exactly the same number of accepted and of rejected steps over the whole cloud."""
+    from oracle import cmm
+    n = 1 << 16
+    P = philox.uniform_box(20250205, np.arange(n, dtype=np.uint64), np.zeros(3), np.full(3, 10.0))
+    want, info = cmm.loglik_progress(P, golden["data_t"], golden["data_P"], golden["data_S0"])
+    got = mm_abi.loglik(1, P)
+    st = mm_abi.stats()
+    assert info["failed"] == 0 and st[3] == 0
+    assert st[1] == info["accepted"] and st[2] == info["rejected"]
+    assert st[11] > 0                                   # some solves went through the tail kernel
+    assert _rel(got, want).max() < 1e-9, _rel(got, want).max()
+
+
 @pytest.mark.parametrize("budget", [1, 7, 64, 100000])
 def test_mm_progress_is_independent_of_the_deferral_budget(mm_abi, golden, budget):
     """Bulk kernel + tail kernel: wherever a solve is finished, the result is the same bits."""
@@ -163,6 +179,41 @@ def test_mm_progress_predictions(mm_abi, golden):
     got = pred.cpu().numpy()
     want = golden["pmodel0"]
     assert np.abs(got - want).max() < 1e-11
+
+
+def test_mm_progress_exact_integrator_matches_its_oracle(mm_abi, golden):
+    """SMCB_MM_EXACT (closed-form progress curves, throughput mode) against oracle.mm.loglik_progress_exact over a
+    prior cloud (stiff particles included: Vmax/Km up to 1e5), a posterior cloud and edge cases; stated bound 1e-9."""
+    a = mm_abi
+    d = (golden["data_t"], golden["data_P"], golden["data_S0"])
+    rs = np.random.RandomState(12)
+    prior = rs.uniform(0, 10, (20000, 3))
+    prior[:50, 1] = 10.0 ** rs.uniform(-6, -2, 50)          # very stiff: S0/Km up to 2e6
+    prior[50, 2] = 0.0
+    post = golden["final_particles"]
+    try:
+        a.ck(a.lib.smcb_set_param(a.h, 7, 1.0))
+        for th, tol in ((prior, 1e-9), (post, 1e-10)):
+            want = mm.loglik_progress_exact(th, *d)
+            got = a.loglik(1, th)
+            assert _rel(got, want).max() < tol, _rel(got, want).max()
+        assert a.loglik(1, prior)[50] == -np.inf
+        # predictions (the reference's C_l_) follow the same curves
+        pred = a.zeros(4, 6, 40)
+        thp = a.t(post[:4].T)
+        a.ck(a.lib.smcb_predict_mm_progress(a.h, thp.data_ptr(), 4, 4, pred.data_ptr(), None))
+        S0 = d[2][None, :, None]
+        from scipy.special import wrightomega
+        z = np.log(S0 / post[:4, 1][:, None, None]) + (S0 - post[:4, 0][:, None, None] * d[0][None]) / post[:4, 1][:, None, None]
+        want_pred = S0 - post[:4, 1][:, None, None] * wrightomega(z).real
+        assert np.abs(pred.cpu().numpy() - want_pred).max() < 1e-12
+        # and the distance to the reference's own (rtol 1e-3) likelihood is what SURVEY.md H1 says it is
+        ref = golden["sweeps_out"][-1]
+        ex = a.loglik(1, golden["sweeps_in"][-1])
+        fin = np.isfinite(ref)
+        assert 1e-8 < _rel(ex[fin], ref[fin]).max() < 1e-2
+    finally:
+        a.ck(a.lib.smcb_set_param(a.h, 7, 0.0))
 
 
 # ------------------------------------------------------------------------------------ K1 MM rate
@@ -317,6 +368,29 @@ def test_transient_reactor_matches_oracle_march(abi):
     bad[0, 0] *= 1e12
     lk_bad = abi.loglik(4, bad)
     assert np.isfinite(lk_bad[0]) and lk_bad[0] < got[0] - 1e3
+
+
+def test_transient_reactor_matches_golden_flows_of_256_particles(abi):
+    """SURVEY.md 8(f) N3 at a size the oracle cannot reach inside a test: 256 particles x the 30 operating conditions of
+    the bench workload (7680 marches) against outlet flows the CPU oracle produced offline
+    (tests/golden/make_dae_flows_fixture.py -> dae_flows_256.npz): 192 particles around the data-generating
+    parameters, 64 from the reference's wide prior box, where some marches fail on both sides."""
+    import os
+    gd = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g, fx = np.load(os.path.join(gd, "dae_synth.npz")), np.load(os.path.join(gd, "dae_flows_256.npz"))
+    cond, base, obs = (np.ascontiguousarray(g[k]) for k in ("cond", "base4", "obs"))
+    est = np.ascontiguousarray(g["est4"], dtype=np.int32)
+    abi.ck(abi.lib.smcb_set_data_kinetic(abi.h, cond.ctypes.data, obs.ctypes.data, cond.shape[0], base.ctypes.data, 4,
+                                         est.ctypes.data, len(est), 1))
+    th, want, flows = fx["theta"], fx["lk"], fx["flows"]
+    got = abi.loglik(4, th)
+    failed = (flows <= -9999).any(axis=(1, 2))          # a march of this particle failed in the oracle: -10000 penalty
+    assert failed[:192].sum() == 0 and 0 < failed.sum() < 64
+    assert np.array_equal(got < -1e6, want < -1e6)      # the same particles are hopeless on both sides
+    ok = ~failed
+    assert ok.sum() >= 192 and _rel(got[ok], want[ok]).max() < 1e-6, _rel(got[ok], want[ok]).max()
+    # a particle with SOME failed conditions carries the penalty for exactly those: still the same number to 1e-6
+    assert _rel(got[failed], want[failed]).max() < 1e-6
 
 
 # ------------------------------------------------------------------------------------ K2 tempering

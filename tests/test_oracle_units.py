@@ -100,3 +100,25 @@ def test_kinetic_model_sane():
     lk = kinetic.loglik(th, cond, obs, base, kinetic.EST_POSITION)
     lk_true = kinetic.loglik(base[None, kinetic.EST_POSITION], cond, obs, base, kinetic.EST_POSITION)[0]
     assert np.all(np.isfinite(lk)) and lk_true > np.max(lk) - 5
+
+
+def test_exact_progress_curve_is_the_converged_solution_of_the_reference_ode(golden):
+    """oracle.mm.loglik_progress_exact (Wright omega closed form, the twin of SMCB_MM_EXACT) against a tight-tolerance
+    integration of the reference's ODE, and its distance from the reference's own rtol-1e-3 likelihood."""
+    from scipy.integrate import solve_ivp
+    from oracle import mm
+    t, P, S0 = golden["data_t"], golden["data_P"], golden["data_S0"]
+    rs = np.random.RandomState(0)
+    th = np.vstack([[1.2, 0.5, 0.02], [1.0, 0.4, 0.05], rs.uniform(0.05, 10, (12, 3))])
+    got = mm.loglik_progress_exact(th, t, P, S0)
+    for i, (Vmax, Km, sigma) in enumerate(th):
+        tot = 0.0
+        for e in range(t.shape[0]):
+            sol = solve_ivp(lambda tt, S: -Vmax * S / (Km + S), (t[e][0], t[e][-1]), [S0[e]], t_eval=t[e], method="DOP853",
+                            rtol=1e-13, atol=1e-15)
+            r = P[e] - (S0[e] - sol.y[0])
+            tot += -0.5 * t.shape[1] * np.log(2 * np.pi * sigma ** 2) - np.sum(r * r) / (2 * sigma ** 2)
+        assert abs(got[i] / tot - 1) < 1e-9, (i, got[i], tot)
+    # the reference's own number at the data-generating point differs in the 6th digit (593.96357 vs 593.96042)
+    ref = mm.loglik_progress_scipy(th[0], t, P, S0)
+    assert abs(ref - 593.96356847) < 1e-6 and 1e-7 < abs(got[0] / ref - 1) < 1e-4
