@@ -558,6 +558,7 @@ def main():
             "bound": "latency", "kernel": "mm_tail_kernel (deferred solves, one per lane; duration = longest solve)",
             "launches": n_sw, "ms_per_step": tail_ms / args.steps, "share_of_step": tail_ms / ms_total if ms_total else None,
             "attempted_steps_in_tail_per_step": tail_attempts / args.steps,
+            "first_sweep_group_ms": round(lik_ms[0], 3) if lik_ms else None,
             "longest_solve": {"attempts": longest >> 32, "cycles_per_attempt": longest & 0xffffffff},
             "floor_cycles_per_attempt": 674,
             "note": "a solve is a strictly serial chain of ~270 dependent FP64/MUFU instructions per attempted step; "

@@ -1,5 +1,11 @@
 """Per-sweep device time of the bulk and the tail kernel of one 2^20-particle run (SMCB_PARAM_PROFILE read after every
-sweep), with the sweep's deferred-solve count and longest solve: what an overlap of tail and bulk could hide."""
+sweep), with the sweep's deferred-solve count, longest solve and early rejections.
+
+profiles/sweeps_r02_baseline.log is its output for the shipped kernels.  profiles/sweeps_r02_direct_tail_experiment_
+ratio64.log is the same run with an experiment of round 2 that was NOT kept: the solves of particles with Vmax/Km >= 64
+were started in the tail kernel on a second stream next to the bulk kernel instead of after it.  It lost by 2.6x:
+those solves then run without what the finished experiments of their particle say about it (the particle-level bound
+of mm_finalize_kernel), so proposals that are rejected after ~1e3 attempts today ran for up to 6e4."""
 import os
 import sys
 
