@@ -92,7 +92,6 @@ extern "C" int smcb_create(int device, smcb_handle** out) {
     e = cudaMalloc(reinterpret_cast<void**>(&h->stats), SMCB_N_STATS * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(h->stats, 0, SMCB_N_STATS * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->seq_carry), 4 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->rs_ctl), 4 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mm_ctl), 8 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(h->mm_ctl, 0, 8 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&h->mm_hist), 2 * 512 * sizeof(unsigned));
@@ -116,7 +115,7 @@ extern "C" int smcb_destroy(smcb_handle* h) {
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     h->prof_ev.clear();
     dev_free(&h->floor_cnt); dev_free(&h->resid_q); dev_free(&h->resid_f); dev_free(&h->tile_tot);
-    dev_free(&h->tile_tot2); dev_free(&h->mark); dev_free(&h->seq_carry); dev_free(&h->rs_ctl);
+    dev_free(&h->tile_tot2); dev_free(&h->mark); dev_free(&h->seq_carry); dev_free(&h->rs_desc);
     dev_free(&h->mmp.t); dev_free(&h->mmp.P); dev_free(&h->mmp.S0);
     dev_free(&h->mmr.S); dev_free(&h->mmr.v); dev_free(&h->mmr.Sv32); dev_free(&h->mmr.suff);
     dev_free(&h->kin.cond); dev_free(&h->kin.obs); dev_free(&h->kin.base); dev_free(&h->kin.est_pos);
@@ -172,6 +171,7 @@ extern "C" int smcb_reserve(smcb_handle* h, int64_t n_max, int d_max) {
     const size_t tiles = (size_t)(n_max + 2047) / 2048 + 8;
     if ((rc = dev_alloc(h, &h->tile_tot, 2 * tiles))) return rc;
     if ((rc = dev_alloc(h, &h->tile_tot2, 2 * tiles))) return rc;
+    if ((rc = dev_alloc(h, &h->rs_desc, 4 * tiles + 8))) return rc;
     h->n_max = n_max;
     h->d_max = d_max;
     return SMCB_OK;

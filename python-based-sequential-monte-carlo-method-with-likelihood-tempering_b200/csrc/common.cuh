@@ -91,7 +91,7 @@ struct smcb_handle {
     int64_t* tile_tot2 = nullptr;    // second tile array (ancestor expansion)
     int32_t* mark = nullptr;         // [n_max] head marks for the ancestor fill
     double* seq_carry = nullptr;     // [4] sequential-scan carry (device)
-    unsigned* rs_ctl = nullptr;      // [4] tile counter of the single-pass resampling kernel
+    unsigned long long* rs_desc = nullptr;   // single-pass resampling: [tile counter | aggregates 2*tiles | inclusive prefixes 2*tiles]
     MmProgressData mmp;
     MmRateData mmr;
     KineticData kin;

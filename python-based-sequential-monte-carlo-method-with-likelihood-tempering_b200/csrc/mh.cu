@@ -332,6 +332,23 @@ __global__ void moments_mean_kernel(const double* __restrict__ colsum, double n_
     if (t < d) mean[t] = colsum[t] / n_local;
 }
 
+// 1/x and 1/sqrt(x) from the MUFU seeds and one cubically convergent correction each (as csrc/kinetic.cuh): the
+// Jacobi rotations below sit on the critical path of every sweep (one warp, strictly serial), where an IEEE FP64
+// division or square root costs ~250 cycles of dependent instructions; the rotation angle needs no last-bit accuracy
+// (Jacobi is self-correcting), the orthogonality of (c, s) is restored to 1 ulp by the correction.
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    const double e = fma(-x, r0, 1.0);
+    return fma(r0, fma(e, e, e), r0);
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+    const double e = fma(-x * y0, y0, 1.0);                 // 1 - x*y0^2
+    return fma(y0, e * fma(0.375, e, 0.5), y0);             // y0*(1 + e/2 + 3e^2/8)
+}
+
 struct WCov {
     double w[SMCB_MAX_DIM * SMCB_MAX_DIM];
     int use;
@@ -423,9 +440,12 @@ moments_merge_factor_kernel(const double* __restrict__ rows, int world, int stri
                 const double apq = A[p][q], app = A[p][p], aqq = A[q][q];
                 __syncwarp();
                 if (apq == 0.0) continue;                       // warp-uniform
-                const double tau = (aqq - app) / (2.0 * apq);
-                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
-                const double c = 1.0 / sqrt(fma(t, t, 1.0)), sn = t * c;
+                // |apq| so small that tau overflows the seeds' range: the rotation is the identity to working precision
+                if (fabs(apq) < 1e-140 * fabs(aqq - app) || fabs(apq) < 1e-290) continue;
+                const double tau = (aqq - app) * rcp_fast(2.0 * apq);
+                const double t2 = fma(tau, tau, 1.0);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) * rcp_fast(fabs(tau) + t2 * rsqrt_fast(t2));
+                const double c = rsqrt_fast(fma(t, t, 1.0)), sn = t * c;
                 if (lane < d) {                                  // columns p, q
                     const double akp = A[lane][p], akq = A[lane][q];
                     A[lane][p] = c * akp - sn * akq;
