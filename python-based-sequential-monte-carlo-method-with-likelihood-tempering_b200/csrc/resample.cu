@@ -397,15 +397,11 @@ gather_kernel(const double* __restrict__ src, int64_t ld_src, const int32_t* __r
 //  and ~150 B for the chain of kernels this replaces on a single GPU.
 constexpr unsigned long long LB_VAL = (1ULL << 62) - 1;
 constexpr unsigned long long LB_READY = 1ULL << 62;
-constexpr int LB_PER = 8;                  // predecessor tiles per lane and look-back step
-constexpr int LB_WIN = 32 * LB_PER;        // ... per warp and step
-constexpr int EXP_PER = 8;                 // consecutive output slots per thread in the expansion
 
 __device__ __forceinline__ unsigned long long ld_volatile(const unsigned long long* p) {
     return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
 
-template <bool ROWS4>   // ROWS4: rows == 4 (d = 3) with the row loop unrolled
 __global__ void __launch_bounds__(SB)
 resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ w_in, int64_t n,
                       const double* __restrict__ max_dev, double gm, const double* __restrict__ sum_w_dev, double Nd,
@@ -416,7 +412,6 @@ resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ 
     __shared__ unsigned long long sm_q[32];
     __shared__ long long sm_f[32];
     __shared__ unsigned s_end[TILE];          // inclusive end offset of every particle of the tile, relative to the tile's first slot
-    __shared__ unsigned short s_anc[TILE];    // ancestors (tile-local) of the output chunk being written
     __shared__ unsigned long long s_base[2];
     __shared__ unsigned s_tile;
     if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
@@ -472,66 +467,29 @@ resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ 
                 __threadfence();
                 atomicExch(&agg[2 * (size_t)tile + 1], LB_READY | (unsigned long long)bf);
             }
-            // Each step looks at LB_WIN = 32 x LB_PER predecessors, LB_PER per lane with all their loads in flight
-            // together (one memory round trip per step; a 2^20-particle resampling is a single step for every tile).
-            // Lane l owns the predecessors look - l - 32 j: the nearest inclusive prefix ends the walk, aggregates
-            // of nearer tiles are added.
             long long look = (long long)tile - 1;
             for (;;) {
-                unsigned long long vq[LB_PER], vf[LB_PER];
-                bool is_inc[LB_PER];
-#pragma unroll
-                for (int j = 0; j < LB_PER; ++j) {
-                    const long long i = look - lane - 32 * j;
-                    is_inc[j] = true;                    // tiles before tile 0: inclusive prefix 0
-                    vq[j] = 0;
-                    vf[j] = 0;
-                    if (i >= 0) {
-                        vf[j] = ld_volatile(&inc[2 * (size_t)i + 1]);
-                        if ((vf[j] >> 62) == 0) {
-                            vf[j] = ld_volatile(&agg[2 * (size_t)i + 1]);
-                            is_inc[j] = false;
+                const long long i = look - lane;
+                bool is_inc = true;                      // tiles before tile 0: inclusive prefix 0
+                unsigned long long vq = 0, vf = 0;
+                if (i >= 0) {
+                    for (;;) {
+                        vf = ld_volatile(&inc[2 * (size_t)i + 1]);
+                        if (vf >> 62) break;
+                        vf = ld_volatile(&agg[2 * (size_t)i + 1]);
+                        if (vf >> 62) {
+                            is_inc = false;
+                            break;
                         }
                     }
+                    __threadfence();
+                    vq = ld_volatile(is_inc ? &inc[2 * (size_t)i] : &agg[2 * (size_t)i]);
+                    vf &= LB_VAL;
                 }
-#pragma unroll
-                for (int j = 0; j < LB_PER; ++j) {
-                    const long long i = look - lane - 32 * j;
-                    if (i >= 0) {
-                        while ((vf[j] >> 62) == 0) {     // neither published yet: poll
-                            vf[j] = ld_volatile(&inc[2 * (size_t)i + 1]);
-                            is_inc[j] = true;
-                            if ((vf[j] >> 62) == 0) {
-                                vf[j] = ld_volatile(&agg[2 * (size_t)i + 1]);
-                                is_inc[j] = false;
-                            }
-                        }
-                    }
-                }
-                __threadfence();
-#pragma unroll
-                for (int j = 0; j < LB_PER; ++j) {
-                    const long long i = look - lane - 32 * j;
-                    if (i >= 0) vq[j] = ld_volatile(is_inc[j] ? &inc[2 * (size_t)i] : &agg[2 * (size_t)i]);
-                    vf[j] &= LB_VAL;
-                }
-                // distance (in tiles) of the nearest inclusive prefix: predecessor index lane + 32 j
-                int near = LB_WIN;
-#pragma unroll
-                for (int j = 0; j < LB_PER; ++j) {
-                    const unsigned m = __ballot_sync(FULL_MASK, is_inc[j]);
-                    if (m != 0) {
-                        const int d = 32 * j + (__ffs(m) - 1);
-                        near = d < near ? d : near;
-                    }
-                }
-                unsigned long long cq = 0, cf = 0;
-#pragma unroll
-                for (int j = 0; j < LB_PER; ++j)
-                    if (lane + 32 * j <= near) {
-                        cq += vq[j];
-                        cf += vf[j];
-                    }
+                // aggregates of the nearer tiles up to, and including, the nearest inclusive prefix
+                const unsigned inc_mask = __ballot_sync(FULL_MASK, is_inc);
+                const int stop = inc_mask ? (__ffs(inc_mask) - 1) : 32;
+                unsigned long long cq = (lane <= stop) ? vq : 0, cf = (lane <= stop) ? vf : 0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     cq += __shfl_xor_sync(FULL_MASK, cq, o);
@@ -539,8 +497,8 @@ resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ 
                 }
                 pre_q += cq;
                 pre_f += cf;
-                if (near < LB_WIN) break;
-                look -= LB_WIN;
+                if (stop < 32) break;
+                look -= 32;
             }
         }
         if (lane == 0) {
@@ -578,72 +536,19 @@ resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ 
     if (tile == (unsigned)(n_tiles - 1) && threadIdx.x == 0) filled_out[0] = tile_off + tile_total;
 
     // ---- 4. cooperative expansion + gather of this tile's output slots ----
-    // Chunks of 2048 slots.  (a) every thread finds the particle of its first slot by one binary search over the
-    // tile's inclusive end offsets and walks forward for its EXP_PER consecutive slots (the offsets are monotone);
-    // the ancestors go to shared memory.  (b) the chunk is written with consecutive threads on consecutive slots:
-    // coalesced stores, near-sorted loads.
     const int64_t tile_first = (int64_t)tile * TILE;
-    for (long long c0 = 0; c0 < tile_total; c0 += TILE) {
-        const long long sl0 = c0 + (long long)threadIdx.x * EXP_PER;
-        if (sl0 < tile_total) {
-            int lo = 0, hi = TILE - 1;             // smallest i with s_end[i] > sl0
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (s_end[mid] > (unsigned)sl0) hi = mid;
-                else lo = mid + 1;
-            }
-#pragma unroll
-            for (int j = 0; j < EXP_PER; ++j) {
-                const long long sl = sl0 + j;
-                if (sl < tile_total) {
-                    while (s_end[lo] <= (unsigned)sl) ++lo;
-                    s_anc[threadIdx.x * EXP_PER + j] = lo;
-                }
-            }
+    for (long long sl = threadIdx.x; sl < tile_total; sl += SB) {
+        const long long slot = tile_off + sl;
+        if (slot >= n) break;                  // copies beyond N are dropped (monotone in sl)
+        int lo = 0, hi = TILE - 1;             // smallest i with s_end[i] > sl
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_end[mid] > (unsigned)sl) hi = mid;
+            else lo = mid + 1;
         }
-        __syncthreads();
-        const long long m_chunk = (tile_total - c0 < TILE) ? tile_total - c0 : TILE;
-        // four slots per thread and step, all their loads issued before the first store (the gather is latency-bound:
-        // what counts is the number of loads in flight)
-        for (int t0 = threadIdx.x; t0 < m_chunk; t0 += 4 * SB) {
-            int64_t a[4];
-            long long slot[4];
-            bool ok[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int t = t0 + u * SB;
-                slot[u] = tile_off + c0 + t;
-                ok[u] = t < m_chunk && slot[u] < n;          // copies beyond N are dropped
-                a[u] = tile_first + (ok[u] ? s_anc[t] : 0);
-            }
-            if (ROWS4) {
-                double v[4][4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) v[u][k] = ok[u] ? src[(int64_t)k * ld_src + a[u]] : 0.0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (ok[u]) {
-                        anc_out[slot[u]] = (int32_t)a[u];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) dst[(int64_t)k * ld_dst + slot[u]] = v[u][k];
-                    }
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (ok[u]) anc_out[slot[u]] = (int32_t)a[u];
-                for (int k = 0; k < rows; ++k) {
-                    double v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) v[u] = ok[u] ? src[(int64_t)k * ld_src + a[u]] : 0.0;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (ok[u]) dst[(int64_t)k * ld_dst + slot[u]] = v[u];
-                }
-            }
-        }
-        __syncthreads();
+        const int64_t a = tile_first + lo;
+        anc_out[slot] = (int32_t)a;
+        for (int k = 0; k < rows; ++k) dst[(int64_t)k * ld_dst + slot] = src[(int64_t)k * ld_src + a];
     }
 }
 
@@ -780,14 +685,9 @@ extern "C" int smcb_resample_fused(smcb_handle* h, const double* lk_dev, const d
     int32_t* anc = ancestors_dev ? ancestors_dev : h->mark;
     const double Nd = (double)n;
     const uint64_t u0q = (uint64_t)llrint(u0 * TWO62);
-    if (rows == 4)
-        resample_fused_kernel<true><<<(unsigned)nt, SB, 0, st>>>(lk_dev, w_dev, n, max_dev, gm, sum_w_dev, Nd, 1.0 / Nd, u0q,
-                                                                agg, inc, counter, src_dev, ld_src, rows, dst_dev, ld_dst,
-                                                                anc, counts_dev, filled_dev);
-    else
-        resample_fused_kernel<false><<<(unsigned)nt, SB, 0, st>>>(lk_dev, w_dev, n, max_dev, gm, sum_w_dev, Nd, 1.0 / Nd,
-                                                                 u0q, agg, inc, counter, src_dev, ld_src, rows, dst_dev,
-                                                                 ld_dst, anc, counts_dev, filled_dev);
+    resample_fused_kernel<<<(unsigned)nt, SB, 0, st>>>(lk_dev, w_dev, n, max_dev, gm, sum_w_dev, Nd, 1.0 / Nd, u0q, agg, inc,
+                                                      counter, src_dev, ld_src, rows, dst_dev, ld_dst, anc, counts_dev,
+                                                      filled_dev);
     LAUNCH_CHECK(h);
     resample_pad_kernel<<<8, 256, 0, st>>>(filled_dev, n, src_dev, ld_src, rows, dst_dev, ld_dst, anc);
     LAUNCH_CHECK(h);
