@@ -372,7 +372,7 @@ def resample_microbench(pkg, eng, torch, flush):
         flush()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        eng._ck(eng.lib.smcb_resample_fused(eng.h, eng.lk.data_ptr(), None, n, eng.scal.data_ptr(), t["gm"],
+        eng._ck(eng.lib.smcb_resample_fused(eng.h, eng.lk.data_ptr(), None, n, n, 0, 0, n, eng.scal.data_ptr(), t["gm"],
                                             eng.scal[1:].data_ptr(), 0.375, eng.state.data_ptr(), n, D1,
                                             eng.state2.data_ptr(), n, eng.anc.data_ptr(), None,
                                             eng.icnt[6:7].data_ptr(), eng._stream))

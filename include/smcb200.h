@@ -221,11 +221,17 @@ int smcb_gather(smcb_handle* h, const double* src_dev, int64_t ld_src, const int
 /* The whole of K3 for one shard in ONE kernel (FIXED arithmetic): weights (from lk_dev, max_dev, gm, sum_w_dev exactly as
  * smcb_weights computes them, or explicit normalised weights w_dev with lk_dev = NULL), floor counts and fixed-point
  * residuals, copy counts, output offsets (decoupled look-back over 2048-particle tiles), ancestors and the gather
- * dst[k*ld_dst+s] = src[k*ld_src+anc[s]] of `rows` rows.  Same counts, ancestors and clamp / pad rule as
- * smcb_resample_counts(SMCB_SCAN_FIXED) + smcb_ancestors + smcb_gather, bit for bit.  ancestors_dev / counts_dev may be
- * NULL; filled_dev int64[1] = sum of the counts. */
-int smcb_resample_fused(smcb_handle* h, const double* lk_dev, const double* w_dev, int64_t n, const double* max_dev,
-                        double gm, const double* sum_w_dev, double u0, const double* src_dev, int64_t ld_src, int rows,
+ * dst[k*ld_dst+s] = src[k*ld_src+anc[s]] of `rows` rows for the first m_out output slots of this shard (more copies
+ * are dropped, fewer are padded with the last ancestor).  Same counts, ancestors and clamp / pad rule as
+ * smcb_resample_counts(SMCB_SCAN_FIXED) + smcb_ancestors + smcb_gather, bit for bit.
+ *   One GPU: n_total = n, carry_q = 0, id_offset = 0, m_out = n.
+ *   Sharded: n_total = N, carry_q = exclusive prefix of the fixed-point residual totals of the lower ranks
+ *   (smcb_resample_totals + all-gather), id_offset = global index of this shard's first particle, m_out = the slots
+ *   this shard fills (the rows of dst then leave with smcb_comm_exchange_rows).
+ * ancestors_dev / counts_dev may be NULL; filled_dev int64[1] = sum of this shard's counts. */
+int smcb_resample_fused(smcb_handle* h, const double* lk_dev, const double* w_dev, int64_t n, int64_t n_total,
+                        uint64_t carry_q, int64_t id_offset, int64_t m_out, const double* max_dev, double gm,
+                        const double* sum_w_dev, double u0, const double* src_dev, int64_t ld_src, int rows,
                         double* dst_dev, int64_t ld_dst, int32_t* ancestors_dev, int32_t* counts_dev,
                         int64_t* filled_dev, void* stream);
 
@@ -326,6 +332,12 @@ int smcb_comm_broadcast(smcb_handle* h, void* buf_dev, int64_t bytes, int root, 
  * of send_dev (rank order), recv_counts_host[q] doubles arrive from rank q into consecutive ranges of recv_dev. */
 int smcb_comm_all_to_all_v(smcb_handle* h, const double* send_dev, const int64_t* send_counts_host,
                            double* recv_dev, const int64_t* recv_counts_host, void* stream);
+/* The same migration straight from / into row-major matrices, without packing: for every rank q the column range
+ * [soff_q, soff_q + send_counts_host[q]) of each of the `rows` rows of send_dev (leading dimension ld_send; soff = running
+ * sum of the send counts) goes to rank q, and what rank q sends lands in the column range [roff_q, roff_q +
+ * recv_counts_host[q]) of the rows of recv_dev (ld_recv).  One grouped NCCL call; the part that stays is a 2-D copy. */
+int smcb_comm_exchange_rows(smcb_handle* h, const double* send_dev, int64_t ld_send, const int64_t* send_counts_host,
+                            double* recv_dev, int64_t ld_recv, const int64_t* recv_counts_host, int rows, void* stream);
 /* Number of NCCL operations this handle has enqueued so far. */
 int64_t smcb_collective_count(const smcb_handle* h);
 

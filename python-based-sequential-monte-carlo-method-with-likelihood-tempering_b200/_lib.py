@@ -38,8 +38,8 @@ _SIGNATURES = {
                              p_void],
     "smcb_resample_totals": [p_void, p_void, c_i64, c_i64, p_void, p_void],
     "smcb_ancestors": [p_void, p_void, c_i64, c_i64, p_void, p_void, p_void],
-    "smcb_resample_fused": [p_void, p_void, p_void, c_i64, p_void, c_dbl, p_void, c_dbl, p_void, c_i64, c_int, p_void,
-                            c_i64, p_void, p_void, p_void, p_void],
+    "smcb_resample_fused": [p_void, p_void, p_void, c_i64, c_i64, c_u64, c_i64, c_i64, p_void, c_dbl, p_void, c_dbl, p_void,
+                            c_i64, c_int, p_void, c_i64, p_void, p_void, p_void, p_void],
     "smcb_gather": [p_void, p_void, c_i64, p_void, c_i64, c_int, p_void, c_i64, p_void],
     "smcb_colsum": [p_void, p_void, c_i64, c_i64, c_int, p_void, p_void],
     "smcb_centered_moments": [p_void, p_void, c_i64, c_i64, c_int, p_void, p_void, p_void],
@@ -71,6 +71,7 @@ _SIGNATURES = {
     "smcb_comm_all_reduce_f64": [p_void, p_void, c_i64, c_int, p_void],
     "smcb_comm_broadcast": [p_void, p_void, c_i64, c_int, p_void],
     "smcb_comm_all_to_all_v": [p_void, p_void, p_void, p_void, p_void, p_void],
+    "smcb_comm_exchange_rows": [p_void, p_void, c_i64, p_void, p_void, c_i64, p_void, c_int, p_void],
     "smcb_collective_count": [p_void],
 }
 # host callback of a user-supplied likelihood (smcb_user_loglik_fn)

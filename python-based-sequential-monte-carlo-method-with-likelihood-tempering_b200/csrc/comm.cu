@@ -224,4 +224,48 @@ extern "C" int smcb_comm_all_to_all_v(smcb_handle* h, const double* send_dev, co
     return SMCB_OK;
 }
 
+extern "C" int smcb_comm_exchange_rows(smcb_handle* h, const double* send_dev, int64_t ld_send,
+                                       const int64_t* send_counts_host, double* recv_dev, int64_t ld_recv,
+                                       const int64_t* recv_counts_host, int rows, void* stream) {
+    REQUIRE(h, h && send_counts_host && recv_counts_host && rows >= 1, SMCB_ERR_INVALID, "bad argument");
+    cudaStream_t st = as_stream(stream);
+    const int W = h->world, me = h->rank;
+    int64_t so = 0, ro = 0, stot = 0, rtot = 0;
+    for (int q = 0; q < W; ++q) {
+        REQUIRE(h, send_counts_host[q] >= 0 && recv_counts_host[q] >= 0, SMCB_ERR_INVALID, "negative count");
+        stot += send_counts_host[q];
+        rtot += recv_counts_host[q];
+    }
+    REQUIRE(h, (stot == 0 || (send_dev && ld_send >= stot)) && (rtot == 0 || (recv_dev && ld_recv >= rtot)),
+            SMCB_ERR_INVALID, "buffer too narrow for the counts");
+    REQUIRE(h, send_counts_host[me] == recv_counts_host[me], SMCB_ERR_INVALID, "self counts differ");
+    ncclComm_t c = static_cast<ncclComm_t>(h->comm);
+    bool group = false;
+    for (int q = 0; q < W; ++q) {
+        const int64_t sc = send_counts_host[q], rc = recv_counts_host[q];
+        if (q == me) {
+            if (sc > 0)
+                CUDA_TRY(h, cudaMemcpy2DAsync(recv_dev + ro, sizeof(double) * (size_t)ld_recv, send_dev + so,
+                                              sizeof(double) * (size_t)ld_send, sizeof(double) * (size_t)sc, (size_t)rows,
+                                              cudaMemcpyDeviceToDevice, st));
+        } else if (sc > 0 || rc > 0) {
+            if (!group) {
+                NCCL_TRY(h, g_nccl.GroupStart());
+                group = true;
+            }
+            for (int k = 0; k < rows; ++k) {
+                if (sc > 0) NCCL_TRY(h, g_nccl.Send(send_dev + (size_t)k * ld_send + so, (size_t)sc, ncclFloat64, q, c, st));
+                if (rc > 0) NCCL_TRY(h, g_nccl.Recv(recv_dev + (size_t)k * ld_recv + ro, (size_t)rc, ncclFloat64, q, c, st));
+            }
+        }
+        so += sc;
+        ro += rc;
+    }
+    if (group) {
+        NCCL_TRY(h, g_nccl.GroupEnd());
+        h->collectives++;
+    }
+    return SMCB_OK;
+}
+
 extern "C" int64_t smcb_collective_count(const smcb_handle* h) { return h ? h->collectives : 0; }

@@ -7,7 +7,6 @@
 #include "common.cuh"
 #include "philox.cuh"
 
-int final_colsum(smcb_handle* h, const double* partial, int nb, int ncol, double* out, cudaStream_t st);
 
 namespace {
 
@@ -107,18 +106,46 @@ moments_general_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, 
     if ((int)threadIdx.x < npair) partial[(int64_t)blockIdx.x * npair + threadIdx.x] = acc;
 }
 
-// expand packed upper triangle to a full symmetric d x d matrix
-__global__ void unpack_sym_kernel(const double* __restrict__ packed, int d, double* __restrict__ out) {
-    const int t = threadIdx.x;
-    if (t >= d * d) return;
-    int a = t / d, b = t - a * d;
-    if (a > b) {
-        const int c = a;
-        a = b;
-        b = c;
+// Final reduction of the centred second moments straight into the full symmetric matrix: one warp per (a <= b) pair
+// sums that column of the block partials (lane-strided, then a shuffle tree: a fixed order) and writes [a][b], [b][a].
+__global__ void __launch_bounds__(256)
+final_sym_kernel(const double* __restrict__ partial, int nb, int d, double* __restrict__ out) {
+    const int npair = d * (d + 1) / 2;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= npair) return;
+    double v = 0.0;
+    for (int b = lane; b < nb; b += 32) v += partial[(int64_t)b * npair + q];
+    v = warp_sum(v);
+    if (lane == 0) {
+        int a = 0, r = q;
+        while (r >= d - a) {
+            r -= d - a;
+            ++a;
+        }
+        const int bb = a + r;
+        out[a * d + bb] = v;
+        out[bb * d + a] = v;
     }
-    const int q = a * d - a * (a - 1) / 2 + (b - a);
-    out[t] = packed[q];
+}
+
+// Final reduction of the column sums of one shard plus the head of its all-gather row (smcb_moments_merged):
+// row[0:4] = MH counters, row[4] = n_r, row[5:5+d] = column sums, mean_r = column sums / n_r.  One warp per column.
+// (row_head == nullptr, mean_r == nullptr: plain column sums into sums, smcb_colsum.)
+__global__ void __launch_bounds__(256)
+colsum_final_row_kernel(const double* __restrict__ partial, int nb, int d, const unsigned long long* __restrict__ counts,
+                        double n_local, double* __restrict__ row_head, double* __restrict__ sums,
+                        double* __restrict__ mean_r) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row_head != nullptr && blockIdx.x == 0 && threadIdx.x < 5)
+        row_head[threadIdx.x] = (threadIdx.x < 4) ? (counts ? (double)counts[threadIdx.x] : 0.0) : n_local;
+    if (k >= d) return;
+    double v = 0.0;
+    for (int b = lane; b < nb; b += 32) v += partial[(int64_t)b * d + k];
+    v = warp_sum(v);
+    if (lane == 0) {
+        sums[k] = v;
+        if (mean_r != nullptr) mean_r[k] = v / n_local;        // IEEE division, as np.cov's X.mean()
+    }
 }
 
 // ---- proposal -------------------------------------------------------------------------------------
@@ -320,18 +347,7 @@ __global__ void sample_box_kernel(double* __restrict__ theta, int64_t ld, int64_
 
 // ---- merged moments + proposal factor ---------------------------------------------------------------------------
 // Row of one shard in the all-gather: [0:4] MH counters, [4] n_r, [5:5+d] column sums, [5+d:5+d+d*d] M2_r (second
-// moments centred on the shard's own mean colsum_r/n_r, full symmetric matrix).
-__global__ void moments_row_kernel(const unsigned long long* __restrict__ counts, double n_local, double* __restrict__ row) {
-    const int t = threadIdx.x;
-    if (t < 4) row[t] = counts ? (double)counts[t] : 0.0;
-    if (t == 4) row[4] = n_local;
-}
-// mean_r = colsum_r / n_r, in place after the column sums (what `mean.div_(N)` did on the host side of round 1)
-__global__ void moments_mean_kernel(const double* __restrict__ colsum, double n_local, int d, double* __restrict__ mean) {
-    const int t = threadIdx.x;
-    if (t < d) mean[t] = colsum[t] / n_local;
-}
-
+// moments centred on the shard's own mean colsum_r/n_r, full symmetric matrix), then that mean (colsum_final_row_kernel).
 // 1/x and 1/sqrt(x) from the MUFU seeds and one cubically convergent correction each (as csrc/kinetic.cuh): the
 // Jacobi rotations below sit on the critical path of every sweep (one warp, strictly serial), where an IEEE FP64
 // division or square root costs ~250 cycles of dependent instructions; the rotation angle needs no last-bit accuracy
@@ -515,7 +531,9 @@ extern "C" int smcb_colsum(smcb_handle* h, const double* theta_dev, int64_t ld, 
     REQUIRE(h, (int64_t)nb * d <= h->partial_len, SMCB_ERR_STATE, "reduction scratch too small");
     colsum_partial_kernel<<<dim3(nb, d), MB, 0, st>>>(theta_dev, ld, n, h->partial);
     LAUNCH_CHECK(h);
-    return final_colsum(h, h->partial, nb, d, out_dev, st);
+    colsum_final_row_kernel<<<(d + 7) / 8, 256, 0, st>>>(h->partial, nb, d, nullptr, (double)n, nullptr, out_dev, nullptr);
+    LAUNCH_CHECK(h);
+    return SMCB_OK;
 }
 
 extern "C" int smcb_centered_moments(smcb_handle* h, const double* theta_dev, int64_t ld, int64_t n, int d,
@@ -541,10 +559,7 @@ extern "C" int smcb_centered_moments(smcb_handle* h, const double* theta_dev, in
         }
     }
     LAUNCH_CHECK(h);
-    double* packed = h->partial + (int64_t)nb * npair;
-    int rc = final_colsum(h, h->partial, nb, npair, packed, st);
-    if (rc) return rc;
-    unpack_sym_kernel<<<1, 1024, 0, st>>>(packed, d, out_dev);
+    final_sym_kernel<<<(npair + 7) / 8, 256, 0, st>>>(h->partial, nb, d, out_dev);
     LAUNCH_CHECK(h);
     return SMCB_OK;
 }
@@ -625,17 +640,27 @@ extern "C" int smcb_moments_merged(smcb_handle* h, const double* theta_dev, int6
     cudaStream_t st = as_stream(stream);
     double* row = h->comm_send;
     double* mean_r = row + 5 + d + d * d;
-    moments_row_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned long long*>(counts_dev), (double)n, row);
+    REQUIRE(h, h->partial != nullptr, SMCB_ERR_STATE, "smcb_reserve has not been called");
+    // five launches (+ the all-gather on more than one GPU): column-sum partials, their final reduction together
+    // with the head of the row and the shard mean, centred partials, their final reduction into the symmetric
+    // matrix, merge + factor
+    const int nbc = moments_grid(h, n);
+    REQUIRE(h, (int64_t)nbc * d <= h->partial_len, SMCB_ERR_STATE, "reduction scratch too small");
+    colsum_partial_kernel<<<dim3(nbc, d), MB, 0, st>>>(theta_dev, ld, n, h->partial);
     LAUNCH_CHECK(h);
-    if ((rc = smcb_colsum(h, theta_dev, ld, n, d, row + 5, stream))) return rc;
-    moments_mean_kernel<<<1, 32, 0, st>>>(row + 5, (double)n, d, mean_r);
+    colsum_final_row_kernel<<<(d + 7) / 8, 256, 0, st>>>(h->partial, nbc, d, reinterpret_cast<const unsigned long long*>(counts_dev),
+                                                       (double)n, row, row + 5, mean_r);
     LAUNCH_CHECK(h);
     if ((rc = smcb_centered_moments(h, theta_dev, ld, n, d, mean_r, row + 5 + d, stream))) return rc;
-    if ((rc = comm_all_gather_f64(h, row, h->comm_recv, stride, st))) return rc;
+    const double* rows = row;
+    if (h->world > 1) {
+        if ((rc = comm_all_gather_f64(h, row, h->comm_recv, stride, st))) return rc;
+        rows = h->comm_recv;
+    }
     WCov wc;
     wc.use = w_cov_host != nullptr;
     if (wc.use) memcpy(wc.w, w_cov_host, sizeof(double) * d * d);
-    moments_merge_factor_kernel<<<1, 32, 0, st>>>(h->comm_recv, h->world, stride, d, (double)n_total, wc, out_dev);
+    moments_merge_factor_kernel<<<1, 32, 0, st>>>(rows, h->world, stride, d, (double)n_total, wc, out_dev);
     LAUNCH_CHECK(h);
     return SMCB_OK;
 }

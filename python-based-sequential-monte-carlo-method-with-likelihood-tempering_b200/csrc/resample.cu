@@ -403,7 +403,8 @@ __device__ __forceinline__ unsigned long long ld_volatile(const unsigned long lo
 }
 
 __global__ void __launch_bounds__(SB)
-resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ w_in, int64_t n,
+resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ w_in, int64_t n, uint64_t N,
+                      unsigned long long carry_q, int first_shard, int64_t m_out,
                       const double* __restrict__ max_dev, double gm, const double* __restrict__ sum_w_dev, double Nd,
                       double inv_Np, uint64_t u0q, unsigned long long* agg /*[2*tiles]: q, floor|ready*/,
                       unsigned long long* inc /*[2*tiles]*/, unsigned* __restrict__ tile_counter, const double* __restrict__ src, int64_t ld_src, int rows,
@@ -419,7 +420,6 @@ resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ 
     const unsigned tile = s_tile;
     const int64_t n_tiles = (n + TILE - 1) / TILE;
     const int64_t base = (int64_t)tile * TILE + (int64_t)threadIdx.x * IPT;   // blocked layout
-    const uint64_t N = (uint64_t)n;
 
     // ---- 1. weights, floor counts, fixed-point residuals (the arithmetic of weights_kernel + prepare_kernel) ----
     unsigned long long q[IPT];
@@ -510,17 +510,20 @@ resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ 
         }
     }
     __syncthreads();
-    const unsigned long long base_q = s_base[0];
+    // residual prefix of the whole run: what the lower ranks hold (carry_q, 0 on one GPU) + this shard's prefix
+    const unsigned long long base_q = carry_q + s_base[0];
     const long long base_f = (long long)s_base[1];
 
     // ---- 3. copy counts and output offsets ----
-    // first output slot of the tile: floor prefix + thresholds crossed before its first particle
-    const long long tile_c0 = (tile == 0) ? 0 : crossings(base_q, N, u0q);
-    const long long tile_off = base_f + tile_c0;
+    // thresholds crossed before this shard's first particle (none before the first particle of the run)
+    const long long c_start = first_shard ? 0 : crossings(carry_q, N, u0q);
+    // first output slot of the tile: floor prefix + thresholds crossed on this shard before its first particle
+    const long long tile_c0 = (tile == 0) ? c_start : crossings(base_q, N, u0q);
+    const long long tile_off = base_f + (tile_c0 - c_start);
     unsigned long long sq = base_q + ex_q;
     long long c_prev = crossings(sq, N, u0q);
-    if (base == 0) c_prev = 0;                 // nothing is crossed before the first particle of the run
-    long long off = base_f + ex_f + c_prev;    // copies placed before this thread's first particle
+    if (base == 0) c_prev = c_start;
+    long long off = base_f + ex_f + (c_prev - c_start);    // copies placed on this shard before this thread's first particle
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         sq += q[k];
@@ -539,7 +542,7 @@ resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ 
     const int64_t tile_first = (int64_t)tile * TILE;
     for (long long sl = threadIdx.x; sl < tile_total; sl += SB) {
         const long long slot = tile_off + sl;
-        if (slot >= n) break;                  // copies beyond N are dropped (monotone in sl)
+        if (slot >= m_out) break;              // copies beyond the slots this shard fills are dropped (monotone in sl)
         int lo = 0, hi = TILE - 1;             // smallest i with s_end[i] > sl
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -663,16 +666,18 @@ extern "C" int smcb_gather(smcb_handle* h, const double* src_dev, int64_t ld_src
 }
 
 
-extern "C" int smcb_resample_fused(smcb_handle* h, const double* lk_dev, const double* w_dev, int64_t n,
-                                   const double* max_dev, double gm, const double* sum_w_dev, double u0,
-                                   const double* src_dev, int64_t ld_src, int rows, double* dst_dev, int64_t ld_dst,
-                                   int32_t* ancestors_dev, int32_t* counts_dev, int64_t* filled_dev, void* stream) {
-    REQUIRE(h, h && src_dev && dst_dev && filled_dev && n > 0 && rows > 0 && ld_src >= n && ld_dst >= n,
-            SMCB_ERR_INVALID, "bad argument");
+extern "C" int smcb_resample_fused(smcb_handle* h, const double* lk_dev, const double* w_dev, int64_t n, int64_t n_total,
+                                   uint64_t carry_q, int64_t id_offset, int64_t m_out, const double* max_dev, double gm,
+                                   const double* sum_w_dev, double u0, const double* src_dev, int64_t ld_src, int rows,
+                                   double* dst_dev, int64_t ld_dst, int32_t* ancestors_dev, int32_t* counts_dev,
+                                   int64_t* filled_dev, void* stream) {
+    REQUIRE(h, h && src_dev && dst_dev && filled_dev && n > 0 && rows > 0 && ld_src >= n, SMCB_ERR_INVALID, "bad argument");
+    REQUIRE(h, n_total >= n && m_out >= 0 && m_out <= n_total && ld_dst >= m_out, SMCB_ERR_INVALID, "bad sizes");
     REQUIRE(h, w_dev != nullptr || (lk_dev && max_dev && sum_w_dev), SMCB_ERR_INVALID,
             "give either normalised weights or (lk, max, sum_w)");
-    REQUIRE(h, h->mark != nullptr && h->rs_desc != nullptr && n <= h->n_max, SMCB_ERR_STATE, "smcb_reserve too small");
-    REQUIRE(h, n < (1LL << 31), SMCB_ERR_UNSUPPORTED, "n must be below 2^31");
+    REQUIRE(h, h->mark != nullptr && h->rs_desc != nullptr && n <= h->n_max && m_out <= h->n_max, SMCB_ERR_STATE,
+            "smcb_reserve too small");
+    REQUIRE(h, n_total < (1LL << 31), SMCB_ERR_UNSUPPORTED, "n_total must be below 2^31");
     REQUIRE(h, u0 >= 0.0 && u0 < 1.0, SMCB_ERR_INVALID, "u0 must lie in [0,1)");
     cudaStream_t st = as_stream(stream);
     const int64_t nt = tiles_of(n);
@@ -683,13 +688,16 @@ extern "C" int smcb_resample_fused(smcb_handle* h, const double* lk_dev, const d
     unsigned long long* inc = agg + 2 * (size_t)nt;
     CUDA_TRY(h, cudaMemsetAsync(desc, 0, sizeof(unsigned long long) * (1 + 4 * (size_t)nt), st));
     int32_t* anc = ancestors_dev ? ancestors_dev : h->mark;
-    const double Nd = (double)n;
+    const double Nd = (double)n_total;
     const uint64_t u0q = (uint64_t)llrint(u0 * TWO62);
-    resample_fused_kernel<<<(unsigned)nt, SB, 0, st>>>(lk_dev, w_dev, n, max_dev, gm, sum_w_dev, Nd, 1.0 / Nd, u0q, agg, inc,
-                                                      counter, src_dev, ld_src, rows, dst_dev, ld_dst, anc, counts_dev,
+    resample_fused_kernel<<<(unsigned)nt, SB, 0, st>>>(lk_dev, w_dev, n, (uint64_t)n_total, carry_q, id_offset == 0 ? 1 : 0,
+                                                      m_out, max_dev, gm, sum_w_dev, Nd, 1.0 / Nd, u0q, agg, inc, counter,
+                                                      src_dev, ld_src, rows, dst_dev, ld_dst, anc, counts_dev,
                                                       filled_dev);
     LAUNCH_CHECK(h);
-    resample_pad_kernel<<<8, 256, 0, st>>>(filled_dev, n, src_dev, ld_src, rows, dst_dev, ld_dst, anc);
-    LAUNCH_CHECK(h);
+    if (m_out > 0) {
+        resample_pad_kernel<<<8, 256, 0, st>>>(filled_dev, m_out, src_dev, ld_src, rows, dst_dev, ld_dst, anc);
+        LAUNCH_CHECK(h);
+    }
     return SMCB_OK;
 }

@@ -150,12 +150,6 @@ inline int reduce_grid(const smcb_handle* h, int64_t n) {
 
 }  // namespace
 
-int final_colsum(smcb_handle* h, const double* partial, int nb, int ncol, double* out, cudaStream_t st) {
-    colsum_final_kernel<<<1, RB, 0, st>>>(partial, nb, ncol, out);
-    LAUNCH_CHECK(h);
-    return SMCB_OK;
-}
-
 extern "C" int smcb_lk_max(smcb_handle* h, const double* lk_dev, int64_t n, double* out_dev, void* stream) {
     REQUIRE(h, h && lk_dev && out_dev && n > 0, SMCB_ERR_INVALID, "null pointer or n<=0");
     REQUIRE(h, h->partial != nullptr, SMCB_ERR_STATE, "smcb_reserve has not been called");

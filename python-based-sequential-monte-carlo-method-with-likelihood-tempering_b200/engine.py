@@ -155,6 +155,13 @@ class NcclComm:
         _lib.check(self.handle, self.lib.smcb_comm_all_to_all_v(self.handle, inp.data_ptr(), sc.ctypes.data,
                                                                out.data_ptr(), rc_.ctypes.data, self._st()))
 
+    def exchange_rows(self, send, ld_send, send_counts, recv, ld_recv, recv_counts, rows):
+        sc = np.ascontiguousarray(send_counts, dtype=np.int64)
+        rc_ = np.ascontiguousarray(recv_counts, dtype=np.int64)
+        _lib.check(self.handle, self.lib.smcb_comm_exchange_rows(self.handle, send.data_ptr(), int(ld_send), sc.ctypes.data,
+                                                                recv.data_ptr(), int(ld_recv), rc_.ctypes.data, int(rows),
+                                                                self._st()))
+
     def broadcast(self, t, src):
         _lib.check(self.handle, self.lib.smcb_comm_broadcast(self.handle, t.data_ptr(), t.numel() * t.element_size(),
                                                             int(src), self._st()))
@@ -221,6 +228,20 @@ def sharded_resample(ops, comm, N, n_local, D1, u0, scan_mode, sendbuf, recvbuf,
                                                    contiguous [D1][len] chunk per destination rank
     Returns the number of slots filled before clamping to N."""
     W, rank = comm.world, comm.rank
+    if scan_mode == "fixed" and hasattr(ops, "fused_expand") and hasattr(comm, "exchange_rows"):
+        # Device path: totals -> all-gather -> integer plan on the host -> ONE kernel from weights to the rows of the
+        # slots this shard fills (smcb_resample_fused with the residual prefix of the lower ranks) -> the column
+        # ranges of those rows travel straight into the destination's state (smcb_comm_exchange_rows): no packing by
+        # destination, no unpacking.
+        allt = comm.all_gather_i64(ops.totals()).cpu().numpy()
+        plan = migration_plan(allt[:, 0], allt[:, 1], N, n_local, u0, W)
+        m_loc, send = plan["M"][rank], plan["send"][rank]
+        recv = [plan["send"][r][rank] for r in range(W)]
+        ld_send = max(m_loc, 1)
+        if m_loc > 0:
+            ops.fused_expand(plan["carry_q"][rank], m_loc, sendbuf, ld_send)
+        comm.exchange_rows(sendbuf, ld_send, send, state_out, state_out.stride(0), recv, D1)
+        return plan["filled"]
     if scan_mode == "fixed":
         allt = comm.all_gather_i64(ops.totals()).cpu().numpy()
         plan = migration_plan(allt[:, 0], allt[:, 1], N, n_local, u0, W)
@@ -288,6 +309,15 @@ class _DeviceShardOps:
                                          carry.ctypes.data, 0, e.id_offset, e.counts.data_ptr(), tot.data_ptr(),
                                          e._stream))
         return carry, tot
+
+    def fused_expand(self, carry_q, m_loc, sendbuf, ld_send):
+        """Counts, offsets, ancestors and the gather of this shard's first m_loc output slots in one kernel; the
+        rows land in sendbuf viewed as [d+1][ld_send]."""
+        e = self.e
+        e._ck(e.lib.smcb_resample_fused(e.h, None, e.w.data_ptr(), e.n, e.N, carry_q, e.id_offset, m_loc, None, 0.0,
+                                        None, 0.0 if e._u0 is None else e._u0, e.state.data_ptr(), e.n, e.d + 1,
+                                        sendbuf.data_ptr(), ld_send, e.anc.data_ptr(), None, e.icnt[6:7].data_ptr(),
+                                        e._stream))
 
     def unpack(self, recvbuf, src_off, width, state_out, dst_off):
         e = self.e
@@ -731,10 +761,10 @@ class Engine:
                 self.w.copy_(torch.as_tensor(weights, dtype=torch.float64))
                 w_ptr = self.w.data_ptr()
             with self._timed("resample_fused"):
-                self._ck(lib.smcb_resample_fused(h, self.lk.data_ptr(), w_ptr, self.n, self.scal.data_ptr(), gm,
-                                                 self.scal[1:].data_ptr(), u0, self.state.data_ptr(), self.n, D1,
-                                                 self.state2.data_ptr(), self.n, self.anc.data_ptr(), None,
-                                                 filled_t.data_ptr(), st))
+                self._ck(lib.smcb_resample_fused(h, self.lk.data_ptr(), w_ptr, self.n, self.n, 0, 0, self.n,
+                                                 self.scal.data_ptr(), gm, self.scal[1:].data_ptr(), u0,
+                                                 self.state.data_ptr(), self.n, D1, self.state2.data_ptr(), self.n,
+                                                 self.anc.data_ptr(), None, filled_t.data_ptr(), st))
             self.state, self.state2 = self.state2, self.state
             return None   # filled count stays on the device (icnt[6]); read lazily
         if weights is not None:

@@ -492,7 +492,7 @@ def _resample_fused(abi, w, u0, D1=4, lk=None, mx=0.0, gm=0.0, sum_w=1.0):
     lkt = abi.t(lk) if lk is not None else None
     sc = abi.t(np.array([mx, sum_w]))
     abi.ck(abi.lib.smcb_resample_fused(abi.h, lkt.data_ptr() if lkt is not None else None,
-                                       wt.data_ptr() if wt is not None else None, n, sc.data_ptr(), gm,
+                                       wt.data_ptr() if wt is not None else None, n, n, 0, 0, n, sc.data_ptr(), gm,
                                        sc[1:].data_ptr(), u0, src.data_ptr(), n, D1, dst.data_ptr(), n, anc.data_ptr(),
                                        counts.data_ptr(), filled.data_ptr(), None))
     torch.cuda.synchronize()
@@ -536,6 +536,43 @@ def test_fused_resampling_skewed_weights_and_weights_on_the_fly(abi):
     c_ref, a_ref, _, f_ref = _resample(abi, wd.cpu().numpy(), 0.7, 1)
     c, a, filled, src, dst = _resample_fused(abi, None, 0.7, lk=lk, mx=mx, gm=gm, sum_w=sum_w)
     assert filled == f_ref and np.array_equal(c, c_ref) and np.array_equal(a, a_ref) and np.array_equal(dst, src[:, a])
+
+
+def test_fused_resampling_shard_by_shard_equals_unsharded(abi):
+    """The sharded form of the single-pass kernel (residual prefix of the lower ranks, global index of the shard's first
+    particle, the slots the shard fills): the shards' outputs concatenated are the unsharded result, bit for bit."""
+    import smcb200
+    n, W, D1 = 1 << 16, 4, 4
+    nl = n // W
+    for seed, u0 in ((11, 0.6180339887), (12, 0.0)):
+        w = _weights(n, seed, conc=0.05)
+        c_full, a_full, tot_full, f_full = _resample(abi, w, u0, 1)
+        src = torch.arange(D1 * n, dtype=torch.float64, device=abi.dev).reshape(D1, n) * 0.25 - 3.0
+        tots = []
+        for r in range(W):
+            wt, tot = abi.t(w[r * nl:(r + 1) * nl]), abi.zeros(2, dtype=torch.int64)
+            abi.ck(abi.lib.smcb_resample_totals(abi.h, wt.data_ptr(), nl, n, tot.data_ptr(), None))
+            tots.append(tot.cpu().numpy())
+        tots = np.array(tots)
+        plan = smcb200.migration_plan(tots[:, 0], tots[:, 1], n, nl, u0, W)
+        assert plan["filled"] == f_full
+        out_rows, out_anc = [], []
+        for r in range(W):
+            m_loc = plan["M"][r]
+            wt = abi.t(w[r * nl:(r + 1) * nl])
+            shard = src[:, r * nl:(r + 1) * nl].contiguous()
+            dst = torch.full((D1, max(m_loc, 1)), -1.0, dtype=torch.float64, device=abi.dev)
+            anc, cnt = abi.zeros(max(m_loc, 1), dtype=torch.int32), abi.zeros(nl, dtype=torch.int32)
+            filled = abi.zeros(1, dtype=torch.int64)
+            abi.ck(abi.lib.smcb_resample_fused(abi.h, None, wt.data_ptr(), nl, n, plan["carry_q"][r], r * nl, m_loc, None, 0.0,
+                                               None, u0, shard.data_ptr(), nl, D1, dst.data_ptr(), max(m_loc, 1),
+                                               anc.data_ptr(), cnt.data_ptr(), filled.data_ptr(), None))
+            torch.cuda.synchronize()
+            assert np.array_equal(cnt.cpu().numpy(), c_full[r * nl:(r + 1) * nl])
+            out_rows.append(dst[:, :m_loc].cpu().numpy())
+            out_anc.append(anc[:m_loc].cpu().numpy().astype(np.int64) + r * nl)
+        assert np.array_equal(np.concatenate(out_anc), a_full)
+        assert np.array_equal(np.concatenate(out_rows, axis=1), src.cpu().numpy()[:, a_full])
 
 
 def test_resample_golden_stage_weights(abi, golden):
