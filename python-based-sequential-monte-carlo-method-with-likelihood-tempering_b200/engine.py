@@ -215,7 +215,7 @@ def migration_plan(floor_tot, q_tot, N, n_local, u0, world):
 
 
 # ------------------------------------------------------------------------------------ sharded resampling
-def sharded_resample(ops, comm, N, n_local, D1, u0, scan_mode, sendbuf, recvbuf, state_out):
+def sharded_resample(ops, comm, N, n_local, D1, u0, scan_mode, sendbuf, recvbuf, state_out, timer=None):
     """Cross-shard residual-systematic resampling: every rank ends up with slots
     [rank*n_local, (rank+1)*n_local) of the globally resampled particle set in state_out[D1, n_local].
 
@@ -228,19 +228,23 @@ def sharded_resample(ops, comm, N, n_local, D1, u0, scan_mode, sendbuf, recvbuf,
                                                    contiguous [D1][len] chunk per destination rank
     Returns the number of slots filled before clamping to N."""
     W, rank = comm.world, comm.rank
+    timer = timer or (lambda name: contextlib.nullcontext())
     if scan_mode == "fixed" and hasattr(ops, "fused_expand") and hasattr(comm, "exchange_rows"):
         # Device path: totals -> all-gather -> integer plan on the host -> ONE kernel from weights to the rows of the
         # slots this shard fills (smcb_resample_fused with the residual prefix of the lower ranks) -> the column
         # ranges of those rows travel straight into the destination's state (smcb_comm_exchange_rows): no packing by
         # destination, no unpacking.
-        allt = comm.all_gather_i64(ops.totals()).cpu().numpy()
+        with timer("rs_totals"):
+            allt = comm.all_gather_i64(ops.totals()).cpu().numpy()
         plan = migration_plan(allt[:, 0], allt[:, 1], N, n_local, u0, W)
         m_loc, send = plan["M"][rank], plan["send"][rank]
         recv = [plan["send"][r][rank] for r in range(W)]
         ld_send = max(m_loc, 1)
-        if m_loc > 0:
-            ops.fused_expand(plan["carry_q"][rank], m_loc, sendbuf, ld_send)
-        comm.exchange_rows(sendbuf, ld_send, send, state_out, state_out.stride(0), recv, D1)
+        with timer("rs_expand"):
+            if m_loc > 0:
+                ops.fused_expand(plan["carry_q"][rank], m_loc, sendbuf, ld_send)
+        with timer("rs_exchange"):
+            comm.exchange_rows(sendbuf, ld_send, send, state_out, state_out.stride(0), recv, D1)
         return plan["filled"]
     if scan_mode == "fixed":
         allt = comm.all_gather_i64(ops.totals()).cpu().numpy()
@@ -788,9 +792,10 @@ class Engine:
         if self.sendbuf is None:
             self.sendbuf = torch.empty(D1 * self.cap, dtype=torch.float64, device=self.device)
             self.recvbuf = torch.empty(D1 * self.n, dtype=torch.float64, device=self.device)
-        filled = sharded_resample(_DeviceShardOps(self), self.comm, self.N, self.n, D1, u0,
-                                  "fixed" if mode == _lib.SCAN_FIXED else "sequential",
-                                  self.sendbuf, self.recvbuf, self.state2)
+        with self._timed("resample_sharded"):
+            filled = sharded_resample(_DeviceShardOps(self), self.comm, self.N, self.n, D1, u0,
+                                      "fixed" if mode == _lib.SCAN_FIXED else "sequential",
+                                      self.sendbuf, self.recvbuf, self.state2, timer=self._timed)
         self.state, self.state2 = self.state2, self.state
         return filled
 
