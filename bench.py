@@ -14,7 +14,7 @@ construction, H2D of the particles from pinned host memory, the run, D2H of post
 Workloads (BASELINE.json configs):
   mm_progress   config 2: Michaelis-Menten progress curves (the reference's six CSVs, 240
                 observations), 2^20 particles per GPU, FP64, scipy-RK45-twin arithmetic.  DEFAULT.
-  mm_progress_exact  the same problem with the closed-form (Wright omega) progress curves: throughput mode, labelled
+  mm_progress_exact  the same problem with the closed-form (Wright omega) progress curves: converged mode, labelled
   mm_rate       config 4 shape: 10 000 rate-law observations, 2^22 particles per GPU (--particles), direct FP32 sum
   mm_rate_suff  config 4, sufficient-statistic form (A(Km), B(Km) tabulated once): 2^23 particles per GPU = 2^26 on 8
   kinetic       config 3: methanation-style reactor, d=5, 30 conditions, RK4 x 50, 2^18 particles
@@ -81,7 +81,7 @@ def make_workload(pkg, name, n_per_gpu):
         prior = pkg.UniformBox([0, 0, 0], [10, 10, 10], names=["Vmax", "Km", "sigma"])
         n = n_per_gpu or (1 << 20)
         cfg = dict()
-        desc = ("THROUGHPUT MODE, not the reference's likelihood: Michaelis-Menten progress curves in closed form (Wright "
+        desc = ("CONVERGED MODE, not the reference's likelihood: Michaelis-Menten progress curves in closed form (Wright "
                 "omega; the converged solution of the reference's ODE, up to 3e-3 relative from its rtol-1e-3 numbers), FP64")
     elif name == "mm_rate":
         lik = pkg.MMRate.synthetic(10000, precision=32)

@@ -145,8 +145,8 @@ int smcb_set_user_likelihood(smcb_handle* h, smcb_user_loglik_fn fn, void* user_
  *   SMCB_MM_RK45_SCIPY (default): scipy's adaptive RK45 taken step for step - the reference's likelihood (parity mode);
  *   SMCB_MM_EXACT: the closed form S(t) = Km*omega(ln(S0/Km) + (S0 - Vmax t)/Km), omega = Wright omega function -
  *   the converged solution of the same ODE (it differs from the reference's rtol-1e-3 result by up to
- *   2.9e-3 relative on the log-likelihood), cost independent of stiffness, no early rejection.  Throughput mode,
- *   labelled as such wherever it is reported. */
+ *   2.9e-3 relative on the log-likelihood), cost independent of stiffness, early rejection per observation.  The mode for
+ *   users who want the ODE's own likelihood; labelled wherever it is reported. */
 #define SMCB_PARAM_MM_INTEGRATOR 7
 #define SMCB_MM_RK45_SCIPY 0
 #define SMCB_MM_EXACT 1

@@ -38,6 +38,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "exp_table.cuh"
 #include "mm_solver.cuh"
 
 namespace {
@@ -542,7 +543,7 @@ mm_predict_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, cons
         for (int i = s.i_eval; i < n_t; ++i) out[i] = NAN;
 }
 
-// ------------------------------------------------------------------------------ exact integrator (throughput mode)
+// ------------------------------------------------------------------------------ exact integrator (converged mode)
 // the progress curve has the closed form  S(t) = Km * omega(z),
 //     z(t) = ln(S0/Km) + (S0 - Vmax t)/Km,      omega + ln(omega) = z   (Wright omega = Lambert W of e^z),
 // which needs no step-size control, has no stiff tail and is the CONVERGED solution of the reference's ODE
@@ -551,37 +552,54 @@ mm_predict_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, cons
 // integrator (SMCB_MM_EXACT) with its own oracle twin (oracle/mm.py: loglik_progress_exact) and is never used for the
 // parity line.
 //
-// omega is evaluated in log space (S0/Km reaches 1e5 and more: e^z overflows) by the Fritsch-Shafer-Crowley
-// iteration (order 4), started along an experiment from the previous observation time through d omega/dz =
-// omega/(1+omega) (third-order Taylor step; one iteration then suffices while |dz| <= 1/2), otherwise from the
-// asymptotic forms e^z/(1+e^z) (z < 1) and z - ln z + ln z / z (z >= 1) with three iterations.
-__device__ __forceinline__ double fsc_step(double w, double z) {
-    const double r = z - w - log(w);
-    const double w1 = 1.0 + w;
-    const double q = w1 * (w1 + (2.0 / 3.0) * r);
-    return w * (1.0 + (r / w1) * ((q - 0.5 * r) / (q - r)));
+// omega is found through L = ln(omega), the root of g(L) = e^L + L - z (S0/Km reaches 1e6: e^z overflows, e^L does
+// not): Halley's iteration L -= 2 g g' / (2 g'^2 - g g''), g' = 1 + e^L, g'' = e^L (order 3), with the table
+// exponential of exp_table.cuh (10 FP64 operations) and a MUFU-seeded reciprocal - no log, no IEEE division on the
+// path.  Along an experiment the start is the previous observation time's L moved by d L/dz = 1/(1+omega)
+// (second-order Taylor step; two iterations then reach 1e-15 while |dz| <= 1/2), otherwise L0 = z - omega0 (the
+// identity L = z - omega) with omega0 = e^z/(1+e^z) for z < 1 and z - ln z + ln z / z (an FP32 logarithm suffices)
+// above, and three iterations (checked against scipy.special.wrightomega over z in [-700, 2e6]: 4e-15 relative).
+// Below z = -37 (substrate exhausted, the usual state of a fast-kinetics particle at most observation times)
+// omega = e^z to the last bit and nothing is iterated.
+__device__ __forceinline__ double halley_step(double& L, double z, const double* __restrict__ etab, double& E) {
+    E = expt::exp_fast(L, etab);
+    const double g = E + (L - z);
+    const double gp = 1.0 + E;
+    const double dL = -(2.0 * g * gp) * mmsolve::rcp64(fma(2.0 * gp, gp, -g * E));
+    L += dL;
+    return dL;
 }
-__device__ __forceinline__ double wright_omega(double z) {
-    if (z < -700.0) return 0.0;                      // omega < 1e-304
-    double w;
-    if (z < 1.0) {
-        const double e = exp(z);
-        w = e / (1.0 + e);
-    } else {
-        const double l = log(z);
-        w = z - l + l / z;
+// omega(z) from scratch; leaves L = ln(omega)
+__device__ __forceinline__ double wright_omega(double z, double& L, const double* __restrict__ etab) {
+    if (z < -37.0) {                                 // substrate exhausted: omega = e^z (1 - e^z + ...), e^z < 1e-16
+        const double w = expt::exp_fast(z, etab);
+        L = z - w;
+        return w;
     }
-    w = fsc_step(w, z);
-    w = fsc_step(w, z);
-    return fsc_step(w, z);
+    double w0;
+    if (z < 1.0) {
+        const double e = expt::exp_fast(z, etab);
+        w0 = e * mmsolve::rcp64(1.0 + e);
+    } else {
+        const double l = (double)__logf((float)z);
+        w0 = z - l + l * mmsolve::rcp64(z);
+    }
+    L = z - w0;
+    double E, dL;
+    halley_step(L, z, etab, E);
+    halley_step(L, z, etab, E);
+    dL = halley_step(L, z, etab, E);
+    return E * fma(dL, fma(0.5, dL, 1.0), 1.0);      // e^(L_before + dL)
 }
 
 __global__ void __launch_bounds__(128)
 mm_exact_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const uint8_t* __restrict__ active,
                 const double* __restrict__ g_t, const double* __restrict__ g_P, const double* __restrict__ g_S0,
-                int n_ex, int n_t, double* __restrict__ lk, double* __restrict__ pred) {
+                int n_ex, int n_t, const double* __restrict__ lkmin, double* __restrict__ lk, double* __restrict__ pred) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const SharedData D = stage_data(smem, g_t, g_P, g_S0, n_ex, n_t);
+    __shared__ double etab[expt::TAB_N];
+    expt::load_table(etab);
+    const SharedData D = stage_data(smem, g_t, g_P, g_S0, n_ex, n_t);     // ends with __syncthreads()
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n || (active != nullptr && !active[p])) return;
     const double Vmax = theta[p], Km = theta[ld + p], sigma = theta[2 * ld + p];
@@ -593,35 +611,42 @@ mm_exact_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const u
     double total = 0.0;
     const double s2 = sigma * sigma;
     const double c0 = -0.5 * n_t * log(2 * M_PI * s2), inv_den = 1.0 / (2 * s2);
+    // exact early rejection (smcb_loglik_bounded): residuals only accumulate, so total so far + c0 for every
+    // experiment not finished - the current one's running residual term is an upper bound of the result
+    const double thr = (lkmin != nullptr && pred == nullptr) ? lkmin[p] : -INFINITY;
     for (int e = 0; e < n_ex; ++e) {
         const mmsolve::ObsPair* obs = D.obs + (size_t)e * n_t;
         const double S0 = D.S0[e];
         const double y0 = S0 * iKm;
-        const double z0 = log(y0) + y0;               // z at t = 0: omega(z0) = y0 exactly
+        const double L0 = log(y0);
+        const double ub0 = total + (n_ex - e) * c0;
+        const double z0 = L0 + y0;                    // z at t = 0: omega(z0) = y0, ln omega = L0
         double t = D.t0[e];
         double z_prev = z0 - k * t;
-        double w = (t == 0.0) ? y0 : wright_omega(z_prev);
+        double L = L0, w = y0;                        // ln(omega) and omega at z_prev
+        if (t != 0.0 && Km > 0.0) w = wright_omega(z_prev, L, etab);
         double ssr = 0.0;
         for (int i = 0; i < n_t; ++i) {
             double S;
             if (!(Km > 0.0)) {
                 S = fmax(S0 - Vmax * t, 0.0);         // Km -> 0: zero-order kinetics until the substrate is gone
             } else {
-                const double z = z0 - k * t;
-                const double dz = z - z_prev;
                 if (i > 0) {
-                    if (fabs(dz) <= 0.5 && w > 0.0) {
-                        // Taylor step along d omega/dz = omega/(1+omega): first derivative d1 = w/(1+w), second
-                        // d2 = d1/(1+w)^2, third d3 = d2 (1-2w)/(1+w)^2; then one order-4 correction
-                        const double a = 1.0 / (1.0 + w), d1 = w * a, a2 = a * a, d2 = d1 * a2;
-                        const double d3 = d2 * (1.0 - 2.0 * w) * a2;
-                        const double wp = w + dz * (d1 + dz * (0.5 * d2 + dz * (1.0 / 6.0) * d3));
-                        w = (wp > 0.0) ? fsc_step(wp, z) : wright_omega(z);
+                    const double z = z0 - k * t;
+                    const double dz = z - z_prev;
+                    if (fabs(dz) <= 0.5) {
+                        // dL/dz = 1/(1+w), d2L/dz2 = -w/(1+w)^3
+                        const double a = mmsolve::rcp64(1.0 + w);
+                        L = fma(dz, fma(-0.5 * dz * w, a * a * a, a), L);
+                        double E;
+                        halley_step(L, z, etab, E);
+                        const double dL = halley_step(L, z, etab, E);
+                        w = E * fma(dL, fma(0.5, dL, 1.0), 1.0);
                     } else {
-                        w = wright_omega(z);
+                        w = wright_omega(z, L, etab);
                     }
+                    z_prev = z;
                 }
-                z_prev = z;
                 S = Km * w;
             }
             const mmsolve::ObsPair o = obs[i];
@@ -631,6 +656,10 @@ mm_exact_kernel(const double* __restrict__ theta, int64_t ld, int64_t n, const u
             } else {
                 const double r = o.P - Pm;
                 ssr = fma(r, r, ssr);
+                if (fma(-ssr, inv_den, ub0) < thr) {  // certainly below the threshold: the proposal is rejected
+                    lk[p] = -INFINITY;
+                    return;
+                }
             }
             t = o.t_next;
         }
@@ -880,10 +909,11 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     REQUIRE(h, smem <= 200 * 1024, SMCB_ERR_UNSUPPORTED, "data set too large for shared-memory staging");
     REQUIRE(h, n * (int64_t)D.n_ex < (1LL << 31), SMCB_ERR_UNSUPPORTED, "too many solves for one launch");
     const unsigned un = (unsigned)n;
-    if (h->mm_integrator == SMCB_MM_EXACT) {          // closed-form progress curves: no ordering, no tail, no bound
+    if (h->mm_integrator == SMCB_MM_EXACT) {          // closed-form progress curves: no ordering, no tail
         if (smem > 48 * 1024)
             CUDA_TRY(h, cudaFuncSetAttribute(mm_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mm_exact_kernel<<<(un + 127) / 128, 128, smem, st>>>(theta, ld, n, active, D.t, D.P, D.S0, D.n_ex, D.n_t, lk, pred);
+        mm_exact_kernel<<<(un + 127) / 128, 128, smem, st>>>(theta, ld, n, active, D.t, D.P, D.S0, D.n_ex, D.n_t, lkmin, lk,
+                                                            pred);
         LAUNCH_CHECK(h);
         return SMCB_OK;
     }

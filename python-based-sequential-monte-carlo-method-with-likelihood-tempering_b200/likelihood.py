@@ -25,7 +25,7 @@ class MMProgress:
     def __init__(self, t, P_obs, S0, integrator="rk45_scipy"):
         """integrator = "rk45_scipy": scipy's adaptive RK45 step for step (the reference's likelihood; parity mode).
         integrator = "exact": the closed form S(t) = Km * wrightomega(ln(S0/Km) + (S0 - Vmax t)/Km), the converged
-        solution of the same ODE (throughput mode: cost independent of stiffness; NOT the reference's rtol-1e-3
+        solution of the same ODE (converged mode: cost independent of stiffness; NOT the reference's rtol-1e-3
         numbers)."""
         self.t, self.P_obs, self.S0 = _f64(t), _f64(P_obs), _f64(S0)
         if self.t.ndim != 2 or self.t.shape != self.P_obs.shape or self.S0.shape != (self.t.shape[0],):

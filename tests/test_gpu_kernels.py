@@ -184,7 +184,7 @@ def test_mm_progress_predictions(mm_abi, golden):
 
 
 def test_mm_progress_exact_integrator_matches_its_oracle(mm_abi, golden):
-    """SMCB_MM_EXACT (closed-form progress curves, throughput mode) against oracle.mm.loglik_progress_exact over a
+    """SMCB_MM_EXACT (closed-form progress curves, converged mode) against oracle.mm.loglik_progress_exact over a
     prior cloud (stiff particles included: Vmax/Km up to 1e5), a posterior cloud and edge cases; stated bound 1e-9."""
     a = mm_abi
     d = (golden["data_t"], golden["data_P"], golden["data_S0"])
@@ -200,6 +200,16 @@ def test_mm_progress_exact_integrator_matches_its_oracle(mm_abi, golden):
             got = a.loglik(1, th)
             assert _rel(got, want).max() < tol, _rel(got, want).max()
         assert a.loglik(1, prior)[50] == -np.inf
+        # early rejection: exact value, or -inf and then the value is certainly below the threshold given
+        full = a.loglik(1, prior)
+        thr = full + rs.normal(0, 300, len(full))
+        thr[:100] = -np.inf
+        thp, lkb, tt = a.t(prior.T), a.zeros(len(full)), a.t(thr)
+        a.ck(a.lib.smcb_loglik_bounded(a.h, 1, thp.data_ptr(), len(full), len(full), 3, None, tt.data_ptr(), lkb.data_ptr(), None))
+        got_b = lkb.cpu().numpy()
+        cut = np.isneginf(got_b) & ~np.isneginf(full)
+        assert np.array_equal(got_b[~cut], full[~cut]) and np.all(full[cut] < thr[cut]) and not cut[:100].any()
+        assert cut.sum() > 1000
         # predictions (the reference's C_l_) follow the same curves
         pred = a.zeros(4, 6, 40)
         thp = a.t(post[:4].T)
