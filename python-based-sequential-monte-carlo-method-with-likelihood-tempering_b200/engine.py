@@ -79,6 +79,23 @@ class TorchComm:
         self.dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits,
                                     group=self.group)
 
+    def exchange_rows(self, send, ld_send, send_counts, recv, ld_recv, recv_counts, rows):
+        """CPU twin of smcb_comm_exchange_rows: column ranges of the rows of `send` (viewed as [rows][ld_send]) go to
+        the ranks, what arrives lands in column ranges of the rows of `recv` ([rows][ld_recv])."""
+        S = send.reshape(-1)[: rows * ld_send].view(rows, ld_send)
+        R = recv if recv.dim() == 2 else recv.reshape(-1)[: rows * ld_recv].view(rows, ld_recv)
+        so = np.concatenate([[0], np.cumsum(send_counts)]).astype(int)
+        ro = np.concatenate([[0], np.cumsum(recv_counts)]).astype(int)
+        inp = torch.cat([S[:, so[q]:so[q + 1]].reshape(-1) for q in range(self.world)])
+        out = torch.empty(rows * int(ro[-1]), dtype=send.dtype, device=send.device)
+        self.dist.all_to_all_single(out, inp, output_split_sizes=[rows * int(c) for c in recv_counts],
+                                    input_split_sizes=[rows * int(c) for c in send_counts], group=self.group)
+        off = 0
+        for q in range(self.world):
+            c = int(recv_counts[q])
+            R[:, ro[q]:ro[q + 1]].copy_(out[off:off + rows * c].view(rows, c))
+            off += rows * c
+
     def broadcast(self, t, src):
         """src is a rank within this communicator's group (torch.distributed wants the global rank)."""
         g_src = src if self.group is None else self.dist.get_global_rank(self.group, src)

@@ -300,7 +300,9 @@ def test_kinetic_matches_oracle(abi, n_pairs, d):
     th_ulp[:, 0] = np.nextafter(th_ulp[:, 0], np.inf)
     sens = _rel(kinetic.loglik(th_ulp, cond, obs, base, est, 50), want)
     good = sens < 1e-12
-    assert good.mean() > 0.9 and good[0]
+    # how many are excluded is part of the statement: 10 of 300 in the reference's 5-parameter box, none of the 300
+    # drawn from the +-10% box of the 32-parameter family (observed; the bound below leaves room for libm changes)
+    assert good[0] and (~good).sum() <= (24 if n_pairs == 4 else 6), (~good).sum()
     assert _rel(got, want)[good].max() < 1e-9, _rel(got, want)[good].max()
     if (~good).any():
         # ... there any ulp-level difference in the arithmetic (NumPy vs CUDA exp(), reciprocal-multiply vs divide)

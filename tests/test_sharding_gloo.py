@@ -55,6 +55,19 @@ class _OracleOps:
                 off += cnt
 
 
+class _OracleFusedOps(_OracleOps):
+    """... plus the stand-in of the single-pass kernel: with it `sharded_resample` takes the device path (one kernel from
+    weights to the rows of the shard's output slots, rows exchanged without packing)."""
+
+    def fused_expand(self, carry_q, m_loc, sendbuf, ld_send):
+        """Stand-in of smcb_resample_fused in its sharded form: rows of this shard's first m_loc output slots."""
+        counts, _, _ = self.smc.resample_fixed_shard(self.w, self.u0, self.N, carry_q, self.rank == 0)
+        anc = self.smc.fit_ancestors(np.repeat(np.arange(len(self.w)), counts), m_loc)
+        D1 = self.state.shape[0]
+        view = sendbuf[: D1 * ld_send].view(D1, ld_send)
+        view[:, :m_loc].copy_(torch.from_numpy(np.ascontiguousarray(self.state[:, anc])))
+
+
 def _worker(rank, world, port, N, d, seed, conc, u0, mode, out):
     import torch.distributed as dist
     import smcb200
@@ -67,7 +80,9 @@ def _worker(rank, world, port, N, d, seed, conc, u0, mode, out):
     n = N // world
     sl = slice(rank * n, (rank + 1) * n)
     D1 = d + 1
-    ops = _OracleOps(smc, w[sl], state[:, sl], N, u0, rank)
+    path = "fused" if mode == "fixed_fused" else "chain"
+    mode = "fixed" if mode == "fixed_fused" else mode
+    ops = (_OracleFusedOps if path == "fused" else _OracleOps)(smc, w[sl], state[:, sl], N, u0, rank)
     sendbuf = torch.zeros(D1 * N, dtype=torch.float64)
     recvbuf = torch.zeros(D1 * n, dtype=torch.float64)
     state_out = torch.zeros((D1, n), dtype=torch.float64)
@@ -77,7 +92,7 @@ def _worker(rank, world, port, N, d, seed, conc, u0, mode, out):
 
 
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("mode", ["fixed", "sequential"])
+@pytest.mark.parametrize("mode", ["fixed", "fixed_fused", "sequential"])
 @pytest.mark.parametrize("conc,u0", [(0.3, 0.37), (0.02, 0.0)])
 def test_sharded_resample_equals_unsharded(tmp_path, world, mode, conc, u0):
     import torch.multiprocessing as mp
@@ -85,7 +100,7 @@ def test_sharded_resample_equals_unsharded(tmp_path, world, mode, conc, u0):
     N, d, seed = 1200, 3, 5
     mp.spawn(_worker, args=(world, _free_port(), N, d, seed, conc, u0, mode, str(tmp_path)), nprocs=world, join=True)
     w, state = _problem(N, d, seed, conc)
-    ref_fn = smc.resample_fixed if mode == "fixed" else smc.resample_sequential
+    ref_fn = smc.resample_sequential if mode == "sequential" else smc.resample_fixed
     anc, counts, info = ref_fn(w, u0)
     want = state[:, smc.fit_ancestors(anc, N)]
     parts = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
