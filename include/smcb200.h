@@ -341,6 +341,19 @@ int smcb_comm_exchange_rows(smcb_handle* h, const double* send_dev, int64_t ld_s
 /* Number of NCCL operations this handle has enqueued so far. */
 int64_t smcb_collective_count(const smcb_handle* h);
 
+/* Several MH sweeps in one call for ANY model, covariance refreshed every sweep (EX/main:212) because the factor stays on
+ * the device: per sweep smcb_mh_propose_dev (factor = the one in blk_dev) -> smcb_mh_threshold (early_reject != 0) ->
+ * smcb_loglik_bounded on the in-box proposals -> smcb_mh_accept -> smcb_moments_merged (counters of all shards +
+ * moments + next factor into blk_dev).  blk_dev must hold the result of a smcb_moments_merged call on the current
+ * particles at entry.  The reference's early-exit and step-halving rules (EX/main:243-248) are the caller's, between
+ * calls (n_sweeps = 1 reproduces them exactly).  Uniform (box) priors, Philox random inputs. */
+int smcb_mh_sweeps(smcb_handle* h, int model, double* theta_dev, int64_t ld, double* lk_dev, int64_t n, int d,
+                   int64_t n_total, const double* w_cov_host, double ratio, const double* low_host,
+                   const double* high_host, double gamma, int n_sweeps, int early_reject, uint64_t seed,
+                   uint64_t id_offset, uint32_t stage, uint32_t sweep0, double* prop_dev, int64_t ld_prop,
+                   double* lk2_dev, double* lkmin_dev, uint8_t* inbox_dev, uint8_t* moved_dev, int64_t* counts_dev,
+                   double* blk_dev, void* stream);
+
 /* ---- utilities ---------------------------------------------------------------------------- */
 /* Philox draws exactly as the kernels make them, for tests: z_dev [n][d], u_dev [n] (either NULL). */
 int smcb_philox_draws(smcb_handle* h, int64_t n, int d, uint64_t seed, uint64_t id_offset, uint32_t stage,

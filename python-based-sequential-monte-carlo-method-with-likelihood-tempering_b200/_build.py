@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsmcb200.so")
-SOURCES = ["api.cu", "loglik_mm.cu", "temper.cu", "resample.cu", "mh.cu", "kinetic.cu", "dae.cu", "comm.cu"]
+SOURCES = ["api.cu", "loglik_mm.cu", "temper.cu", "resample.cu", "mh.cu", "kinetic.cu", "dae.cu", "comm.cu", "sweep.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 

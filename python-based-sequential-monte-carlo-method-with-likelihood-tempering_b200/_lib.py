@@ -52,6 +52,9 @@ _SIGNATURES = {
                           p_void],
     "smcb_mh_fused": [p_void, c_int, p_void, c_i64, p_void, c_i64, c_int, p_void, c_dbl, p_void, p_void, c_dbl,
                       c_int, c_u64, c_u64, c_u32, c_u32, p_void, p_void, p_void],
+    "smcb_mh_sweeps": [p_void, c_int, p_void, c_i64, p_void, c_i64, c_int, c_i64, p_void, c_dbl, p_void, p_void, c_dbl,
+                       c_int, c_int, c_u64, c_u64, c_u32, c_u32, p_void, c_i64, p_void, p_void, p_void, p_void, p_void,
+                       p_void, p_void],
     "smcb_philox_draws": [p_void, c_i64, c_int, c_u64, c_u64, c_u32, c_u32, p_void, p_void, p_void],
     "smcb_sample_uniform_box": [p_void, p_void, c_i64, c_i64, c_int, p_void, p_void, c_u64, c_u64, p_void],
     "smcb_measure_fma_peak": [p_void, p_void],

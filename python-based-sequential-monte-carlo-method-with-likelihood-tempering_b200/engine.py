@@ -534,7 +534,7 @@ class Engine:
         self.dlp = None           # log prior ratio of the current proposals (priors with normal components only)
         if getattr(prior, "has_normal", False):
             if self.cfg.fused_sweeps > 0:
-                raise NotImplementedError("fused sweeps support uniform priors only")
+                raise NotImplementedError("several sweeps per call support uniform priors only")
             self.dlp = torch.zeros(self.n, dtype=f64, device=dev)
 
     # -------------------------------------------------------------------------------- helpers
@@ -923,6 +923,9 @@ class Engine:
                     ends exactly where the uninterrupted run would have.
         """
         cfg, N, d = self.cfg, self.N, self.d
+        if cfg.fused_sweeps > 0 and stream is not None:
+            raise ValueError("several sweeps per call (fused_sweeps > 0) draw their random inputs on the device; "
+                             "supplied random inputs need fused_sweeps = 0")
         if particles is not None:
             self.set_particles(particles)
         host_rng = np.random.RandomState(cfg.seed)
@@ -963,7 +966,30 @@ class Engine:
             # Host-side factor (NumPy's SVD, reproduces the reference's proposals for given normals) in parity mode
             # and for the fused kernel, which takes a host factor; the device's own Jacobi factor otherwise.
             host_factor = cfg.factor == "host" or (cfg.factor == "auto" and (stream is not None or hook is not None))
-            if cfg.fused_sweeps > 0:
+            if cfg.fused_sweeps > 0 and self.lik.model_id != _lib.MODEL_KINETIC_RK:
+                # any model: batches of sweeps with the covariance refreshed every sweep (smcb_mh_sweeps); the
+                # reference's early-exit and step-halving rules act between batches
+                self._launch_moments()
+                done = 0
+                while done < n_mh:
+                    k = min(cfg.fused_sweeps, n_mh - done)
+                    with self._timed("mh_sweeps"):
+                        self._ck(self.lib.smcb_mh_sweeps(
+                            self.h, self.lik.model_id, self.state.data_ptr(), self.n, self.lk.data_ptr(), self.n, d,
+                            self.N, self._w_cov_c.ctypes.data, ratio, self._low.ctypes.data, self._high.ctypes.data,
+                            gamma_new, k, 1 if cfg.early_reject else 0, cfg.seed, self.id_offset, step, done,
+                            self.prop.data_ptr(), self.n, self.lk2.data_ptr(), self.lkmin.data_ptr(),
+                            self.inbox.data_ptr(), self.moved.data_ptr(), self.icnt.data_ptr(), self.blk.data_ptr(),
+                            self._stream))
+                    done += k
+                    n_run += k
+                    blk = self._read_block(False)
+                    moved, stage_evals, stage_cut = int(blk[1]), int(blk[2]), int(blk[3])
+                    if cfg.early_exit and moved > r_th * N:
+                        break
+                    if moved < cfg.r_threshold_min * N:
+                        ratio = ratio * 0.5
+            elif cfg.fused_sweeps > 0:
                 F, _ = self.proposal_factor()
                 done = 0
                 while done < n_mh:

@@ -38,7 +38,9 @@ class Settings:
     mm_tail_warps: int = 32             # MM_PROGRESS: one-warp blocks per SM of the tail kernel
     mm_chunk: int = 32                  # MM_PROGRESS: particles per work-queue item of the bulk kernel
     mm_patience: int = 3                # ... and for how many steps (results do not depend on these three)
-    fused_sweeps: int = 0               # >0: run this many sweeps per launch with a frozen proposal factor
+    fused_sweeps: int = 0               # >0: this many sweeps per library call (smcb_mh_sweeps: covariance refreshed every
+                                        # sweep; kinetic model: smcb_mh_fused with a frozen factor); the early-exit and
+                                        # step-halving rules then act between batches
     bisect_iters: int = 60
     factor: str = "auto"                # proposal factor: "host" = NumPy's SVD factor on the host (reproduces the reference's
                                         # proposals for given normals), "device" = Jacobi eigen-factor on the device (same

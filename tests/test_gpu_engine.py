@@ -110,6 +110,35 @@ def test_philox_run_matches_oracle_loop_mm_rate(pkg, scan_mode):
     eng.close()
 
 
+@pytest.mark.parametrize("model", ["mm_rate", "mm_progress"])
+def test_several_sweeps_per_call_equal_the_sweep_by_sweep_run(pkg, golden, model):
+    """smcb_mh_sweeps (any model, covariance refreshed every sweep on the device): with the early exit off and the
+    step-halving rule idle (more than 10 % of the particles move in every sweep here) a run in batches of 2 or 5
+    sweeps per call is the sweep-by-sweep run, bit for bit."""
+    N, seed = 4096, 3
+    if model == "mm_rate":
+        lik = pkg.MMRate.synthetic(200)
+    else:
+        lik = pkg.MMProgress(golden["data_t"], golden["data_P"], golden["data_S0"])
+    prior = pkg.UniformBox([0, 0, 0], [10, 10, 10])
+    out = []
+    for k in (0, 2, 5):
+        eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=N, seed=seed, fused_sweeps=k, early_exit=False,
+                                                  mhstep_num=4, ad_mhstep_num=6))
+        eng.sample_prior()
+        out.append(eng.run())
+        eng.close()
+    ref = out[0]
+    assert ref.reached_one and min(ref.n_moved) > 0.1 * N
+    for r in out[1:]:
+        assert r.betas == ref.betas and r.n_mh == ref.n_mh and r.n_moved == ref.n_moved
+        assert r.log_evidence == ref.log_evidence and r.n_eval == ref.n_eval and r.n_eval_cut == ref.n_eval_cut
+        assert np.array_equal(r.particles, ref.particles) and np.array_equal(r.lk, ref.lk)
+    with pytest.raises(ValueError):
+        eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=64, fused_sweeps=2))
+        eng.run(np.full((64, 3), 1.0), stream=smc.ReferenceStream(1))
+
+
 def test_exact_integrator_run_matches_oracle_loop(pkg, golden):
     """MMProgress(integrator="exact") through the whole sampler against the oracle loop on the closed-form likelihood."""
     N, seed = 2048, 9
