@@ -36,29 +36,50 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source and link the shared library.  Returns its path."""
+    """Compile every CUDA source and link the shared library.  Returns its path.
+
+    Safe under concurrent callers (one process per GPU imports the package at the same time): the build runs under
+    an exclusive file lock, staleness is re-checked inside it, objects go to a per-process directory and the library
+    is moved into place atomically."""
     if not force and not _stale():
         return LIB
-    nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
-    os.makedirs(objdir, exist_ok=True)
+    import fcntl
+    import shutil
+    import tempfile
+    objroot = os.path.join(HERE, "build")
+    os.makedirs(objroot, exist_ok=True)
+    with open(os.path.join(objroot, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():          # another process built it while this one waited
+                return LIB
+            nvcc = _nvcc()
+            objdir = tempfile.mkdtemp(prefix="obj_", dir=objroot)
 
-    def one(src):
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
-        if verbose:
-            sys.stderr.write(r.stderr)
-        return obj
+            def one(src):
+                obj = os.path.join(objdir, src.replace(".cu", ".o"))
+                cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+                r = subprocess.run(cmd, capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+                if verbose:
+                    sys.stderr.write(r.stderr)
+                return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+            try:
+                with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+                    objs = list(ex.map(one, SOURCES))
+                tmp_lib = os.path.join(objdir, "libsmcb200.so")
+                cmd = [nvcc, "-shared", "-o", tmp_lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart",
+                                                                 "static", "-ldl"]
+                r = subprocess.run(cmd, capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+                os.replace(tmp_lib, LIB)
+            finally:
+                shutil.rmtree(objdir, ignore_errors=True)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
