@@ -548,10 +548,11 @@ def main():
             flop_model="84/attempted step + 34/accepted step + 18/observation + 30/solve (DESIGN.md K1), step counts "
                        "from the device counters; proposals rejected early are not counted",
             # DRAM bytes of one launch from the ncu --set full capture of a posterior-cloud sweep at 2^20 particles
-            # (profiles/ncu_full_r01_bulk_posterior_v2.md: 41.8 MB read + 21.9 MB written), scaled to this shard's
+            # (profiles/ncu_full_r02_bulk.md: 60.7 MB read + 41.4 MB written), scaled to this shard's
             # particle count - not re-measured here; the kernel moves 61 B per particle and is nowhere near HBM-bound
-            traffic=(63.72e6 / (1 << 20)) * eng.n,
-            traffic_source="ncu capture profiles/ncu_full_r01_bulk_posterior_v2.md, per particle x particles of a sweep")
+            traffic=(102.12e6 / (1 << 20)) * eng.n,
+            traffic_source="ncu --set full capture profiles/ncu_full_r02_bulk.md (a posterior-cloud sweep at 2^20 particles), per "
+                           "particle x particles of a sweep; the kernel moves ~100 B per particle and is nowhere near HBM-bound")
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
         longest = int(st1[16])
         roofline_tail = {
@@ -615,7 +616,12 @@ def main():
         roofline_hbm = {"bound": "hbm", "kernel": "resample_fused_kernel (all of K3 in one launch: weights, counts, look-back "
                                                   "scan, ancestors, gather of the particle state)",
                         "achieved": g_bytes / (g_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                        "frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak,
+                        # DRAM bytes of one launch from the ncu --set full capture (profiles/ncu_full_r02_resample.md:
+                        # 33.6 MB read + 1.0 MB written at 2^20 particles, d = 3: inside a run the 32 MiB state and its
+                        # copy live in the 126 MB L2), scaled to this launch's particle count - not re-measured here
+                        "traffic": (34.6e6 / (1 << 20)) * eng.n if eng.d == 3 else None,
+                        "traffic_source": "ncu capture profiles/ncu_full_r02_resample.md (L2-resident state), per particle",
                         "bytes_model": "8 (weight) + 4 + 4 (ancestor) + 2 (d+1) 8 (state) per particle, SURVEY.md 8(d)",
                         "peak_source": hbm_src, "launch_ms": g_ms, "bytes": g_bytes}
 
