@@ -548,6 +548,8 @@ class Engine:
     def close(self):
         """Park the library handle (with its device scratch) for the next Engine on this device."""
         if getattr(self, "h", None):
+            if self.lik.model_id == _lib.MODEL_USER:      # the callback must not outlive the likelihood object
+                self.lib.smcb_set_user_likelihood(self.h, None, None)
             if self._own_handle:
                 _release_handle(self.device.index, self.h)
             self.h = None
