@@ -402,7 +402,12 @@ __device__ __forceinline__ unsigned long long ld_volatile(const unsigned long lo
     return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
 
-__global__ void __launch_bounds__(SB)
+// MINB: blocks per SM the register allocation aims at.  6 (42 registers, a few spilled words) beats the unconstrained
+// 58 registers / 4 blocks once the launch has several waves of tiles - the kernel is bound by memory latency, and
+// more resident warps hide more of it: 208 -> 187 us at 2^23 particles, 124 -> 116 at 2^22 - and loses at 2^20, where
+// all 512 tiles are resident at once either way (45 -> 48 us; profiles/resample_variants.py).
+template <int MINB>
+__global__ void __launch_bounds__(SB, MINB)
 resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ w_in, int64_t n, uint64_t N,
                       unsigned long long carry_q, int first_shard, int64_t m_out,
                       const double* __restrict__ max_dev, double gm, const double* __restrict__ sum_w_dev, double Nd,
@@ -690,10 +695,11 @@ extern "C" int smcb_resample_fused(smcb_handle* h, const double* lk_dev, const d
     int32_t* anc = ancestors_dev ? ancestors_dev : h->mark;
     const double Nd = (double)n_total;
     const uint64_t u0q = (uint64_t)llrint(u0 * TWO62);
-    resample_fused_kernel<<<(unsigned)nt, SB, 0, st>>>(lk_dev, w_dev, n, (uint64_t)n_total, carry_q, id_offset == 0 ? 1 : 0,
-                                                      m_out, max_dev, gm, sum_w_dev, Nd, 1.0 / Nd, u0q, agg, inc, counter,
-                                                      src_dev, ld_src, rows, dst_dev, ld_dst, anc, counts_dev,
-                                                      filled_dev);
+#define RS_ARGS lk_dev, w_dev, n, (uint64_t)n_total, carry_q, id_offset == 0 ? 1 : 0, m_out, max_dev, gm, sum_w_dev, Nd, \
+                1.0 / Nd, u0q, agg, inc, counter, src_dev, ld_src, rows, dst_dev, ld_dst, anc, counts_dev, filled_dev
+    if (nt > 2 * (int64_t)h->sm_count * 4) resample_fused_kernel<6><<<(unsigned)nt, SB, 0, st>>>(RS_ARGS);
+    else resample_fused_kernel<1><<<(unsigned)nt, SB, 0, st>>>(RS_ARGS);
+#undef RS_ARGS
     LAUNCH_CHECK(h);
     if (m_out > 0) {
         resample_pad_kernel<<<8, 256, 0, st>>>(filled_dev, m_out, src_dev, ld_src, rows, dst_dev, ld_dst, anc);
