@@ -254,6 +254,180 @@ counts_sequential_kernel(const int32_t* __restrict__ floor_cnt, const double* __
     }
 }
 
+// SEQUENTIAL mode at block speed.  The reference's running sum S_j = fl(S_{j-1} + r_j) and its threshold
+// T_k = fl(T_{k-1} + 1/N) look inherently serial, but inside one binade [2^e, 2^(e+1)) every FP64 value is an integer
+// multiple of u = 2^(e-52), so fl(S + r) = S + rn(r/u)*u as long as the result stays in the binade and r/u is not
+// exactly half-way between two integers: the sequentially ROUNDED sum of a chunk is an exact INTEGER prefix sum of
+// q_j = rn(r_j/u), which a block scans in parallel; likewise the thresholds of a chunk are T + i*rn((1/N)/u_T)*u_T,
+// and the number of thresholds at or below S_j is one integer division.  One block of 1024 threads walks the
+// particles in chunks of 1024, carrying (S, T) exactly; a chunk that breaks an assumption (a binade boundary of S
+// or T inside it, a half-way case, S still tiny against the residuals, a particle crossing two thresholds) is done
+// by thread 0 with the literal loop, 2.4% of the chunks at 2^20 particles.  Result: the reference's counts bit for
+// bit (tests/test_gpu_kernels.py, oracle/smc.py::resample_sequential) in 2.65 ms instead of 4.4 ms at 2^20 and 8.6
+// instead of 17.6 ms at 2^22 (profiles/resample_sequential_timing.py): the chain over the chunks keeps the work on
+// ONE SM, whose issue rate (~150 instructions per particle) is now the limit, not the latency of 2^20 dependent adds.
+constexpr int SQB = 1024;
+__device__ __forceinline__ double pow2i(int k) { return __hiloint2double((k + 1023) << 20, 0); }   // -1022 <= k <= 1023
+__device__ __forceinline__ int unit_exp(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1023 - 52; }
+
+__global__ void __launch_bounds__(SQB)
+counts_sequential_block_kernel(const int32_t* __restrict__ floor_cnt, const double* __restrict__ resid_f, int64_t n,
+                               double inv_Np, double* __restrict__ carry /*[2]: sum, wrand*/,
+                               int32_t* __restrict__ counts, int64_t* __restrict__ totals_out,
+                               unsigned long long* __restrict__ dbg /*[2] chunks, literal chunks; may be null*/) {
+    __shared__ double s_r[SQB];
+    __shared__ unsigned long long s_c[SQB];
+    __shared__ long long s_w[32];
+    __shared__ double sh_S, sh_T;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        sh_S = carry[0];
+        sh_T = carry[1];
+    }
+    long long nfloor = 0, ncross = 0, n_lit = 0, n_chunks = 0;   // ncross, n_lit, n_chunks: thread 0 / uniform
+    __syncthreads();
+    // the chunks depend on one another through (S, T), so nothing hides a load but the previous chunk's work: the
+    // next chunk's residuals and floor counts are fetched while the current one is scanned
+    double r_next = (tid < n) ? resid_f[tid] : 0.0;
+    int32_t f_next = (tid < n) ? floor_cnt[tid] : 0;
+    for (int64_t b0 = 0; b0 < n; b0 += SQB) {
+        const int m = (int)((n - b0 < SQB) ? (n - b0) : SQB);
+        const double r = r_next;
+        const int32_t f_cur = f_next;
+        {
+            const int64_t jn = b0 + SQB + tid;
+            r_next = (jn < n) ? resid_f[jn] : 0.0;
+            f_next = (jn < n) ? floor_cnt[jn] : 0;
+        }
+        s_r[tid] = r;
+        const double S = sh_S, T = sh_T;
+        ++n_chunks;
+        // ---- can the chunk be scanned in integers? (every condition is checked, none is assumed) ----
+        bool bad = !(S > 0.0 && T > 0.0 && S < 1e300 && T < 1e300 && S > 1e-280 && T > 1e-280);
+        const int uS = bad ? 0 : unit_exp(S), uT = bad ? 0 : unit_exp(T);
+        const int emin = uS < uT ? uS : uT;
+        const int dS = uS - emin, dT = uT - emin;
+        bad = bad || (dS > 10) || (dT > 10);
+        bad = bad || !(fabs(r) < S * 1024.0);                    // also catches NaN
+        double t = 0.0;
+        long long q = 0;
+        if (!bad) {
+            t = r * pow2i(-uS);                                  // exact scaling: |t| < 2^63
+            bad = (t - floor(t) == 0.5);                         // half-way: the rounding would depend on the sum's parity
+            q = __double2ll_rn(t);
+        }
+        // thresholds: T + i*step*u_T
+        long long step = 0, Mt = 0, M = 0;
+        if (!bad) {
+            const double st = inv_Np * pow2i(-uT);
+            bad = !(st >= 1.0 && st < 4.0e18) || (st - floor(st) == 0.5);
+            step = __double2ll_rn(st);
+            Mt = (long long)(T * pow2i(-uT));                    // exact: an integer in [2^52, 2^53)
+            M = (long long)(S * pow2i(-uS));
+        }
+        // inclusive block scan of q
+        long long incl = q;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long up = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_w[wid] = incl;
+        int any_bad = __syncthreads_or(bad ? 1 : 0);
+        if (wid == 0) {
+            long long w = s_w[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long up = __shfl_up_sync(FULL_MASK, w, o);
+                if (lane >= o) w += up;
+            }
+            s_w[lane] = w;
+        }
+        __syncthreads();
+        const long long cum = incl + (wid > 0 ? s_w[wid - 1] : 0);
+        const long long total = s_w[31];
+        unsigned long long c = 0;
+        const double inv_sc = (!any_bad) ? 1.0 / (double)((unsigned long long)step << dT) : 0.0;
+        if (!any_bad) {
+            const long long Mj = M + cum;
+            bad = (Mj < (1LL << 52)) || (M + total >= (1LL << 53));       // S leaves its binade inside the chunk
+            if (!bad) {
+                const unsigned long long A = (unsigned long long)Mj << dS, B = (unsigned long long)Mt << dT,
+                                         sc = (unsigned long long)step << dT;
+                // thresholds T + i*step at or below S_j: floor((A-B)/sc) + 1, the quotient (<= 1024 here) from a
+                // double estimate corrected by exact integer products (a 64-bit division costs ~100 instructions)
+                if (A >= B) {
+                    const unsigned long long D = A - B;
+                    unsigned long long qd = (unsigned long long)((double)D * inv_sc);
+                    if (qd * sc > D) --qd;
+                    if ((qd + 1ULL) * sc <= D) ++qd;
+                    bad = bad || (qd * sc > D) || ((qd + 1ULL) * sc <= D) || qd > 4096ULL;   // estimate off by more than one
+                    c = qd + 1ULL;
+                }
+            }
+        }
+        s_c[tid] = c;
+        any_bad = __syncthreads_or((any_bad || bad) ? 1 : 0);
+        int flag = 0;
+        if (!any_bad) {
+            const unsigned long long c_prev = (tid > 0) ? s_c[tid - 1] : 0ULL;
+            bad = (c < c_prev) || (c - c_prev > 1ULL);                     // the literal loop takes one threshold per particle
+            flag = (int)(c - c_prev);
+            // every threshold that was compared with (index <= c_last) must lie in T's binade
+            if (tid == SQB - 1) bad = bad || (Mt + (long long)(c + 1) * step >= (1LL << 53));
+        }
+        any_bad = __syncthreads_or((any_bad || bad) ? 1 : 0);
+        if (any_bad) {
+            // ---- literal loop of the reference for this chunk (Micmem_SMC_main.py:165-174) ----
+            if (tid == 0) {
+                double run = S, wrand = T;
+#pragma unroll 8
+                for (int i = 0; i < m; ++i) {
+                    run = __dadd_rn(run, s_r[i]);
+                    const bool hit = run >= wrand;
+                    s_c[i] = hit ? 1ULL : 0ULL;
+                    if (hit) {
+                        wrand = __dadd_rn(wrand, inv_Np);
+                        ++ncross;
+                    }
+                }
+                sh_S = run;
+                sh_T = wrand;
+                ++n_lit;
+            }
+            __syncthreads();
+            flag = (tid < m) ? (int)s_c[tid] : 0;
+        } else if (tid == SQB - 1) {
+            sh_S = (double)(M + total) * pow2i(uS);                        // exact: below 2^53 in units of u_S
+            sh_T = (double)(Mt + (long long)c * step) * pow2i(uT);
+            s_w[0] = (long long)c;
+        }
+        __syncthreads();
+        if (!any_bad && tid == 0) ncross += s_w[0];
+        if (tid < m) {
+            counts[b0 + tid] = f_cur + flag;
+            nfloor += f_cur;
+        }
+        __syncthreads();
+    }
+    nfloor = warp_sum_ll(nfloor);
+    if (lane == 0) s_w[wid] = nfloor;
+    __syncthreads();
+    if (tid == 0) {
+        long long tf = 0;
+        for (int k = 0; k < SQB / 32; ++k) tf += s_w[k];
+        carry[0] = sh_S;
+        carry[1] = sh_T;
+        totals_out[0] = tf;
+        totals_out[1] = ncross;
+        if (dbg != nullptr) {
+            dbg[0] = (unsigned long long)n_chunks;
+            dbg[1] = (unsigned long long)n_lit;
+        }
+
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // ancestor expansion
 __global__ void __launch_bounds__(SB)
@@ -614,8 +788,10 @@ extern "C" int smcb_resample_counts(smcb_handle* h, const double* w_dev, int64_t
             carry[1] = carry_host[1];
         }
         CUDA_TRY(h, cudaMemcpyAsync(h->seq_carry, carry, sizeof(carry), cudaMemcpyHostToDevice, st));
-        counts_sequential_kernel<<<1, 32, 0, st>>>(h->floor_cnt, h->resid_f, n, inv_Np, h->seq_carry, counts_dev,
-                                                  totals_dev);
+        // [2], [3] of seq_carry: chunks walked / chunks that needed the literal loop (diagnostics, as doubles' bits)
+        counts_sequential_block_kernel<<<1, SQB, 0, st>>>(h->floor_cnt, h->resid_f, n, inv_Np, h->seq_carry, counts_dev,
+                                                         totals_dev,
+                                                         reinterpret_cast<unsigned long long*>(h->seq_carry + 2));
         LAUNCH_CHECK(h);
         if (carry_host != nullptr) {
             CUDA_TRY(h, cudaMemcpyAsync(carry_host, h->seq_carry, sizeof(carry), cudaMemcpyDeviceToHost, st));

@@ -482,6 +482,20 @@ def test_resample_sequential_is_bit_exact(abi, n, seed, u0):
     assert np.array_equal(a, smc.fit_ancestors(a_ref, n))
 
 
+@pytest.mark.parametrize("n,conc,u0", [((1 << 20) + 3, 0.3, 0.37), (1 << 20, 0.02, 0.0), (300007, 5.0, 0.999999),
+                                       (1 << 18, 1.0, 0.5)])
+def test_resample_sequential_is_bit_exact_at_full_size(abi, n, conc, u0):
+    """The block-parallel form of the reference's sequentially rounded running sum (integer scans inside a binade,
+    literal loop where a chunk breaks an assumption) against the literal Python loop at BASELINE config 2's size,
+    with even, concentrated and very concentrated weights: counts and ancestors bit for bit."""
+    w = _weights(n, 21, conc=conc)
+    a_ref, c_ref, info = smc.resample_sequential(w, u0)
+    c, a, tot, filled = _resample(abi, w, u0, 0)
+    assert np.array_equal(c, c_ref)
+    assert filled == info["n_filled"] and tot[0] == info["n_floor"] and tot[1] == info["n_cross"]
+    assert np.array_equal(a, smc.fit_ancestors(a_ref, n))
+
+
 @pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (7, 2), (1000, 3), (2048, 4), (2049, 5), (5000, 6), (65536, 7)])
 @pytest.mark.parametrize("u0", [0.0, 0.37, 0.999999])
 def test_resample_fixed_matches_integer_twin(abi, n, seed, u0):
