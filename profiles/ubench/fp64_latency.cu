@@ -102,6 +102,27 @@ __global__ void solve_many(double* out, long long* cyc, unsigned* natt, double V
     if (threadIdx.x == 0 && blockIdx.x == 0) { cyc[0] = t1 - t0; natt[0] = a + r; }
 }
 
+// the tail kernel's spelling (mmsolve::solve_lat): lanes other than 0 integrate neighbouring problems
+template <bool HOIST>
+__global__ void solve_lat_many(double* out, long long* cyc, unsigned* natt, double Vmax, double Km, double S0, int active_lanes,
+                               double spread) {
+    __shared__ mmsolve::ObsPair obs[40];
+    __shared__ double s_coef[mmsolve::LAT_NCOEF];
+    if (threadIdx.x == 0) mmsolve::lat_coef_fill(s_coef);
+    for (int i = threadIdx.x; i < 40; i += blockDim.x) { obs[i].P = 0.05; obs[i].t_next = (i < 39) ? 10.0 * (i + 1) / 39.0 : INFINITY; }
+    __syncthreads();
+    if ((int)threadIdx.x >= active_lanes) return;
+    mmsolve::Solve s;
+    s.nVmax = -Vmax; s.Km = Km * (1.0 + spread * threadIdx.x); s.S0 = S0; s.cut_lim = INFINITY;
+    unsigned a = 0, r = 0;
+    long long t0 = clock64();
+    int st = mmsolve::setup(s, 0.0, 10.0) ? mmsolve::RUNNING : mmsolve::FAILED;
+    if (st == mmsolve::RUNNING) st = mmsolve::solve_lat<HOIST>(s, obs, a, r, s_coef);
+    long long t1 = clock64();
+    out[blockIdx.x * 32 + threadIdx.x] = s.ssr;
+    if (threadIdx.x == 0 && blockIdx.x == 0) { cyc[0] = t1 - t0; natt[0] = a + r; cyc[1] = (long long)__double_as_longlong(s.ssr); }
+}
+
 int main() {
     double* out; long long* cyc; unsigned* natt;
     cudaMalloc(&out, 1 << 24); cudaMallocManaged(&cyc, 64); cudaMallocManaged(&natt, 64);
@@ -140,6 +161,28 @@ int main() {
     for (int lanes = 2; lanes <= 32; lanes *= 4) {
         solve_many<<<148 * 4, 32>>>(out, cyc, natt, 9.88869508e+00, 4.28267643e-04, 0.1, lanes); cudaDeviceSynchronize();
         printf("4 warps per SM, %2d lanes with neighbouring stiff problems: %.1f cycles per attempt of lane 0 (%u attempts)\n", lanes, (double)cyc[0] / natt[0], natt[0]);
+    }
+    // ---- round 2: the latency spelling of the tail kernel (solve_lat), registers-resident coefficients or not
+    solve_steps<<<1, 32>>>(out, cyc, natt, 9.88869508e+00, 4.28267643e-04, 0.1, 1); cudaDeviceSynchronize();
+    printf("attempt() loop, worst solve, 1 lane            : %u attempts, %.1f cycles per attempt, ssr bits %016llx\n", natt[0], (double)cyc[0] / natt[0],
+           (unsigned long long)0);
+    for (int lanes = 1; lanes <= 32; lanes *= 8) {
+        if (lanes == 64) break;
+        solve_lat_many<false><<<1, 32>>>(out, cyc, natt, 9.88869508e+00, 4.28267643e-04, 0.1, lanes, 0.01); cudaDeviceSynchronize();
+        printf("solve_lat<false>, %2d lane(s), 1 warp             : %u attempts, %.1f cycles per attempt\n", lanes, natt[0], (double)cyc[0] / natt[0]);
+        solve_lat_many<true><<<1, 32>>>(out, cyc, natt, 9.88869508e+00, 4.28267643e-04, 0.1, lanes, 0.01); cudaDeviceSynchronize();
+        printf("solve_lat<true>,  %2d lane(s), 1 warp             : %u attempts, %.1f cycles per attempt\n", lanes, natt[0], (double)cyc[0] / natt[0]);
+    }
+    // lanes of very different stiffness in one warp (Km spread 10x per lane: the other lanes finish early or wait at the loop's exit)
+    solve_lat_many<false><<<1, 32>>>(out, cyc, natt, 9.88869508e+00, 4.28267643e-04, 0.1, 8, 3.0); cudaDeviceSynchronize();
+    printf("solve_lat<false>, 8 lanes of mixed stiffness      : %u attempts of lane 0, %.1f cycles per attempt\n", natt[0], (double)cyc[0] / natt[0]);
+    solve_lat_many<true><<<1, 32>>>(out, cyc, natt, 9.88869508e+00, 4.28267643e-04, 0.1, 8, 3.0); cudaDeviceSynchronize();
+    printf("solve_lat<true>,  8 lanes of mixed stiffness      : %u attempts of lane 0, %.1f cycles per attempt\n", natt[0], (double)cyc[0] / natt[0]);
+    for (int wps = 4; wps <= 16; wps *= 2) {
+        solve_lat_many<false><<<148 * wps, 32>>>(out, cyc, natt, 9.88869508e+00, 4.28267643e-04, 0.1, 1, 0.01); cudaDeviceSynchronize();
+        printf("solve_lat<false>, lane 0 of %2d warps per SM       : %.1f cycles per attempt\n", wps, (double)cyc[0] / natt[0]);
+        solve_lat_many<true><<<148 * wps, 32>>>(out, cyc, natt, 9.88869508e+00, 4.28267643e-04, 0.1, 1, 0.01); cudaDeviceSynchronize();
+        printf("solve_lat<true>,  lane 0 of %2d warps per SM       : %.1f cycles per attempt\n", wps, (double)cyc[0] / natt[0]);
     }
     solve_steps<<<1, 32>>>(out, cyc, natt, 1.2, 0.5, 2.0, 1); cudaDeviceSynchronize();
     printf("posterior solve, 1 lane   : %u attempts, %.1f cycles per attempt\n", natt[0], (double)cyc[0] / natt[0]);

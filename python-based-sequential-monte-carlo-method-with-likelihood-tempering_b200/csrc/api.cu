@@ -197,6 +197,7 @@ extern "C" int smcb_set_data_mm_progress(smcb_handle* h, const double* t_host, c
     h->mmp.n_ex = n_ex;
     h->mmp.n_t = n_t;
     h->mm_bulk_blocks_per_sm = 0;   // shared-memory footprint changed: query the occupancy again
+    h->mm_tail_blocks_per_sm = 0;
     h->mm_smem_set = false;
     if (h->n_max > 0 && n_ex > h->ssr_rows) return smcb_reserve(h, h->n_max, h->d_max);
     return SMCB_OK;

@@ -83,6 +83,7 @@ struct smcb_handle {
     int mm_patience = 3;             // ... for this many attempted steps (unless the whole warp is free)
     int mm_refill_min = 8;           // free lanes a warp of the bulk kernel waits for before setting up new solves
     int mm_bulk_blocks_per_sm = 0;   // occupancy of the bulk kernel (queried once)
+    int mm_tail_blocks_per_sm = 0;   // occupancy of the tail kernel (queried once)
     bool mm_smem_set = false;
     int32_t* floor_cnt = nullptr;    // [n_max]
     uint64_t* resid_q = nullptr;     // [n_max] fixed-point residuals

@@ -45,6 +45,14 @@ namespace {
 
 using mmsolve::Solve;
 
+// The tail kernel takes its steps in the latency spelling of mm_solver.cuh (attempt_lat); 0 = the bulk kernel's spelling
+#ifndef SMCB_TAIL_LATENCY_FORM
+#define SMCB_TAIL_LATENCY_FORM 1
+#endif
+#ifndef SMCB_TAIL_HOIST
+#define SMCB_TAIL_HOIST 1
+#endif
+
 constexpr int BULK_BLOCK = 128;
 constexpr int TAIL_BLOCK = 32;
 constexpr double DEFERRED = -1.0;   // marker in the per-solve result array (a residual sum is >= 0)
@@ -435,6 +443,12 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
         return;
     }
     extern __shared__ __align__(16) unsigned char smem[];
+#if SMCB_TAIL_HOIST
+    __shared__ double s_coef[mmsolve::LAT_NCOEF];
+    if (threadIdx.x == 0) mmsolve::lat_coef_fill(s_coef);   // stage_data ends with a block-wide barrier
+#else
+    const double* s_coef = nullptr;
+#endif
     const SharedData D = stage_data(smem, g_t, g_P, g_S0, n_ex, n_t);
 
     unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, mx = 0, mx_cyc = 0;
@@ -454,7 +468,11 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
         n_set++;
         const long long c0 = clock64();
         int st = mmsolve::setup(s, D.t0[e], D.tb[e]) ? mmsolve::RUNNING : mmsolve::FAILED;
+#if SMCB_TAIL_LATENCY_FORM
+        if (st == mmsolve::RUNNING) st = mmsolve::solve_lat<SMCB_TAIL_HOIST != 0>(s, obs, n_acc, n_rej, s_coef);
+#else
         while (st == mmsolve::RUNNING) st = mmsolve::attempt<false>(s, obs, nullptr, n_acc, n_rej);
+#endif
         const long long c1 = clock64();
         ssr[g] = (st == mmsolve::DONE) ? s.ssr : INFINITY;
         if (st == mmsolve::FAILED) n_fail++;
@@ -938,6 +956,8 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
         int a = 0;
         CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, mm_bulk_kernel, BULK_BLOCK, smem));
         h->mm_bulk_blocks_per_sm = a > 0 ? a : 1;
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, mm_tail_kernel<false>, TAIL_BLOCK, smem));
+        h->mm_tail_blocks_per_sm = a > 0 ? a : 1;
     }
     {
         const int rc = prof_begin_sweep(h);
@@ -985,7 +1005,8 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     // One-warp blocks, one deferred solve per thread.  The grid holds the larger of mm_tail_warps (32) blocks per
     // SM and one lane per 32 solves of the sweep (a prior cloud defers 0.5% of its solves: 33 618 of 6.3e6 at 2^20
     // particles); blocks without entries exit at once, so the long chains end up alone on their schedulers.
-    unsigned tail_grid = (unsigned)h->sm_count * (unsigned)h->mm_tail_warps;
+    // (never more blocks per SM than are resident together: a block of a second wave would start its solves late)
+    unsigned tail_grid = (unsigned)h->sm_count * (unsigned)std::min(h->mm_tail_warps, h->mm_tail_blocks_per_sm);
     if (tasks / 32 / TAIL_BLOCK > tail_grid) tail_grid = tasks / 32 / TAIL_BLOCK;
     prof_mark(h, 2, st);
     mm_tail_kernel<false><<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, h->mm_cutlim, D.t, D.P, D.S0, D.n_ex, D.n_t,

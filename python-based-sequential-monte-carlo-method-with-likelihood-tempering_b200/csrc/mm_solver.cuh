@@ -213,6 +213,18 @@ MM_HD bool setup(Solve& s, double t0, double t_bound) {
 // One attempted step (rk.py:111-176).  obs: the experiment's observation grid (ObsPair).  PRED: write
 // P_model = S0 - S(t_eval) to pred[i] instead of accumulating residuals.  n_acc / n_rej count accepted /
 // rejected attempts.
+#define MM_UNLIKELY(c) __builtin_expect(!!(c), 0)
+// c ? a : b as a single select that the optimiser cannot re-distribute
+MM_HD double select_late(bool c, double a, double b) {
+#if defined(__CUDA_ARCH__)
+    double o;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(o) : "d"(a), "d"(b), "r"((int)c));
+    return o;
+#else
+    return c ? a : b;
+#endif
+}
+
 template <bool PRED>
 MM_HD int attempt(Solve& s, const ObsPair* obs, double* pred, unsigned& n_acc, unsigned& n_rej) {
     const double t = s.t, y = s.y;
@@ -301,6 +313,239 @@ MM_HD int attempt(Solve& s, const ObsPair* obs, double* pred, unsigned& n_acc, u
     s.rejected = 1;
     n_rej++;
     return RUNNING;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// solve_lat: a whole solve, spelt for LATENCY (mm_tail_kernel: one long solve per lane, 1e3 .. 1e5 strictly
+// sequential attempts and nothing to overlap them with; attempt() above is spelt for instruction count, which is
+// what bounds mm_bulk_kernel).  Steps that need anything beyond the plain RK45 attempt - a step that reaches an
+// observation time or t_bound, a step at the min_step floor, a step that exploded - are handed to attempt() as
+// they are.  All others (all but ~50 of the 1e3 .. 1e5 attempts of a stiff solve) run in a loop whose dependent chain
+// is as short as the arithmetic allows.  Same tableau, same controller; what differs from attempt() is where roundings
+// fall, never by more than the ulp or two that already separate either spelling from scipy's operation order:
+//   * a stage's rate is K = q + q*p with q = (hn*S)*r0 and p = e + e^2 the reciprocal correction.  The NEXT stage's
+//     denominator Km + y + sum a_j K_j is formed as fma(a*q, p, fma(a, q, Km + partial sum)): it needs only p from
+//     the chain - not K, not the stage argument, no separate Km + S - so a stage costs MUFU.RCP64H -> e -> p -> den
+//     (~40 cycles) instead of ... -> K -> S -> den (~56);
+//   * the error estimate takes k7 the same way (one FMA after p7);
+//   * err^(-1/5): the FP32 seed is 2^(-0.2*(lg2|ee| - lg2 scale)), so the logarithm starts as soon as ee is known
+//     and 1/scale (needed only by the FP64 correction) is off the chain;
+//   * the new step size is fma((0.9*ha*r)*e, poly(e), 0.9*ha*r) instead of ha*(0.9*root), chosen against the
+//     clamped alternatives by ONE select;
+//   * accept / reject is a select on the state, and the loop is rotated: t + h, the first stage and the test
+//     "is the next step a plain one" are issued at the end of the previous step, so the only branch of a step is
+//     the loop's own and its predicate is ready before it is needed.
+// A solve takes the same accepted / rejected steps as with attempt() alone (tests/test_host_twin.py compares both
+// spellings with the C twin of scipy's RK45 solve by solve, the stiffest solves of the bench's prior cloud included);
+// residual sums differ by rounding only.  Which spelling performs a step is a function of the solve's own state, so
+// results are reproducible and independent of sharding, grid and scheduling.
+struct QP {
+    double q, p;
+};
+// q = (cS)/den to 20 bits and the correction p = e + e^2, e = 1 - den*r0:  cS/den = q + q*p  (error < 1 ulp)
+MM_HD QP rate_qp(double cS, double den) {
+    const double r0 = rcp_seed(den);
+    QP o;
+    o.q = cS * r0;
+    const double e = fma(-den, r0, 1.0);
+    o.p = fma(e, e, e);
+    return o;
+}
+// lg2 of |x| truncated to FP32 by moving bits (the sign leaves through the shift); garbage outside the FP32 range
+MM_HD float lg2_trunc(double x) {
+#if defined(__CUDA_ARCH__)
+    const unsigned hi = (unsigned)__double2hiint(x);
+    const float xf = __uint_as_float(((hi - 0x38000000u) << 3) | ((unsigned)__double2loint(x) >> 29));
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(xf));
+    return l;
+#else
+    return log2f((float)fabs(x));
+#endif
+}
+MM_HD double ex2_widen(float a) {
+#if defined(__CUDA_ARCH__)
+    float rf;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(a));
+    const unsigned rb = __float_as_uint(rf);
+    return __hiloint2double((int)((rb >> 3) + 0x38000000u), (int)(rb << 29));
+#else
+    return (double)exp2f(a);
+#endif
+}
+
+MM_HD double mul_early(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    double o;
+    asm("mul.f64 %0, %1, %2;" : "=d"(o) : "d"(a), "d"(b));
+    return o;
+#else
+    return a * b;
+#endif
+}
+
+// The coefficients of solve_lat's loop, in the order the loop names them.  HOIST: the caller has copied them to
+// `tab` (any memory that is not constant memory, e.g. shared) with lat_coef_fill and the loop keeps them in registers:
+// read through a volatile pointer so that the loads can neither be folded back into constant operands nor be repeated
+// inside the loop.
+constexpr int LAT_NCOEF = 36;
+MM_HD void lat_coef_fill(double* tab) {
+    tab[0] = A21;
+    tab[1] = A31;
+    tab[2] = A32;
+    tab[3] = A41;
+    tab[4] = A42;
+    tab[5] = A43;
+    tab[6] = A51;
+    tab[7] = A52;
+    tab[8] = A53;
+    tab[9] = A54;
+    tab[10] = A61;
+    tab[11] = A62;
+    tab[12] = A63;
+    tab[13] = A64;
+    tab[14] = A65;
+    tab[15] = B1;
+    tab[16] = B3;
+    tab[17] = B4;
+    tab[18] = B5;
+    tab[19] = B6;
+    tab[20] = E1;
+    tab[21] = E3;
+    tab[22] = E4;
+    tab[23] = E5;
+    tab[24] = E6;
+    tab[25] = E7;
+    tab[26] = RTOL;
+    tab[27] = ATOL;
+    tab[28] = SAFETY;
+    tab[29] = MAX_FACTOR;
+    tab[30] = MIN_FACTOR;
+    tab[31] = ERR_LO;
+    tab[32] = ERR_ONE;
+    tab[33] = ERR_HI;
+    tab[34] = C_ROOT_A;
+    tab[35] = C_ROOT_B;
+}
+template <bool HOIST>
+MM_HD double coef(double c, const double* tab, int i) {
+    return HOIST ? *reinterpret_cast<const volatile double*>(tab + i) : c;
+}
+
+// Returns DONE, FAILED or CUT.  s: a solve after setup() (or after any number of attempts).
+// HOIST: keep the 36 coefficients of the loop in registers (the tail kernel has registers to spare) instead of
+// re-reading them from constant memory in every step; tab: see lat_coef_fill.
+template <bool HOIST>
+MM_HD int solve_lat(Solve& s, const ObsPair* obs, unsigned& n_acc, unsigned& n_rej, const double* tab = nullptr) {
+    const double Km = s.Km, nVmax = s.nVmax, t_bound = s.t_bound;
+    // a step size at or above this is above attempt()'s min_step test at every t of the solve
+    const double h_floor = fma(fmax(fabs(s.t), fabs(t_bound)), C_MINSTEP_REL, C_MINSTEP_ABS);
+    // loop coefficients (registers if HOIST)
+    const double c_a21 = coef<HOIST>(A21, tab, 0), c_a31 = coef<HOIST>(A31, tab, 1), c_a32 = coef<HOIST>(A32, tab, 2), c_a41 = coef<HOIST>(A41, tab, 3);
+    const double c_a42 = coef<HOIST>(A42, tab, 4), c_a43 = coef<HOIST>(A43, tab, 5), c_a51 = coef<HOIST>(A51, tab, 6), c_a52 = coef<HOIST>(A52, tab, 7);
+    const double c_a53 = coef<HOIST>(A53, tab, 8), c_a54 = coef<HOIST>(A54, tab, 9), c_a61 = coef<HOIST>(A61, tab, 10), c_a62 = coef<HOIST>(A62, tab, 11);
+    const double c_a63 = coef<HOIST>(A63, tab, 12), c_a64 = coef<HOIST>(A64, tab, 13), c_a65 = coef<HOIST>(A65, tab, 14), c_b1 = coef<HOIST>(B1, tab, 15);
+    const double c_b3 = coef<HOIST>(B3, tab, 16), c_b4 = coef<HOIST>(B4, tab, 17), c_b5 = coef<HOIST>(B5, tab, 18), c_b6 = coef<HOIST>(B6, tab, 19);
+    const double c_e1 = coef<HOIST>(E1, tab, 20), c_e3 = coef<HOIST>(E3, tab, 21), c_e4 = coef<HOIST>(E4, tab, 22), c_e5 = coef<HOIST>(E5, tab, 23);
+    const double c_e6 = coef<HOIST>(E6, tab, 24), c_e7 = coef<HOIST>(E7, tab, 25), c_rtol = coef<HOIST>(RTOL, tab, 26), c_atol = coef<HOIST>(ATOL, tab, 27);
+    const double c_safety = coef<HOIST>(SAFETY, tab, 28), c_max_factor = coef<HOIST>(MAX_FACTOR, tab, 29), c_min_factor = coef<HOIST>(MIN_FACTOR, tab, 30), c_err_lo = coef<HOIST>(ERR_LO, tab, 31);
+    const double c_err_one = coef<HOIST>(ERR_ONE, tab, 32), c_err_hi = coef<HOIST>(ERR_HI, tab, 33), c_c_root_a = coef<HOIST>(C_ROOT_A, tab, 34), c_c_root_b = coef<HOIST>(C_ROOT_B, tab, 35);
+    for (;;) {
+        // plain step: not tiny, and t + h_abs lies before the next observation time and before t_bound
+        // (then attempt() would neither clip the step, nor finish, nor emit an observation)
+        const double lim = fmin(s.t_next, t_bound);
+        double t = s.t, y = s.y, f = s.f, ha = s.h_abs;
+        double tn = t + ha;
+        if (tn < lim) {
+            bool rej = s.rejected != 0, plain;
+            unsigned nt = 0, na = 0;
+            double h = tn - t;
+            double K1 = h * f, hn = h * nVmax;
+            double d2 = fma(c_a21, K1, Km + y), cS2 = hn * fma(c_a21, K1, y);
+            do {
+                // ---- stages 2..6, y_new, f(y_new)
+                // the candidates of the next step size that need no root (opaque products: the optimiser would fold
+                // them into one late multiplication by a conditionally loaded constant)
+                const double ha_in = ha;
+                const double haS = mul_early(h, c_safety), ha_max = mul_early(h, c_max_factor), ha_min = mul_early(h, c_min_factor);
+                const QP s2 = rate_qp(cS2, d2);
+                const double y3 = fma(c_a31, K1, y);
+                const double d3 = fma(c_a32 * s2.q, s2.p, fma(c_a32, s2.q, Km + y3));
+                const double K2 = fma(s2.q, s2.p, s2.q);
+                const QP s3 = rate_qp(hn * fma(c_a32, K2, y3), d3);
+                const double y4 = fma(c_a42, K2, fma(c_a41, K1, y));
+                const double d4 = fma(c_a43 * s3.q, s3.p, fma(c_a43, s3.q, Km + y4));
+                const double K3 = fma(s3.q, s3.p, s3.q);
+                const QP s4 = rate_qp(hn * fma(c_a43, K3, y4), d4);
+                const double y5 = fma(c_a53, K3, fma(c_a52, K2, fma(c_a51, K1, y)));
+                const double d5 = fma(c_a54 * s4.q, s4.p, fma(c_a54, s4.q, Km + y5));
+                const double K4 = fma(s4.q, s4.p, s4.q);
+                const QP s5 = rate_qp(hn * fma(c_a54, K4, y5), d5);
+                const double y6 = fma(c_a64, K4, fma(c_a63, K3, fma(c_a62, K2, fma(c_a61, K1, y))));
+                const double d6 = fma(c_a65 * s5.q, s5.p, fma(c_a65, s5.q, Km + y6));
+                const double K5 = fma(s5.q, s5.p, s5.q);
+                const QP s6 = rate_qp(hn * fma(c_a65, K5, y6), d6);
+                const double yn = fma(c_b5, K5, fma(c_b4, K4, fma(c_b3, K3, fma(c_b1, K1, y))));
+                const double d7 = fma(c_b6 * s6.q, s6.p, fma(c_b6, s6.q, Km + yn));
+                const double K6 = fma(s6.q, s6.p, s6.q);
+                const double y_new = fma(c_b6, K6, yn);
+                const QP s7 = rate_qp(nVmax * y_new, d7);
+                const double k7 = fma(s7.q, s7.p, s7.q);
+                // ---- error estimate sum_j E_j K_j, the last term (c_e7*h)*k7 entering through p7
+                const double pe = fma(c_e6, K6, fma(c_e5, K5, fma(c_e4, K4, fma(c_e3, K3, c_e1 * K1))));
+                const double E7h = c_e7 * h;
+                const double ee = fma(E7h * s7.q, s7.p, fma(E7h, s7.q, pe));
+                const double scale = fma(fmax(fabs(y), fabs(y_new)), c_rtol, c_atol);
+                const float l_scale = lg2_trunc(scale);
+                const double err = fabs(ee * rcp64(scale));
+                // ---- h * 0.9 * err^(-1/5)
+                const double r = ex2_widen(fmaf(lg2_trunc(ee), -0.2f, 0.2f * l_scale));
+                const double r2 = r * r, r4 = r2 * r2;
+                const double e = fma(-err * r, r4, 1.0);
+                const double har = haS * r;
+                const double h_fr = fma(har * e, fma(c_c_root_a, e, c_c_root_b), har);
+                // ---- rk.py:156-170.  accepted: min(c_max_factor, .), no growth right after a rejection;
+                //      rejected: max(c_min_factor, .), a NaN error estimate included (Python's max()).
+                // bad: the step exploded out of the range in which the FP32 seed means anything, or it was entered with
+                // a step size at attempt()'s min_step floor (tested here, in the shadow of the stages, not between two
+                // steps); nothing of such a step is kept and attempt() repeats it.
+                const bool bad = !(scale < 1e30) || ha_in < h_floor;
+                const bool acc = err < 1.0 && !bad;
+                const bool use_max = acc && err <= c_err_lo;
+                const bool use_one = acc && rej && err < c_err_one;
+                const bool use_min = !acc && !(err < c_err_hi);
+                double h_other = use_max ? ha_max : ha_min;
+                h_other = use_one ? h : h_other;
+                h_other = bad ? ha_in : h_other;
+                // ONE select after the root (the optimiser otherwise spreads the conditions over a cascade of five)
+                ha = select_late(use_max || use_one || use_min || bad, h_other, h_fr);
+                nt += bad ? 0u : 1u;
+                na += acc ? 1u : 0u;
+                rej = bad ? rej : !acc;
+                t = acc ? tn : t;
+                y = acc ? y_new : y;
+                f = acc ? k7 : f;
+                // ---- head of the next step
+                tn = t + ha;
+                h = tn - t;
+                K1 = h * f;
+                hn = h * nVmax;
+                d2 = fma(c_a21, K1, Km + y);
+                cS2 = hn * fma(c_a21, K1, y);
+                plain = tn < lim && !bad;
+            } while (plain);
+            s.t = t;
+            s.y = y;
+            s.f = f;
+            s.h_abs = ha;
+            s.rejected = rej ? 1 : 0;
+            n_acc += na;
+            n_rej += nt - na;
+        }
+        const int st = attempt<false>(s, obs, nullptr, n_acc, n_rej);
+        if (st != RUNNING) return st;
+    }
 }
 
 }  // namespace mmsolve

@@ -11,8 +11,10 @@
 
 #include "../python-based-sequential-monte-carlo-method-with-likelihood-tempering_b200/csrc/mm_solver.cuh"
 
-extern "C" void twin_loglik(const double* theta, int64_t n, const double* t, const double* P, const double* S0,
-                            int n_ex, int n_t, double* lk, int64_t* counters, int32_t* steps) {
+// form 0: attempt() alone (the bulk kernel), form 1: solve_lat() (the tail kernel)
+template <int FORM>
+static void loglik_form(const double* theta, int64_t n, const double* t, const double* P, const double* S0,
+                        int n_ex, int n_t, double* lk, int64_t* counters, int32_t* steps) {
     using namespace mmsolve;
     std::vector<ObsPair> obs((size_t)n_ex * n_t);
     for (int e = 0; e < n_ex; ++e)
@@ -35,7 +37,11 @@ extern "C" void twin_loglik(const double* theta, int64_t n, const double* t, con
             s.cut_lim = INFINITY;
             unsigned n_acc = 0, n_rej = 0;
             int st = setup(s, t[e * n_t], t[e * n_t + n_t - 1]) ? RUNNING : FAILED;
-            while (st == RUNNING) st = attempt<false>(s, obs.data() + (size_t)e * n_t, nullptr, n_acc, n_rej);
+            if (FORM) {
+                if (st == RUNNING) st = solve_lat<false>(s, obs.data() + (size_t)e * n_t, n_acc, n_rej);
+            } else {
+                while (st == RUNNING) st = attempt<false>(s, obs.data() + (size_t)e * n_t, nullptr, n_acc, n_rej);
+            }
             if (counters) {
                 counters[0] += 2 + 6 * (int64_t)(n_acc + n_rej);
                 counters[1] += n_acc;
@@ -47,6 +53,15 @@ extern "C" void twin_loglik(const double* theta, int64_t n, const double* t, con
         }
         lk[p] = total;
     }
+}
+
+extern "C" void twin_loglik(const double* theta, int64_t n, const double* t, const double* P, const double* S0,
+                            int n_ex, int n_t, double* lk, int64_t* counters, int32_t* steps) {
+    loglik_form<0>(theta, n, t, P, S0, n_ex, n_t, lk, counters, steps);
+}
+extern "C" void twin_loglik_lat(const double* theta, int64_t n, const double* t, const double* P, const double* S0,
+                                int n_ex, int n_t, double* lk, int64_t* counters, int32_t* steps) {
+    loglik_form<1>(theta, n, t, P, S0, n_ex, n_t, lk, counters, steps);
 }
 
 extern "C" void twin_predict(const double* theta, int64_t n, const double* t, const double* S0, int n_ex,

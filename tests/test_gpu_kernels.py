@@ -85,7 +85,10 @@ def test_mm_progress_prior_cloud_of_65536_particles_matches_c_oracle(mm_abi, gol
 
 @pytest.mark.parametrize("budget", [1, 7, 64, 100000])
 def test_mm_progress_is_independent_of_the_deferral_budget(mm_abi, golden, budget):
-    """Bulk kernel + tail kernel: wherever a solve is finished, the result is the same bits."""
+    """Bulk kernel + tail kernel: wherever a solve is finished it takes the same steps and gives the same result up
+    to rounding.  (Round 1 had the same bits: both kernels called mmsolve::attempt.  The tail kernel now runs the
+    latency spelling mmsolve::solve_lat, whose roundings fall elsewhere; with a fixed budget - the product never
+    changes it during a run - which kernel finishes a solve is a function of the solve alone.)"""
     P = np.concatenate([golden["sweeps_in"][0], golden["sweeps_in"][33]])
     mm_abi.ck(mm_abi.lib.smcb_set_param(mm_abi.h, 1, 256.0))
     base = mm_abi.loglik(1, P)
@@ -94,7 +97,8 @@ def test_mm_progress_is_independent_of_the_deferral_budget(mm_abi, golden, budge
     got = mm_abi.loglik(1, P)
     st = mm_abi.stats()
     mm_abi.ck(mm_abi.lib.smcb_set_param(mm_abi.h, 1, 256.0))
-    assert np.array_equal(got, base)
+    assert _rel(got, base).max() < 1e-11, _rel(got, base).max()
+    assert st[1] == st0[1] and st[2] == st0[2]            # the same accepted / rejected steps wherever a solve runs
     if budget < 100000:
         assert st[11] > st0[11] and st[13] > 0          # more solves deferred, the tail kernel had work
     else:
@@ -106,15 +110,15 @@ def test_mm_progress_bounded_sweep_is_exact_or_certainly_below(mm_abi, golden):
     certainly below the threshold it was given (prior cloud, thresholds spread around the likelihoods)."""
     P = golden["sweeps_in"][0]
     n = len(P)
-    full = mm_abi.loglik(1, P)
     rs = np.random.RandomState(4)
-    thr = full + rs.normal(0, 300, n)
+    thr = mm_abi.loglik(1, P) + rs.normal(0, 300, n)
     thr[:50] = -np.inf
     thr[50:60] = np.inf
     th = mm_abi.t(np.asarray(P).T)
     lk, tt = mm_abi.zeros(n), mm_abi.t(thr)
     for budget in (256.0, 3.0):
         mm_abi.ck(mm_abi.lib.smcb_set_param(mm_abi.h, 1, budget))
+        full = mm_abi.loglik(1, P)              # the unbounded evaluation at the same budget: same kernels, same bits
         mm_abi.ck(mm_abi.lib.smcb_loglik_bounded(mm_abi.h, 1, th.data_ptr(), n, n, 3, None, tt.data_ptr(), lk.data_ptr(), None))
         got = lk.cpu().numpy()
         cut = np.isneginf(got) & ~np.isneginf(full)

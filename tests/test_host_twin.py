@@ -22,12 +22,12 @@ def twin(tmp_path_factory):
                     os.path.join(HERE, "host_twin.cpp")], check=True)
     lib = C.CDLL(so)
 
-    def loglik(theta, t, P, S0):
+    def loglik(theta, t, P, S0, fn="twin_loglik"):
         th = np.ascontiguousarray(theta, dtype=np.float64)
         t, P, S0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, P, S0))
         n, (n_ex, n_t) = len(th), t.shape
         lk, cnt, steps = np.empty(n), np.zeros(4, dtype=np.int64), np.zeros((n, n_ex), dtype=np.int32)
-        lib.twin_loglik(C.c_void_p(th.ctypes.data), C.c_int64(n), C.c_void_p(t.ctypes.data), C.c_void_p(P.ctypes.data),
+        getattr(lib, fn)(C.c_void_p(th.ctypes.data), C.c_int64(n), C.c_void_p(t.ctypes.data), C.c_void_p(P.ctypes.data),
                         C.c_void_p(S0.ctypes.data), C.c_int(n_ex), C.c_int(n_t), C.c_void_p(lk.ctypes.data),
                         C.c_void_p(cnt.ctypes.data), C.c_void_p(steps.ctypes.data))
         return lk, cnt, steps
@@ -70,6 +70,27 @@ def test_device_arithmetic_takes_scipys_steps(twin, golden):
     assert cnt[1] == info["accepted"] and cnt[2] == info["rejected"] and cnt[0] == info["nfev"]
     assert steps.max() > 2000                                  # the cloud does contain stiff solves
     assert np.max(np.abs(got - want) / np.abs(want)) < 1e-9
+
+
+def test_tail_kernel_spelling_takes_scipys_steps(twin, golden):
+    """mmsolve::solve_lat (the tail kernel: plain steps in the latency spelling, steps that touch an observation time
+    through attempt()) against the C twin of scipy's RK45 and against attempt() alone: the same accepted / rejected
+    steps solve by solve - the two stiffest solves of the bench's 2^20-particle prior cloud included (83 133 and
+    62 913 attempts) - and log-likelihoods that differ by rounding only."""
+    from oracle import cmm
+    loglik, _ = twin
+    d = (golden["data_t"], golden["data_P"], golden["data_S0"])
+    th = np.concatenate([np.random.RandomState(1).uniform(0, 10, (1 << 14, 3)),
+                         [[9.88869508e+00, 4.28267643e-04, 4.53281765e+00], [7.30644405, 4.35543917e-04, 1.0]],
+                         golden["sweeps_in"][33][:64]])
+    std, cnt0, steps0 = loglik(th, *d)
+    got, cnt, steps = loglik(th, *d, fn="twin_loglik_lat")
+    want, info = cmm.loglik_progress(th, *d, want_steps=True)
+    assert np.array_equal(steps, info["steps"]) and np.array_equal(steps, steps0)
+    assert cnt[1] == info["accepted"] and cnt[2] == info["rejected"] and cnt[3] == 0
+    assert steps.max() == 83133
+    assert np.max(np.abs(got - want) / np.abs(want)) < 1e-7         # 6e-9 observed on the stiffest solves; bar 1e-5
+    assert np.max(np.abs(got - std) / np.abs(std)) < 1e-11          # the two spellings: rounding only
 
 
 def test_device_predictions_match_reference(twin, golden):
