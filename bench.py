@@ -561,9 +561,11 @@ def main():
             "attempted_steps_in_tail_per_step": tail_attempts / args.steps,
             "first_sweep_group_ms": round(lik_ms[0], 3) if lik_ms else None,
             "longest_solve": {"attempts": longest >> 32, "cycles_per_attempt": longest & 0xffffffff},
-            "floor_cycles_per_attempt": 674,
-            "note": "a solve is a strictly serial chain of ~270 dependent FP64/MUFU instructions per attempted step; "
-                    "674 cycles is the same step measured alone on the GPU (profiles/ubench_fp64_r01.log)"}
+            "floor_cycles_per_attempt": 456,
+            "note": "a solve is a strictly serial chain: per attempted step 6 x (MUFU.RCP64H + 3 dependent FMAs) and the "
+                    "step-size controller (2 MUFU + ~12 dependent FP64 operations), ~430 cycles of dependent latency; 456 "
+                    "cycles is the same step measured with the solve alone on the GPU (profiles/ncu_full_r02_tail.md); "
+                    "round 1's spelling took 707"}
     if args.workload == "mm_rate":
         # SURVEY 8(d) form A: 6 flop per (particle, observation) with the reciprocal counted as one; the kernel
         # spends 5.5 FMA-pipe lane slots + 0.5 MUFU per term, so lane-slot occupancy is the tighter figure

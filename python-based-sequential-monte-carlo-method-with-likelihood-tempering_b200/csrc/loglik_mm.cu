@@ -22,8 +22,9 @@
 //   mm_finalize_kernel  one thread per evaluated particle: sums the experiments in the reference's order
 //                       (Micmem_likelihood.py:70-73), applies the particle-level bound, or lists the particle's
 //                       deferred solves for the tail kernel.
-//   mm_tail_kernel      one deferred solve per thread, restarted without a budget.  These few thousand solves
-//                       are latency-bound (~0.37 us per step); the kernel lasts as long as its longest solve.
+//   mm_tail_kernel      one deferred solve per lane, restarted without a budget, stepped by mmsolve::solve_lat (the
+//                       latency spelling of the step).  These few thousand solves are latency-bound (~0.23 us per
+//                       step); the kernel lasts as long as its longest solve.
 //   mm_collect_kernel   ordered sum for the particles the tail kernel finished.
 //
 // Early rejection (MH sweeps).  Residuals only accumulate, so with c0 = -n_t/2 log(2 pi sigma^2)
@@ -417,28 +418,40 @@ mm_finalize_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, con
 }
 
 // ------------------------------------------------------------------------------ tail
-// One lane per deferred solve, restarted from t0 without a budget.  These are the 1e3 .. 1e5-step solves: each
-// is a strictly serial chain (~680 cycles per attempted step), so the kernel lasts as long as its longest
-// solve.  Everything here serves that chain:
-//   * one-warp blocks, mm_tail_warps (4) per SM = one per scheduler;
-//   * entry k of the (roughly heaviest-first) list goes to lane k / n_blocks of block k % n_blocks, so the
-//     longest solves each lead a different warp and soon have it to themselves;
-//   * NO warp collective, __syncthreads or value-returning atomic after the data is staged: with any of those
-//     downstream the compiler fences every divergent region of the step with BSSY/BSYNC reconvergence
-//     barriers, which cost ~140 cycles per step (811 against 674 cycles, profiles/ubench_fp64_r01.log).  Work
-//     counters therefore go to a per-thread record that mm_collect_kernel adds up.
-constexpr int TAIL_REC = 4;   // per-thread record: set-ups | failed << 32, accepted, rejected, max attempts << 32 | its cycles/attempt
+// One lane per deferred solve, restarted from t0 without a budget.  These are the 1e3 .. 1e5-step solves: each is a
+// strictly serial chain (~460 cycles per attempted step for a lane that has its scheduler to itself), so the kernel
+// lasts as long as its longest solve.  Everything here serves that chain:
+//   * the steps are taken by mmsolve::solve_lat (mm_solver.cuh): plain steps in a loop that is ONE basic block
+//     (accept / reject are selects), steps that touch an observation time through attempt();
+//   * lanes of a warp are free, warps are not: inside that loop the lanes of a warp run in lockstep whatever their
+//     solves do, while a second warp on the same scheduler competes for the FP64 pipe and the issue slot (the lone
+//     chain runs at 456 cycles per step, next to the three other warps of a 16-block-per-SM launch at 554).  So the
+//     list is dealt to as FEW warps as possible: entry k of the (roughly heaviest-first) list goes to lane
+//     (k / nb) % 32 of block k % nb, where nb = one block per scheduler (4 per SM) as long as that gives a lane at
+//     most TAIL_DEPTH entries to work through, and more blocks only beyond that.  The heaviest solves thus each lead
+//     a different warp; the entries a lane takes after its first are the light end of the list.  Blocks >= nb exit.
+//   * a lane that leaves the loop (every solve does, once per observation time) waits at the loop's exit for the
+//     other lanes of its warp, so a warp advances in rounds of [plain steps until every lane needs attempt()] +
+//     [one attempt()].  The stiffest lane of a warp sets the length of nearly every round (the number of steps
+//     between two observation times grows with Vmax/Km), so the warp's time is that lane's own.
+//   * NO warp collective, __syncthreads or value-returning atomic after the data is staged (work counters go to a
+//     per-thread record that mm_collect_kernel adds up).
+constexpr int TAIL_REC = 4;     // per-thread record: set-ups | failed << 32, accepted, rejected, max attempts << 32 | its cycles/attempt
+constexpr unsigned TAIL_DEPTH = 4;
 
-template <bool LOOP>
 __global__ void __launch_bounds__(TAIL_BLOCK)
 mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const double* __restrict__ cutlim,
                const double* __restrict__ g_t, const double* __restrict__ g_P, const double* __restrict__ g_S0,
                int n_ex, int n_t, double* __restrict__ ssr, const unsigned* __restrict__ solve_list,
-               const unsigned* __restrict__ ctl, unsigned long long* __restrict__ rec, unsigned first) {
+               const unsigned* __restrict__ ctl, unsigned long long* __restrict__ rec, unsigned min_blocks) {
     const unsigned count = ctl[1];
     const unsigned tid = blockIdx.x * TAIL_BLOCK + threadIdx.x;
     unsigned long long* my = rec + (size_t)tid * TAIL_REC;
-    if (first + blockIdx.x >= count) {   // no entry for any lane of this block
+    // blocks in use (see above)
+    unsigned nb = (count + TAIL_BLOCK * TAIL_DEPTH - 1) / (TAIL_BLOCK * TAIL_DEPTH);
+    nb = max(nb, min(min_blocks, count));
+    nb = min(nb, gridDim.x);
+    if (blockIdx.x >= nb) {
         my[0] = 0;
         return;
     }
@@ -452,10 +465,8 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
     const SharedData D = stage_data(smem, g_t, g_P, g_S0, n_ex, n_t);
 
     unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, mx = 0, mx_cyc = 0;
-    // LOOP = false: one entry per thread (the normal case; the launch has more threads than there are entries
-    // in any sweep seen so far).  LOOP = true: grid-stride over whatever lies beyond that launch's reach.
-    const unsigned stride = LOOP ? gridDim.x * TAIL_BLOCK : ~0u;
-    for (unsigned idx = first + threadIdx.x * gridDim.x + blockIdx.x; idx < count; idx += stride) {
+    const unsigned stride = nb * TAIL_BLOCK;
+    for (unsigned idx = threadIdx.x * nb + blockIdx.x; idx < count; idx += stride) {
         const unsigned g = solve_list[idx];
         const unsigned e = g / n, p = g - e * n;
         Solve s;
@@ -481,7 +492,6 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
             mx = att;
             mx_cyc = (unsigned)((c1 - c0) / (att ? att : 1u));
         }
-        if (!LOOP) break;
     }
     my[0] = (unsigned long long)n_set | ((unsigned long long)n_fail << 32);
     my[1] = n_acc;
@@ -948,15 +958,14 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     const bool bounded = lkmin != nullptr;
     if (smem > 48 * 1024 && !h->mm_smem_set) {
         CUDA_TRY(h, cudaFuncSetAttribute(mm_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(h, cudaFuncSetAttribute(mm_tail_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(h, cudaFuncSetAttribute(mm_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(h, cudaFuncSetAttribute(mm_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->mm_smem_set = true;
     }
     if (h->mm_bulk_blocks_per_sm == 0) {
         int a = 0;
         CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, mm_bulk_kernel, BULK_BLOCK, smem));
         h->mm_bulk_blocks_per_sm = a > 0 ? a : 1;
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, mm_tail_kernel<false>, TAIL_BLOCK, smem));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, mm_tail_kernel, TAIL_BLOCK, smem));
         h->mm_tail_blocks_per_sm = a > 0 ? a : 1;
     }
     {
@@ -1002,29 +1011,22 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
                                                                    h->ssr, lk, h->mm_cutlim, solve_list, part_list,
                                                                    h->mm_ctl, h->stats);
     LAUNCH_CHECK(h);
-    // One-warp blocks, one deferred solve per thread.  The grid holds the larger of mm_tail_warps (32) blocks per
-    // SM and one lane per 32 solves of the sweep (a prior cloud defers 0.5% of its solves: 33 618 of 6.3e6 at 2^20
-    // particles); blocks without entries exit at once, so the long chains end up alone on their schedulers.
-    // (never more blocks per SM than are resident together: a block of a second wave would start its solves late)
-    unsigned tail_grid = (unsigned)h->sm_count * (unsigned)std::min(h->mm_tail_warps, h->mm_tail_blocks_per_sm);
-    if (tasks / 32 / TAIL_BLOCK > tail_grid) tail_grid = tasks / 32 / TAIL_BLOCK;
+    // One-warp blocks.  The grid is what is resident together (at most mm_tail_warps blocks per SM); the kernel itself
+    // decides from the length of the list how many of those blocks it uses (one per scheduler unless the list is very
+    // long) and walks the list with a stride, so one launch covers any list.
+    const unsigned tail_grid = (unsigned)h->sm_count * (unsigned)std::min(h->mm_tail_warps, h->mm_tail_blocks_per_sm);
     prof_mark(h, 2, st);
-    mm_tail_kernel<false><<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, h->mm_cutlim, D.t, D.P, D.S0, D.n_ex, D.n_t,
-                                                              h->ssr, solve_list, h->mm_ctl, h->mm_tailrec, 0u);
-    LAUNCH_CHECK(h);
-    // entries beyond the reach of that launch (none in practice): grid-stride, records in the second half
-    mm_tail_kernel<true><<<(unsigned)h->sm_count * 4, TAIL_BLOCK, smem, st>>>(
-        theta, ld, un, h->mm_cutlim, D.t, D.P, D.S0, D.n_ex, D.n_t, h->ssr, solve_list, h->mm_ctl,
-        h->mm_tailrec + (size_t)tail_grid * TAIL_BLOCK * TAIL_REC, tail_grid * TAIL_BLOCK);
+    mm_tail_kernel<<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, h->mm_cutlim, D.t, D.P, D.S0, D.n_ex, D.n_t, h->ssr,
+                                                       solve_list, h->mm_ctl, h->mm_tailrec, 4u * (unsigned)h->sm_count);
     LAUNCH_CHECK(h);
     prof_mark(h, 3, st);
     const unsigned cgrid = (unsigned)h->sm_count * 8;
     if (bounded)
         mm_collect_kernel<true><<<cgrid, 256, 0, st>>>(theta, ld, un, D.n_ex, D.n_t, h->ssr, lk, part_list, h->mm_ctl,
-                                                      h->stats, h->mm_tailrec, (tail_grid + (unsigned)h->sm_count * 4) * TAIL_BLOCK);
+                                                      h->stats, h->mm_tailrec, tail_grid * TAIL_BLOCK);
     else
         mm_collect_kernel<false><<<cgrid, 256, 0, st>>>(theta, ld, un, D.n_ex, D.n_t, h->ssr, lk, part_list, h->mm_ctl,
-                                                       h->stats, h->mm_tailrec, (tail_grid + (unsigned)h->sm_count * 4) * TAIL_BLOCK);
+                                                       h->stats, h->mm_tailrec, tail_grid * TAIL_BLOCK);
     LAUNCH_CHECK(h);
     if (h->prof_on) h->prof_sweeps++;
     return SMCB_OK;
