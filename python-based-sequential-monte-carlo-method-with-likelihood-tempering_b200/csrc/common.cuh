@@ -77,7 +77,7 @@ struct smcb_handle {
     double prof_acc[2] = {0.0, 0.0}; // bulk / tail milliseconds of the sweeps already drained
     long long prof_acc_sweeps = 0;
     int mm_integrator = 0;           // SMCB_MM_RK45_SCIPY (reference parity) | SMCB_MM_EXACT (closed form)
-    int mm_budget = 256;             // attempted steps after which the bulk kernel defers a solve
+    int mm_budget = 512;             // attempted steps after which the bulk kernel defers a solve
     int mm_tail_warps = 32;          // one-warp blocks per SM of the tail kernel
     int mm_chunk = 32;               // particles per queue item of the bulk kernel
     int mm_patience = 3;             // ... for this many attempted steps (unless the whole warp is free)

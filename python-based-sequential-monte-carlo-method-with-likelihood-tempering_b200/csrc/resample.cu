@@ -576,11 +576,14 @@ __device__ __forceinline__ unsigned long long ld_volatile(const unsigned long lo
     return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
 
-// MINB: blocks per SM the register allocation aims at.  6 (42 registers, a few spilled words) beats the unconstrained
-// 58 registers / 4 blocks once the launch has several waves of tiles - the kernel is bound by memory latency, and
-// more resident warps hide more of it: 208 -> 187 us at 2^23 particles, 124 -> 116 at 2^22 - and loses at 2^20, where
-// all 512 tiles are resident at once either way (45 -> 48 us; profiles/resample_variants.py).
-template <int MINB>
+// MINB: blocks per SM the register allocation aims at; U: output slots a thread expands at a time.  The kernel issues
+// ~340 instructions per particle (the FP64 exponential and division of the weight, nine 128-bit crossing counts per
+// thread, an 11-step search per output slot) and waits on memory in between: ncu at 2^23 particles shows the issue
+// slot 43 % busy and 5 long-scoreboard stalls per issue.  More resident warps hide more of that latency (6 blocks per SM
+// at 42 registers beat the unconstrained 58 registers / 4 blocks above 2^21 particles), two independent searches and
+// eight row loads in flight per thread a little more: <5, 2> measures 46 / 110 / 184 us at 2^20 / 2^22 / 2^23 particles
+// against 56 / 118 / 192 for <6, 1>; <4, 4> 46 / 114 / 196; <3, 8> 67 / 153 / 265 (profiles/resample_variants_r02.log).
+template <int MINB, int U>
 __global__ void __launch_bounds__(SB, MINB)
 resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ w_in, int64_t n, uint64_t N,
                       unsigned long long carry_q, int first_shard, int64_t m_out,
@@ -718,19 +721,44 @@ resample_fused_kernel(const double* __restrict__ lk, const double* __restrict__ 
     if (tile == (unsigned)(n_tiles - 1) && threadIdx.x == 0) filled_out[0] = tile_off + tile_total;
 
     // ---- 4. cooperative expansion + gather of this tile's output slots ----
+    // U slots per thread at a time: their searches are independent chains of shared-memory loads and their row loads
+    // are all in flight together (U = 1: one search, then one particle's rows, per trip).
     const int64_t tile_first = (int64_t)tile * TILE;
-    for (long long sl = threadIdx.x; sl < tile_total; sl += SB) {
-        const long long slot = tile_off + sl;
-        if (slot >= m_out) break;              // copies beyond the slots this shard fills are dropped (monotone in sl)
-        int lo = 0, hi = TILE - 1;             // smallest i with s_end[i] > sl
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (s_end[mid] > (unsigned)sl) hi = mid;
-            else lo = mid + 1;
+    long long lim = tile_total;                                  // slots of this tile that this shard fills
+    if (m_out - tile_off < lim) lim = m_out - tile_off;          // (copies beyond m_out are dropped)
+    for (long long sl0 = threadIdx.x; sl0 < lim; sl0 += (long long)U * SB) {
+        int pos[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) pos[u] = 0;
+        // number of end offsets <= sl  =  smallest i with s_end[i] > sl   (TILE is a power of two: fixed trip count)
+#pragma unroll
+        for (int step = TILE / 2; step > 0; step >>= 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned sl = (unsigned)(sl0 + (long long)u * SB);
+                if (s_end[pos[u] + step - 1] <= sl) pos[u] += step;
+            }
         }
-        const int64_t a = tile_first + lo;
-        anc_out[slot] = (int32_t)a;
-        for (int k = 0; k < rows; ++k) dst[(int64_t)k * ld_dst + slot] = src[(int64_t)k * ld_src + a];
+        int64_t a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            a[u] = tile_first + (pos[u] < TILE - 1 ? pos[u] : TILE - 1);
+            if (sl0 + (long long)u * SB < lim) anc_out[tile_off + sl0 + (long long)u * SB] = (int32_t)a[u];
+        }
+        for (int k0 = 0; k0 < rows; k0 += 4) {
+            double v[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k0 + k < rows && sl0 + (long long)u * SB < lim) v[u][k] = src[(int64_t)(k0 + k) * ld_src + a[u]];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k0 + k < rows && sl0 + (long long)u * SB < lim)
+                        dst[(int64_t)(k0 + k) * ld_dst + tile_off + sl0 + (long long)u * SB] = v[u][k];
+        }
     }
 }
 
@@ -873,8 +901,7 @@ extern "C" int smcb_resample_fused(smcb_handle* h, const double* lk_dev, const d
     const uint64_t u0q = (uint64_t)llrint(u0 * TWO62);
 #define RS_ARGS lk_dev, w_dev, n, (uint64_t)n_total, carry_q, id_offset == 0 ? 1 : 0, m_out, max_dev, gm, sum_w_dev, Nd, \
                 1.0 / Nd, u0q, agg, inc, counter, src_dev, ld_src, rows, dst_dev, ld_dst, anc, counts_dev, filled_dev
-    if (nt > 2 * (int64_t)h->sm_count * 4) resample_fused_kernel<6><<<(unsigned)nt, SB, 0, st>>>(RS_ARGS);
-    else resample_fused_kernel<1><<<(unsigned)nt, SB, 0, st>>>(RS_ARGS);
+    resample_fused_kernel<5, 2><<<(unsigned)nt, SB, 0, st>>>(RS_ARGS);
 #undef RS_ARGS
     LAUNCH_CHECK(h);
     if (m_out > 0) {

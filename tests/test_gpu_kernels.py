@@ -96,7 +96,7 @@ def test_mm_progress_is_independent_of_the_deferral_budget(mm_abi, golden, budge
     mm_abi.ck(mm_abi.lib.smcb_set_param(mm_abi.h, 1, float(budget)))
     got = mm_abi.loglik(1, P)
     st = mm_abi.stats()
-    mm_abi.ck(mm_abi.lib.smcb_set_param(mm_abi.h, 1, 256.0))
+    mm_abi.ck(mm_abi.lib.smcb_set_param(mm_abi.h, 1, 512.0))          # the default
     assert _rel(got, base).max() < 1e-11, _rel(got, base).max()
     assert st[1] == st0[1] and st[2] == st0[2]            # the same accepted / rejected steps wherever a solve runs
     if budget < 100000:
@@ -127,7 +127,7 @@ def test_mm_progress_bounded_sweep_is_exact_or_certainly_below(mm_abi, golden):
         assert not cut[:50].any() and cut[50:60].all()
         assert cut.sum() >= 10
         assert mm_abi.stats()[8] == np.isneginf(got).sum()
-    mm_abi.ck(mm_abi.lib.smcb_set_param(mm_abi.h, 1, 256.0))
+    mm_abi.ck(mm_abi.lib.smcb_set_param(mm_abi.h, 1, 512.0))          # the default
 
 
 def test_mh_threshold_is_conservative(abi):
