@@ -107,7 +107,7 @@ extern "C" int smcb_create(int device, smcb_handle** out) {
 extern "C" int smcb_destroy(smcb_handle* h) {
     if (!h) return SMCB_OK;
     cudaSetDevice(h->device);
-    dev_free(&h->ssr); dev_free(&h->partial); dev_free(&h->stats); dev_free(&h->mm_ctl); dev_free(&h->mm_defer); dev_free(&h->mm_cutlim);
+    dev_free(&h->ssr); dev_free(&h->partial); dev_free(&h->stats); dev_free(&h->mm_ctl); dev_free(&h->mm_defer); dev_free(&h->mm_cutlim); dev_free(&h->mm_park);
     dev_free(&h->mm_bins); dev_free(&h->mm_perm); dev_free(&h->mm_hist); dev_free(&h->mm_tailrec);
     dev_free(&h->fused_plist); dev_free(&h->fused_owner);
     if (h->fused_ctl) cudaFree(h->fused_ctl);
@@ -160,6 +160,12 @@ extern "C" int smcb_reserve(smcb_handle* h, int64_t n_max, int d_max) {
     if ((rc = dev_alloc(h, &h->mark, (size_t)n_max))) return rc;
     if ((rc = dev_alloc(h, &h->mm_defer, (size_t)(rows + 1) * n_max))) return rc;   // deferred solves + particles
     if ((rc = dev_alloc(h, &h->mm_cutlim, (size_t)n_max))) return rc;
+    {   // parked solves: 48 bytes each; a sweep that hands over more than this restarts the excess from t0
+        size_t cap = (size_t)(h->mmp.n_ex > 0 ? h->mmp.n_ex : 1) * n_max / 16;   // (progress-curve model only)
+        if (cap < 65536) cap = 65536;
+        if ((rc = dev_alloc(h, &h->mm_park, cap * 6))) return rc;
+        h->mm_park_cap = (unsigned)cap;
+    }
     if ((rc = dev_alloc(h, &h->mm_bins, (size_t)n_max))) return rc;
     if ((rc = dev_alloc(h, &h->mm_perm, (size_t)n_max))) return rc;
     {   // tail kernel: one 4-word record per thread of max(32 warps per SM, one lane per 32 solves) + the loop launch

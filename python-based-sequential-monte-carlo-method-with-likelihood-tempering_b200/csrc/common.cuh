@@ -58,9 +58,11 @@ struct smcb_handle {
     double* partial = nullptr;       // block partials for reductions
     int64_t partial_len = 0;
     unsigned long long* stats = nullptr;  // SMCB_N_STATS counters (device)
-    unsigned* mm_ctl = nullptr;      // [0] bulk queue head, [1] deferred solves, [2] deferred particles, [3] particles to evaluate, [4] tail queue head
+    unsigned* mm_ctl = nullptr;      // [0] bulk queue head, [1] deferred solves, [2] deferred particles, [3] particles to evaluate, [4] parked solves
     unsigned* mm_defer = nullptr;    // [ssr_rows*n_max] deferred solves, then [n_max] their particles
     double* mm_cutlim = nullptr;     // [n_max] per-particle residual limit of a bounded sweep
+    double* mm_park = nullptr;       // [mm_park_cap][6] state of the solves the bulk kernel handed over (the tail kernel resumes them)
+    unsigned mm_park_cap = 0;
     unsigned short* mm_bins = nullptr;   // [n_max] cost bin of every particle (0xFFFF = no solve needed)
     unsigned* mm_perm = nullptr;     // [n_max] particles to evaluate, heaviest cost bin first
     unsigned long long* mm_tailrec = nullptr;   // [lanes of the tail launches][4] per-thread work record of the tail kernel (sized in smcb_reserve)

@@ -56,7 +56,36 @@ using mmsolve::Solve;
 
 constexpr int BULK_BLOCK = 128;
 constexpr int TAIL_BLOCK = 32;
-constexpr double DEFERRED = -1.0;   // marker in the per-solve result array (a residual sum is >= 0)
+// markers in the per-solve result array (a residual sum is >= 0): DEFERRED = restart the solve in the tail kernel,
+// PARKED - slot = resume it from park[slot]
+constexpr double DEFERRED = -1.0;
+constexpr double PARKED = -2.0;
+constexpr int PARK_WORDS = 6;       // t, y, f, h_abs, ssr, (i_eval | rejected << 16 | attempts << 32)
+
+__device__ __forceinline__ void park_store(double* rec, const Solve& s, unsigned n_att) {
+    rec[0] = s.t;
+    rec[1] = s.y;
+    rec[2] = s.f;
+    rec[3] = s.h_abs;
+    rec[4] = s.ssr;
+    rec[5] = __longlong_as_double((long long)((unsigned long long)(unsigned)s.i_eval | ((unsigned long long)(s.rejected != 0) << 16) |
+                                              ((unsigned long long)n_att << 32)));
+}
+// restores what park_store saved (the fields setup() would have set); returns the attempts already made
+__device__ __forceinline__ unsigned park_load(const double* rec, Solve& s, const mmsolve::ObsPair* obs, double t_bound) {
+    s.t = rec[0];
+    s.y = rec[1];
+    s.f = rec[2];
+    s.h_abs = rec[3];
+    s.ssr = rec[4];
+    const unsigned long long w = (unsigned long long)__double_as_longlong(rec[5]);
+    s.i_eval = (int)(w & 0xffffu);
+    s.rejected = (int)((w >> 16) & 1u);
+    s.t_bound = t_bound;
+    // next observation time: the pair before it carries it (obs[i].t_next = t[i+1]); nothing emitted yet: t[0] = t0 <= t
+    s.t_next = (s.i_eval > 0) ? obs[s.i_eval - 1].t_next : s.t;
+    return (unsigned)(w >> 32);
+}
 
 // Shared-memory image of the data set: obs[n_ex][n_t] (P_obs[i], t[i+1]) pairs, then per experiment
 // (S0, t[0], t[n_t-1]).
@@ -240,7 +269,8 @@ __global__ void __launch_bounds__(BULK_BLOCK)
 mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const unsigned* __restrict__ perm,
                const double* __restrict__ g_t, const double* __restrict__ g_P,
                const double* __restrict__ g_S0, int n_ex, int n_t, unsigned budget, int refill_min,
-               int patience, unsigned chunk, double* __restrict__ ssr_out, unsigned* __restrict__ queue, unsigned long long* __restrict__ stats) {
+               int patience, unsigned chunk, double* __restrict__ ssr_out, unsigned* __restrict__ queue,
+               double* __restrict__ park, unsigned park_cap, unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SharedData D = stage_data(smem, g_t, g_P, g_S0, n_ex, n_t);
 
@@ -337,11 +367,19 @@ mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const u
                 mx = max(mx, n_att);
                 have = false;
             } else if (n_att >= budget) {
-                ssr_out[task] = DEFERRED;
+                // over budget: the solve is parked (its state goes to `park`, the result array names the slot) and the
+                // tail kernel takes it from here; without a free slot it is marked DEFERRED and restarted there
+                const unsigned slot = atomicAdd(queue + 4, 1u);
+                if (slot < park_cap) {
+                    park_store(park + (size_t)slot * PARK_WORDS, s, n_att);
+                    ssr_out[task] = PARKED - (double)slot;
+                } else {
+                    ssr_out[task] = DEFERRED;
+                    n_set--;            // redone from scratch by the tail kernel: its attempts here are dropped again
+                    n_acc = acc0;
+                    n_rej = rej0;
+                }
                 n_def++;
-                n_set--;
-                n_acc = acc0;
-                n_rej = rej0;
                 have = false;
             }
         }
@@ -454,7 +492,8 @@ __global__ void __launch_bounds__(TAIL_BLOCK)
 mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const double* __restrict__ cutlim,
                const double* __restrict__ g_t, const double* __restrict__ g_P, const double* __restrict__ g_S0,
                int n_ex, int n_t, double* __restrict__ ssr, const unsigned* __restrict__ solve_list,
-               const unsigned* __restrict__ ctl, unsigned long long* __restrict__ rec, unsigned min_blocks) {
+               const unsigned* __restrict__ ctl, const double* __restrict__ park, unsigned long long* __restrict__ rec,
+               unsigned min_blocks) {
     const unsigned count = ctl[1];
     const unsigned tid = blockIdx.x * TAIL_BLOCK + threadIdx.x;
     unsigned long long* my = rec + (size_t)tid * TAIL_REC;
@@ -487,9 +526,16 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
         s.cut_lim = cutlim[p];
         const mmsolve::ObsPair* obs = D.obs + (size_t)e * n_t;
         const unsigned att0 = n_acc + n_rej;
-        n_set++;
+        const double mark = ssr[g];
         const long long c0 = clock64();
-        int st = mmsolve::setup(s, D.t0[e], D.tb[e]) ? mmsolve::RUNNING : mmsolve::FAILED;
+        int st = mmsolve::RUNNING;
+        unsigned att_parked = 0;
+        if (mark <= PARKED) {     // handed over with its state: resume
+            att_parked = park_load(park + (size_t)(unsigned)(PARKED - mark) * PARK_WORDS, s, obs, D.tb[e]);
+        } else {                  // restart
+            n_set++;
+            if (!mmsolve::setup(s, D.t0[e], D.tb[e])) st = mmsolve::FAILED;
+        }
 #if SMCB_TAIL_LATENCY_FORM
         if (st == mmsolve::RUNNING) st = mmsolve::solve_lat<SMCB_TAIL_HOIST != 0>(s, obs, n_acc, n_rej, s_coef);
 #else
@@ -499,12 +545,12 @@ mm_tail_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const d
         ssr[g] = (st == mmsolve::DONE) ? s.ssr : INFINITY;
         if (st == mmsolve::FAILED) n_fail++;
         const unsigned att = n_acc + n_rej - att0;
-        if (att > mx) {
-            mx = att;
-            mx_cyc = (unsigned)((c1 - c0) / (att ? att : 1u));
+        if (att + att_parked > mx) {
+            mx = att + att_parked;                                   // attempts of the whole solve,
+            mx_cyc = (unsigned)((c1 - c0) / (att ? att : 1u));      // cycles per attempt of the part taken here
         }
     }
-    my[0] = (unsigned long long)n_set | ((unsigned long long)n_fail << 32);
+    my[0] = (unsigned long long)n_set | ((unsigned long long)n_fail << 32) | (1ull << 63);   // bit 63: record in use
     my[1] = n_acc;
     my[2] = n_rej;
     my[3] = ((unsigned long long)mx << 32) | mx_cyc;
@@ -529,7 +575,7 @@ mm_collect_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, int 
             fev += (long long)(2ull * n_set + 6ull * (r[1] + r[2]));
             acc += (long long)r[1];
             rej += (long long)r[2];
-            fail += (long long)(r[0] >> 32);
+            fail += (long long)((r[0] >> 32) & 0x7fffffffull);
             mx = max(mx, r[3] >> 32);
             if ((r[3] >> 32) > 1024) mxrec = max(mxrec, r[3]);
         }
@@ -1025,7 +1071,8 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     const unsigned budget = (unsigned)h->mm_budget;
     prof_mark(h, 0, st);
     mm_bulk_kernel<<<grid, BULK_BLOCK, smem, st>>>(theta, ld, un, h->mm_perm, D.t, D.P, D.S0, D.n_ex, D.n_t, budget,
-                                                  h->mm_refill_min, h->mm_patience, (unsigned)h->mm_chunk, h->ssr, queue, h->stats);
+                                                  h->mm_refill_min, h->mm_patience, (unsigned)h->mm_chunk, h->ssr, queue,
+                                                  h->mm_park, h->mm_park_cap, h->stats);
     LAUNCH_CHECK(h);
     prof_mark(h, 1, st);
     unsigned* solve_list = h->mm_defer;                              // [n_ex * n_max]
@@ -1045,7 +1092,8 @@ int launch_loglik_mm_progress(smcb_handle* h, const double* theta, int64_t ld, i
     const unsigned tail_grid = (unsigned)h->sm_count * (unsigned)std::min(h->mm_tail_warps, h->mm_tail_blocks_per_sm);
     prof_mark(h, 2, st);
     mm_tail_kernel<<<tail_grid, TAIL_BLOCK, smem, st>>>(theta, ld, un, h->mm_cutlim, D.t, D.P, D.S0, D.n_ex, D.n_t, h->ssr,
-                                                       solve_list, h->mm_ctl, h->mm_tailrec, 4u * (unsigned)h->sm_count);
+                                                       solve_list, h->mm_ctl, h->mm_park, h->mm_tailrec,
+                                                       4u * (unsigned)h->sm_count);
     LAUNCH_CHECK(h);
     prof_mark(h, 3, st);
     const unsigned cgrid = (unsigned)h->sm_count * 8;
