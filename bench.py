@@ -538,7 +538,7 @@ def main():
         att_all = float(d_stats[1] + d_stats[2])
         flops_bulk = flops_all * (1.0 - tail_attempts / max(att_all, 1.0))
         roofline.update(
-            kernel=f"mm_bulk_kernel (one launch per likelihood sweep; all solves of up to {cfg.mm_budget} attempted steps)",
+            kernel=f"mm_bulk_kernel (one launch per likelihood sweep; all solves of up to {eng.mm_budget} attempted steps)",
             achieved=flops_bulk / (bulk_ms * 1e-3) / 1e12, launches=n_sw, avg_launch_ms=bulk_ms / max(n_sw, 1),
             share_of_step=bulk_ms / ms_total if ms_total else None,
             sweep_group_ms_last_step=[round(x, 3) for x in lik_ms[-per:]],

@@ -20,7 +20,7 @@ g = np.load(os.path.join(ROOT, "tests", "golden", "mm_reference_run.npz"))
 lik = pkg.MMProgress(g["data_t"], g["data_P"], g["data_S0"])
 prior = pkg.UniformBox([0, 0, 0], [10, 10, 10])
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-budget = int(sys.argv[2]) if len(sys.argv) > 2 else 256       # attempted steps before a solve moves to the tail kernel
+budget = int(sys.argv[2]) if len(sys.argv) > 2 else 0         # attempted steps before a solve moves to the tail kernel
 eng = pkg.Engine(lik, prior, pkg.Settings(n_particle=n, mm_budget=budget))
 eng.sample_prior()
 eng.run()                     # warm

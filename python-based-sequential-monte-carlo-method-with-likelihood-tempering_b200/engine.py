@@ -491,7 +491,9 @@ class Engine:
             self.h, self._own_handle = self.comm.handle, False      # the communicator lives in this handle
         else:
             self.h, self._own_handle = _acquire_handle(self.lib, self.device.index), True
-        for key, val in ((_lib.PARAM_MM_BUDGET, self.cfg.mm_budget), (_lib.PARAM_MM_REFILL_MIN, self.cfg.mm_refill_min),
+        n_local = self.cfg.n_particle // max(self.comm.world, 1)
+        self.mm_budget = self.cfg.mm_budget or self._auto_mm_budget(n_local, likelihood)
+        for key, val in ((_lib.PARAM_MM_BUDGET, self.mm_budget), (_lib.PARAM_MM_REFILL_MIN, self.cfg.mm_refill_min),
                          (_lib.PARAM_MM_PATIENCE, self.cfg.mm_patience), (_lib.PARAM_MM_CHUNK, self.cfg.mm_chunk),
                          (_lib.PARAM_MM_TAIL_WARPS, self.cfg.mm_tail_warps)):
             self._ck(self.lib.smcb_set_param(self.h, key, float(val)))
@@ -684,6 +686,25 @@ class Engine:
         return self.lk
 
     # -------------------------------------------------------------------------------- K2
+    def _auto_mm_budget(self, n_local, likelihood):
+        """Deferral budget of the progress-curve likelihood by size.  While the solves of a sweep outnumber the lanes of
+        the bulk kernel (6 blocks of 128 threads per SM) many times over, a long budget keeps solves of a few hundred
+        steps out of the tail kernel (2^20 particles: 512 -> 72.0 ms per run, 256 -> 73.7, 128 -> 74.5); when every solve
+        has a lane to itself the bulk kernel lasts as long as its slowest solve is allowed to and the tail kernel takes
+        the same steps faster (N = 1000: 16 -> 13.9 ms, 64 -> 14.7, 512 -> 17.3; N = 2^18: 128 -> 44.3, 512 -> 48.0;
+        profiles/budget_by_size_r02.log).  Results do not depend on it beyond rounding."""
+        t = getattr(likelihood, "t", None)
+        n_ex = int(t.shape[0]) if isinstance(t, np.ndarray) and t.ndim == 2 else 1
+        lanes = torch.cuda.get_device_properties(self.device).multi_processor_count * 6 * 128
+        waves = n_local * n_ex / lanes
+        if waves <= 1.0:
+            return 32
+        if waves <= 20.0:
+            return 128
+        if waves <= 40.0:
+            return 256
+        return 512
+
     def temper(self, gamma_old):
         """Next gamma by the configured rule.  Returns dict(gamma_new, gm, ess, sum_w, max_lk, n_backoff)
         and leaves max in scal[0], the accepted sum_w in scal[1]."""

@@ -33,7 +33,9 @@ class Settings:
     cand_batch: int = 8                 # tempering candidates evaluated per pass (<=16)
     early_exit: bool = True             # stop sweeps when moved fraction exceeds r_threshold (reference)
     early_reject: bool = True           # let the likelihood stop once the MH rejection is certain (exact decisions)
-    mm_budget: int = 512                # MM_PROGRESS: attempted RK steps before a solve moves to the tail kernel
+    mm_budget: int = 0                  # MM_PROGRESS: attempted RK steps before a solve moves to the tail kernel;
+                                        # 0 = by size (Engine.mm_budget: 512 when the solves outnumber the lanes of the
+                                        # bulk kernel many times over, down to 32 when every solve has a lane to itself)
     mm_refill_min: int = 8              # MM_PROGRESS: free lanes a warp waits for before setting up new solves ...
     mm_tail_warps: int = 32             # MM_PROGRESS: one-warp blocks per SM of the tail kernel
     mm_chunk: int = 32                  # MM_PROGRESS: particles per work-queue item of the bulk kernel
