@@ -17,12 +17,12 @@
 //                       one experiment from a global queue (all experiments of the heavy bins come first), so
 //                       its lanes take nearly the same steps; a lane whose solve ends waits until a few lanes
 //                       of its warp have been free for a few steps (or none is busy) and they are then set up
-//                       together.  A solve that needs more than `budget` attempts is marked DEFERRED, which
+//                       together.  A solve that needs more than `budget` attempts is parked (its state saved), which
 //                       bounds the drain time of the kernel.
 //   mm_finalize_kernel  one thread per evaluated particle: sums the experiments in the reference's order
 //                       (Micmem_likelihood.py:70-73), applies the particle-level bound, or lists the particle's
 //                       deferred solves for the tail kernel.
-//   mm_tail_kernel      one deferred solve per lane, restarted without a budget, stepped by mmsolve::solve_lat (the
+//   mm_tail_kernel      one deferred solve per lane, resumed where the bulk kernel left it, stepped by mmsolve::solve_lat (the
 //                       latency spelling of the step).  These few thousand solves are latency-bound (~0.23 us per
 //                       step); the kernel lasts as long as its longest solve.
 //   mm_collect_kernel   ordered sum for the particles the tail kernel finished.
@@ -291,7 +291,7 @@ mm_bulk_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, const u
     bool have = false;
     unsigned task = 0, n_att = 0;
     const mmsolve::ObsPair* obs = D.obs;
-    // work counters: a deferred solve is redone from scratch by the tail kernel, so its attempts here are
+    // work counters: a solve that cannot be parked is redone from scratch by the tail kernel, so its attempts here are
     // dropped again (acc0/rej0 = counters when the solve started) and every step is counted once
     unsigned n_set = 0, n_acc = 0, n_rej = 0, n_fail = 0, n_def = 0, mx = 0, acc0 = 0, rej0 = 0;
 
@@ -467,7 +467,7 @@ mm_finalize_kernel(const double* __restrict__ theta, int64_t ld, unsigned n, con
 }
 
 // ------------------------------------------------------------------------------ tail
-// One lane per deferred solve, restarted from t0 without a budget.  These are the 1e3 .. 1e5-step solves: each is a
+// One lane per deferred solve, resumed from its parked state and run to its end.  These are the 1e3 .. 1e5-step solves: each is a
 // strictly serial chain (~460 cycles per attempted step for a lane that has its scheduler to itself), so the kernel
 // lasts as long as its longest solve.  Everything here serves that chain:
 //   * the steps are taken by mmsolve::solve_lat (mm_solver.cuh): plain steps in a loop that is ONE basic block
