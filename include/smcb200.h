@@ -125,7 +125,10 @@ int smcb_loglik_bounded(smcb_handle* h, int model, const double* theta_dev, int6
 /* Registers the callback smcb_loglik(..., SMCB_MODEL_USER, ...) dispatches to (NULL removes it). */
 int smcb_set_user_likelihood(smcb_handle* h, smcb_user_loglik_fn fn, void* user_data);
 /* Tunables.  SMCB_PARAM_MM_BUDGET: attempted RK steps after which the bulk MM_PROGRESS kernel hands a
- * solve to the tail kernel (default 256; results do not depend on it). */
+ * solve, with its state, to the tail kernel (default 512; the Python engine picks 32 .. 512 by particle count).
+ * A solve takes the same accepted / rejected steps whichever kernel finishes it; the two kernels spell the
+ * arithmetic of a step differently (throughput / latency, csrc/mm_solver.cuh), so results depend on the budget
+ * by rounding only (<= 1e-11 relative on a log-likelihood). */
 #define SMCB_PARAM_MM_BUDGET 1
 /* SMCB_PARAM_MM_REFILL_MIN: free lanes a warp of the bulk kernel waits for before it sets up new solves
  * (default 8, 1..32; results do not depend on it). */
@@ -139,7 +142,8 @@ int smcb_set_user_likelihood(smcb_handle* h, smcb_user_loglik_fn fn, void* user_
 #define SMCB_PARAM_PROFILE 4
 /* SMCB_PARAM_MM_CHUNK: particles per work-queue item of the bulk kernel (default 32). */
 #define SMCB_PARAM_MM_CHUNK 5
-/* SMCB_PARAM_MM_TAIL_WARPS: one-warp blocks per SM of the tail kernel (default 32, 1..32). */
+/* SMCB_PARAM_MM_TAIL_WARPS: upper limit of the one-warp blocks per SM the tail kernel may use (default 32,
+ * 1..32; it uses one per scheduler unless a sweep leaves it more than 128 solves per warp). */
 #define SMCB_PARAM_MM_TAIL_WARPS 6
 /* SMCB_PARAM_MM_INTEGRATOR: how MM_PROGRESS integrates dS/dt = -Vmax S/(Km+S) (EX/lik:14-33).
  *   SMCB_MM_RK45_SCIPY (default): scipy's adaptive RK45 taken step for step - the reference's likelihood (parity mode);
