@@ -468,6 +468,24 @@ atexit.register(release_pool)
 
 
 # ------------------------------------------------------------------------------------ engine
+def auto_mm_budget(n_local, n_ex, sm_count):
+    """Attempted RK steps after which the bulk MM_PROGRESS kernel hands a solve to the tail kernel, by size
+    (`Settings.mm_budget = 0`).  While the solves of a sweep outnumber the lanes of the bulk kernel (6 blocks of 128
+    threads per SM) many times over, a long budget keeps solves of a few hundred steps out of the tail kernel (2^20
+    particles: 512 -> 72.0 ms per run, 256 -> 73.7, 128 -> 74.5); when every solve has a lane to itself the bulk kernel
+    lasts as long as its slowest solve is allowed to and the tail kernel takes the same steps faster (N = 1000: 16 ->
+    13.9 ms, 64 -> 14.7, 512 -> 17.3; N = 2^18: 128 -> 44.3, 512 -> 48.0; profiles/budget_by_size_r02.log).  Results do
+    not depend on it beyond rounding."""
+    waves = n_local * n_ex / float(sm_count * 6 * 128)
+    if waves <= 1.0:
+        return 32
+    if waves <= 20.0:
+        return 128
+    if waves <= 40.0:
+        return 256
+    return 512
+
+
 class Engine:
     def __init__(self, likelihood, prior, settings=None, device=None, comm=None):
         if not torch.cuda.is_available():
@@ -687,23 +705,10 @@ class Engine:
 
     # -------------------------------------------------------------------------------- K2
     def _auto_mm_budget(self, n_local, likelihood):
-        """Deferral budget of the progress-curve likelihood by size.  While the solves of a sweep outnumber the lanes of
-        the bulk kernel (6 blocks of 128 threads per SM) many times over, a long budget keeps solves of a few hundred
-        steps out of the tail kernel (2^20 particles: 512 -> 72.0 ms per run, 256 -> 73.7, 128 -> 74.5); when every solve
-        has a lane to itself the bulk kernel lasts as long as its slowest solve is allowed to and the tail kernel takes
-        the same steps faster (N = 1000: 16 -> 13.9 ms, 64 -> 14.7, 512 -> 17.3; N = 2^18: 128 -> 44.3, 512 -> 48.0;
-        profiles/budget_by_size_r02.log).  Results do not depend on it beyond rounding."""
+        """Deferral budget of the progress-curve likelihood by size (auto_mm_budget)."""
         t = getattr(likelihood, "t", None)
         n_ex = int(t.shape[0]) if isinstance(t, np.ndarray) and t.ndim == 2 else 1
-        lanes = torch.cuda.get_device_properties(self.device).multi_processor_count * 6 * 128
-        waves = n_local * n_ex / lanes
-        if waves <= 1.0:
-            return 32
-        if waves <= 20.0:
-            return 128
-        if waves <= 40.0:
-            return 256
-        return 512
+        return auto_mm_budget(n_local, n_ex, torch.cuda.get_device_properties(self.device).multi_processor_count)
 
     def temper(self, gamma_old):
         """Next gamma by the configured rule.  Returns dict(gamma_new, gm, ess, sum_w, max_lk, n_backoff)
