@@ -46,7 +46,8 @@ namespace {
 
 using mmsolve::Solve;
 
-// The tail kernel takes its steps in the latency spelling of mm_solver.cuh (attempt_lat); 0 = the bulk kernel's spelling
+// Build switches kept for A/B runs: the tail kernel takes its steps in the latency spelling of mm_solver.cuh (solve_lat;
+// 0 = the bulk kernel's attempt() alone) with the loop's coefficients in registers (0 = wherever the compiler puts them)
 #ifndef SMCB_TAIL_LATENCY_FORM
 #define SMCB_TAIL_LATENCY_FORM 1
 #endif

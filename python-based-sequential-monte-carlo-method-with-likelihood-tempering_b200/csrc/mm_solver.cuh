@@ -213,7 +213,6 @@ MM_HD bool setup(Solve& s, double t0, double t_bound) {
 // One attempted step (rk.py:111-176).  obs: the experiment's observation grid (ObsPair).  PRED: write
 // P_model = S0 - S(t_eval) to pred[i] instead of accumulating residuals.  n_acc / n_rej count accepted /
 // rejected attempts.
-#define MM_UNLIKELY(c) __builtin_expect(!!(c), 0)
 // c ? a : b as a single select that the optimiser cannot re-distribute
 MM_HD double select_late(bool c, double a, double b) {
 #if defined(__CUDA_ARCH__)
