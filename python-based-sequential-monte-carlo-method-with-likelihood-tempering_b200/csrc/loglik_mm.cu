@@ -58,35 +58,12 @@ using mmsolve::Solve;
 constexpr int BULK_BLOCK = 128;
 constexpr int TAIL_BLOCK = 32;
 // markers in the per-solve result array (a residual sum is >= 0): DEFERRED = restart the solve in the tail kernel,
-// PARKED - slot = resume it from park[slot]
+// PARKED - slot = resume it from park[slot] (mmsolve::park_store / park_load, mm_solver.cuh)
 constexpr double DEFERRED = -1.0;
 constexpr double PARKED = -2.0;
-constexpr int PARK_WORDS = 6;       // t, y, f, h_abs, ssr, (i_eval | rejected << 16 | attempts << 32)
-
-__device__ __forceinline__ void park_store(double* rec, const Solve& s, unsigned n_att) {
-    rec[0] = s.t;
-    rec[1] = s.y;
-    rec[2] = s.f;
-    rec[3] = s.h_abs;
-    rec[4] = s.ssr;
-    rec[5] = __longlong_as_double((long long)((unsigned long long)(unsigned)s.i_eval | ((unsigned long long)(s.rejected != 0) << 16) |
-                                              ((unsigned long long)n_att << 32)));
-}
-// restores what park_store saved (the fields setup() would have set); returns the attempts already made
-__device__ __forceinline__ unsigned park_load(const double* rec, Solve& s, const mmsolve::ObsPair* obs, double t_bound) {
-    s.t = rec[0];
-    s.y = rec[1];
-    s.f = rec[2];
-    s.h_abs = rec[3];
-    s.ssr = rec[4];
-    const unsigned long long w = (unsigned long long)__double_as_longlong(rec[5]);
-    s.i_eval = (int)(w & 0xffffu);
-    s.rejected = (int)((w >> 16) & 1u);
-    s.t_bound = t_bound;
-    // next observation time: the pair before it carries it (obs[i].t_next = t[i+1]); nothing emitted yet: t[0] = t0 <= t
-    s.t_next = (s.i_eval > 0) ? obs[s.i_eval - 1].t_next : s.t;
-    return (unsigned)(w >> 32);
-}
+constexpr int PARK_WORDS = mmsolve::PARK_WORDS;
+using mmsolve::park_load;
+using mmsolve::park_store;
 
 // Shared-memory image of the data set: obs[n_ex][n_t] (P_obs[i], t[i+1]) pairs, then per experiment
 // (S0, t[0], t[n_t-1]).

@@ -547,4 +547,44 @@ MM_HD int solve_lat(Solve& s, const ObsPair* obs, unsigned& n_acc, unsigned& n_r
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Handing a running solve from one kernel to another (mm_bulk_kernel parks a solve that exceeds its budget,
+// mm_tail_kernel resumes it): everything setup() and the attempts so far have put into the Solve, in six words.
+constexpr int PARK_WORDS = 6;       // t, y, f, h_abs, ssr, (i_eval | rejected << 16 | attempts << 32)
+
+MM_HD double bits_to_double(uint64_t w) {
+    union { double d; uint64_t u; } v;
+    v.u = w;
+    return v.d;
+}
+MM_HD uint64_t double_to_bits(double d) {
+    union { double d; uint64_t u; } v;
+    v.d = d;
+    return v.u;
+}
+MM_HD void park_store(double* rec, const Solve& s, unsigned n_att) {
+    rec[0] = s.t;
+    rec[1] = s.y;
+    rec[2] = s.f;
+    rec[3] = s.h_abs;
+    rec[4] = s.ssr;
+    rec[5] = bits_to_double((uint64_t)(unsigned)s.i_eval | ((uint64_t)(s.rejected != 0) << 16) | ((uint64_t)n_att << 32));
+}
+// restores what park_store saved (nVmax, Km, S0, cut_lim are the caller's, as before setup()); returns the attempts
+// already made
+MM_HD unsigned park_load(const double* rec, Solve& s, const ObsPair* obs, double t_bound) {
+    s.t = rec[0];
+    s.y = rec[1];
+    s.f = rec[2];
+    s.h_abs = rec[3];
+    s.ssr = rec[4];
+    const uint64_t w = double_to_bits(rec[5]);
+    s.i_eval = (int)(w & 0xffffu);
+    s.rejected = (int)((w >> 16) & 1u);
+    s.t_bound = t_bound;
+    // next observation time: the pair before it carries it (obs[i].t_next = t[i+1]); nothing emitted yet: t[0] = t0 <= t
+    s.t_next = (s.i_eval > 0) ? obs[s.i_eval - 1].t_next : s.t;
+    return (unsigned)(w >> 32);
+}
+
 }  // namespace mmsolve

@@ -64,6 +64,56 @@ extern "C" void twin_loglik_lat(const double* theta, int64_t n, const double* t,
     loglik_form<1>(theta, n, t, P, S0, n_ex, n_t, lk, counters, steps);
 }
 
+// The hand-over between the two kernels: attempt() for at most `budget` attempts (mm_bulk_kernel), then the solve is
+// parked (park_store), restored into a fresh Solve (park_load) and finished by solve_lat (mm_tail_kernel).
+extern "C" void twin_loglik_parked(const double* theta, int64_t n, const double* t, const double* P, const double* S0,
+                                   int n_ex, int n_t, int budget, double* lk, int64_t* counters, int32_t* steps) {
+    using namespace mmsolve;
+    std::vector<ObsPair> obs((size_t)n_ex * n_t);
+    for (int e = 0; e < n_ex; ++e)
+        for (int i = 0; i < n_t; ++i) fill_pairs(obs.data() + (size_t)e * n_t, t + e * n_t, P + e * n_t, n_t, i);
+    for (int64_t p = 0; p < n; ++p) {
+        const double Vmax = theta[3 * p], Km = theta[3 * p + 1], sigma = theta[3 * p + 2];
+        const double s2 = sigma * sigma;
+        const double c0 = -0.5 * n_t * log(2 * M_PI * s2);
+        const double inv_den = 1.0 / (2 * s2);
+        double total = 0.0;
+        for (int e = 0; e < n_ex; ++e) {
+            const ObsPair* ob = obs.data() + (size_t)e * n_t;
+            Solve s;
+            s.nVmax = -Vmax;
+            s.Km = Km;
+            s.S0 = S0[e];
+            s.cut_lim = INFINITY;
+            unsigned n_acc = 0, n_rej = 0, n_att = 0;
+            int st = setup(s, t[e * n_t], t[e * n_t + n_t - 1]) ? RUNNING : FAILED;
+            while (st == RUNNING && n_att < (unsigned)budget) {
+                st = attempt<false>(s, ob, nullptr, n_acc, n_rej);
+                ++n_att;
+            }
+            if (st == RUNNING) {
+                double rec[PARK_WORDS];
+                park_store(rec, s, n_att);
+                Solve r;
+                r.nVmax = -Vmax;
+                r.Km = Km;
+                r.S0 = S0[e];
+                r.cut_lim = INFINITY;
+                const unsigned parked = park_load(rec, r, ob, t[e * n_t + n_t - 1]);
+                if (parked != n_att) counters[3] += 1000;      // the record lost the attempt count
+                st = solve_lat<false>(r, ob, n_acc, n_rej);
+                s = r;
+            }
+            counters[1] += n_acc;
+            counters[2] += n_rej;
+            counters[3] += (st == FAILED);
+            steps[p * n_ex + e] = (int32_t)(n_acc + n_rej);
+            total += (st == DONE) ? c0 - s.ssr * inv_den : -INFINITY;
+        }
+        lk[p] = total;
+    }
+}
+
 extern "C" void twin_predict(const double* theta, int64_t n, const double* t, const double* S0, int n_ex,
                              int n_t, double* pred) {
     using namespace mmsolve;

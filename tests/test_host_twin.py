@@ -41,6 +41,17 @@ def twin(tmp_path_factory):
                          C.c_int(n_ex), C.c_int(n_t), C.c_void_p(out.ctypes.data))
         return out
 
+    def loglik_parked(theta, t, P, S0, budget):
+        th = np.ascontiguousarray(theta, dtype=np.float64)
+        t, P, S0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, P, S0))
+        n, (n_ex, n_t) = len(th), t.shape
+        lk, cnt, steps = np.empty(n), np.zeros(4, dtype=np.int64), np.zeros((n, n_ex), dtype=np.int32)
+        lib.twin_loglik_parked(C.c_void_p(th.ctypes.data), C.c_int64(n), C.c_void_p(t.ctypes.data), C.c_void_p(P.ctypes.data),
+                               C.c_void_p(S0.ctypes.data), C.c_int(n_ex), C.c_int(n_t), C.c_int(budget),
+                               C.c_void_p(lk.ctypes.data), C.c_void_p(cnt.ctypes.data), C.c_void_p(steps.ctypes.data))
+        return lk, cnt, steps
+
+    loglik.parked = loglik_parked
     return loglik, predict
 
 
@@ -91,6 +102,28 @@ def test_tail_kernel_spelling_takes_scipys_steps(twin, golden):
     assert steps.max() == 83133
     assert np.max(np.abs(got - want) / np.abs(want)) < 1e-7         # 6e-9 observed on the stiffest solves; bar 1e-5
     assert np.max(np.abs(got - std) / np.abs(std)) < 1e-11          # the two spellings: rounding only
+
+
+@pytest.mark.parametrize("budget", [1, 7, 64, 512])
+def test_parked_solves_resume_where_they_stopped(twin, golden, budget):
+    """The hand-over between the two kernels (mm_bulk_kernel parks a solve that exceeds its budget, mm_tail_kernel
+    resumes it: mmsolve::park_store / park_load): whatever the budget, a solve takes the steps of the C twin of scipy's
+    RK45 - before, across and after the hand-over - and the log-likelihood moves by rounding only."""
+    from oracle import cmm
+    loglik, _ = twin
+    d = (golden["data_t"], golden["data_P"], golden["data_S0"])
+    th = np.concatenate([np.random.RandomState(2).uniform(0, 10, (4096, 3)), golden["sweeps_in"][33][:64],
+                         [[7.30644405, 4.35543917e-04, 1.0]]])
+    th[:, 2] = np.maximum(th[:, 2], 1e-3)
+    base, _, steps0 = loglik(th, *d)
+    got, cnt, steps = loglik.parked(th, *d, budget)
+    want, info = cmm.loglik_progress(th, *d, want_steps=True)
+    assert cnt[3] == 0
+    assert np.array_equal(steps, info["steps"]) and np.array_equal(steps, steps0)
+    assert cnt[1] == info["accepted"] and cnt[2] == info["rejected"]
+    assert (steps > budget).any()                                    # some solves were handed over
+    assert np.max(np.abs(got - base) / np.abs(base)) < 1e-11
+    assert np.max(np.abs(got - want) / np.abs(want)) < 1e-7
 
 
 def test_device_predictions_match_reference(twin, golden):
